@@ -1,0 +1,333 @@
+"""Restatement of the R side of AM() (the caller of the hot path).  TEST INFRASTRUCTURE ONLY.
+
+R is not installed in this image, so the forward-selection driver that surrounds the three
+hot-path exports is restated in numpy so that a full multi-locus search can be run with EITHER
+the CPU oracle or the GPU library plugged in as `backend` (an object exposing
+calculateMMt_rcpp / calculate_a_and_vara_rcpp / extract_geno_rcpp with the reference's
+argument lists).  In a real deployment none of this exists: the untouched R package calls the
+Rcpp exports.  Paths below are relative to /root/reference/MyPackage/Eagle/R/.
+
+Single trait, no Z matrix (Z never reaches find_qtl in this snapshot: AM.R:450-452,
+find_qtl.R:1-2, calculateP.R:22-25).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from scipy.linalg import lapack
+from scipy.special import gammaln
+
+NA = float("nan")
+
+
+# ----------------------------------------------------------------------------- base-R helpers
+def r_eigen_sym(A):
+    """eigen(A, symmetric=TRUE): eigenvalues in DEcreasing order."""
+    w, v = np.linalg.eigh(A)
+    return w[::-1].copy(), v[:, ::-1].copy()
+
+
+def r_chol2inv_chol(A):
+    """chol2inv(chol(A)) == LAPACK dpotrf + dpotri."""
+    c, info = lapack.dpotrf(np.asfortranarray(A), lower=0)
+    if info != 0:
+        raise np.linalg.LinAlgError(f"chol: leading minor of order {info} is not positive definite")
+    inv, info = lapack.dpotri(c, lower=0)
+    if info != 0:
+        raise np.linalg.LinAlgError("dpotri failed")
+    iu = np.triu_indices_from(inv, 1)
+    inv[(iu[1], iu[0])] = inv[iu]
+    return inv
+
+
+def r_uniroot(f, lower, upper, tol=np.finfo(float).eps ** 0.25, maxiter=1000):
+    """uniroot() -> R_zeroin2: the Brent/Dekker 'zeroin' of Forsythe, Malcolm & Moler
+    (published algorithm, netlib zeroin.c), default tol = .Machine$double.eps^0.25."""
+    a, b = float(lower), float(upper)
+    fa, fb = f(a), f(b)
+    c, fc = a, fa
+    EPS = np.finfo(float).eps
+    if fa == 0.0:
+        return a
+    if fb == 0.0:
+        return b
+    it = maxiter + 1
+    while it > 0:
+        it -= 1
+        prev_step = b - a
+        if abs(fc) < abs(fb):
+            a, b, c = b, c, b
+            fa, fb, fc = fb, fc, fb
+        tol_act = 2 * EPS * abs(b) + tol / 2
+        new_step = (c - b) / 2
+        if abs(new_step) <= tol_act or fb == 0.0:
+            return b
+        if abs(prev_step) >= tol_act and abs(fa) > abs(fb):
+            cb = c - b
+            if a == c:
+                t1 = fb / fa
+                p = cb * t1
+                q = 1.0 - t1
+            else:
+                q = fa / fc
+                t1 = fb / fc
+                t2 = fb / fa
+                p = t2 * (cb * q * (q - t1) - (b - a) * (t1 - 1.0))
+                q = (q - 1.0) * (t1 - 1.0) * (t2 - 1.0)
+            if p > 0:
+                q = -q
+            else:
+                p = -p
+            if p < (0.75 * cb * q - abs(tol_act * q) / 2) and p < abs(prev_step * q / 2):
+                new_step = p / q
+        if abs(new_step) < tol_act:
+            new_step = tol_act if new_step > 0 else -tol_act
+        a, fa = b, fb
+        b += new_step
+        fb = f(b)
+        if (fb > 0 and fc > 0) or (fb < 0 and fc < 0):
+            c, fc = a, fa
+    return b
+
+
+def lchoose(n, k):
+    return gammaln(n + 1) - gammaln(k + 1) - gammaln(n - k + 1)
+
+
+# ----------------------------------------------------------------------------- EMMA (emma_*.R)
+def emma_eigen_R_wo_Z(K, X):
+    """emma_eigen_R_wo_Z.R:4-20"""
+    n, q = X.shape
+    dn = np.eye(n)
+    S = dn - X @ np.linalg.inv(X.T @ X) @ X.T
+    w, v = r_eigen_sym(S @ (K + dn) @ S)
+    return w[: n - q] - 1.0, v[:, : n - q]
+
+
+def _grid_opt(dLL, logdelta, llim, ulim, esp, LLfun, dLLfun):
+    """emma_REMLE.R:54-76 / emma_MLE.R:34-56 (identical control flow)."""
+    m = len(logdelta)
+    opt_ld, opt_ll = [], []
+    if dLL[0] < esp:
+        opt_ld.append(llim)
+        opt_ll.append(LLfun(llim))
+    if dLL[m - 2] > 0 - esp:  # R: dLL[m - 1], 1-based
+        opt_ld.append(ulim)
+        opt_ll.append(LLfun(ulim))
+    for i in range(m - 1):
+        if dLL[i] * dLL[i + 1] < 0 - esp * esp and dLL[i] > 0 and dLL[i + 1] < 0:
+            r = r_uniroot(dLLfun, logdelta[i], logdelta[i + 1])
+            opt_ld.append(r)
+            opt_ll.append(LLfun(r))
+    k = int(np.argmax(opt_ll))  # which.max: first maximum
+    return math.exp(opt_ld[k]), opt_ll[k]
+
+
+def emma_REMLE(y, X, K, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
+    """emma_REMLE.R:27-131 (Z = NULL branch)."""
+    n, q = len(y), X.shape[1]
+    if np.linalg.det(X.T @ X) == 0:
+        return dict(REML=0.0, delta=0.0, ve=0.0, vg=0.0)
+    lam, U = emma_eigen_R_wo_Z(K, X)
+    etas = U.T @ y
+    etasq = etas * etas
+    logdelta = np.arange(ngrids + 1) / ngrids * (ulim - llim) + llim
+    delta = np.exp(logdelta)
+    Lambdas = lam[:, None] + delta[None, :]
+    Etasq = etasq[:, None]
+    dLL = 0.5 * delta * ((n - q) * (Etasq / (Lambdas * Lambdas)).sum(0) / (Etasq / Lambdas).sum(0)
+                         - (1.0 / Lambdas).sum(0))
+
+    def LLfun(ld):  # emma.delta.REML.LL.wo.Z  :144-150
+        nq = len(etas)
+        d = math.exp(ld)
+        return 0.5 * (nq * (math.log(nq / (2 * math.pi)) - 1 - math.log((etasq / (lam + d)).sum()))
+                      - np.log(lam + d).sum())
+
+    def dLLfun(ld):  # emma.delta.REML.dLL.wo.Z :134-142
+        nq = len(etas)
+        d = math.exp(ld)
+        ldel = lam + d
+        return 0.5 * (nq * (etasq / (ldel * ldel)).sum() / (etasq / ldel).sum() - (1.0 / ldel).sum())
+
+    maxdelta, maxLL = _grid_opt(dLL, logdelta, llim, ulim, esp, LLfun, dLLfun)
+    maxva = (etasq / (lam + maxdelta)).sum() / (n - q)
+    return dict(REML=maxLL, delta=maxdelta, ve=maxva * maxdelta, vg=maxva)
+
+
+def emma_MLE(y, X, K, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
+    """emma_MLE.R:2-117 (Z = NULL branch)."""
+    n, q = len(y), X.shape[1]
+    if np.linalg.det(X.T @ X) == 0:
+        return dict(ML=0.0, delta=0.0, ve=0.0, vg=0.0)
+    xi, _ = r_eigen_sym(K)  # emma_eigen_L_wo_Z.R:9
+    lam, U = emma_eigen_R_wo_Z(K, X)
+    etas = U.T @ y
+    etasq = etas * etas
+    logdelta = np.arange(ngrids + 1) / ngrids * (ulim - llim) + llim
+    delta = np.exp(logdelta)
+    Lambdas = lam[:, None] + delta[None, :]
+    Xis = xi[:, None] + delta[None, :]
+    Etasq = etasq[:, None]
+    dLL = 0.5 * delta * (n * (Etasq / (Lambdas * Lambdas)).sum(0) / (Etasq / Lambdas).sum(0)
+                         - (1.0 / Xis).sum(0))
+
+    def LLfun(ld):  # emma_delta_ML_LL_wo_Z.R:2-8
+        nn = len(xi)
+        d = math.exp(ld)
+        return 0.5 * (nn * (math.log(nn / (2 * math.pi)) - 1 - math.log((etasq / (lam + d)).sum()))
+                      - np.log(xi + d).sum())
+
+    def dLLfun(ld):  # emma_misc.R:10-18
+        nn = len(xi)
+        d = math.exp(ld)
+        ldel = lam + d
+        return 0.5 * (nn * (etasq / (ldel * ldel)).sum() / (etasq / ldel).sum() - (1.0 / (xi + d)).sum())
+
+    maxdelta, maxLL = _grid_opt(dLL, logdelta, llim, ulim, esp, LLfun, dLLfun)
+    maxva = (etasq / (lam + maxdelta)).sum() / n
+    return dict(ML=maxLL, delta=maxdelta, ve=maxva * maxdelta, vg=maxva)
+
+
+# ----------------------------------------------------------------------------- n x n algebra
+def calculateH(MMt, varE, varG):
+    """calculateH.R:36"""
+    return varE * np.eye(MMt.shape[0]) + varG * MMt
+
+
+def calculateP(H, X):
+    """calculateP.R:27-28"""
+    Hinv = r_chol2inv_chol(H)
+    return Hinv - Hinv @ X @ np.linalg.inv(X.T @ Hinv @ X) @ X.T @ Hinv
+
+
+def is_positive_definite(A, tol=1e-8):
+    """matrixcalc::is.positive.definite (third-party, un-vendored; published behaviour):
+    exact symmetry required, eigenvalues with |ev| < tol set to 0, all must be > 0."""
+    if not np.array_equal(A, A.T):
+        raise ValueError("argument x is not a symmetric matrix")
+    ev = np.linalg.eigvalsh(A)
+    ev[np.abs(ev) < tol] = 0.0
+    return bool(np.all(ev > 0))
+
+
+def calculateMMt_sqrt_and_sqrtinv(MMt):
+    """calculateMMt_sqrt_and_sqrtinv.R:15-31"""
+    if not is_positive_definite(MMt):
+        raise ValueError("M %*% t(M) is not positive definite")
+    w, v = r_eigen_sym(MMt)
+    sq = v @ np.diag(np.sqrt(w)) @ v.T
+    return sq, r_chol2inv_chol(sq)
+
+
+def calculate_reduced_a(varG, P, MMtsqrt, y):
+    """calculate_reduced_a.R:31  --  `varG * MMtsqrt %*% P %*% y` is left-associative."""
+    return ((varG * MMtsqrt) @ P) @ y
+
+
+def calculate_reduced_vara(X, varE, varG, invMMt, MMtsqrt):
+    """calculate_reduced_vara.R:21-35"""
+    n = invMMt.shape[0]
+    Ze = MMtsqrt
+    R1 = np.linalg.inv(varE * np.eye(n))
+    G1 = np.linalg.inv(varG * np.eye(n))
+    A = X.T @ R1 @ X
+    B = X.T @ R1 @ Ze
+    Cc = Ze.T @ R1 @ X
+    D = Ze.T @ R1 @ Ze + G1
+    D1 = np.linalg.inv(D)
+    return varG * np.eye(n) - (D1 + D1 @ Cc @ np.linalg.inv(A - B @ D1 @ Cc) @ B @ D1)
+
+
+# ----------------------------------------------------------------------------- the hot-path callers
+def calcMMt(backend, geno, availmemGb, ncpu, selected_loci):
+    """calcMMt.R:5-13 + calculateMMt.R:24-27"""
+    sel = np.asarray(selected_loci, dtype=np.float64)
+    if not np.any(np.isnan(sel)):
+        sel = sel - 1
+    MMt = backend.calculateMMt_rcpp(geno["asciifileM"], availmemGb, ncpu, sel, geno["dim_of_ascii_M"], True, None)
+    MMt = np.asarray(MMt)
+    return MMt / MMt.max() + np.diag(np.full(MMt.shape[0], 0.95))
+
+
+def scan_inputs(MMt, invMMt, X, y, ve, vg):
+    """find_qtl.R:5-45: everything the scan export consumes (S = K^-1/2, V, a_hat)."""
+    H = calculateH(MMt, ve, vg)
+    P = calculateP(H, X)
+    sq, sqinv = calculateMMt_sqrt_and_sqrtinv(MMt)
+    hat_a = calculate_reduced_a(vg, P, sq, y)
+    var_hat_a = calculate_reduced_vara(X, ve, vg, invMMt, sq)
+    return sqinv, var_hat_a, hat_a
+
+
+def pick_locus(a, vara):
+    """find_qtl.R:71-83: tsq = a^2/vara; first index of max (NaN ignored); returns 1-based index."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tsq = (np.asarray(a).reshape(-1) ** 2) / np.asarray(vara).reshape(-1)
+    mx = np.nanmax(tsq)
+    return int(np.flatnonzero(tsq == mx)[0]) + 1, tsq
+
+
+def find_qtl(backend, geno, availmemGb, selected_loci, MMt, invMMt, ve, vg, X, y, trace=None):
+    S, V, hat_a = scan_inputs(MMt, invMMt, X, y, ve, vg)
+    n, L = geno["dim_of_ascii_M"]
+    sel = np.asarray(selected_loci, dtype=np.float64)
+    if not np.any(np.isnan(sel)):  # calculate_a_and_vara.R:23 (never true under AM(): AM.R:260)
+        sel = sel - 1
+    res = backend.calculate_a_and_vara_rcpp(geno["asciifileMt"], sel, S, V, availmemGb, (L, n), hat_a, True, None)
+    idx, tsq = pick_locus(res["a"], res["vara"])
+    if trace is not None:
+        trace.append(dict(S=S, V=V, hat_a=hat_a, a=np.asarray(res["a"]).reshape(-1).copy(),
+                          vara=np.asarray(res["vara"]).reshape(-1).copy(), tsq=tsq, picked=idx))
+    return idx
+
+
+def calc_extBIC(y, X, MMt, L):
+    """calc_extBIC.R:6-9"""
+    res_p = emma_MLE(y, X, MMt, llim=-100.0, ulim=100.0)
+    BIC = -2 * res_p["ML"] + (X.shape[1] + 1) * math.log(len(y))
+    return BIC + 2 * lchoose(L, X.shape[1] - 1)
+
+
+def AM(backend, geno, y, X0=None, availmemGb=8, ncpu=1, maxit=20, keep_trace=False):
+    """AM.R:260, 395-504.  geno = dict(asciifileM, asciifileMt, dim_of_ascii_M=(n, L));
+    y = trait vector (no NAs); X0 = design matrix before marker effects (default: intercept).
+    Returns dict(selected=[1-based loci], extBIC=[...], trace=[per-iteration scan inputs/outputs])."""
+    y = np.asarray(y, dtype=np.float64)
+    n, L = geno["dim_of_ascii_M"]
+    X = np.ones((n, 1)) if X0 is None else np.asarray(X0, dtype=np.float64)
+    selected_loci = [NA]      # AM.R:260
+    new_selected_locus = NA   # AM.R:261
+    extBIC = []
+    trace = [] if keep_trace else None
+    itnum = 1
+    cont = True
+    MMt = invMMt = None
+    while cont:
+        if not math.isnan(new_selected_locus):  # constructX.R:11-20
+            col = backend.extract_geno_rcpp(geno["asciifileM"], availmemGb, int(new_selected_locus) - 1, (n, L))
+            X = np.column_stack([X, np.asarray(col, dtype=np.float64)])
+        if itnum == 1:  # AM.R:414-423
+            MMt = calcMMt(backend, geno, availmemGb, ncpu, selected_loci)
+            invMMt = r_chol2inv_chol(MMt)
+        vc = emma_REMLE(y, X, MMt)                      # AM.R:428
+        extBIC.append(calc_extBIC(y, X, MMt, L))         # AM.R:436
+        if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) == len(extBIC) - 1:  # AM.R:448
+            new_selected_locus = find_qtl(backend, geno, availmemGb, selected_loci, MMt, invMMt,
+                                          vc["ve"], vc["vg"], X, y, trace)
+            selected_loci.append(new_selected_locus)     # AM.R:455
+        else:
+            cont = False
+        itnum += 1
+        if itnum > maxit:                                # AM.R:465
+            cont = False
+    if itnum > maxit:                                    # AM.R:477-481
+        final = selected_loci
+    elif len(selected_loci) > 1:                         # AM.R:485-492
+        final = selected_loci[:-1]
+    else:
+        final = selected_loci
+    return dict(selected=[int(s) for s in final if not math.isnan(s)],
+                all_picked=[int(s) for s in selected_loci if not math.isnan(s)],
+                extBIC=extBIC, trace=trace, vc=vc)

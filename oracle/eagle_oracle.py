@@ -1,0 +1,148 @@
+"""ctypes front-end of the CPU ORACLE (oracle/eagle_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Function names, argument order and meaning follow the reference's Rcpp exports
+(/root/reference/MyPackage/Eagle/src/RcppExports.cpp:9, 37, 54, 73, 129) so the parity
+tests can call oracle and GPU path with the same arguments.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libeagle_oracle.so")
+
+#: R's NA_real_ (a NaN with low word 1954, see R_IsNA); selected_loci = [NA] means "none".
+NA_REAL = struct.unpack("<d", struct.pack("<Q", 0x7FF00000000007A2))[0]
+
+ERRORS = {1: "ERROR: Could not open ", 2: "short line / truncated file", 3: "allocation failed",
+          4: "soft failure (reference returns zeros)", 5: "block size 0 (reference divides by zero)"}
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "eagle_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        dp, lp, ip = C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_int)
+        L.eo_ReadBlock.argtypes = [C.c_char_p, C.c_long, C.c_long, C.c_long, dp]
+        L.eo_calculateMMt.argtypes = [C.c_char_p, C.c_double, C.c_int, dp, C.c_long, lp, dp, ip]
+        L.eo_calculate_a_and_vara.argtypes = [C.c_char_p, dp, C.c_long, dp, dp, C.c_double, lp, dp, dp, dp, ip]
+        L.eo_calculate_reduced_a.argtypes = [C.c_char_p, C.c_double, dp, dp, C.c_double, lp, dp, C.c_long, dp]
+        L.eo_extract_geno.argtypes = [C.c_char_p, C.c_double, C.c_long, lp, ip, ip]
+        L.eo_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _check(rc, what):
+    if rc:
+        raise OracleError(f"{what}: {ERRORS.get(rc, rc)}")
+
+
+def _sel(selected_loci):
+    s = np.atleast_1d(np.asarray(selected_loci, dtype=np.float64)).copy()
+    return s
+
+
+def _dims(dims):
+    return (C.c_long * 2)(int(dims[0]), int(dims[1]))
+
+
+def ReadBlock(asciifname, start_row, numcols, numrows_in_block):
+    """ReadBlock.cpp:16-68 -> (numrows x numcols) float64, column-major (Fortran order)."""
+    M = np.empty((numrows_in_block, numcols), dtype=np.float64, order="F")
+    _check(lib().eo_ReadBlock(os.fsencode(asciifname), start_row, numcols, numrows_in_block, _d(M)),
+           f"ReadBlock({asciifname})")
+    return M
+
+
+def calculateMMt_rcpp(f_name_ascii, max_memory_in_Gbytes, num_cores, selected_loci, dims,
+                      quiet=True, message=None, return_branch=False):
+    """calculateMMt_rcpp.cpp:19-185.  dims = (n, L)."""
+    n = int(dims[0])
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    s = _sel(selected_loci)
+    br = C.c_int(-1)
+    _check(lib().eo_calculateMMt(os.fsencode(f_name_ascii), float(max_memory_in_Gbytes), int(num_cores),
+                                 _d(s), len(s), _dims(dims), _d(out), C.byref(br)), "calculateMMt_rcpp")
+    return (out, br.value) if return_branch else out
+
+
+def calculate_a_and_vara_rcpp(f_name_ascii, selected_loci, inv_MMt_sqrt, dim_reduced_vara,
+                              max_memory_in_Gbytes, dims, a, quiet=True, message=None,
+                              return_branch=False):
+    """calculate_a_and_vara_rcpp.cpp:22-241.  dims = (L, n) = dims of Mt.  -> dict(a, vara) of L x 1."""
+    Lm, n = int(dims[0]), int(dims[1])
+    S = np.asfortranarray(inv_MMt_sqrt, dtype=np.float64)
+    V = np.asfortranarray(dim_reduced_vara, dtype=np.float64)
+    av = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    assert S.shape == (n, n) and V.shape == (n, n) and av.shape == (n,)
+    oa = np.empty(Lm, dtype=np.float64)
+    ov = np.empty(Lm, dtype=np.float64)
+    s = _sel(selected_loci)
+    br = C.c_int(-1)
+    rc = lib().eo_calculate_a_and_vara(os.fsencode(f_name_ascii), _d(s), len(s), _d(S), _d(V),
+                                       float(max_memory_in_Gbytes), _dims(dims), _d(av), _d(oa), _d(ov),
+                                       C.byref(br))
+    if rc == 4:  # :141-142  List(a=0, vara=0)
+        res = {"a": 0, "vara": 0}
+    else:
+        _check(rc, "calculate_a_and_vara_rcpp")
+        res = {"a": oa.reshape(Lm, 1), "vara": ov.reshape(Lm, 1)}
+    return (res, br.value) if return_branch else res
+
+
+def calculate_reduced_a_rcpp(f_name_ascii, varG, P, y, max_memory_in_Gbytes, dims, selected_loci,
+                             quiet=True, message=None):
+    """calculate_reduced_a_rcpp.cpp:20-171.  dims = (n, L) = dims of M (file is Mt.ascii)."""
+    n, Lm = int(dims[0]), int(dims[1])
+    Pm = np.asfortranarray(P, dtype=np.float64)
+    yv = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    out = np.empty(Lm, dtype=np.float64)
+    s = _sel(selected_loci)
+    rc = lib().eo_calculate_reduced_a(os.fsencode(f_name_ascii), float(varG), _d(Pm), _d(yv),
+                                      float(max_memory_in_Gbytes), _dims(dims), _d(s), len(s), _d(out))
+    if rc == 4:
+        return np.zeros((1, 1))
+    _check(rc, "calculate_reduced_a_rcpp")
+    return out.reshape(Lm, 1)
+
+
+def extract_geno_rcpp(f_name_ascii, max_memory_in_Gbytes, selected_locus, dims, return_branch=False):
+    """extract_geno_rcpp.cpp:17-86.  dims = (n, L); selected_locus 0-based.  -> int32[n]."""
+    n = int(dims[0])
+    out = np.empty(n, dtype=np.int32)
+    br = C.c_int(-1)
+    _check(lib().eo_extract_geno(os.fsencode(f_name_ascii), float(max_memory_in_Gbytes), int(selected_locus),
+                                 _dims(dims), out.ctypes.data_as(C.POINTER(C.c_int)), C.byref(br)),
+           "extract_geno_rcpp")
+    return (out, br.value) if return_branch else out
+
+
+def num_threads() -> int:
+    return int(lib().eo_num_threads())
