@@ -1,0 +1,102 @@
+"""ctypes binding of libeaglegpu.so (C ABI declared in include/eagle_gpu.h).
+
+The shared library is built in-tree by `__graft_entry__.build()` / `make -C eagleeverything_b200/csrc`.
+There is no fallback of any kind: if the library is missing, or no B200 is visible when a compute
+entry point is called, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libeaglegpu.so")
+
+EG_OK, EG_ERR_CUDA, EG_ERR_OPEN, EG_ERR_FORMAT, EG_ERR_ARG, EG_ERR_ALLOC = range(6)
+
+
+class EagleGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+MESSAGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+
+_i64 = C.c_int64
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/eagle_gpu.h declares
+SIGNATURES = {
+    "eg_init": (C.c_int, [C.c_int]),
+    "eg_shutdown": (C.c_int, []),
+    "eg_last_error": (C.c_char_p, []),
+    "eg_abi_version": (C.c_int, []),
+    "eg_device_count": (C.c_int, []),
+    "eg_cache_clear": (None, []),
+    "eg_ReadBlock": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _dp]),
+    "eg_calculateMMt_rcpp": (C.c_int, [C.c_char_p, C.c_double, C.c_int, _dp, _i64, _lp, C.c_int, MESSAGE_FN, _vp, _dp]),
+    "eg_calculate_a_and_vara_rcpp": (C.c_int, [C.c_char_p, _dp, _i64, _dp, _dp, C.c_double, _lp, _dp, C.c_int,
+                                               MESSAGE_FN, _vp, _dp, _dp]),
+    "eg_calculate_reduced_a_rcpp": (C.c_int, [C.c_char_p, C.c_double, _dp, _dp, C.c_double, _lp, _dp, _i64, C.c_int,
+                                              MESSAGE_FN, _vp, _dp]),
+    "eg_extract_geno_rcpp": (C.c_int, [C.c_char_p, C.c_double, _i64, _lp, _ip]),
+    "eg_store_from_host_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
+    "eg_store_from_host_ascii_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
+    "eg_store_from_file": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
+    "eg_store_transpose": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "eg_store_free": (C.c_int, [_vp]),
+    "eg_store_info": (C.c_int, [_vp, _lp, _lp, _lp, C.POINTER(_vp)]),
+    "eg_store_mmt": (C.c_int, [_vp, _lp, _i64, _dp]),
+    "eg_store_a_and_vara": (C.c_int, [_vp, _lp, _i64, _dp, _dp, _dp, _dp, _dp]),
+    "eg_store_extract_col": (C.c_int, [_vp, _i64, _ip]),
+    "eg_dev_decode": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "eg_dev_transpose_i8": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "eg_dev_syrk_i8": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "eg_dev_syrk_zero_cols": (C.c_int, [_vp, _i64, _i64, _lp, _i64, _vp, _i64, _vp]),
+    "eg_dev_mmt_finalize": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "eg_scan_wp_elems": (_i64, [_i64]),
+    "eg_dev_scan_prepare": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "eg_dev_scan": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _lp, _i64, _vp, _vp, _vp]),
+    "eg_dev_argmax_tsq": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "eg_dev_gemv_i8": (C.c_int, [_vp, _i64, _i64, _i64, _vp, C.c_double, _vp, _vp]),
+    "eg_dev_extract_col": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "eg_dev_synth_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, C.c_uint64, _vp]),
+    "eg_last_timing": (C.c_int, [_dp, C.c_int]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libeaglegpu.so and attach signatures.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C eagleeverything_b200/csrc`).  There is no CPU fallback.")
+        lib = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != EG_OK:
+        msg = load().eg_last_error()
+        raise EagleGpuError(rc, (msg or b"").decode("utf-8", "replace") or f"libeaglegpu error {rc}")
+
+
+def require_gpu():
+    """Fail loudly when the CUDA path cannot run (no silent fallback anywhere in this package)."""
+    lib = load()
+    if lib.eg_device_count() <= 0:
+        raise EagleGpuError(EG_ERR_CUDA, "no CUDA device visible: the Eagle hot path has no CPU fallback")
+    return lib

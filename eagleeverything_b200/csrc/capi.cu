@@ -1,0 +1,713 @@
+// Host side of libeaglegpu.so: context, resident genotype stores + path cache, and the five
+// reference-facing entry points declared in include/eagle_gpu.h.  No CPU compute path exists
+// here: every entry point either runs the CUDA kernels or fails with an error code.
+#include <cublas_v2.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct eg_store {
+    int8_t* d = nullptr;
+    int64_t rows = 0, cols = 0, pitch = 0;
+};
+
+namespace eg {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return EG_OK;
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return set_error(EG_ERR_ALLOC, "CUDA out of memory in %s", what);
+    }
+    return set_error(EG_ERR_CUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+int check_launch(const char* kernel) { return check_cuda(cudaGetLastError(), kernel); }
+
+// ------------------------------------------------------------------ context
+struct CacheEntry {
+    std::string key;
+    eg_store* store;
+    uint64_t stamp;
+};
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cublasHandle_t cublas = nullptr;
+    std::vector<CacheEntry> cache;
+    uint64_t clock = 0;
+    int32_t* d_err = nullptr;
+    double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+static Context g_ctx;
+
+int num_sms() {
+    if (g_ctx.sms > 0) return g_ctx.sms;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        return sms;
+    return 148;
+}
+
+static int ensure_init() {
+    if (g_ctx.ready) return check_cuda(cudaSetDevice(g_ctx.device), "cudaSetDevice");
+    const char* env = getenv("EAGLE_GPU_DEVICE");
+    return eg_init(env ? atoi(env) : 0);
+}
+
+void syrk_release_cache();
+int launch_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp,
+                const int64_t* d_zero_rows, int n_zero, double* d_a, double* d_vara, cudaStream_t st);
+
+// RAII device buffer
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes, const char* what) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return set_error(EG_ERR_ALLOC, "out of device memory allocating %zu bytes for %s", bytes, what);
+        }
+        return EG_OK;
+    }
+    template <class T>
+    T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Timer {
+    cudaEvent_t a, b;
+    cudaStream_t st;
+    Timer(cudaStream_t s) : st(s) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    double stop() {
+        float ms = 0;
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+    ~Timer() {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+};
+
+static bool is_na(double x) { return std::isnan(x); }  // NA_real_ is a NaN; see header
+
+// selected_loci (doubles, NA sentinel) -> validated 0-based index list
+static int parse_selected(const double* sel, int64_t nsel, int64_t limit, std::vector<int64_t>& out, const char* who) {
+    out.clear();
+    if (!sel || nsel <= 0 || is_na(sel[0])) return EG_OK;
+    for (int64_t i = 0; i < nsel; i++) {
+        if (is_na(sel[i]) || sel[i] < 0 || sel[i] >= (double)limit)
+            return set_error(EG_ERR_ARG, "%s: selected_loci[%lld] = %g is outside [0, %lld)", who, (long long)i,
+                             sel[i], (long long)limit);
+        out.push_back((int64_t)sel[i]);
+    }
+    return EG_OK;
+}
+
+// ------------------------------------------------------------------ stores
+static int store_alloc(int64_t rows, int64_t cols, eg_store** out) {
+    eg_store* s = new eg_store();
+    s->rows = rows;
+    s->cols = cols;
+    s->pitch = store_pitch(cols);
+    cudaError_t e = cudaMalloc(&s->d, (size_t)rows * (size_t)s->pitch + 256);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        // evict cached stores (least recently used first) and retry once per eviction
+        while (e != cudaSuccess && !g_ctx.cache.empty()) {
+            size_t lru = 0;
+            for (size_t i = 1; i < g_ctx.cache.size(); i++)
+                if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
+            cudaFree(g_ctx.cache[lru].store->d);
+            delete g_ctx.cache[lru].store;
+            g_ctx.cache.erase(g_ctx.cache.begin() + lru);
+            e = cudaMalloc(&s->d, (size_t)rows * (size_t)s->pitch + 256);
+            if (e != cudaSuccess) cudaGetLastError();
+        }
+        if (e != cudaSuccess) {
+            delete s;
+            return set_error(EG_ERR_ALLOC, "out of device memory for a %lld x %lld genotype store", (long long)rows,
+                             (long long)cols);
+        }
+    }
+    *out = s;
+    return EG_OK;
+}
+
+// Host ASCII image -> store.  Rows [row0,row1), columns [col0,col1) of an image with `cols_total`
+// characters per line.  Row blocks are staged through two device buffers so that the H2D copy of
+// block k+1 overlaps the decode of block k.
+static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t row0, int64_t row1, int64_t col0,
+                            int64_t col1, eg_store** out) {
+    EG_TRY(ensure_init());
+    const int64_t rows = row1 - row0, w = col1 - col0, src_pitch_host = cols_total + 1;
+    if (!image || rows <= 0 || w <= 0 || col0 < 0 || col1 > cols_total || row0 < 0)
+        return set_error(EG_ERR_ARG, "genotype store: bad image range");
+    eg_store* s = nullptr;
+    EG_TRY(store_alloc(rows, w, &s));
+    const bool full_width = (w == cols_total);
+    const int64_t dev_pitch = full_width ? src_pitch_host : round_up(w, 16);
+    int64_t block_rows = (int64_t)(256LL << 20) / dev_pitch;
+    if (block_rows < 1) block_rows = 1;
+    if (block_rows > rows) block_rows = rows;
+    DevBuf stg[2];
+    cudaEvent_t copied[2], decoded[2];
+    int rc = EG_OK;
+    for (int i = 0; i < 2 && rc == EG_OK; i++) rc = stg[i].alloc((size_t)block_rows * dev_pitch + 64, "ASCII staging");
+    if (rc != EG_OK) {
+        eg_store_free(s);
+        return rc;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&decoded[i], cudaEventDisableTiming);
+    }
+    cudaMemsetAsync(g_ctx.d_err, 0, 4 * sizeof(int32_t), g_ctx.stream);
+    double t_h2d = 0, t_dec = 0;
+    Timer total(g_ctx.stream);
+    int k = 0;
+    for (int64_t r = 0; r < rows && rc == EG_OK; r += block_rows, k++) {
+        const int b = k & 1;
+        const int64_t nr = (r + block_rows <= rows) ? block_rows : rows - r;
+        if (k >= 2) cudaStreamWaitEvent(g_ctx.copy_stream, decoded[b], 0);  // staging buffer free again
+        const uint8_t* src = image + (row0 + r) * src_pitch_host + col0;
+        cudaError_t e;
+        if (full_width) {
+            // the very last line of a file may lack its '\n': never read past row1*pitch - 1
+            size_t bytes = (size_t)nr * src_pitch_host;
+            if (r + nr == rows) bytes -= 1;
+            e = cudaMemcpyAsync(stg[b].p, src, bytes, cudaMemcpyHostToDevice, g_ctx.copy_stream);
+        } else {
+            e = cudaMemcpy2DAsync(stg[b].p, dev_pitch, src, src_pitch_host, w, nr, cudaMemcpyHostToDevice,
+                                  g_ctx.copy_stream);
+        }
+        rc = check_cuda(e, "H2D copy of the ASCII genotype image");
+        if (rc != EG_OK) break;
+        cudaEventRecord(copied[b], g_ctx.copy_stream);
+        cudaStreamWaitEvent(g_ctx.stream, copied[b], 0);
+        rc = eg_dev_decode(stg[b].as<uint8_t>(), dev_pitch, (int64_t)block_rows * dev_pitch + 64, nr, w,
+                           s->d + r * s->pitch, s->pitch, g_ctx.d_err, g_ctx.stream);
+        cudaEventRecord(decoded[b], g_ctx.stream);
+    }
+    int32_t h_err[4] = {0, 0, 0, 0};
+    if (rc == EG_OK)
+        rc = check_cuda(cudaMemcpyAsync(h_err, g_ctx.d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream),
+                        "decode status D2H");
+    if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "genotype decode");
+    cudaStreamSynchronize(g_ctx.copy_stream);
+    t_h2d = total.stop();
+    (void)t_dec;
+    g_ctx.timing[0] = t_h2d;  // H2D + decode (overlapped)
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(copied[i]);
+        cudaEventDestroy(decoded[i]);
+    }
+    if (rc == EG_OK && h_err[0]) {
+        const int64_t brow = ((int64_t)h_err[3] << 31) | (int64_t)h_err[1];
+        rc = set_error(EG_ERR_FORMAT,
+                       "genotype file is not in no-space ASCII format: byte outside {'0','1','2'} near row %lld, column %lld "
+                       "(wrong dims / line pitch?)",
+                       (long long)(row0 + brow), (long long)(col0 + h_err[2]));
+    }
+    if (rc != EG_OK) {
+        eg_store_free(s);
+        return rc;
+    }
+    *out = s;
+    return EG_OK;
+}
+
+struct MappedFile {
+    int fd = -1;
+    const uint8_t* p = nullptr;
+    size_t size = 0;
+    struct stat st;
+    ~MappedFile() {
+        if (p) munmap(const_cast<uint8_t*>(p), size);
+        if (fd >= 0) close(fd);
+    }
+    int open_ro(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s", path);  // ReadBlock.cpp:43
+        if (fstat(fd, &st) != 0) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s", path);
+        size = (size_t)st.st_size;
+        if (size == 0) return set_error(EG_ERR_FORMAT, "%s is empty", path);
+        void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return set_error(EG_ERR_OPEN, "could not map %s", path);
+        p = static_cast<const uint8_t*>(m);
+        madvise(m, size, MADV_SEQUENTIAL);
+        return EG_OK;
+    }
+};
+
+static int check_image_size(const MappedFile& f, const char* path, int64_t rows, int64_t cols) {
+    const size_t want = (size_t)rows * (size_t)(cols + 1);
+    if (f.size != want && f.size + 1 != want)
+        return set_error(EG_ERR_FORMAT, "%s has %zu bytes; %lld rows x %lld columns of no-space ASCII need %zu", path,
+                         f.size, (long long)rows, (long long)cols, want);
+    if (rows > 1 && f.p[cols] != '\n')
+        return set_error(EG_ERR_FORMAT, "%s: first line is not %lld characters long", path, (long long)cols);
+    return EG_OK;
+}
+
+// cache lookup by (realpath, size, mtime, dims)
+static int cached_store(const char* path, int64_t rows, int64_t cols, eg_store** out) {
+    EG_TRY(ensure_init());
+    if (!path) return set_error(EG_ERR_ARG, "null file name");
+    if (rows <= 0 || cols <= 0) return set_error(EG_ERR_ARG, "dims must be positive");
+    struct stat st;
+    if (stat(path, &st) != 0) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s", path);
+    char* rp = realpath(path, nullptr);
+    char key[4400];
+    snprintf(key, sizeof(key), "%s|%lld|%lld.%09ld|%lldx%lld", rp ? rp : path, (long long)st.st_size,
+             (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (long long)rows, (long long)cols);
+    free(rp);
+    for (auto& e : g_ctx.cache)
+        if (e.key == key) {
+            e.stamp = ++g_ctx.clock;
+            *out = e.store;
+            return EG_OK;
+        }
+    MappedFile f;
+    EG_TRY(f.open_ro(path));
+    EG_TRY(check_image_size(f, path, rows, cols));
+    eg_store* s = nullptr;
+    EG_TRY(store_from_image(f.p, cols, 0, rows, 0, cols, &s));
+    const char* envmax = getenv("EAGLE_GPU_CACHE_ENTRIES");
+    const size_t maxe = envmax ? (size_t)atoi(envmax) : 4;
+    while (g_ctx.cache.size() >= (maxe ? maxe : 1)) {
+        size_t lru = 0;
+        for (size_t i = 1; i < g_ctx.cache.size(); i++)
+            if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
+        cudaFree(g_ctx.cache[lru].store->d);
+        delete g_ctx.cache[lru].store;
+        g_ctx.cache.erase(g_ctx.cache.begin() + lru);
+    }
+    g_ctx.cache.push_back({key, s, ++g_ctx.clock});
+    *out = s;
+    return EG_OK;
+}
+
+// ------------------------------------------------------------------ small conversion kernel for eg_ReadBlock
+__global__ void __launch_bounds__(256) i8_to_f64_colmajor_kernel(const int8_t* __restrict__ in, int64_t rows,
+                                                                 int64_t cols, int64_t pitch,
+                                                                 double* __restrict__ out) {
+    __shared__ int8_t tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? in[r * pitch + c] : (int8_t)0;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t c = c0 + i, r = r0 + tx;
+        if (r < rows && c < cols) out[r + c * rows] = (double)tile[tx][i];
+    }
+}
+
+// ------------------------------------------------------------------ compute helpers on stores
+static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols, double* out_host) {
+    const int64_t n = M->rows;
+    DevBuf C, D;
+    EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
+    EG_TRY(D.alloc((size_t)n * n * sizeof(double), "MMt output"));
+    cudaStream_t st = g_ctx.stream;
+    EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
+    {
+        Timer t(st);
+        EG_TRY(eg_dev_syrk_i8(M->d, n, M->cols, M->pitch, C.as<int32_t>(), n, st));
+        g_ctx.timing[1] = t.stop();
+    }
+    if (!zero_cols.empty())
+        EG_TRY(eg_dev_syrk_zero_cols(M->d, n, M->pitch, zero_cols.data(), (int64_t)zero_cols.size(), C.as<int32_t>(), n, st));
+    {
+        Timer t(st);
+        EG_TRY(eg_dev_mmt_finalize(C.as<int32_t>(), n, n, D.as<double>(), st));
+        g_ctx.timing[2] = t.stop();
+    }
+    {
+        Timer t(st);
+        EG_CUDA(cudaMemcpyAsync(out_host, D.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        g_ctx.timing[3] = t.stop();
+    }
+    return EG_OK;
+}
+
+static int scan_of_store(const eg_store* Mt, const std::vector<int64_t>& zero_rows, const double* S, const double* V,
+                         const double* a, double* out_a, double* out_vara) {
+    const int64_t L = Mt->rows, n = Mt->cols;
+    cudaStream_t st = g_ctx.stream;
+    DevBuf dS, dV, da, dT, dW, oa, ov;
+    EG_TRY(dS.alloc((size_t)n * n * 8, "inv_MMt_sqrt"));
+    EG_TRY(dV.alloc((size_t)n * n * 8, "dim_reduced_vara"));
+    EG_TRY(dT.alloc((size_t)n * n * 8, "scan scratch"));
+    EG_TRY(da.alloc((size_t)n * 8, "a"));
+    EG_TRY(dW.alloc((size_t)eg_scan_wp_elems(n) * 8, "packed W"));
+    EG_TRY(oa.alloc((size_t)L * 8, "a out"));
+    EG_TRY(ov.alloc((size_t)L * 8, "vara out"));
+    {
+        Timer t(st);
+        EG_CUDA(cudaMemcpyAsync(dS.p, S, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
+        EG_CUDA(cudaMemcpyAsync(dV.p, V, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
+        EG_CUDA(cudaMemcpyAsync(da.p, a, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        g_ctx.timing[4] = t.stop();
+    }
+    {
+        Timer t(st);
+        EG_TRY(eg_dev_scan_prepare(dS.as<double>(), dV.as<double>(), da.as<double>(), n, dT.as<double>(),
+                                   dW.as<double>(), st));
+        g_ctx.timing[5] = t.stop();
+    }
+    {
+        Timer t(st);
+        EG_TRY(eg_dev_scan(Mt->d, L, n, Mt->pitch, dW.as<double>(), zero_rows.empty() ? nullptr : zero_rows.data(),
+                           (int64_t)zero_rows.size(), oa.as<double>(), ov.as<double>(), st));
+        g_ctx.timing[6] = t.stop();
+    }
+    {
+        Timer t(st);
+        EG_CUDA(cudaMemcpyAsync(out_a, oa.p, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaMemcpyAsync(out_vara, ov.p, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        g_ctx.timing[7] = t.stop();
+    }
+    return EG_OK;
+}
+
+static void say(eg_message_fn message, void* ctx, const char* fmt, ...) {
+    if (!message) return;
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    message(ctx, buf);
+}
+
+}  // namespace eg
+
+using namespace eg;
+
+// ================================================================== lifecycle
+extern "C" int eg_abi_version(void) { return 1; }
+
+extern "C" const char* eg_last_error(void) { return g_err; }
+
+extern "C" int eg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int eg_init(int device) {
+    if (g_ctx.ready && g_ctx.device == device) return check_cuda(cudaSetDevice(device), "cudaSetDevice");
+    if (g_ctx.ready) eg_shutdown();
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(EG_ERR_CUDA, "no usable CUDA device (%s); libeaglegpu has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return set_error(EG_ERR_ARG, "eg_init: device %d of %d", device, ndev);
+    EG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(EG_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device,
+                         prop.major, prop.minor);
+    g_ctx.sms = prop.multiProcessorCount;
+    EG_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    EG_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    if (cublasCreate(&g_ctx.cublas) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasCreate failed");
+    EG_CUDA(cudaMalloc(&g_ctx.d_err, 4 * sizeof(int32_t)));
+    g_ctx.device = device;
+    g_ctx.ready = true;
+    return EG_OK;
+}
+
+extern "C" void eg_cache_clear(void) {
+    for (auto& e : g_ctx.cache) {
+        cudaFree(e.store->d);
+        delete e.store;
+    }
+    g_ctx.cache.clear();
+}
+
+extern "C" int eg_shutdown(void) {
+    if (!g_ctx.ready) return EG_OK;
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    eg_cache_clear();
+    syrk_release_cache();
+    if (g_ctx.cublas) cublasDestroy(g_ctx.cublas);
+    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
+    if (g_ctx.d_err) cudaFree(g_ctx.d_err);
+    g_ctx = Context();
+    return EG_OK;
+}
+
+extern "C" int eg_last_timing(double* out_ms, int n_out) {
+    if (!out_ms) return set_error(EG_ERR_ARG, "eg_last_timing: null");
+    for (int i = 0; i < n_out && i < 8; i++) out_ms[i] = g_ctx.timing[i];
+    return EG_OK;
+}
+
+// ================================================================== stores
+extern "C" int eg_store_from_host_ascii(const uint8_t* image, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
+                                        eg_store_t** out) {
+    if (!out) return set_error(EG_ERR_ARG, "null out");
+    return store_from_image(image, cols, 0, rows, col0, col1, out);
+}
+extern "C" int eg_store_from_host_ascii_rows(const uint8_t* image, int64_t rows, int64_t cols, int64_t row0,
+                                             int64_t row1, eg_store_t** out) {
+    if (!out || row1 > rows) return set_error(EG_ERR_ARG, "bad row range");
+    return store_from_image(image, cols, row0, row1, 0, cols, out);
+}
+extern "C" int eg_store_from_file(const char* path, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
+                                  eg_store_t** out) {
+    if (!out || !path) return set_error(EG_ERR_ARG, "null argument");
+    MappedFile f;
+    EG_TRY(f.open_ro(path));
+    EG_TRY(check_image_size(f, path, rows, cols));
+    return store_from_image(f.p, cols, 0, rows, col0, col1, out);
+}
+extern "C" int eg_store_transpose(const eg_store_t* in, eg_store_t** out) {
+    if (!in || !out) return set_error(EG_ERR_ARG, "null argument");
+    EG_TRY(ensure_init());
+    eg_store* s = nullptr;
+    EG_TRY(store_alloc(in->cols, in->rows, &s));
+    int rc = eg_dev_transpose_i8(in->d, in->rows, in->cols, in->pitch, s->d, s->pitch, g_ctx.stream);
+    if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "transpose");
+    if (rc != EG_OK) {
+        eg_store_free(s);
+        return rc;
+    }
+    *out = s;
+    return EG_OK;
+}
+extern "C" int eg_store_free(eg_store_t* s) {
+    if (!s) return EG_OK;
+    if (s->d) cudaFree(s->d);
+    delete s;
+    return EG_OK;
+}
+extern "C" int eg_store_info(const eg_store_t* s, int64_t* rows, int64_t* cols, int64_t* pitch, void** device_ptr) {
+    if (!s) return set_error(EG_ERR_ARG, "null store");
+    if (rows) *rows = s->rows;
+    if (cols) *cols = s->cols;
+    if (pitch) *pitch = s->pitch;
+    if (device_ptr) *device_ptr = s->d;
+    return EG_OK;
+}
+extern "C" int eg_store_mmt(const eg_store_t* M, const int64_t* zero_cols, int64_t n_zero, double* out_MMt_host) {
+    if (!M || !out_MMt_host || n_zero < 0) return set_error(EG_ERR_ARG, "eg_store_mmt: bad argument");
+    EG_TRY(ensure_init());
+    std::vector<int64_t> z;
+    for (int64_t i = 0; i < n_zero; i++) {
+        if (zero_cols[i] < 0 || zero_cols[i] >= M->cols) return set_error(EG_ERR_ARG, "zero column out of range");
+        z.push_back(zero_cols[i]);
+    }
+    return mmt_of_store(M, z, out_MMt_host);
+}
+extern "C" int eg_store_a_and_vara(const eg_store_t* Mt, const int64_t* zero_rows, int64_t n_zero,
+                                   const double* inv_MMt_sqrt, const double* dim_reduced_vara, const double* a,
+                                   double* out_a, double* out_vara) {
+    if (!Mt || !inv_MMt_sqrt || !dim_reduced_vara || !a || !out_a || !out_vara || n_zero < 0)
+        return set_error(EG_ERR_ARG, "eg_store_a_and_vara: bad argument");
+    EG_TRY(ensure_init());
+    std::vector<int64_t> z;
+    for (int64_t i = 0; i < n_zero; i++) {
+        if (zero_rows[i] < 0 || zero_rows[i] >= Mt->rows) return set_error(EG_ERR_ARG, "zero row out of range");
+        z.push_back(zero_rows[i]);
+    }
+    return scan_of_store(Mt, z, inv_MMt_sqrt, dim_reduced_vara, a, out_a, out_vara);
+}
+extern "C" int eg_store_extract_col(const eg_store_t* M, int64_t col, int32_t* out) {
+    if (!M || !out || col < 0 || col >= M->cols) return set_error(EG_ERR_ARG, "eg_store_extract_col: bad argument");
+    EG_TRY(ensure_init());
+    DevBuf d;
+    EG_TRY(d.alloc((size_t)M->rows * 4, "column"));
+    EG_TRY(eg_dev_extract_col(M->d, M->rows, M->pitch, col, d.as<int32_t>(), g_ctx.stream));
+    EG_CUDA(cudaMemcpyAsync(out, d.p, (size_t)M->rows * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    EG_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return EG_OK;
+}
+
+// ================================================================== device-level: scan pre-products (cuBLAS)
+extern "C" int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a, int64_t n, double* d_tmp,
+                                   double* d_Wp, void* stream) {
+    if (!d_S || !d_V || !d_a || !d_tmp || !d_Wp || n <= 0) return set_error(EG_ERR_ARG, "eg_dev_scan_prepare: bad argument");
+    EG_TRY(ensure_init());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Kpad = round_up(n, 32);
+    const double one = 1.0, zero = 0.0;
+    EG_CUDA(cudaMemsetAsync(d_Wp, 0, (size_t)eg_scan_wp_elems(n) * 8, st));
+    if (cublasSetStream(g_ctx.cublas, st) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasSetStream");
+    // calculate_a_and_vara_rcpp.cpp:97   tmp = dim_reduced_vara * inv_MMt_sqrt
+    if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_V, (int)n, d_S, (int)n,
+                    &zero, d_tmp, (int)n) != CUBLAS_STATUS_SUCCESS)
+        return set_error(EG_ERR_CUDA, "cublasDgemm(V*S) failed");
+    // :98   W = inv_MMt_sqrt * tmp, written straight into the packed layout (ld = Kpad)
+    if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_S, (int)n, d_tmp, (int)n,
+                    &zero, d_Wp, (int)Kpad) != CUBLAS_STATUS_SUCCESS)
+        return set_error(EG_ERR_CUDA, "cublasDgemm(S*tmp) failed");
+    // :90   v = inv_MMt_sqrt * a  -> column n of Wp
+    if (cublasDgemv(g_ctx.cublas, CUBLAS_OP_N, (int)n, (int)n, &one, d_S, (int)n, d_a, 1, &zero, d_Wp + n * Kpad, 1) !=
+        CUBLAS_STATUS_SUCCESS)
+        return set_error(EG_ERR_CUDA, "cublasDgemv(S*a) failed");
+    return EG_OK;
+}
+
+// ================================================================== reference-facing entry points
+extern "C" int eg_ReadBlock(const char* asciifname, int64_t start_row, int64_t numcols, int64_t numrows_in_block,
+                            double* out_colmajor) {
+    if (!asciifname || !out_colmajor || start_row < 0 || numcols <= 0 || numrows_in_block <= 0)
+        return set_error(EG_ERR_ARG, "ReadBlock: bad argument");
+    EG_TRY(ensure_init());
+    MappedFile f;
+    EG_TRY(f.open_ro(asciifname));
+    const void* nl = memchr(f.p, '\n', f.size);
+    const int64_t line = nl ? (const uint8_t*)nl - f.p : (int64_t)f.size;  // characters per line
+    if (numcols > line) return set_error(EG_ERR_FORMAT, "ReadBlock: lines of %s have %lld characters, %lld requested",
+                                         asciifname, (long long)line, (long long)numcols);
+    const int64_t nrows_file = ((int64_t)f.size + 1) / (line + 1);
+    if (start_row + numrows_in_block > nrows_file)
+        return set_error(EG_ERR_FORMAT, "ReadBlock: %s has %lld lines, rows [%lld,%lld) requested", asciifname,
+                         (long long)nrows_file, (long long)start_row, (long long)(start_row + numrows_in_block));
+    eg_store* s = nullptr;
+    EG_TRY(store_from_image(f.p, line, start_row, start_row + numrows_in_block, 0, numcols, &s));
+    DevBuf d;
+    int rc = d.alloc((size_t)numrows_in_block * numcols * 8, "ReadBlock output");
+    if (rc == EG_OK) {
+        dim3 grid((unsigned)((numcols + 31) / 32), (unsigned)((numrows_in_block + 31) / 32));
+        if (grid.y > 65535) rc = set_error(EG_ERR_ARG, "ReadBlock: block of %lld rows is too tall", (long long)numrows_in_block);
+        if (rc == EG_OK) {
+            i8_to_f64_colmajor_kernel<<<grid, 256, 0, g_ctx.stream>>>(s->d, numrows_in_block, numcols, s->pitch, d.as<double>());
+            rc = check_launch("i8_to_f64_colmajor_kernel");
+        }
+        if (rc == EG_OK)
+            rc = check_cuda(cudaMemcpyAsync(out_colmajor, d.p, (size_t)numrows_in_block * numcols * 8,
+                                            cudaMemcpyDeviceToHost, g_ctx.stream), "ReadBlock D2H");
+        if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "ReadBlock");
+    }
+    eg_store_free(s);
+    return rc;
+}
+
+extern "C" int eg_calculateMMt_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, int num_cores,
+                                    const double* selected_loci, int64_t n_selected_loci, const int64_t* dims,
+                                    int quiet, eg_message_fn message, void* message_ctx, double* out_MMt) {
+    (void)max_memory_in_Gbytes;
+    (void)num_cores;
+    if (!dims || !out_MMt) return set_error(EG_ERR_ARG, "calculateMMt_rcpp: null argument");
+    eg_store* M = nullptr;
+    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], &M));
+    std::vector<int64_t> z;
+    EG_TRY(parse_selected(selected_loci, n_selected_loci, dims[1], z, "calculateMMt_rcpp"));
+    if (!quiet) say(message, message_ctx, " M %%*%% t(M) on GPU %d (int8 tensor cores, exact) ", g_ctx.device);
+    return mmt_of_store(M, z, out_MMt);
+}
+
+extern "C" int eg_calculate_a_and_vara_rcpp(const char* f_name_ascii, const double* selected_loci,
+                                            int64_t n_selected_loci, const double* inv_MMt_sqrt,
+                                            const double* dim_reduced_vara, double max_memory_in_Gbytes,
+                                            const int64_t* dims, const double* a, int quiet, eg_message_fn message,
+                                            void* message_ctx, double* out_a, double* out_vara) {
+    (void)max_memory_in_Gbytes;
+    if (!dims || !inv_MMt_sqrt || !dim_reduced_vara || !a || !out_a || !out_vara)
+        return set_error(EG_ERR_ARG, "calculate_a_and_vara_rcpp: null argument");
+    eg_store* Mt = nullptr;
+    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], &Mt));  // dims of Mt: (L, n)
+    std::vector<int64_t> z;
+    EG_TRY(parse_selected(selected_loci, n_selected_loci, dims[0], z, "calculate_a_and_vara_rcpp"));
+    if (!quiet)
+        say(message, message_ctx, "Inside internal function calculate_a_and_vara_rcpp: GPU %d, no blocking needed ",
+            g_ctx.device);
+    return scan_of_store(Mt, z, inv_MMt_sqrt, dim_reduced_vara, a, out_a, out_vara);
+}
+
+extern "C" int eg_calculate_reduced_a_rcpp(const char* f_name_ascii, double varG, const double* P, const double* y,
+                                           double max_memory_in_Gbytes, const int64_t* dims,
+                                           const double* selected_loci, int64_t n_selected_loci, int quiet,
+                                           eg_message_fn message, void* message_ctx, double* out_ar) {
+    (void)max_memory_in_Gbytes;
+    if (!dims || !P || !y || !out_ar) return set_error(EG_ERR_ARG, "calculate_reduced_a_rcpp: null argument");
+    const int64_t n = dims[0], L = dims[1];  // dims of M; the file is Mt.ascii (L lines of n characters)
+    eg_store* Mt = nullptr;
+    EG_TRY(cached_store(f_name_ascii, L, n, &Mt));
+    std::vector<int64_t> z;
+    EG_TRY(parse_selected(selected_loci, n_selected_loci, L, z, "calculate_reduced_a_rcpp"));
+    if (!quiet) say(message, message_ctx, "Inside internal function calculate_reduced_a_rcpp. GPU %d ", g_ctx.device);
+    cudaStream_t st = g_ctx.stream;
+    DevBuf dP, dy, dpy, dout;
+    EG_TRY(dP.alloc((size_t)n * n * 8, "P"));
+    EG_TRY(dy.alloc((size_t)n * 8, "y"));
+    EG_TRY(dpy.alloc((size_t)n * 8, "P*y"));
+    EG_TRY(dout.alloc((size_t)L * 8, "ar"));
+    EG_CUDA(cudaMemcpyAsync(dP.p, P, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
+    EG_CUDA(cudaMemcpyAsync(dy.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    const double one = 1.0, zero = 0.0;
+    if (cublasSetStream(g_ctx.cublas, st) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasSetStream");
+    if (cublasDgemv(g_ctx.cublas, CUBLAS_OP_N, (int)n, (int)n, &one, dP.as<double>(), (int)n, dy.as<double>(), 1, &zero,
+                    dpy.as<double>(), 1) != CUBLAS_STATUS_SUCCESS)  // :82  ar = P * y
+        return set_error(EG_ERR_CUDA, "cublasDgemv(P*y) failed");
+    EG_TRY(eg_dev_gemv_i8(Mt->d, L, n, Mt->pitch, dpy.as<double>(), varG, dout.as<double>(), st));  // :83-84
+    EG_CUDA(cudaMemcpyAsync(out_ar, dout.p, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+    EG_CUDA(cudaStreamSynchronize(st));
+    for (int64_t r : z) out_ar[r] = varG * 0.0;  // :74-78 zeroed rows of Mt
+    return EG_OK;
+}
+
+extern "C" int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, int64_t selected_locus,
+                                    const int64_t* dims, int32_t* out) {
+    (void)max_memory_in_Gbytes;
+    if (!dims || !out) return set_error(EG_ERR_ARG, "extract_geno_rcpp: null argument");
+    if (selected_locus < 0 || selected_locus >= dims[1])
+        return set_error(EG_ERR_ARG, "extract_geno_rcpp: locus %lld outside [0, %lld)", (long long)selected_locus,
+                         (long long)dims[1]);
+    eg_store* M = nullptr;
+    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], &M));
+    return eg_store_extract_col(M, selected_locus, out);
+}

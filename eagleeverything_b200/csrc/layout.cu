@@ -1,0 +1,294 @@
+// Small bandwidth-bound kernels around the two tensor-core kernels:
+//   transpose_i8      M (n x L int8) -> Mt (L x n int8)        replaces createMt_ASCII_rcpp.cpp:99-118
+//   mmt_finalize      int32 upper triangle -> symmetric double  (Rcpp::wrap of MMt, calculateMMt_rcpp.cpp:183)
+//   syrk_zero_cols    rank-k correction for zeroed loci         calculateMMt_rcpp.cpp:88-92
+//   extract_col       one marker column of M as int32           extract_geno_rcpp.cpp:46-48
+//   argmax_tsq        tsq = a^2/vara, first index of the max    R/find_qtl.R:71-80
+//   gemv_i8           y = scale * Mt * x                        calculate_reduced_a_rcpp.cpp:83-84
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace eg {
+
+// ------------------------------------------------------------------ transpose (64 x 64 byte tiles)
+constexpr int TR_TILE = 64;
+__global__ void __launch_bounds__(256) transpose_i8_kernel(const int8_t* __restrict__ in, int64_t rows, int64_t cols,
+                                                           int64_t in_pitch, int8_t* __restrict__ out,
+                                                           int64_t out_pitch, int64_t tiles_c) {
+    __shared__ __align__(16) uint8_t tile[TR_TILE][TR_TILE + 16];
+    const int t = threadIdx.x;
+    for (int64_t tix = blockIdx.x; ; tix += gridDim.x) {
+        const int64_t tr = tix / tiles_c, tc = tix - tr * tiles_c;
+        if (tr * TR_TILE >= rows) break;
+        const int64_t r0 = tr * TR_TILE, c0 = tc * TR_TILE;
+        __syncthreads();
+        {   // load 64 rows x 64 bytes: thread -> (row t/4, 16-byte segment t%4); pitch padding is readable
+            const int r = t >> 2, sgm = t & 3;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (r0 + r < rows && c0 + sgm * 16 < in_pitch)
+                v = *reinterpret_cast<const uint4*>(in + (r0 + r) * in_pitch + c0 + sgm * 16);
+            *reinterpret_cast<uint4*>(&tile[r][sgm * 16]) = v;
+        }
+        __syncthreads();
+        {   // store: out row = input column c0 + t/4, 16 consecutive input rows per thread
+            const int c = t >> 2, sgm = t & 3;
+            if (c0 + c < cols) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int rb = sgm * 16 + k * 4;
+                    w[k] = (uint32_t)tile[rb][c] | ((uint32_t)tile[rb + 1][c] << 8) | ((uint32_t)tile[rb + 2][c] << 16) |
+                           ((uint32_t)tile[rb + 3][c] << 24);
+                }
+                // rows beyond `rows` were loaded as 0, so the output pad stays zero
+                if (r0 + sgm * 16 < out_pitch)
+                    *reinterpret_cast<uint4*>(out + (c0 + c) * out_pitch + r0 + sgm * 16) =
+                        make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ finalize: mirror + int32 -> double
+__global__ void __launch_bounds__(256) mmt_finalize_kernel(const int32_t* __restrict__ C, int64_t n, int64_t ldc,
+                                                           double* __restrict__ out) {
+    // block (bx, by) with bx >= by handles the 32x32 tile rows by*32.., cols bx*32.. of the upper
+    // triangle and writes both out[r][c] and out[c][r] (out is symmetric: row- == column-major).
+    __shared__ int32_t tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx < by) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t r0 = (int64_t)by * 32, c0 = (int64_t)bx * 32;
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r0 + i, c = c0 + tx;
+        int32_t v = 0;
+        if (r < n && c < n) v = (c >= r) ? C[r * ldc + c] : C[c * ldc + r];
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r0 + i, c = c0 + tx;
+        if (r < n && c < n) out[r * n + c] = (double)tile[i][tx];
+    }
+    if (bx != by) {
+        for (int i = ty; i < 32; i += 8) {
+            const int64_t r = c0 + i, c = r0 + tx;  // transposed tile
+            if (r < n && c < n) out[r * n + c] = (double)tile[tx][i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ zeroed loci as a rank-k update
+__global__ void gather_cols_kernel(const int8_t* __restrict__ M, int64_t n, int64_t pitch,
+                                   const int64_t* __restrict__ cols, int ncols, int8_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int s = 0; s < ncols; s++) out[i * ncols + s] = M[i * pitch + cols[s]];
+}
+__global__ void __launch_bounds__(256) syrk_zero_cols_kernel(const int8_t* __restrict__ G, int64_t n, int ncols,
+                                                             int32_t* __restrict__ C, int64_t ldc) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c >= n || c < r) return;
+    int32_t acc = 0;
+    for (int s = 0; s < ncols; s++) acc += (int32_t)G[r * ncols + s] * (int32_t)G[c * ncols + s];
+    if (acc) C[r * ldc + c] -= acc;
+}
+
+// ------------------------------------------------------------------ extract one marker column
+__global__ void extract_col_kernel(const int8_t* __restrict__ M, int64_t n, int64_t pitch, int64_t col,
+                                   int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)M[i * pitch + col];
+}
+
+// ------------------------------------------------------------------ tsq argmax
+struct Best {
+    double v;
+    int64_t i;
+};
+__device__ __forceinline__ Best better(Best a, Best b) {
+    // larger value wins; ties -> lower index (which(tsq == max)[1]); i < 0 marks "nothing yet"
+    if (b.i < 0) return a;
+    if (a.i < 0) return b;
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+__device__ __forceinline__ Best warp_best(Best x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best y;
+        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+        x = better(x, y);
+    }
+    return x;
+}
+__global__ void __launch_bounds__(256) argmax_tsq_kernel(const double* __restrict__ a, const double* __restrict__ vara,
+                                                         int64_t L, Best* __restrict__ partial) {
+    Best b;
+    b.v = 0.0;
+    b.i = -1;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (int64_t)gridDim.x * blockDim.x) {
+        const double av = a[j];
+        const double t = (av * av) / vara[j];  // a**2/vara, IEEE division as in R
+        if (t == t) {                          // max(tsq, na.rm=TRUE): NaN ignored, +-Inf kept
+            Best c;
+            c.v = t;
+            c.i = j;
+            b = better(b, c);
+        }
+    }
+    __shared__ Best sh[8];
+    b = warp_best(b);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Best c;
+        c.v = 0.0;
+        c.i = -1;
+        if (threadIdx.x < 8) c = sh[threadIdx.x];
+        c = warp_best(c);
+        if (threadIdx.x == 0) partial[blockIdx.x] = c;
+    }
+}
+__global__ void argmax_final_kernel(const Best* __restrict__ partial, int nparts, double* best, int64_t* best_idx) {
+    Best b;
+    b.v = 0.0;
+    b.i = -1;
+    for (int k = threadIdx.x; k < nparts; k += 32) b = better(b, partial[k]);
+    b = warp_best(b);
+    if (threadIdx.x == 0) {
+        *best = b.i >= 0 ? b.v : nan("");
+        *best_idx = b.i;
+    }
+}
+
+// ------------------------------------------------------------------ y = scale * Mt * x  (one warp per marker row)
+__global__ void __launch_bounds__(256) gemv_i8_kernel(const int8_t* __restrict__ Mt, int64_t L, int64_t n,
+                                                      int64_t pitch, const double* __restrict__ x, double scale,
+                                                      double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nvec = (n + 15) >> 4;  // 16 genotypes per 16-byte vector; the pitch padding is zero
+    for (int64_t j = warp_global; j < L; j += nwarps) {
+        const uint4* row = reinterpret_cast<const uint4*>(Mt + j * pitch);
+        double acc = 0.0;
+        for (int64_t v = lane; v < nvec; v += 32) {
+            const uint4 q = row[v];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const int64_t base = v * 16;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int g = (int)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xFF);
+                if (base + k < n) acc += (double)g * x[base + k];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[j] = scale * acc;
+    }
+}
+
+}  // namespace eg
+
+using namespace eg;
+
+extern "C" int eg_dev_transpose_i8(const int8_t* d_in, int64_t rows, int64_t cols, int64_t in_pitch, int8_t* d_out,
+                                   int64_t out_pitch, void* stream) {
+    if (!d_in || !d_out || rows < 0 || cols < 0 || (in_pitch & 15) || (out_pitch & 15) || in_pitch < cols ||
+        out_pitch < rows)
+        return set_error(EG_ERR_ARG, "eg_dev_transpose_i8: bad argument");
+    if (rows == 0 || cols == 0) return EG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // zero the whole output first so that every pad byte (columns >= rows of the input) is 0
+    EG_CUDA(cudaMemsetAsync(d_out, 0, (size_t)cols * (size_t)out_pitch, st));
+    const int64_t tiles_r = (rows + TR_TILE - 1) / TR_TILE, tiles_c = (cols + TR_TILE - 1) / TR_TILE;
+    const int64_t total = tiles_r * tiles_c;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    transpose_i8_kernel<<<(unsigned)(total < cap ? total : cap), 256, 0, st>>>(d_in, rows, cols, in_pitch, d_out,
+                                                                              out_pitch, tiles_c);
+    return check_launch("transpose_i8_kernel");
+}
+
+extern "C" int eg_dev_mmt_finalize(const int32_t* d_C, int64_t n, int64_t ldc, double* d_out, void* stream) {
+    if (!d_C || !d_out || n <= 0 || ldc < n) return set_error(EG_ERR_ARG, "eg_dev_mmt_finalize: bad argument");
+    const unsigned nb = (unsigned)((n + 31) / 32);
+    mmt_finalize_kernel<<<dim3(nb, nb), 256, 0, (cudaStream_t)stream>>>(d_C, n, ldc, d_out);
+    return check_launch("mmt_finalize_kernel");
+}
+
+extern "C" int eg_dev_syrk_zero_cols(const int8_t* d_M, int64_t n, int64_t pitch, const int64_t* h_zero_cols,
+                                     int64_t n_zero, int32_t* d_C, int64_t ldc, void* stream) {
+    if (n_zero <= 0) return EG_OK;
+    if (!d_M || !d_C || !h_zero_cols) return set_error(EG_ERR_ARG, "eg_dev_syrk_zero_cols: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    // a locus listed twice must only be removed once (setZero is idempotent in the reference)
+    std::vector<int64_t> uniq;
+    for (int64_t i = 0; i < n_zero; i++) {
+        bool seen = false;
+        for (int64_t u : uniq) seen |= (u == h_zero_cols[i]);
+        if (!seen) uniq.push_back(h_zero_cols[i]);
+    }
+    const int k = (int)uniq.size();
+    int64_t* d_cols = nullptr;
+    int8_t* d_G = nullptr;
+    EG_CUDA(cudaMalloc(&d_cols, k * sizeof(int64_t)));
+    if (cudaMalloc(&d_G, (size_t)n * k) != cudaSuccess) {
+        cudaFree(d_cols);
+        return set_error(EG_ERR_ALLOC, "eg_dev_syrk_zero_cols: out of device memory");
+    }
+    int rc = check_cuda(cudaMemcpyAsync(d_cols, uniq.data(), k * sizeof(int64_t), cudaMemcpyHostToDevice, st), "memcpy");
+    if (rc == EG_OK) {
+        gather_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_M, n, pitch, d_cols, k, d_G);
+        syrk_zero_cols_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, st>>>(d_G, n, k, d_C, ldc);
+        rc = check_launch("syrk_zero_cols_kernel");
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(d_cols);
+    cudaFree(d_G);
+    return rc;
+}
+
+extern "C" int eg_dev_extract_col(const int8_t* d_M, int64_t n, int64_t pitch, int64_t col, int32_t* d_out,
+                                  void* stream) {
+    if (!d_M || !d_out || n <= 0 || col < 0 || col >= pitch)
+        return set_error(EG_ERR_ARG, "eg_dev_extract_col: bad argument");
+    extract_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_M, n, pitch, col, d_out);
+    return check_launch("extract_col_kernel");
+}
+
+extern "C" int eg_dev_argmax_tsq(const double* d_a, const double* d_vara, int64_t L, double* d_best,
+                                 int64_t* d_best_idx, void* stream) {
+    if (!d_a || !d_vara || !d_best || !d_best_idx || L <= 0)
+        return set_error(EG_ERR_ARG, "eg_dev_argmax_tsq: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local Best* d_partial = nullptr;
+    static thread_local int d_partial_dev = -1;
+    int dev = 0;
+    EG_CUDA(cudaGetDevice(&dev));
+    const int maxblocks = 1024;
+    if (!d_partial || d_partial_dev != dev) {
+        EG_CUDA(cudaMalloc(&d_partial, maxblocks * sizeof(Best)));
+        d_partial_dev = dev;
+    }
+    int64_t nb = (L + 255) / 256;
+    if (nb > maxblocks) nb = maxblocks;
+    argmax_tsq_kernel<<<(unsigned)nb, 256, 0, st>>>(d_a, d_vara, L, d_partial);
+    argmax_final_kernel<<<1, 32, 0, st>>>(d_partial, (int)nb, d_best, d_best_idx);
+    return check_launch("argmax_tsq_kernel");
+}
+
+extern "C" int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_x,
+                              double scale, double* d_y, void* stream) {
+    if (!d_Mt || !d_x || !d_y || L <= 0 || n <= 0 || (pitch & 15) || pitch < n)
+        return set_error(EG_ERR_ARG, "eg_dev_gemv_i8: bad argument");
+    int64_t nb = (L + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (nb > cap) nb = cap;
+    gemv_i8_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(d_Mt, L, n, pitch, d_x, scale, d_y);
+    return check_launch("gemv_i8_kernel");
+}

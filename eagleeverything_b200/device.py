@@ -1,0 +1,140 @@
+"""Device-resident pipeline: torch owns the HBM buffers and streams (plumbing), libeaglegpu's
+`eg_dev_*` entry points do all of the work.  Used by bench.py (inputs already resident in HBM), by
+the multi-GPU layer (dist.py) and by the device-level parity tests.
+
+Nothing here computes on the CPU or with torch ops on the hot path; torch is used for
+allocation, the current stream, and (in dist.py) the NCCL all-reduce.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def store_pitch(cols: int) -> int:
+    """Row pitch of a genotype store: one spare zero column, rounded to 128 bytes."""
+    return (cols + 1 + 127) // 128 * 128
+
+
+def init(device: int):
+    lib = _lib.require_gpu()
+    torch.cuda.set_device(device)
+    _lib.check(lib.eg_init(int(device)))
+    return lib
+
+
+def synth_ascii(rows, cols, seed, col_offset=0, n_total=None, row_offset=0, device=None):
+    """Synthetic M.ascii image in HBM: uint8 tensor of rows*(cols+1) bytes (+64 bytes of slack)."""
+    lib = _lib.load()
+    img = torch.empty(rows * (cols + 1) + 64, dtype=torch.uint8, device=device or "cuda")
+    img[rows * (cols + 1):].zero_()
+    _lib.check(lib.eg_dev_synth_ascii(_ptr(img), rows, cols, col_offset, rows if n_total is None else n_total,
+                                      row_offset, C.c_uint64(seed), _stream()))
+    return img
+
+
+def decode(img, src_pitch, rows, cols, out=None, err=None, src_offset=0):
+    """K1.  img: uint8 tensor holding the ASCII bytes; returns int8 tensor (rows, pitch)."""
+    lib = _lib.load()
+    pitch = store_pitch(cols)
+    if out is None:
+        out = torch.empty((rows, pitch), dtype=torch.int8, device=img.device)
+    if err is None:
+        err = torch.zeros(4, dtype=torch.int32, device=img.device)
+    _lib.check(lib.eg_dev_decode(C.c_void_p(img.data_ptr() + src_offset), src_pitch, img.numel() - src_offset, rows, cols,
+                                 _ptr(out), out.stride(0), _ptr(err), _stream()))
+    return out, err
+
+
+def transpose(store, rows, cols, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((cols, store_pitch(rows)), dtype=torch.int8, device=store.device)
+    _lib.check(lib.eg_dev_transpose_i8(_ptr(store), rows, cols, store.stride(0), _ptr(out), out.stride(0), _stream()))
+    return out
+
+
+def syrk(store, n, kcols, C32=None, zero=True):
+    """K2.  store: int8 (n, pitch).  Returns int32 (n, n) whose upper triangle holds M*M^T."""
+    lib = _lib.load()
+    if C32 is None:
+        C32 = torch.empty((n, n), dtype=torch.int32, device=store.device)
+    if zero:
+        C32.zero_()
+    _lib.check(lib.eg_dev_syrk_i8(_ptr(store), n, kcols, store.stride(0), _ptr(C32), C32.stride(0), _stream()))
+    return C32
+
+
+def syrk_zero_cols(store, n, zero_cols, C32):
+    lib = _lib.load()
+    z = np.asarray(list(zero_cols), dtype=np.int64)
+    _lib.check(lib.eg_dev_syrk_zero_cols(_ptr(store), n, store.stride(0), z.ctypes.data_as(C.POINTER(C.c_int64)), len(z),
+                                         _ptr(C32), C32.stride(0), _stream()))
+    return C32
+
+
+def mmt_finalize(C32, n, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.float64, device=C32.device)
+    _lib.check(lib.eg_dev_mmt_finalize(_ptr(C32), n, C32.stride(0), _ptr(out), _stream()))
+    return out
+
+
+def scan_prepare(S, V, a, n, Wp=None, tmp=None):
+    """Pre-products of K3 (cuBLAS): v = S a, W = S (V S), packed.  S, V: (n, n) column-major content."""
+    lib = _lib.load()
+    if Wp is None:
+        Wp = torch.empty(lib.eg_scan_wp_elems(n), dtype=torch.float64, device=S.device)
+    if tmp is None:
+        tmp = torch.empty(n * n, dtype=torch.float64, device=S.device)
+    _lib.check(lib.eg_dev_scan_prepare(_ptr(S), _ptr(V), _ptr(a), n, _ptr(tmp), _ptr(Wp), _stream()))
+    return Wp
+
+
+def scan(storeT, L, n, Wp, zero_rows=(), out_a=None, out_vara=None):
+    """K3.  storeT: int8 (L, pitch >= round_up(n+1,128)) holding Mt."""
+    lib = _lib.load()
+    if out_a is None:
+        out_a = torch.empty(L, dtype=torch.float64, device=storeT.device)
+    if out_vara is None:
+        out_vara = torch.empty(L, dtype=torch.float64, device=storeT.device)
+    z = np.asarray(list(zero_rows), dtype=np.int64)
+    _lib.check(lib.eg_dev_scan(_ptr(storeT), L, n, storeT.stride(0), _ptr(Wp), z.ctypes.data_as(C.POINTER(C.c_int64)),
+                               len(z), _ptr(out_a), _ptr(out_vara), _stream()))
+    return out_a, out_vara
+
+
+def argmax_tsq(a, vara, out=None):
+    """K5.  Returns (best: float64[1], idx: int64[1]) device tensors."""
+    lib = _lib.load()
+    best = torch.empty(1, dtype=torch.float64, device=a.device)
+    idx = torch.empty(1, dtype=torch.int64, device=a.device)
+    _lib.check(lib.eg_dev_argmax_tsq(_ptr(a), _ptr(vara), a.numel(), _ptr(best), _ptr(idx), _stream()))
+    return best, idx
+
+
+def gemv_i8(storeT, L, n, x, scale=1.0):
+    lib = _lib.load()
+    y = torch.empty(L, dtype=torch.float64, device=storeT.device)
+    _lib.check(lib.eg_dev_gemv_i8(_ptr(storeT), L, n, storeT.stride(0), _ptr(x), float(scale), _ptr(y), _stream()))
+    return y
+
+
+def extract_col(store, n, col):
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.int32, device=store.device)
+    _lib.check(lib.eg_dev_extract_col(_ptr(store), n, store.stride(0), col, _ptr(out), _stream()))
+    return out

@@ -1,0 +1,168 @@
+/*
+ * eagle_gpu.h -- C ABI of libeaglegpu.so, the B200 (sm_100a) implementation of the genome-scan
+ * hot path of Eagle / WMAM v1.0.3.  This library replaces the nvblas / Makevars.gpu route
+ * (reference: MyPackage/Makevars.gpu:1-2, nvblas.conf, ReadMe_GPU:57-71).  Plain pointers and
+ * sizes only; no R, Rcpp, Eigen or torch types.  INTEGRATION.md shows the Rcpp glue that binds it.
+ *
+ * Reference paths below are relative to /root/reference/MyPackage/Eagle/.
+ *
+ * Conventions
+ *   - every function returns EG_OK (0) or an EG_ERR_* code; eg_last_error() holds the text of the
+ *     last failure on the calling thread (what the Rcpp glue passes to Rcpp::stop);
+ *   - matrices crossing the ABI on the host side are column-major doubles, exactly the memory of
+ *     an R numeric matrix / Eigen::MatrixXd (RcppExports.cpp:61-62 Eigen::Map is zero-copy);
+ *   - `selected_loci` follows the reference: 0-based indices as doubles, element 0 == NA_real_
+ *     (any NaN) means "none" (calculateMMt_rcpp.cpp:88, calculate_a_and_vara_rcpp.cpp:79);
+ *   - `max_memory_in_Gbytes` and `num_cores` are accepted and ignored: GPU residency of the int8
+ *     genotypes (1 byte/genotype instead of 8) replaces the host row-blocking they drive;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails
+ *     with EG_ERR_CUDA.
+ */
+#ifndef EAGLE_GPU_H_INCLUDED
+#define EAGLE_GPU_H_INCLUDED
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EG_OK 0
+#define EG_ERR_CUDA 1     /* CUDA runtime / cuBLAS failure, or no device */
+#define EG_ERR_OPEN 2     /* "ERROR: Could not open <file>" (ReadBlock.cpp:42-45) */
+#define EG_ERR_FORMAT 3   /* byte outside {'0','1','2'} or wrong line pitch (reference: undefined behaviour) */
+#define EG_ERR_ARG 4      /* bad argument (null pointer, negative size, index out of range) */
+#define EG_ERR_ALLOC 5    /* out of device / host memory */
+
+/* message(...) callback of the reference's exports (Rcpp::Function message); called only on the
+ * calling thread.  May be NULL. */
+typedef void (*eg_message_fn)(void* ctx, const char* text);
+
+/* ---------------------------------------------------------------- lifecycle */
+int eg_init(int device);            /* bind this process/thread to one GPU; idempotent */
+int eg_shutdown(void);              /* frees every cached genotype store and workspace */
+const char* eg_last_error(void);
+int eg_abi_version(void);
+int eg_device_count(void);          /* 0 when no CUDA device is usable */
+void eg_cache_clear(void);          /* drop device-resident genotype stores keyed by file path */
+
+/* ================================================================ reference-facing entry points
+ * One per Rcpp export on the hot path; same argument order and meaning. */
+
+/* ReadBlock(asciifname, start_row, numcols, numrows_in_block)          src/ReadBlock.cpp:16-68
+ * out: numrows_in_block x numcols doubles, column-major, values -1/0/1. */
+int eg_ReadBlock(const char* asciifname, int64_t start_row, int64_t numcols, int64_t numrows_in_block,
+                 double* out_colmajor);
+
+/* calculateMMt_rcpp(...)                                           src/calculateMMt_rcpp.cpp:19-185
+ * dims = (n, L) of M.ascii.  out_MMt: n x n doubles (exact integers, exactly symmetric). */
+int eg_calculateMMt_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, int num_cores,
+                         const double* selected_loci, int64_t n_selected_loci, const int64_t* dims, int quiet,
+                         eg_message_fn message, void* message_ctx, double* out_MMt);
+
+/* calculate_a_and_vara_rcpp(...)                           src/calculate_a_and_vara_rcpp.cpp:22-241
+ * f_name_ascii = Mt.ascii, dims = (L, n) of Mt.  inv_MMt_sqrt, dim_reduced_vara: n x n; a: n.
+ * out_a, out_vara: L doubles each (the reference's List(a = Lx1, vara = Lx1)). */
+int eg_calculate_a_and_vara_rcpp(const char* f_name_ascii, const double* selected_loci, int64_t n_selected_loci,
+                                 const double* inv_MMt_sqrt, const double* dim_reduced_vara,
+                                 double max_memory_in_Gbytes, const int64_t* dims, const double* a, int quiet,
+                                 eg_message_fn message, void* message_ctx, double* out_a, double* out_vara);
+
+/* calculate_reduced_a_rcpp(...)                             src/calculate_reduced_a_rcpp.cpp:20-171
+ * f_name_ascii = Mt.ascii, dims = (n, L) of M (sic, :37,:71).  P: n x n, y: n.  out_ar: L doubles
+ * = varG * Mt * (P * y). */
+int eg_calculate_reduced_a_rcpp(const char* f_name_ascii, double varG, const double* P, const double* y,
+                                double max_memory_in_Gbytes, const int64_t* dims, const double* selected_loci,
+                                int64_t n_selected_loci, int quiet, eg_message_fn message, void* message_ctx,
+                                double* out_ar);
+
+/* extract_geno_rcpp(...)                                          src/extract_geno_rcpp.cpp:17-86
+ * dims = (n, L) of M.ascii; selected_locus 0-based.  out: n ints in {-1,0,1}. */
+int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, int64_t selected_locus,
+                         const int64_t* dims, int32_t* out);
+
+/* ================================================================ resident genotype stores
+ * A store is a decoded genotype matrix held in HBM as int8 in {-1,0,1}: `rows` x `cols`, row
+ * pitch `pitch` bytes (multiple of 128, > cols; the tail of every row is zero).  The entry points
+ * above keep stores in a cache keyed by (path, size, mtime, dims); these calls manage them
+ * explicitly (host buffers in, handles out). */
+typedef struct eg_store eg_store_t;
+
+/* `image` is a byte-exact no-space ASCII file image in host memory (CreateASCIInospace.cpp:119-122):
+ * `rows` lines of `cols` chars + '\n'.  Only columns [col0, col1) are transferred and decoded (a
+ * marker shard when the image is M.ascii); pass 0, cols for everything. */
+int eg_store_from_host_ascii(const uint8_t* image, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
+                             eg_store_t** out);
+int eg_store_from_file(const char* path, int64_t rows, int64_t cols, int64_t col0, int64_t col1, eg_store_t** out);
+/* rows [row0,row1) of the image (a marker shard when the image is Mt.ascii) */
+int eg_store_from_host_ascii_rows(const uint8_t* image, int64_t rows, int64_t cols, int64_t row0, int64_t row1,
+                                  eg_store_t** out);
+int eg_store_transpose(const eg_store_t* in, eg_store_t** out); /* replaces createMt_ASCII_rcpp.cpp:99 on device */
+int eg_store_free(eg_store_t* s);
+int eg_store_info(const eg_store_t* s, int64_t* rows, int64_t* cols, int64_t* pitch, void** device_ptr);
+
+/* M.Mt of a store holding M (n x L_shard), with optional zeroed columns (store-local indices).
+ * out_MMt_host: n x n doubles. */
+int eg_store_mmt(const eg_store_t* M, const int64_t* zero_cols, int64_t n_zero, double* out_MMt_host);
+/* a / vara scan of a store holding Mt (L_shard x n); zero_rows are store-local. */
+int eg_store_a_and_vara(const eg_store_t* Mt, const int64_t* zero_rows, int64_t n_zero, const double* inv_MMt_sqrt,
+                        const double* dim_reduced_vara, const double* a, double* out_a, double* out_vara);
+int eg_store_extract_col(const eg_store_t* M, int64_t col, int32_t* out);
+
+/* ================================================================ device-level entry points
+ * Device pointers + a CUDA stream (cudaStream_t passed as void*, NULL = default stream).  Used by
+ * the host-level calls above, by bench.py (inputs resident in HBM) and by the multi-GPU
+ * plumbing, which owns the buffers and runs the NCCL all-reduce between eg_dev_syrk_i8 and
+ * eg_dev_mmt_finalize. */
+
+/* K1: ASCII bytes -> int8.  src byte (r,c) at src + r*src_pitch + c; writes dst[r*dst_pitch + c] = byte - '1'
+ * for c < cols and 0 for cols <= c < dst_pitch.  src must be readable up to src_bytes_avail (>= the
+ * last needed byte, ideally +32).  d_err: 4 ints, [0] != 0 when a byte outside {'0','1','2'} was seen. */
+int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_avail, int64_t rows, int64_t cols,
+                  int8_t* d_dst, int64_t dst_pitch, int32_t* d_err, void* stream);
+int eg_dev_transpose_i8(const int8_t* d_in, int64_t rows, int64_t cols, int64_t in_pitch, int8_t* d_out,
+                        int64_t out_pitch, void* stream);
+/* K2: C (int32, n x n row-major, ld = ldc, must be zeroed by the caller) += M * M^T over columns
+ * [0, kcols) of M (int8 n x kcols, row pitch multiple of 128 and padded with zeros).  Only entries
+ * with col >= row are complete. */
+int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64_t pitch, int32_t* d_C, int64_t ldc,
+                   void* stream);
+/* C[r][c] -= sum_s M[r][zero_cols[s]] * M[c][zero_cols[s]]  (calculateMMt_rcpp.cpp:88-92 as a rank-k fix) */
+int eg_dev_syrk_zero_cols(const int8_t* d_M, int64_t n, int64_t pitch, const int64_t* h_zero_cols, int64_t n_zero,
+                          int32_t* d_C, int64_t ldc, void* stream);
+/* mirror the upper triangle and convert: out (n x n doubles, column-major == row-major, symmetric) */
+int eg_dev_mmt_finalize(const int32_t* d_C, int64_t n, int64_t ldc, double* d_out, void* stream);
+
+/* K3 pre-products (calculate_a_and_vara_rcpp.cpp:90, 97-98): v = S*a; W = S*(V*S); packed for K3.
+ * d_S, d_V: n x n column-major doubles; d_a: n.  d_Wp: eg_scan_wp_elems(n) doubles;
+ * d_tmp: n*n doubles scratch. */
+int64_t eg_scan_wp_elems(int64_t n);
+int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a, int64_t n, double* d_tmp,
+                        double* d_Wp, void* stream);
+/* K3: a = Mt*v, vara_j = (Mt*W)_j . Mt_j for marker rows of an Mt store (L x n int8, pitch >=
+ * round_up(n+1,128)); zero rows get a = vara = 0. */
+int eg_dev_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp,
+                const int64_t* h_zero_rows, int64_t n_zero, double* d_a, double* d_vara, void* stream);
+/* K5: tsq = a^2/vara; maximum ignoring NaN and lowest index attaining it (find_qtl.R:71-80).
+ * d_out: {max tsq (double), index (int64 bits in a double slot)}; index -1 if all NaN. */
+int eg_dev_argmax_tsq(const double* d_a, const double* d_vara, int64_t L, double* d_best, int64_t* d_best_idx,
+                      void* stream);
+/* y = scale * Mt * x  (calculate_reduced_a_rcpp.cpp:82-84 second product) */
+int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_x, double scale,
+                   double* d_y, void* stream);
+int eg_dev_extract_col(const int8_t* d_M, int64_t n, int64_t pitch, int64_t col, int32_t* d_out, void* stream);
+
+/* Bench / test utility: write a synthetic M.ascii image (rows x (cols+1) bytes, Binomial(2,p_j)
+ * genotypes from a counter-based hash; same bytes as eagleeverything_b200/synth.py) into device memory.
+ * Column c is marker col_offset + c, row r is individual row_offset + r of an n_total-individual data set. */
+int eg_dev_synth_ascii(uint8_t* d_img, int64_t rows, int64_t cols, int64_t col_offset, int64_t n_total,
+                       int64_t row_offset, uint64_t seed, void* stream);
+
+/* timing of the last host-level call, milliseconds per stage (h2d, decode, syrk, finalize, d2h,
+ * prepare, scan); n_out entries written. */
+int eg_last_timing(double* out_ms, int n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAGLE_GPU_H_INCLUDED */

@@ -1,0 +1,158 @@
+"""GPU tests of the device-level entry points (eg_dev_*), and full-size (BASELINE config 2)
+checks through size-independent properties plus an independent torch evaluation on the device."""
+import numpy as np
+import pytest
+
+from eagleeverything_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    from eagleeverything_b200 import device
+    device.init(0)
+    return device, torch
+
+
+def test_synth_kernel_matches_numpy_twin(dev):
+    device, torch = dev
+    n, L = 77, 1001
+    img = device.synth_ascii(n, L, synth.GENO_SEED)
+    torch.cuda.synchronize()
+    got = img[: n * (L + 1)].cpu().numpy().reshape(n, L + 1)
+    assert np.array_equal(got, synth.ascii_image(synth.genotypes(n, L)))
+    shard = device.synth_ascii(n, 300, synth.GENO_SEED, col_offset=512, n_total=n)
+    assert np.array_equal(shard[: n * 301].cpu().numpy().reshape(n, 301)[:, :300], got[:, 512:812])
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 15), (5, 16), (7, 17), (150, 4998), (4998, 150), (33, 8191),
+                                       (9, 8192), (4, 8193), (2, 20000), (1000, 2000), (3, 127), (2, 128)])
+def test_decode_bit_exact_all_alignments(dev, rows, cols):
+    device, torch = dev
+    G = synth.genotypes(rows, cols, seed=rows * 31 + cols)
+    img_np = synth.ascii_image(G).reshape(-1)
+    for lead in (0, 1, 5, 16):  # shift the image inside the buffer: every source misalignment class
+        buf = torch.zeros(lead + img_np.size + 64, dtype=torch.uint8, device="cuda")
+        buf[lead:lead + img_np.size] = torch.from_numpy(img_np).cuda()
+        out, err = device.decode(buf, cols + 1, rows, cols, src_offset=lead)
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        assert err.cpu().numpy()[0] == 0
+        assert np.array_equal(o[:, :cols], G.astype(np.int8) - 1)
+        assert not o[:, cols:].any(), "row padding must be zero"
+
+
+def test_decode_column_shard_and_bad_byte(dev):
+    device, torch = dev
+    rows, cols = 40, 5000
+    G = synth.genotypes(rows, cols, seed=5)
+    img_np = synth.ascii_image(G).reshape(-1).copy()
+    buf = torch.from_numpy(np.concatenate([img_np, np.zeros(64, np.uint8)])).cuda()
+    out, err = device.decode(buf, cols + 1, rows, 1111, src_offset=777)  # columns [777, 1888)
+    assert np.array_equal(out.cpu().numpy()[:, :1111], G[:, 777:1888].astype(np.int8) - 1) and err[0].item() == 0
+    img_np[13 * (cols + 1) + 4000] = ord("3")
+    buf = torch.from_numpy(np.concatenate([img_np, np.zeros(64, np.uint8)])).cuda()
+    out, err = device.decode(buf, cols + 1, rows, cols)
+    e = err.cpu().numpy()
+    assert e[0] == 1 and e[1] == 13 and 4000 - 16 < e[2] <= 4000
+
+
+def test_transpose_and_extract(dev):
+    device, torch = dev
+    for rows, cols in [(1, 1), (63, 65), (64, 64), (150, 4998), (1000, 333)]:
+        G = synth.genotypes(rows, cols, seed=rows + cols)
+        buf = torch.from_numpy(np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+        st, _ = device.decode(buf, cols + 1, rows, cols)
+        tt = device.transpose(st, rows, cols)
+        t = tt.cpu().numpy()
+        assert np.array_equal(t[:, :rows], (G.astype(np.int8) - 1).T) and not t[:, rows:].any()
+        c = device.extract_col(st, rows, cols // 2).cpu().numpy()
+        assert np.array_equal(c, G[:, cols // 2].astype(np.int32) - 1)
+
+
+def test_argmax_semantics(dev):
+    device, torch = dev
+    rng = np.random.default_rng(1)
+    L = 100003
+    a = rng.standard_normal(L)
+    v = rng.random(L) + 0.5
+    a[[10, 50000, 99999]] = 9.0
+    v[[10, 50000, 99999]] = 1.0            # three-way tie at 81 -> first index
+    a[5], v[5] = np.nan, 1.0               # NaN ignored
+    a[7], v[7] = 0.0, 0.0                  # 0/0 -> NaN ignored
+    best, idx = device.argmax_tsq(torch.from_numpy(a).cuda(), torch.from_numpy(v).cuda())
+    assert idx.item() == 10 and best.item() == 81.0
+    a[20], v[20] = 1.0, 0.0                # +Inf is kept by max(na.rm=TRUE)
+    best, idx = device.argmax_tsq(torch.from_numpy(a).cuda(), torch.from_numpy(v).cuda())
+    assert idx.item() == 20 and np.isinf(best.item())
+    nan = torch.full((1000,), float("nan"), dtype=torch.float64, device="cuda")
+    best, idx = device.argmax_tsq(nan, nan)
+    assert idx.item() == -1
+
+
+def test_gemv_matches_float64(dev):
+    device, torch = dev
+    rows, cols = 3000, 517
+    G = synth.genotypes(cols, rows, seed=8)  # Mt = G.T is rows x cols
+    buf = torch.from_numpy(np.concatenate([synth.ascii_image(G.T).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    st, _ = device.decode(buf, cols + 1, rows, cols)
+    x = np.random.default_rng(2).standard_normal(cols)
+    y = device.gemv_i8(st, rows, cols, torch.from_numpy(x).cuda(), 2.5).cpu().numpy()
+    np.testing.assert_allclose(y, 2.5 * ((G.T.astype(np.float64) - 1) @ x), rtol=1e-12, atol=1e-11)
+
+
+def test_config2_full_size_properties(dev):
+    """BASELINE config 2 (n=2,000 x L=500,000) on one GPU: decode -> M.Mt -> scan, checked by
+    properties the domain offers and by an independent torch evaluation on the device."""
+    device, torch = dev
+    n, L = 2000, 500000
+    img = device.synth_ascii(n, L, synth.GENO_SEED)
+    st, err = device.decode(img, L + 1, n, L)
+    assert err[0].item() == 0
+    # decode == image - '1' (torch elementwise as the independent checker)
+    view = img[: n * (L + 1)].view(n, L + 1)
+    assert torch.equal(st[:, :L], (view[:, :L].to(torch.int16) - 49).to(torch.int8))
+    assert not st[:, L:].any()
+    C32 = device.syrk(st, n, L)
+    K = device.mmt_finalize(C32, n)
+    torch.cuda.synchronize()
+    assert torch.equal(K, K.T)
+    # trace = number of non-heterozygous genotypes; exact
+    assert K.diagonal().sum().item() == float((st[:, :L] != 0).sum().item())
+    # independent evaluation: fp32 GEMM on +-1/0 values is exact while |entries| <= L < 2^24
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = torch.zeros((n, n), dtype=torch.float32, device="cuda")
+    for c0 in range(0, L, 50000):
+        blk = st[:, c0:c0 + 50000].float()
+        ref += blk @ blk.T
+    assert torch.equal(K, ref.double())
+    del ref, blk
+    # linearity over marker shards (what the multi-GPU all-reduce relies on)
+    half = (L // 2) // 128 * 128
+    Ca = device.syrk(st[:, :half], n, half)
+    stb = st[:, half:].contiguous()
+    Cb = device.syrk(stb, n, L - half)
+    assert torch.equal(torch.triu(Ca + Cb), torch.triu(C32))
+    del Ca, Cb, stb
+    # scan on the transposed store, against torch float64 on sampled marker rows
+    tt = device.transpose(st, n, L)
+    S, V, a = synth.scan_inputs(n)
+    Sd, Vd, ad = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (S, V, a))
+    Wp = device.scan_prepare(Sd, Vd, ad, n)
+    oa, ov = device.scan(tt, L, n, Wp)
+    torch.cuda.synchronize()
+    W = Sd @ (Vd @ Sd)      # S, V symmetric: row-major view == column-major content
+    v = Sd @ ad
+    rows = torch.from_numpy(np.random.default_rng(0).choice(L, 4096, replace=False)).cuda()
+    Mr = tt[rows, :n].double()
+    ra = Mr @ v
+    rv = ((Mr @ W) * Mr).sum(1)
+    tol = 1e-9
+    assert ((oa[rows] - ra).abs() <= tol * torch.maximum(ra.abs(), tol * ra.abs().max())).all()
+    assert ((ov[rows] - rv).abs() <= tol * torch.maximum(rv.abs(), tol * rv.abs().max())).all()
+    # argmax kernel == torch on the full vectors
+    best, idx = device.argmax_tsq(oa, ov)
+    tsq = oa * oa / ov
+    assert best.item() == tsq.max().item() and idx.item() == int((tsq == tsq.max()).nonzero()[0].item())

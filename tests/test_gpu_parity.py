@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libeaglegpu.so) against the CPU oracle and
+the committed golden fixtures.  Bit-exact for decode / M.Mt / extract; a and var(a) within
+    |x - x_ref| <= 1e-9 * max(|x_ref|, 1e-9 * max|x_ref|)
+(the north-star tolerance, with the floor SURVEY.md section 7 motivates for cancelling sums)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from eagleeverything_b200 import _lib, api, synth
+from oracle import am_driver as am
+from oracle import eagle_oracle as eo
+from oracle import np_oracle as npo
+
+pytestmark = pytest.mark.gpu
+NA = api.NA_REAL
+RTOL = 1e-9
+
+
+def assert_close(x, ref, what=""):
+    x, ref = np.asarray(x, dtype=np.float64).reshape(-1), np.asarray(ref, dtype=np.float64).reshape(-1)
+    tol = RTOL * np.maximum(np.abs(ref), RTOL * np.abs(ref).max())
+    bad = np.abs(x - ref) > tol
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst rel err " \
+                          f"{(np.abs(x - ref) / np.maximum(np.abs(ref), 1e-300)).max():.3e}"
+
+
+def write_pair(tmp_path, G, tag):
+    m, mt = str(tmp_path / f"{tag}.M.ascii"), str(tmp_path / f"{tag}.Mt.ascii")
+    npo.write_ascii(m, G)
+    npo.write_ascii(mt, G.T)
+    return m, mt
+
+
+# ------------------------------------------------------------------------------- decode
+def test_readblock_bit_exact(synth_small):
+    s = synth_small
+    for (f, start, ncols, nrows) in [(s["M"], 0, s["L"], s["n"]), (s["M"], 7, s["L"], 50), (s["M"], 200, 1, 3),
+                                     (s["Mt"], 100, 60, 9), (s["Mt"], 0, s["n"], s["L"]), (s["Mt"], 2999, s["n"], 2)]:
+        got = api.ReadBlock(f, start, ncols, nrows)
+        ref = eo.ReadBlock(f, start, ncols, nrows)
+        assert got.flags.f_contiguous and got.shape == ref.shape
+        assert np.array_equal(got, ref)
+
+
+def test_open_and_format_errors(tmp_path, synth_small):
+    with pytest.raises(_lib.EagleGpuError, match="Could not open") as e:
+        api.ReadBlock(str(tmp_path / "nope.ascii"), 0, 3, 3)
+    assert e.value.code == _lib.EG_ERR_OPEN
+    with pytest.raises(_lib.EagleGpuError, match="Could not open"):
+        api.calculateMMt_rcpp(str(tmp_path / "nope.ascii"), 8, 1, [NA], (3, 3))
+    bad = tmp_path / "bad.ascii"
+    bad.write_bytes(b"0120\n01X0\n2210\n")
+    with pytest.raises(_lib.EagleGpuError, match="no-space ASCII") as e:
+        api.calculateMMt_rcpp(str(bad), 8, 1, [NA], (3, 4))
+    assert e.value.code == _lib.EG_ERR_FORMAT
+    s = synth_small
+    with pytest.raises(_lib.EagleGpuError) as e:  # dims swapped: the file size does not fit
+        api.calculateMMt_rcpp(s["M"], 8, 1, [NA], (s["n"] + 1, s["L"]))
+    assert e.value.code == _lib.EG_ERR_FORMAT
+    with pytest.raises(_lib.EagleGpuError) as e:
+        api.calculateMMt_rcpp(s["M"], 8, 1, [float(s["L"])], (s["n"], s["L"]))  # locus out of range
+    assert e.value.code == _lib.EG_ERR_ARG
+
+
+# ------------------------------------------------------------------------------- M.Mt
+def test_mmt_demo_bit_exact(demo):
+    z = demo["z"]
+    msgs = []
+    MMt = api.calculateMMt_rcpp(demo["M"], 8, 4, [NA], (demo["n"], demo["L"]), quiet=False, message=msgs.append)
+    assert hashlib.sha256(MMt.astype("<i4").tobytes()).hexdigest() == str(z["mmt_sha256"])
+    assert np.array_equal(MMt, eo.calculateMMt_rcpp(demo["M"], 8, 4, [NA], (demo["n"], demo["L"])))
+    assert np.array_equal(MMt, MMt.T) and MMt.dtype == np.float64
+    assert msgs and "GPU" in msgs[0]
+
+
+def test_mmt_selected_loci(synth_small):
+    s = synth_small
+    dims = (s["n"], s["L"])
+    for sel in ([5.0], [5.0, 17.0, 2999.0], [0.0, 0.0, 3000.0]):
+        assert np.array_equal(api.calculateMMt_rcpp(s["M"], 8, 1, sel, dims), eo.calculateMMt_rcpp(s["M"], 8, 1, sel, dims))
+    # NA anywhere but position 0 is not "none": only element 0 is the sentinel (calculateMMt_rcpp.cpp:88)
+    assert np.array_equal(api.calculateMMt_rcpp(s["M"], 8, 1, [NA, 5.0], dims), eo.calculateMMt_rcpp(s["M"], 8, 1, [NA], dims))
+
+
+@pytest.mark.parametrize("n,L", [(1, 1), (1, 200), (2, 127), (3, 128), (129, 129), (128, 4096), (257, 1000),
+                                 (300, 5000), (513, 777), (640, 20000)])
+def test_mmt_ragged_sizes(tmp_path, n, L):
+    G = synth.genotypes(n, L, seed=n * 7919 + L)
+    m, _ = write_pair(tmp_path, G, f"r{n}x{L}")
+    Gi = G.astype(np.int64) - 1
+    got = api.calculateMMt_rcpp(m, 8, 1, [NA], (n, L))
+    assert np.array_equal(got, (Gi @ Gi.T).astype(np.float64))
+
+
+def test_mmt_split_k_and_many_tiles(tmp_path):
+    """n small / L large exercises the K split (atomic int32 accumulation); n large the tile table."""
+    for n, L in [(150, 300000), (1500, 3000)]:
+        G = synth.genotypes(n, L, seed=42)
+        m, _ = write_pair(tmp_path, G, f"s{n}")
+        Gf = G.astype(np.float32) - 1  # exact in fp32: |entries| <= L < 2^24
+        ref = (Gf @ Gf.T).astype(np.float64)
+        got = api.calculateMMt_rcpp(m, 8, 1, [NA], (n, L))
+        assert np.array_equal(got, ref)
+        api.cache_clear()
+
+
+# ------------------------------------------------------------------------------- scan
+def test_scan_demo_against_golden(demo):
+    z = demo["z"]
+    r = api.calculate_a_and_vara_rcpp(demo["Mt"], [NA], z["it1_S"], z["it1_V"], 8, (demo["L"], demo["n"]), z["it1_hat_a"])
+    assert r["a"].shape == (demo["L"], 1) and r["vara"].shape == (demo["L"], 1)
+    assert_close(r["a"], z["it1_a"], "a")
+    assert_close(r["vara"], z["it1_vara"], "vara")
+    idx, _ = am.pick_locus(r["a"], r["vara"])
+    assert idx == 2207  # columns 2207 and 2209 are identical: the tie must go to the first
+
+
+def test_scan_synth_with_selected_rows(synth_small):
+    s = synth_small
+    S, V, a = synth.scan_inputs(s["n"], 3)
+    dims = (s["L"], s["n"])
+    for sel in ([NA], [3.0, 2500.0]):
+        got = api.calculate_a_and_vara_rcpp(s["Mt"], sel, S, V, 8, dims, a)
+        ref = eo.calculate_a_and_vara_rcpp(s["Mt"], sel, S, V, 8, dims, a)
+        assert_close(got["a"], ref["a"], "a")
+        assert_close(got["vara"], ref["vara"], "vara")
+    assert got["a"][3, 0] == 0 and got["vara"][2500, 0] == 0
+
+
+@pytest.mark.parametrize("n,L", [(1, 5), (31, 1), (127, 300), (128, 257), (129, 1000), (255, 129), (640, 1500)])
+def test_scan_ragged_sizes(tmp_path, n, L):
+    G = synth.genotypes(n, L, seed=n + L)
+    _, mt = write_pair(tmp_path, G, f"q{n}x{L}")
+    S, V, a = synth.scan_inputs(n, n)
+    got = api.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
+    ref = npo.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
+    assert_close(got["a"], ref["a"], "a")
+    assert_close(got["vara"], ref["vara"], "vara")
+
+
+def test_scan_identical_and_mirrored_markers_are_bit_identical(tmp_path):
+    """Tie hazard: duplicates / mirror images anywhere in the file must give
+    bit-identical tsq, so that the first index wins exactly as in the reference."""
+    n, L = 300, 2000
+    G = synth.genotypes(n, L, seed=99)
+    dup = [(5, 6), (5, 127), (5, 128), (5, 1999), (700, 1413)]
+    for src, dst in dup:
+        G[:, dst] = G[:, src]
+    G[:, 300] = 2 - G[:, 5]  # mirror image: m -> -m
+    _, mt = write_pair(tmp_path, G, "dup")
+    S, V, a = synth.scan_inputs(n, 1)
+    r = api.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
+    av, vv = r["a"][:, 0], r["vara"][:, 0]
+    for src, dst in dup:
+        assert av[src] == av[dst] and vv[src] == vv[dst]
+    assert av[300] == -av[5] and vv[300] == vv[5]
+    tsq = av ** 2 / vv
+    assert tsq[300] == tsq[5] == tsq[1999]
+
+
+def test_reduced_a_and_extract(synth_small):
+    s = synth_small
+    rng = np.random.default_rng(5)
+    P, y = rng.standard_normal((s["n"], s["n"])), rng.standard_normal(s["n"])
+    for sel in ([NA], [10.0, 11.0]):
+        got = api.calculate_reduced_a_rcpp(s["Mt"], 1.7, P, y, 8, (s["n"], s["L"]), sel)
+        ref = eo.calculate_reduced_a_rcpp(s["Mt"], 1.7, P, y, 8, (s["n"], s["L"]), sel)
+        assert got.shape == (s["L"], 1)
+        assert_close(got, ref, "ar")
+    for col in (0, 1234, s["L"] - 1):
+        got = api.extract_geno_rcpp(s["M"], 8, col, (s["n"], s["L"]))
+        assert got.dtype == np.int32 and np.array_equal(got, eo.extract_geno_rcpp(s["M"], 8, col, (s["n"], s["L"])))
+    with pytest.raises(_lib.EagleGpuError):
+        api.extract_geno_rcpp(s["M"], 8, s["L"], (s["n"], s["L"]))
+
+
+# ------------------------------------------------------------------------------- end to end
+def test_forward_search_matches_oracle(demo):
+    """Full multi-locus AM() forward search with the GPU library plugged into the restated driver:
+    identical selected-QTL sequence, extBIC trace and per-iteration scores."""
+    z = demo["z"]
+    r = am.AM(api, demo["geno"], z["trait1"], keep_trace=True)
+    assert r["selected"] == list(z["am1_selected"]) and r["all_picked"] == list(z["am1_all_picked"])
+    np.testing.assert_allclose(r["extBIC"], z["am1_extBIC"], rtol=1e-9)
+    ro = am.AM(eo, demo["geno"], z["trait1"], keep_trace=True)
+    for tg, to in zip(r["trace"], ro["trace"]):
+        assert tg["picked"] == to["picked"]
+        assert_close(tg["a"], to["a"], "a")
+        assert_close(tg["vara"], to["vara"], "vara")
+    X0 = np.column_stack([np.ones(demo["n"]), z["pc1"], z["pc2"]])
+    r2 = am.AM(api, demo["geno"], z["trait2"], X0=X0)
+    assert r2["selected"] == [] and r2["all_picked"] == [1200]
+
+
+def test_forward_search_synthetic(synth_small):
+    s = synth_small
+    y, qtl = synth.phenotype(s["G"])
+    rg = am.AM(api, s["geno"], y, maxit=6)
+    ro = am.AM(eo, s["geno"], y, maxit=6)
+    assert rg["all_picked"] == ro["all_picked"] and rg["selected"] == ro["selected"]
+    np.testing.assert_allclose(rg["extBIC"], ro["extBIC"], rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------- stores / shards
+def test_store_shards_sum_to_full_and_transpose(synth_small):
+    from eagleeverything_b200 import dist as egd
+    s = synth_small
+    img = synth.ascii_image(s["G"])
+    full = api.GenotypeStore.from_host_ascii(img, s["n"], s["L"])
+    ref = eo.calculateMMt_rcpp(s["M"], 8, 1, [NA], (s["n"], s["L"]))
+    assert np.array_equal(full.mmt(), ref)
+    acc = np.zeros_like(ref)
+    S, V, a = synth.scan_inputs(s["n"], 3)
+    ra, rv = full.transpose().a_and_vara(S, V, a)
+    for world in (3,):
+        pa, pv = [], []
+        for r in range(world):
+            c0, c1 = egd.shard_range(s["L"], world, r)
+            sh = api.GenotypeStore.from_host_ascii(img, s["n"], s["L"], c0, c1)
+            assert sh.info()["cols"] == c1 - c0
+            acc += sh.mmt()
+            x, v = sh.transpose().a_and_vara(S, V, a)
+            pa.append(x)
+            pv.append(v)
+        assert np.array_equal(acc, ref)
+        # marker scores do not depend on the shard a marker lives in: bit-identical
+        assert np.array_equal(np.concatenate(pa), ra) and np.array_equal(np.concatenate(pv), rv)
+    # Mt decoded from Mt.ascii rows == transpose of the M store
+    mt_img = synth.ascii_image(s["G"].T)
+    rows = api.GenotypeStore.from_host_rows(mt_img, s["L"], s["n"], 1000, 2000)
+    xa, xv = rows.a_and_vara(S, V, a)
+    assert np.array_equal(xa, ra[1000:2000]) and np.array_equal(xv, rv[1000:2000])
+    assert np.array_equal(full.extract_col(77), s["G"][:, 77].astype(np.int32) - 1)
