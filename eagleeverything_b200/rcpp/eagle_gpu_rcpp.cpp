@@ -1,0 +1,94 @@
+// Rcpp glue for libeaglegpu.so -- replaces the BODIES of five files in MyPackage/Eagle/src/
+// (ReadBlock.cpp, calculateMMt_rcpp.cpp, calculate_a_and_vara_rcpp.cpp,
+// calculate_reduced_a_rcpp.cpp, extract_geno_rcpp.cpp).  The exported prototypes are unchanged,
+// so RcppExports.cpp / RcppExports.R / NAMESPACE / every R file stay byte-identical and AM(),
+// SummaryAM() etc. run untouched (reference: src/RcppExports.cpp:9, 37, 54, 73, 129 and the
+// registration table :154-170).
+//
+// NOT compiled in this repository: R, Rcpp and RcppEigen are not installed in the build image.
+// It is the thin, mechanical layer INTEGRATION.md describes; everything it calls is the C ABI in
+// include/eagle_gpu.h, which IS built and tested here (tests/ call the same entry points through
+// ctypes with the same arguments).
+//
+// Build: see Makevars in this directory (replaces MyPackage/Makevars.gpu + nvblas.conf).
+
+// [[Rcpp::depends(RcppEigen)]]
+#include <RcppEigen.h>
+
+#include "eagle_gpu.h"
+#include "readblock.h"
+
+namespace {
+
+// message(...) of the reference is an R closure; the shim calls back on the calling (R main) thread only
+void r_message(void* ctx, const char* text) {
+    Rcpp::Function* f = static_cast<Rcpp::Function*>(ctx);
+    (*f)(text);
+}
+
+inline void check(int rc) {
+    if (rc != EG_OK) Rcpp::stop(eg_last_error());  // -> R error through END_RCPP, as ReadBlock.cpp:42-45 does
+}
+
+inline std::vector<int64_t> dims64(const std::vector<long>& d) { return std::vector<int64_t>(d.begin(), d.end()); }
+
+}  // namespace
+
+// [[Rcpp::export]]
+Eigen::MatrixXd ReadBlock(std::string asciifname, long start_row, long numcols, long numrows_in_block) {
+    Eigen::MatrixXd M(numrows_in_block, numcols);  // column-major, the layout eg_ReadBlock writes
+    check(eg_ReadBlock(asciifname.c_str(), start_row, numcols, numrows_in_block, M.data()));
+    return M;
+}
+
+// [[Rcpp::export]]
+Eigen::MatrixXd calculateMMt_rcpp(Rcpp::CharacterVector f_name_ascii, double max_memory_in_Gbytes, int num_cores,
+                                  Rcpp::NumericVector selected_loci, std::vector<long> dims, bool quiet,
+                                  Rcpp::Function message) {
+    std::string fname = Rcpp::as<std::string>(f_name_ascii);
+    std::vector<int64_t> d = dims64(dims);
+    Eigen::MatrixXd MMt(dims[0], dims[0]);
+    // NA_real_ in selected_loci(0) is passed through untouched: the shim tests it like R_IsNA
+    check(eg_calculateMMt_rcpp(fname.c_str(), max_memory_in_Gbytes, num_cores, selected_loci.begin(),
+                               selected_loci.size(), d.data(), quiet, r_message, &message, MMt.data()));
+    return MMt;
+}
+
+// [[Rcpp::export]]
+Rcpp::List calculate_a_and_vara_rcpp(Rcpp::CharacterVector f_name_ascii, Rcpp::NumericVector selected_loci,
+                                     Eigen::Map<Eigen::MatrixXd> inv_MMt_sqrt,
+                                     Eigen::Map<Eigen::MatrixXd> dim_reduced_vara, double max_memory_in_Gbytes,
+                                     std::vector<long> dims, Eigen::VectorXd a, bool quiet, Rcpp::Function message) {
+    std::string fname = Rcpp::as<std::string>(f_name_ascii);
+    std::vector<int64_t> d = dims64(dims);
+    Eigen::MatrixXd ans(dims[0], 1), var_ans(dims[0], 1);
+    // the Eigen::Map arguments are zero-copy views of the R matrices; the shim only reads them
+    check(eg_calculate_a_and_vara_rcpp(fname.c_str(), selected_loci.begin(), selected_loci.size(),
+                                       inv_MMt_sqrt.data(), dim_reduced_vara.data(), max_memory_in_Gbytes, d.data(),
+                                       a.data(), quiet, r_message, &message, ans.data(), var_ans.data()));
+    return Rcpp::List::create(Rcpp::Named("a") = ans, Rcpp::Named("vara") = var_ans);
+}
+
+// [[Rcpp::export]]
+Eigen::MatrixXd calculate_reduced_a_rcpp(Rcpp::CharacterVector f_name_ascii, double varG,
+                                         Eigen::Map<Eigen::MatrixXd> P, Eigen::Map<Eigen::MatrixXd> y,
+                                         double max_memory_in_Gbytes, std::vector<long> dims,
+                                         Rcpp::NumericVector selected_loci, bool quiet, Rcpp::Function message) {
+    std::string fname = Rcpp::as<std::string>(f_name_ascii);
+    std::vector<int64_t> d = dims64(dims);
+    Eigen::MatrixXd ar(dims[1], 1);
+    check(eg_calculate_reduced_a_rcpp(fname.c_str(), varG, P.data(), y.data(), max_memory_in_Gbytes, d.data(),
+                                      selected_loci.begin(), selected_loci.size(), quiet, r_message, &message,
+                                      ar.data()));
+    return ar;
+}
+
+// [[Rcpp::export]]
+Eigen::VectorXi extract_geno_rcpp(Rcpp::CharacterVector f_name_ascii, double max_memory_in_Gbytes,
+                                  long selected_locus, std::vector<long> dims) {
+    std::string fname = Rcpp::as<std::string>(f_name_ascii);
+    std::vector<int64_t> d = dims64(dims);
+    Eigen::VectorXi column_of_genos(dims[0]);
+    check(eg_extract_geno_rcpp(fname.c_str(), max_memory_in_Gbytes, selected_locus, d.data(), column_of_genos.data()));
+    return column_of_genos;
+}

@@ -1,7 +1,14 @@
 """GPU parity tests: the CUDA path (through the C ABI of libeaglegpu.so) against the CPU oracle and
-the committed golden fixtures.  Bit-exact for decode / M.Mt / extract; a and var(a) within
-    |x - x_ref| <= 1e-9 * max(|x_ref|, 1e-9 * max|x_ref|)
-(the north-star tolerance, with the floor SURVEY.md section 7 motivates for cancelling sums)."""
+the committed golden fixtures.  Bit-exact for decode / M.Mt / extract.  a and var(a):
+
+    |x - x_ref| <= 1e-9 * |x_ref|  +  4 (n + 10) eps * cond_j
+
+The first term is the north-star tolerance (1e-9 relative).  The second is the floating-point
+floor for sums that cancel: markers in span(X) (monomorphic or already selected) have a TRUE value
+of 0, and both the reference's Eigen arithmetic and any other summation order return rounding
+noise of size gamma_n * sum|terms| there (demo: |a_j| ~ 1e-14 against max|a| ~ 40).  cond_j is that
+sum of absolute terms: |m_j| . (|S||a_hat|) for a, |m_j|^T (|S||V||S|) |m_j| for var(a).  For every
+marker whose value is not dominated by cancellation the floor is ~1e-12 relative, far inside 1e-9."""
 import hashlib
 import os
 
@@ -18,12 +25,30 @@ NA = api.NA_REAL
 RTOL = 1e-9
 
 
-def assert_close(x, ref, what=""):
+EPS = np.finfo(np.float64).eps
+
+
+def scan_conds(G012, S, V, a, zero_rows=()):
+    """Rounding-error scales of a_j and vara_j (sums of absolute terms); G012 is n x L."""
+    Mabs = np.abs(np.asarray(G012).T.astype(np.float64) - 1.0)  # L x n
+    for r in zero_rows:
+        Mabs[int(r)] = 0.0
+    Sa, Va = np.abs(np.asarray(S)), np.abs(np.asarray(V))
+    ca = Mabs @ (Sa @ np.abs(np.asarray(a).reshape(-1)))
+    cv = np.einsum("ij,ij->i", Mabs @ (Sa @ (Va @ Sa)), Mabs)
+    return ca, cv
+
+
+def assert_close(x, ref, cond, n, what=""):
     x, ref = np.asarray(x, dtype=np.float64).reshape(-1), np.asarray(ref, dtype=np.float64).reshape(-1)
-    tol = RTOL * np.maximum(np.abs(ref), RTOL * np.abs(ref).max())
-    bad = np.abs(x - ref) > tol
-    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst rel err " \
-                          f"{(np.abs(x - ref) / np.maximum(np.abs(ref), 1e-300)).max():.3e}"
+    tol = RTOL * np.abs(ref) + 4.0 * (n + 10) * EPS * np.asarray(cond).reshape(-1)
+    err = np.abs(x - ref)
+    bad = ~(err <= tol)
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst err/tol " \
+                          f"{(err / np.maximum(tol, 1e-300)).max():.3e}"
+    # report-style sanity: where the value is not cancellation noise, plain 1e-9 relative holds
+    solid = np.abs(ref) > 1e-6 * np.abs(ref).max()
+    assert (err[solid] <= RTOL * np.abs(ref[solid])).all(), f"{what}: 1e-9 relative violated on a well-conditioned entry"
 
 
 def write_pair(tmp_path, G, tag):
@@ -111,8 +136,9 @@ def test_scan_demo_against_golden(demo):
     z = demo["z"]
     r = api.calculate_a_and_vara_rcpp(demo["Mt"], [NA], z["it1_S"], z["it1_V"], 8, (demo["L"], demo["n"]), z["it1_hat_a"])
     assert r["a"].shape == (demo["L"], 1) and r["vara"].shape == (demo["L"], 1)
-    assert_close(r["a"], z["it1_a"], "a")
-    assert_close(r["vara"], z["it1_vara"], "vara")
+    ca, cv = scan_conds(demo["G"], z["it1_S"], z["it1_V"], z["it1_hat_a"])
+    assert_close(r["a"], z["it1_a"], ca, demo["n"], "a")
+    assert_close(r["vara"], z["it1_vara"], cv, demo["n"], "vara")
     idx, _ = am.pick_locus(r["a"], r["vara"])
     assert idx == 2207  # columns 2207 and 2209 are identical: the tie must go to the first
 
@@ -121,11 +147,12 @@ def test_scan_synth_with_selected_rows(synth_small):
     s = synth_small
     S, V, a = synth.scan_inputs(s["n"], 3)
     dims = (s["L"], s["n"])
+    ca, cv = scan_conds(s["G"], S, V, a)
     for sel in ([NA], [3.0, 2500.0]):
         got = api.calculate_a_and_vara_rcpp(s["Mt"], sel, S, V, 8, dims, a)
         ref = eo.calculate_a_and_vara_rcpp(s["Mt"], sel, S, V, 8, dims, a)
-        assert_close(got["a"], ref["a"], "a")
-        assert_close(got["vara"], ref["vara"], "vara")
+        assert_close(got["a"], ref["a"], ca, s["n"], "a")
+        assert_close(got["vara"], ref["vara"], cv, s["n"], "vara")
     assert got["a"][3, 0] == 0 and got["vara"][2500, 0] == 0
 
 
@@ -136,8 +163,9 @@ def test_scan_ragged_sizes(tmp_path, n, L):
     S, V, a = synth.scan_inputs(n, n)
     got = api.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
     ref = npo.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
-    assert_close(got["a"], ref["a"], "a")
-    assert_close(got["vara"], ref["vara"], "vara")
+    ca, cv = scan_conds(G, S, V, a)
+    assert_close(got["a"], ref["a"], ca, n, "a")
+    assert_close(got["vara"], ref["vara"], cv, n, "vara")
 
 
 def test_scan_identical_and_mirrored_markers_are_bit_identical(tmp_path):
@@ -168,7 +196,8 @@ def test_reduced_a_and_extract(synth_small):
         got = api.calculate_reduced_a_rcpp(s["Mt"], 1.7, P, y, 8, (s["n"], s["L"]), sel)
         ref = eo.calculate_reduced_a_rcpp(s["Mt"], 1.7, P, y, 8, (s["n"], s["L"]), sel)
         assert got.shape == (s["L"], 1)
-        assert_close(got, ref, "ar")
+        cond = 1.7 * (np.abs(s["G"].T.astype(np.float64) - 1) @ (np.abs(P) @ np.abs(y)))
+        assert_close(got, ref, cond, s["n"], "ar")
     for col in (0, 1234, s["L"] - 1):
         got = api.extract_geno_rcpp(s["M"], 8, col, (s["n"], s["L"]))
         assert got.dtype == np.int32 and np.array_equal(got, eo.extract_geno_rcpp(s["M"], 8, col, (s["n"], s["L"])))
@@ -187,8 +216,9 @@ def test_forward_search_matches_oracle(demo):
     ro = am.AM(eo, demo["geno"], z["trait1"], keep_trace=True)
     for tg, to in zip(r["trace"], ro["trace"]):
         assert tg["picked"] == to["picked"]
-        assert_close(tg["a"], to["a"], "a")
-        assert_close(tg["vara"], to["vara"], "vara")
+        ca, cv = scan_conds(demo["G"], to["S"], to["V"], to["hat_a"])
+        assert_close(tg["a"], to["a"], ca, demo["n"], "a")
+        assert_close(tg["vara"], to["vara"], cv, demo["n"], "vara")
     X0 = np.column_stack([np.ones(demo["n"]), z["pc1"], z["pc2"]])
     r2 = am.AM(api, demo["geno"], z["trait2"], X0=X0)
     assert r2["selected"] == [] and r2["all_picked"] == [1200]
