@@ -7,7 +7,7 @@
 // HBM-bound: algorithmic traffic = 1 byte read + 1 byte written per genotype.
 // Source rows start at arbitrary byte alignment (pitch = L+1), so each work unit (one row chunk,
 // or a few whole short rows) is staged into shared memory with ONE 16-byte-aligned bulk-async
-// copy (cp.async.bulk, completion on an mbarrier, 4-stage ring per CTA); warps then read aligned
+// copy (cp.async.bulk, completion on an mbarrier, 4-stage ring of 16 KB per CTA, 3 CTAs per SM); warps then read aligned
 // 16-byte vectors, realign them with funnel shifts (the misalignment is warp-uniform), subtract
 // '1' bytewise, validate and emit aligned 16-byte stores into the padded int8 matrix.
 #include "common.cuh"
@@ -16,9 +16,11 @@
 namespace eg {
 
 constexpr int DEC_THREADS = 256;
+constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int DEC_STAGES = 4;
-constexpr int DEC_SPAN = 8192;                 // max bytes of source per unit (before alignment slack)
+constexpr int DEC_SPAN = 16384;                // max bytes of source per unit (before alignment slack)
 constexpr int DEC_STAGE_BYTES = DEC_SPAN + 64; // 16 B head slack + 32 B tail over-read slack, 16-B multiple
+constexpr int DEC_SMEM_BYTES = DEC_STAGES * DEC_STAGE_BYTES + 1024;
 
 struct DecodeParams {
     const uint8_t* src;
@@ -33,17 +35,17 @@ struct DecodeParams {
     int64_t num_units;
 };
 
-struct UnitGeom {
+// geometry of one unit, computed once by the producer thread and published through shared memory
+struct __align__(16) UnitGeom {
     int64_t r0;
-    int32_t nrows;
     int64_t c0;
-    int32_t out_bytes;   // output bytes per row in this chunk (multiple of 16, includes zero pad)
-    const uint8_t* a0;   // 16-B aligned start of the staged span
-    uint32_t o0;         // misalignment of (row r0, col c0) inside the span
+    int32_t nrows;
+    int32_t out_bytes;   // output bytes per row in this chunk (multiple of 16, includes the zero pad)
+    uint32_t o0;         // misalignment of (row r0, col c0) inside the staged span
     uint32_t bytes;      // span length (multiple of 16), 0 when the chunk is pure padding
 };
 
-__device__ __forceinline__ UnitGeom unit_geom(const DecodeParams& p, int64_t u) {
+__device__ __forceinline__ UnitGeom unit_geom(const DecodeParams& p, int64_t u, const uint8_t** a0_out) {
     UnitGeom g;
     int64_t ru = u / p.chunks_per_row;
     int32_t ch = (int32_t)(u - ru * p.chunks_per_row);
@@ -56,7 +58,7 @@ __device__ __forceinline__ UnitGeom unit_geom(const DecodeParams& p, int64_t u) 
     int64_t cend = g.c0 + p.chunk_bytes;
     if (cend > p.cols) cend = p.cols;
     if (cend <= g.c0) {
-        g.a0 = nullptr; g.o0 = 0; g.bytes = 0;
+        *a0_out = nullptr; g.o0 = 0; g.bytes = 0;
         return g;
     }
     const uint8_t* first = p.src + g.r0 * p.src_pitch + g.c0;
@@ -64,15 +66,62 @@ __device__ __forceinline__ UnitGeom unit_geom(const DecodeParams& p, int64_t u) 
     uintptr_t fa = (uintptr_t)first;
     uintptr_t a0 = fa & ~(uintptr_t)15;
     uintptr_t a1 = ((uintptr_t)last + 15) & ~(uintptr_t)15;
-    g.a0 = (const uint8_t*)a0;
+    *a0_out = (const uint8_t*)a0;
     g.o0 = (uint32_t)(fa - a0);
     g.bytes = (uint32_t)(a1 - a0);
     return g;
 }
 
+// 16 source bytes starting at staged offset `soff` (any alignment; soff & 15 is warp-uniform) ->
+// 16 genotypes in {-1,0,1}.  `bad` collects bits of bytes outside {'0','1','2'} among the first
+// `nvalid` bytes; bytes beyond nvalid are forced to 0 (row padding).
+__device__ __forceinline__ uint4 decode16(const uint8_t* sb, uint32_t soff, int nvalid, uint32_t& bad) {
+    const uint32_t al = soff & ~15u, o = soff & 15u;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(sb + al);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(sb + al + 16);
+    const uint32_t sh = (o & 3u) * 8u;
+    uint32_t x[4];
+    switch (o >> 2) {
+        case 0:
+            x[0] = __funnelshift_r(q0.x, q0.y, sh); x[1] = __funnelshift_r(q0.y, q0.z, sh);
+            x[2] = __funnelshift_r(q0.z, q0.w, sh); x[3] = __funnelshift_r(q0.w, q1.x, sh);
+            break;
+        case 1:
+            x[0] = __funnelshift_r(q0.y, q0.z, sh); x[1] = __funnelshift_r(q0.z, q0.w, sh);
+            x[2] = __funnelshift_r(q0.w, q1.x, sh); x[3] = __funnelshift_r(q1.x, q1.y, sh);
+            break;
+        case 2:
+            x[0] = __funnelshift_r(q0.z, q0.w, sh); x[1] = __funnelshift_r(q0.w, q1.x, sh);
+            x[2] = __funnelshift_r(q1.x, q1.y, sh); x[3] = __funnelshift_r(q1.y, q1.z, sh);
+            break;
+        default:
+            x[0] = __funnelshift_r(q0.w, q1.x, sh); x[1] = __funnelshift_r(q1.x, q1.y, sh);
+            x[2] = __funnelshift_r(q1.y, q1.z, sh); x[3] = __funnelshift_r(q1.z, q1.w, sh);
+            break;
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t d = x[k] ^ 0x30303030u;                         // '0','1','2' -> 0,1,2
+        uint32_t b = (d & 0xFCFCFCFCu) | ((d & (d >> 1)) & 0x01010101u);  // any byte > 2
+        uint32_t v = ((d | 0x80808080u) - 0x01010101u) ^ 0x80808080u;  // bytewise d - 1, no inter-byte borrow
+        if (nvalid < 16) {
+            const int nvk = nvalid - 4 * k;
+            const uint32_t m = nvk >= 4 ? 0xFFFFFFFFu : (nvk > 0 ? ((1u << (8 * nvk)) - 1u) : 0u);
+            b &= m;
+            v &= m;
+        }
+        bad |= b;
+        out[k] = v;
+    }
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 __global__ void __launch_bounds__(DEC_THREADS) decode_ascii_kernel(const DecodeParams p) {
-    __shared__ __align__(128) uint8_t stage[DEC_STAGES][DEC_STAGE_BYTES];
-    __shared__ __align__(8) uint64_t full[DEC_STAGES];
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint8_t* stage0 = dsm;
+    UnitGeom* geom = reinterpret_cast<UnitGeom*>(dsm + DEC_STAGES * DEC_STAGE_BYTES);      // [DEC_STAGES]
+    uint64_t* full = reinterpret_cast<uint64_t*>(dsm + DEC_STAGES * DEC_STAGE_BYTES + 512); // [DEC_STAGES]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -83,93 +132,68 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_ascii_kernel(const DecodeP
 
     const int64_t first_unit = blockIdx.x;
     const int64_t stride = gridDim.x;
-    int64_t my_units = p.num_units > first_unit ? (p.num_units - first_unit + stride - 1) / stride : 0;
+    const int64_t my_units = p.num_units > first_unit ? (p.num_units - first_unit + stride - 1) / stride : 0;
 
     auto issue = [&](int64_t i) {  // thread 0 only
-        UnitGeom g = unit_geom(p, first_unit + i * stride);
-        uint64_t* bar = &full[i % DEC_STAGES];
+        const int s = (int)(i % DEC_STAGES);
+        const uint8_t* a0;
+        UnitGeom g = unit_geom(p, first_unit + i * stride, &a0);
+        geom[s] = g;  // published by the release of the arrive below
         if (g.bytes) {
-            ptx::mbar_expect_tx(bar, g.bytes);
-            ptx::bulk_g2s(stage[i % DEC_STAGES], g.a0, g.bytes, bar);
+            ptx::mbar_expect_tx(&full[s], g.bytes);
+            ptx::bulk_g2s(stage0 + s * DEC_STAGE_BYTES, a0, g.bytes, &full[s]);
         } else {
-            ptx::mbar_arrive(bar);
+            ptx::mbar_arrive(&full[s]);
         }
     };
     if (tid == 0)
         for (int64_t i = 0; i < DEC_STAGES - 1 && i < my_units; i++) issue(i);
 
-    uint32_t bad_any = 0;
-    int64_t bad_row = 0, bad_col = 0;
+    uint32_t bad = 0;
+    const uint32_t src_pitch32 = (uint32_t)p.src_pitch;
     for (int64_t i = 0; i < my_units; i++) {
-        __syncthreads();  // everyone is done with unit i-1, whose stage is refilled next
+        __syncthreads();  // everyone is done with unit i-1, whose stage (and geometry slot) is refilled next
         if (tid == 0 && i + DEC_STAGES - 1 < my_units) issue(i + DEC_STAGES - 1);
         const int s = (int)(i % DEC_STAGES);
         ptx::mbar_wait(&full[s], (uint32_t)((i / DEC_STAGES) & 1));
 
-        const UnitGeom g = unit_geom(p, first_unit + i * stride);
-        const uint8_t* sb = stage[s];
-        const int segs_per_row = (g.out_bytes + 511) >> 9;
-        const int nseg = g.nrows * segs_per_row;
-        for (int sidx = warp; sidx < nseg; sidx += DEC_THREADS / 32) {
-            const int rr = sidx / segs_per_row;
-            const int sg = sidx - rr * segs_per_row;
-            const int vbyte = (sg * 32 + lane) * 16;  // byte offset inside the chunk
-            if (vbyte >= g.out_bytes) continue;
-            const int64_t col = g.c0 + vbyte;
-            int64_t nv64 = p.cols - col;
-            const int nvalid = nv64 >= 16 ? 16 : (nv64 > 0 ? (int)nv64 : 0);
-            uint4 out = make_uint4(0, 0, 0, 0);
-            if (nvalid > 0) {
-                const uint32_t soff = g.o0 + (uint32_t)rr * (uint32_t)p.src_pitch + (uint32_t)vbyte;
-                const uint32_t al = soff & ~15u, o = soff & 15u;  // o is warp-uniform
-                const uint4 q0 = *reinterpret_cast<const uint4*>(sb + al);
-                const uint4 q1 = *reinterpret_cast<const uint4*>(sb + al + 16);
-                const uint32_t sh = (o & 3u) * 8u;
-                uint32_t x0, x1, x2, x3;
-                switch (o >> 2) {
-                    case 0:
-                        x0 = __funnelshift_r(q0.x, q0.y, sh); x1 = __funnelshift_r(q0.y, q0.z, sh);
-                        x2 = __funnelshift_r(q0.z, q0.w, sh); x3 = __funnelshift_r(q0.w, q1.x, sh);
-                        break;
-                    case 1:
-                        x0 = __funnelshift_r(q0.y, q0.z, sh); x1 = __funnelshift_r(q0.z, q0.w, sh);
-                        x2 = __funnelshift_r(q0.w, q1.x, sh); x3 = __funnelshift_r(q1.x, q1.y, sh);
-                        break;
-                    case 2:
-                        x0 = __funnelshift_r(q0.z, q0.w, sh); x1 = __funnelshift_r(q0.w, q1.x, sh);
-                        x2 = __funnelshift_r(q1.x, q1.y, sh); x3 = __funnelshift_r(q1.y, q1.z, sh);
-                        break;
-                    default:
-                        x0 = __funnelshift_r(q0.w, q1.x, sh); x1 = __funnelshift_r(q1.x, q1.y, sh);
-                        x2 = __funnelshift_r(q1.y, q1.z, sh); x3 = __funnelshift_r(q1.z, q1.w, sh);
-                        break;
-                }
-                uint32_t xs[4] = {x0, x1, x2, x3};
-                uint32_t os[4];
-                uint32_t bad = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int nvk = nvalid - 4 * k;
-                    const uint32_t m = nvk >= 4 ? 0xFFFFFFFFu : (nvk > 0 ? ((1u << (8 * nvk)) - 1u) : 0u);
-                    const uint32_t d = __vsub4(xs[k], 0x30303030u);           // byte - '0'
-                    bad |= __vcmpgtu4(d, 0x02020202u) & m;                     // not in {0,1,2}
-                    os[k] = __vsub4(d, 0x01010101u) & m;                       // -> {-1,0,1}, pad = 0
-                }
-                out = make_uint4(os[0], os[1], os[2], os[3]);
-                if (bad) {
-                    bad_any = 1;
-                    bad_row = g.r0 + rr;
-                    bad_col = col;
+        const UnitGeom g = geom[s];
+        const uint8_t* sb = stage0 + s * DEC_STAGE_BYTES;
+        const int nvec = g.out_bytes >> 4;                       // 16-byte vectors per row in this chunk
+        int64_t ncol = p.cols - g.c0;                            // valid source bytes per row in this chunk
+        const int nvalid_row = ncol >= g.out_bytes ? g.out_bytes : (ncol > 0 ? (int)ncol : 0);
+        uint32_t bad_here = 0;
+        if (g.nrows == 1) {
+            int8_t* drow = p.dst + g.r0 * p.dst_pitch + g.c0;
+            for (int v = warp * 32 + lane; v < nvec; v += DEC_THREADS) {
+                const int vb = v << 4;
+                int nv = nvalid_row - vb;
+                nv = nv > 16 ? 16 : nv;
+                uint4 out = make_uint4(0, 0, 0, 0);
+                if (nv > 0) out = decode16(sb, g.o0 + (uint32_t)vb, nv, bad_here);
+                *reinterpret_cast<uint4*>(drow + vb) = out;
+            }
+        } else {
+            for (int rr = warp; rr < g.nrows; rr += DEC_WARPS) {   // one warp per (short) row
+                int8_t* drow = p.dst + (g.r0 + rr) * p.dst_pitch + g.c0;
+                const uint32_t rbase = g.o0 + (uint32_t)rr * src_pitch32;
+                for (int v = lane; v < nvec; v += 32) {
+                    const int vb = v << 4;
+                    int nv = nvalid_row - vb;
+                    nv = nv > 16 ? 16 : nv;
+                    uint4 out = make_uint4(0, 0, 0, 0);
+                    if (nv > 0) out = decode16(sb, rbase + (uint32_t)vb, nv, bad_here);
+                    *reinterpret_cast<uint4*>(drow + vb) = out;
                 }
             }
-            *reinterpret_cast<uint4*>(p.dst + (g.r0 + rr) * p.dst_pitch + col) = out;
         }
-    }
-    if (bad_any) {
-        if (atomicExch(&p.err[0], 1) == 0) {
-            p.err[1] = (int32_t)(bad_row & 0x7FFFFFFF);
-            p.err[2] = (int32_t)(bad_col & 0x7FFFFFFF);
-            p.err[3] = (int32_t)(bad_row >> 31);
+        if (bad_here && !bad) {
+            bad = 1;
+            if (atomicExch(&p.err[0], 1) == 0) {  // first reporter records the unit (row of the chunk, chunk column)
+                p.err[1] = (int32_t)(g.r0 & 0x7FFFFFFF);
+                p.err[2] = (int32_t)(g.c0 & 0x7FFFFFFF);
+                p.err[3] = (int32_t)(g.r0 >> 31);
+            }
         }
     }
 }
@@ -193,7 +217,7 @@ extern "C" int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t sr
     DecodeParams p;
     p.src = d_src; p.src_pitch = src_pitch; p.rows = rows; p.cols = cols;
     p.dst = d_dst; p.dst_pitch = dst_pitch; p.err = d_err;
-    if (dst_pitch >= 4096 || src_pitch > DEC_SPAN) {
+    if (dst_pitch >= 4096 || src_pitch > DEC_SPAN / 2) {
         p.rows_per_unit = 1;
         p.chunk_bytes = DEC_SPAN;
     } else {
@@ -204,7 +228,8 @@ extern "C" int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t sr
     }
     p.chunks_per_row = (int32_t)((dst_pitch + p.chunk_bytes - 1) / p.chunk_bytes);
     p.num_units = ((rows + p.rows_per_unit - 1) / p.rows_per_unit) * p.chunks_per_row;
-    int64_t grid = p.num_units < (int64_t)num_sms() * 6 ? p.num_units : (int64_t)num_sms() * 6;
-    decode_ascii_kernel<<<(unsigned)grid, DEC_THREADS, 0, (cudaStream_t)stream>>>(p);
+    EG_CUDA(cudaFuncSetAttribute(decode_ascii_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
+    int64_t grid = p.num_units < (int64_t)num_sms() * 3 ? p.num_units : (int64_t)num_sms() * 3;
+    decode_ascii_kernel<<<(unsigned)grid, DEC_THREADS, DEC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
     return check_launch("decode_ascii_kernel");
 }

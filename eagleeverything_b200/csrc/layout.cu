@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) transpose_i8_kernel(const int8_t* __restr
     const int t = threadIdx.x;
     for (int64_t tix = blockIdx.x; ; tix += gridDim.x) {
         const int64_t tr = tix / tiles_c, tc = tix - tr * tiles_c;
-        if (tr * TR_TILE >= rows) break;
+        if (tr * TR_TILE >= out_pitch) break;
         const int64_t r0 = tr * TR_TILE, c0 = tc * TR_TILE;
         __syncthreads();
         {   // load 64 rows x 64 bytes: thread -> (row t/4, 16-byte segment t%4); pitch padding is readable
@@ -199,14 +199,13 @@ using namespace eg;
 
 extern "C" int eg_dev_transpose_i8(const int8_t* d_in, int64_t rows, int64_t cols, int64_t in_pitch, int8_t* d_out,
                                    int64_t out_pitch, void* stream) {
-    if (!d_in || !d_out || rows < 0 || cols < 0 || (in_pitch & 15) || (out_pitch & 15) || in_pitch < cols ||
+    if (!d_in || !d_out || rows < 0 || cols < 0 || (in_pitch & 15) || (out_pitch & 63) || in_pitch < cols ||
         out_pitch < rows)
         return set_error(EG_ERR_ARG, "eg_dev_transpose_i8: bad argument");
     if (rows == 0 || cols == 0) return EG_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    // zero the whole output first so that every pad byte (columns >= rows of the input) is 0
-    EG_CUDA(cudaMemsetAsync(d_out, 0, (size_t)cols * (size_t)out_pitch, st));
-    const int64_t tiles_r = (rows + TR_TILE - 1) / TR_TILE, tiles_c = (cols + TR_TILE - 1) / TR_TILE;
+    // tiles run over the whole output pitch: input rows >= `rows` are read as 0, which zero-fills the pad
+    const int64_t tiles_r = (out_pitch + TR_TILE - 1) / TR_TILE, tiles_c = (cols + TR_TILE - 1) / TR_TILE;
     const int64_t total = tiles_r * tiles_c;
     const int64_t cap = (int64_t)num_sms() * 16;
     transpose_i8_kernel<<<(unsigned)(total < cap ? total : cap), 256, 0, st>>>(d_in, rows, cols, in_pitch, d_out,

@@ -18,6 +18,15 @@
 // when there are too few tiles to fill the SMs; integer atomics keep the result exact and
 // order independent.  Tiles are ordered in compact super-rows so that one wave of CTAs shares
 // operand rows in L2 while all of them stream along K together.
+//
+// K-phase flow control.  The L2 reuse above only happens if the CTAs of a wave stay within the L2
+// window along K (126 MB / (rows of the wave x 128 B) ~ 200 k-blocks); measured without it at
+// n=10k, L=1M: 372 GB of DRAM reads for a 10 GB operand (L2 hit 38 %), DRAM-bound at 47 % of the
+// tensor roofline.  So K is cut into phases of SY_PHASE k-blocks; a CTA publishes "phase p landed
+// in my shared memory" with one red.release.gpu, and no producer starts phase p before every
+// active CTA has published phase p - SY_LAG.  The grid is launched cooperatively (all CTAs
+// co-resident), so the soft barrier cannot deadlock.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -34,6 +43,8 @@ constexpr int SY_B_BYTES = SY_BN * SY_BK;
 constexpr int SY_STAGE_BYTES = SY_A_BYTES + SY_B_BYTES;
 constexpr int SY_THREADS = 192;
 constexpr int SY_TMEM_COLS = 512;
+constexpr int SY_PHASE = 16;  // k-blocks per flow-control phase (2 KB of K)
+constexpr int SY_LAG = 2;     // a producer may run at most this many phases ahead of the slowest CTA
 constexpr int SY_SMEM_BYTES = SY_STAGES * SY_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct SyrkParams {
@@ -45,7 +56,18 @@ struct SyrkParams {
     int32_t kblocks_total;
     int32_t kblocks_per_chunk;
     int32_t nunits;
+    uint32_t* phase_ctr;       // [rounds * phases_per_unit], zeroed before the launch; null = no flow control
+    int32_t phases_per_unit;
 };
+
+__device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
 syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
@@ -83,12 +105,29 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            int round = 0;
+            for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
                 const int kc = u / p.ntiles;
                 const int2 t = p.tiles[u - kc * p.ntiles];
                 const int kb0 = kc * p.kblocks_per_chunk;
                 const int kb1 = min(kb0 + p.kblocks_per_chunk, p.kblocks_total);
                 for (int kb = kb0; kb < kb1; kb++) {
+                    if (p.phase_ctr && ((kb - kb0) % SY_PHASE) == 0) {
+                        // do not start this phase before everybody has landed phase (this - SY_LAG)
+                        const int pid = round * p.phases_per_unit + (kb - kb0) / SY_PHASE - SY_LAG;
+                        if (pid >= 0) {
+                            const int r = pid / p.phases_per_unit;
+                            const int left = p.nunits - r * (int)gridDim.x;
+                            const uint32_t need = (uint32_t)(left < (int)gridDim.x ? left : (int)gridDim.x);
+                            uint32_t spins = 0;
+                            while (ld_acquire(p.phase_ctr + pid) < need) {
+                                if (++spins > (1u << 24)) {
+                                    printf("eagle: syrk flow control timed out (block %d phase %d)\n", (int)blockIdx.x, pid);
+                                    __trap();
+                                }
+                            }
+                        }
+                    }
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * SY_STAGE_BYTES;
                     uint8_t* sB = sA + SY_A_BYTES;
@@ -108,7 +147,8 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            int round = 0;
+            for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
                 const int kc = u / p.ntiles;
                 const int kb0 = kc * p.kblocks_per_chunk;
                 const int kb1 = min(kb0 + p.kblocks_per_chunk, p.kblocks_total);
@@ -117,6 +157,17 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SY_BN);
                 for (int kb = kb0; kb < kb1; kb++) {
                     ptx::mbar_wait(&full[stage], phase);
+                    if (p.phase_ctr) {
+                        // the operands of this k-block are in shared memory: this CTA no longer needs them in L2
+                        const int rel = kb - kb0;
+                        if ((rel % SY_PHASE) == SY_PHASE - 1 || kb == kb1 - 1) {
+                            const int ph = rel / SY_PHASE;
+                            uint32_t* c = p.phase_ctr + (int64_t)round * p.phases_per_unit;
+                            red_release_add(c + ph, 1u);
+                            if (kb == kb1 - 1)  // short last chunk: publish the phases this unit does not have
+                                for (int q = ph + 1; q < p.phases_per_unit; q++) red_release_add(c + q, 1u);
+                        }
+                    }
                     ptx::tc_fence_after();
                     const uint32_t a_addr = ptx::smem_u32(smem + stage * SY_STAGE_BYTES);
                     const uint64_t a_desc = ptx::make_desc_k_sw128(a_addr);
@@ -198,6 +249,8 @@ struct TileTable {
     int device = -1;
     int2* d_tiles = nullptr;
     int ntiles = 0;
+    uint32_t* d_phase = nullptr;  // flow-control counters
+    size_t phase_cap = 0;
 };
 static thread_local TileTable g_tiles;
 
@@ -207,6 +260,11 @@ static int build_tiles(int64_t n, cudaStream_t st) {
     int dev = 0;
     EG_CUDA(cudaGetDevice(&dev));
     if (g_tiles.n == n && g_tiles.device == dev && g_tiles.d_tiles) return EG_OK;
+    if (g_tiles.device != dev && g_tiles.d_phase) {
+        cudaFree(g_tiles.d_phase);
+        g_tiles.d_phase = nullptr;
+        g_tiles.phase_cap = 0;
+    }
     const int TM = (int)((n + SY_BM - 1) / SY_BM), TN = (int)((n + SY_BN - 1) / SY_BN);
     std::vector<int2> h;
     for (int sr = 0; sr < TM; sr += 16)
@@ -226,6 +284,7 @@ static int build_tiles(int64_t n, cudaStream_t st) {
 
 void syrk_release_cache() {
     if (g_tiles.d_tiles) cudaFree(g_tiles.d_tiles);
+    if (g_tiles.d_phase) cudaFree(g_tiles.d_phase);
     g_tiles = TileTable();
 }
 
@@ -273,12 +332,36 @@ extern "C" int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64
     kchunks = (p.kblocks_total + p.kblocks_per_chunk - 1) / p.kblocks_per_chunk;
     p.nunits = p.ntiles * kchunks;
 
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        EG_CUDA(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
-        attr_set = true;
-    }
+    EG_CUDA(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
     const int grid = p.nunits < sms ? p.nunits : sms;
-    syrk_i8_kernel<<<grid, SY_THREADS, SY_SMEM_BYTES, st>>>(tmap, p);
+
+    // flow-control counters: one per (round, phase); zeroed on the launch stream
+    p.phases_per_unit = (p.kblocks_per_chunk + SY_PHASE - 1) / SY_PHASE;
+    const int rounds = (p.nunits + grid - 1) / grid;
+    const size_t nctr = (size_t)rounds * p.phases_per_unit;
+    const char* env_fc = getenv("EAGLE_SYRK_FLOWCTL");
+    const bool flow = !(env_fc && env_fc[0] == '0') && grid > 1;
+    p.phase_ctr = nullptr;
+    if (flow) {
+        if (nctr > g_tiles.phase_cap) {
+            if (g_tiles.d_phase) cudaFree(g_tiles.d_phase);
+            g_tiles.d_phase = nullptr;
+            EG_CUDA(cudaMalloc(&g_tiles.d_phase, nctr * sizeof(uint32_t)));
+            g_tiles.phase_cap = nctr;
+        }
+        EG_CUDA(cudaMemsetAsync(g_tiles.d_phase, 0, nctr * sizeof(uint32_t), st));
+        p.phase_ctr = g_tiles.d_phase;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SY_THREADS);
+    cfg.dynamicSmemBytes = SY_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the soft barrier cannot deadlock
+    attr[0].val.cooperative = flow ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EG_CUDA(cudaLaunchKernelEx(&cfg, syrk_i8_kernel, tmap, p));
     return check_launch("syrk_i8_kernel");
 }
