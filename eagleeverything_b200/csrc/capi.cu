@@ -341,6 +341,36 @@ __global__ void __launch_bounds__(256) i8_to_f64_colmajor_kernel(const int8_t* _
     }
 }
 
+// ------------------------------------------------------------------ W -> U (symmetric half) for the scan
+// In place on the packed Wp (column-major, ld = Kpad): for i < k  U[i][k] = W[i][k] + W[k][i], U[k][i] = 0.
+__global__ void __launch_bounds__(256) symmetrize_upper_kernel(double* __restrict__ Wp, int64_t n, int64_t ld) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;  // tile (rows by*32.., cols bx*32..) with bx >= by
+    if (bx < by) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)by * 32, c0 = (int64_t)bx * 32;
+    // stage the mirrored tile W[c0.., r0..] (rows of the lower part) through shared memory
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = c0 + tx, c = r0 + i;  // element (r, c) of the lower tile, r fastest (coalesced)
+        tile[i][tx] = (r < n && c < n) ? Wp[r + c * ld] : 0.0;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r0 + tx, c = c0 + i;  // element (r, c) of the upper tile
+        if (r < n && c < n) {
+            if (r < c) Wp[r + c * ld] = Wp[r + c * ld] + tile[tx][i];   // W[r][c] + W[c][r]
+            else if (r > c) Wp[r + c * ld] = 0.0;                        // inside a diagonal tile
+        }
+    }
+    if (bx != by) {
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8) {
+            const int64_t r = c0 + tx, c = r0 + i;
+            if (r < n && c < n) Wp[r + c * ld] = 0.0;  // strictly lower tile
+        }
+    }
+}
+
 // ------------------------------------------------------------------ compute helpers on stores
 static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols, double* out_host) {
     const int64_t n = M->rows;
@@ -597,7 +627,10 @@ extern "C" int eg_dev_scan_prepare(const double* d_S, const double* d_V, const d
     if (cublasDgemv(g_ctx.cublas, CUBLAS_OP_N, (int)n, (int)n, &one, d_S, (int)n, d_a, 1, &zero, d_Wp + n * Kpad, 1) !=
         CUBLAS_STATUS_SUCCESS)
         return set_error(EG_ERR_CUDA, "cublasDgemv(S*a) failed");
-    return EG_OK;
+    // vara_j = m^T W m only sees the symmetric part of W: fold it into the upper triangle (scan_f64.cu)
+    const unsigned nb = (unsigned)((n + 31) / 32);
+    symmetrize_upper_kernel<<<dim3(nb, nb), 256, 0, st>>>(d_Wp, n, Kpad);
+    return check_launch("symmetrize_upper_kernel");
 }
 
 // ================================================================== reference-facing entry points

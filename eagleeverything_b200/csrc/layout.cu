@@ -166,30 +166,59 @@ __global__ void argmax_final_kernel(const Best* __restrict__ partial, int nparts
     }
 }
 
-// ------------------------------------------------------------------ y = scale * Mt * x  (one warp per marker row)
+// ------------------------------------------------------------------ y = scale * Mt * x
+// HBM-bound: reads the Mt store once.  x is staged in shared memory chunk by chunk, transposed so
+// that the 32 lanes of a warp (each holding one 16-genotype vector) read consecutive doubles
+// (conflict-free).  A warp owns 8 marker rows; per row the reduction order is fixed (lane-private
+// sums in vector order, then a shuffle tree), so identical rows give bit-identical results.
+constexpr int GV_CHUNK_VEC = 256;                  // 16-genotype vectors per x chunk (4096 doubles, 32 KB)
+constexpr int GV_ROWS_PER_WARP = 8;
+constexpr int GV_ROWS_PER_BLOCK = 8 * GV_ROWS_PER_WARP;
+__device__ __forceinline__ double gv_s8_to_f64(uint32_t w, int b) {  // byte b of w in {-1,0,1} -> double, integer ops only
+    const uint32_t g = (uint32_t)((int32_t)(w << (24 - 8 * b)) >> 24);
+    const uint32_t hi = (g & 0x80000000u) | ((g & 1u) * 0x3FF00000u);
+    return __hiloint2double((int)hi, 0);
+}
 __global__ void __launch_bounds__(256) gemv_i8_kernel(const int8_t* __restrict__ Mt, int64_t L, int64_t n,
                                                       int64_t pitch, const double* __restrict__ x, double scale,
                                                       double* __restrict__ y) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t nvec = (n + 15) >> 4;  // 16 genotypes per 16-byte vector; the pitch padding is zero
-    for (int64_t j = warp_global; j < L; j += nwarps) {
-        const uint4* row = reinterpret_cast<const uint4*>(Mt + j * pitch);
-        double acc = 0.0;
-        for (int64_t v = lane; v < nvec; v += 32) {
-            const uint4 q = row[v];
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            const int64_t base = v * 16;
+    __shared__ double xs[16 * GV_CHUNK_VEC];  // xs[k * GV_CHUNK_VEC + v] = x[chunk0 + 16 v + k]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nvec = (n + 15) >> 4;
+    for (int64_t rb = (int64_t)blockIdx.x * GV_ROWS_PER_BLOCK; rb < L; rb += (int64_t)gridDim.x * GV_ROWS_PER_BLOCK) {
+        const int64_t r0 = rb + warp * GV_ROWS_PER_WARP;
+        double acc[GV_ROWS_PER_WARP];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const int g = (int)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xFF);
-                if (base + k < n) acc += (double)g * x[base + k];
+        for (int r = 0; r < GV_ROWS_PER_WARP; r++) acc[r] = 0.0;
+        for (int64_t v0 = 0; v0 < nvec; v0 += GV_CHUNK_VEC) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < 16 * GV_CHUNK_VEC; e += 256) {
+                const int64_t i = v0 * 16 + e;
+                xs[(e & 15) * GV_CHUNK_VEC + (e >> 4)] = i < n ? x[i] : 0.0;  // zero beyond n: no bounds checks below
+            }
+            __syncthreads();
+            const int nv = (int)((nvec - v0) < GV_CHUNK_VEC ? (nvec - v0) : GV_CHUNK_VEC);
+#pragma unroll
+            for (int r = 0; r < GV_ROWS_PER_WARP; r++) {
+                if (r0 + r >= L) break;
+                const uint4* row = reinterpret_cast<const uint4*>(Mt + (r0 + r) * pitch) + v0;
+                double a = acc[r];
+                for (int v = lane; v < nv; v += 32) {
+                    const uint4 q = row[v];
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int k = 0; k < 16; k++) a += gv_s8_to_f64(w[k >> 2], k & 3) * xs[k * GV_CHUNK_VEC + v];
+                }
+                acc[r] = a;
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) y[j] = scale * acc;
+        for (int r = 0; r < GV_ROWS_PER_WARP; r++) {
+            double a = acc[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0 && r0 + r < L) y[r0 + r] = scale * a;
+        }
     }
 }
 
@@ -285,8 +314,8 @@ extern "C" int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t 
                               double scale, double* d_y, void* stream) {
     if (!d_Mt || !d_x || !d_y || L <= 0 || n <= 0 || (pitch & 15) || pitch < n)
         return set_error(EG_ERR_ARG, "eg_dev_gemv_i8: bad argument");
-    int64_t nb = (L + 7) / 8;
-    const int64_t cap = (int64_t)num_sms() * 8;
+    int64_t nb = (L + GV_ROWS_PER_BLOCK - 1) / GV_ROWS_PER_BLOCK;
+    const int64_t cap = (int64_t)num_sms() * 6;
     if (nb > cap) nb = cap;
     gemv_i8_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(d_Mt, L, n, pitch, d_x, scale, d_y);
     return check_launch("gemv_i8_kernel");

@@ -23,8 +23,8 @@
 // window along K (126 MB / (rows of the wave x 128 B) ~ 200 k-blocks); measured without it at
 // n=10k, L=1M: 372 GB of DRAM reads for a 10 GB operand (L2 hit 38 %), DRAM-bound at 47 % of the
 // tensor roofline.  So K is cut into phases of SY_PHASE k-blocks; a CTA publishes "phase p landed
-// in my shared memory" with one red.release.gpu, and no producer starts phase p before every
-// active CTA has published phase p - SY_LAG.  The grid is launched cooperatively (all CTAs
+// in my shared memory" with one relaxed red.global.add, and no producer starts phase p before every
+// active CTA has published phase p - SY_LAG (probed optimistically, a few phases per round trip).  The grid is launched cooperatively (all CTAs
 // co-resident), so the soft barrier cannot deadlock.
 #include <cstdlib>
 #include <vector>
@@ -44,7 +44,7 @@ constexpr int SY_STAGE_BYTES = SY_A_BYTES + SY_B_BYTES;
 constexpr int SY_THREADS = 192;
 constexpr int SY_TMEM_COLS = 512;
 constexpr int SY_PHASE = 16;  // k-blocks per flow-control phase (2 KB of K)
-constexpr int SY_LAG = 2;     // a producer may run at most this many phases ahead of the slowest CTA
+constexpr int SY_LAG = 4;     // a producer may run at most this many phases ahead of the slowest CTA
 constexpr int SY_SMEM_BYTES = SY_STAGES * SY_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct SyrkParams {
@@ -60,12 +60,13 @@ struct SyrkParams {
     int32_t phases_per_unit;
 };
 
-__device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// The counters are a throttle only (no data is passed through them): relaxed, GPU-scope accesses.
+__device__ __forceinline__ void red_relaxed_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -106,6 +107,11 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             int stage = 0;
             uint32_t phase = 0;
             int round = 0;
+            int known = -1;  // every active CTA is known to have landed all global phases <= known
+            auto need_of = [&](int gp) -> uint32_t {
+                const int left = p.nunits - (gp / p.phases_per_unit) * (int)gridDim.x;
+                return (uint32_t)(left < (int)gridDim.x ? left : (int)gridDim.x);
+            };
             for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
                 const int kc = u / p.ntiles;
                 const int2 t = p.tiles[u - kc * p.ntiles];
@@ -113,16 +119,21 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
                 const int kb1 = min(kb0 + p.kblocks_per_chunk, p.kblocks_total);
                 for (int kb = kb0; kb < kb1; kb++) {
                     if (p.phase_ctr && ((kb - kb0) % SY_PHASE) == 0) {
-                        // do not start this phase before everybody has landed phase (this - SY_LAG)
-                        const int pid = round * p.phases_per_unit + (kb - kb0) / SY_PHASE - SY_LAG;
-                        if (pid >= 0) {
-                            const int r = pid / p.phases_per_unit;
-                            const int left = p.nunits - r * (int)gridDim.x;
-                            const uint32_t need = (uint32_t)(left < (int)gridDim.x ? left : (int)gridDim.x);
+                        // do not start global phase gp before everybody has landed phase gp - SY_LAG
+                        const int gp = round * p.phases_per_unit + (kb - kb0) / SY_PHASE;
+                        if (gp - SY_LAG > known) {
+                            // optimistic probes (independent loads, one round trip): newest first
+                            uint32_t v[SY_LAG];
+#pragma unroll
+                            for (int q = 0; q < SY_LAG; q++) v[q] = ld_relaxed(p.phase_ctr + max(gp - 1 - q, 0));
+#pragma unroll
+                            for (int q = SY_LAG - 1; q >= 0; q--)
+                                if (gp - 1 - q >= 0 && gp - 1 - q > known && v[q] >= need_of(gp - 1 - q)) known = gp - 1 - q;
                             uint32_t spins = 0;
-                            while (ld_acquire(p.phase_ctr + pid) < need) {
-                                if (++spins > (1u << 24)) {
-                                    printf("eagle: syrk flow control timed out (block %d phase %d)\n", (int)blockIdx.x, pid);
+                            while (gp - SY_LAG > known) {
+                                if (ld_relaxed(p.phase_ctr + gp - SY_LAG) >= need_of(gp - SY_LAG)) known = gp - SY_LAG;
+                                else if (++spins > (1u << 24)) {
+                                    printf("eagle: syrk flow control timed out (block %d phase %d)\n", (int)blockIdx.x, gp);
                                     __trap();
                                 }
                             }
@@ -163,9 +174,9 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
                         if ((rel % SY_PHASE) == SY_PHASE - 1 || kb == kb1 - 1) {
                             const int ph = rel / SY_PHASE;
                             uint32_t* c = p.phase_ctr + (int64_t)round * p.phases_per_unit;
-                            red_release_add(c + ph, 1u);
+                            red_relaxed_add(c + ph, 1u);
                             if (kb == kb1 - 1)  // short last chunk: publish the phases this unit does not have
-                                for (int q = ph + 1; q < p.phases_per_unit; q++) red_release_add(c + q, 1u);
+                                for (int q = ph + 1; q < p.phases_per_unit; q++) red_relaxed_add(c + q, 1u);
                         }
                     }
                     ptx::tc_fence_after();
