@@ -13,12 +13,14 @@ find_qtl.R:1-2, calculateP.R:22-25).
 from __future__ import annotations
 
 import math
+import struct
 
 import numpy as np
 from scipy.linalg import lapack
 from scipy.special import gammaln
 
-NA = float("nan")
+#: R's NA_real_ (NaN with low word 1954): the reference tests it with R_IsNA, which a plain NaN fails
+NA = struct.unpack("<d", struct.pack("<Q", 0x7FF00000000007A2))[0]
 
 
 # ----------------------------------------------------------------------------- base-R helpers

@@ -6,17 +6,24 @@
  * cpu_baseline / --impl reference legs of bench.py may load this library.  The
  * product path (eagleeverything_b200/csrc) never links, loads or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or
- * known-answer fixtures for this path and its sources
- * need R + Rcpp + RcppEigen, none of which exist in this image, so the real
- * thing cannot be run here.  What pins this file instead:
- *   - M.Mt is exact integer arithmetic (|entry| <= L < 2^53): any correct
- *     implementation, in any summation order, produces the same bits;
- *   - an independent numpy restatement (oracle/np_oracle.py) and, when
- *     /root/reference is mounted, the reference's own .cpp files compiled
- *     against a stand-in for the Rcpp/Eigen headers (oracle/refshim ->
- *     oracle/_ref) are checked against it in tests/test_oracle.py;
- *   - a / var(a) are additionally checked against a long-double evaluation.
+ * PINNING.  The reference ships no tests, golden vectors or known-answer fixtures for this path
+ * (SURVEY.md section 4), and the package itself needs R + Rcpp + RcppEigen, none of which exist in
+ * this image.  What pins this file:
+ *   - the reference's OWN five hot-path sources (ReadBlock.cpp, calculateMMt_rcpp.cpp,
+ *     calculate_a_and_vara_rcpp.cpp, calculate_reduced_a_rcpp.cpp, extract_geno_rcpp.cpp) are compiled
+ *     from where they lie under /root/reference against a stand-in for the RcppEigen headers
+ *     (oracle/refshim -> oracle/_ref/libeagle_ref.so) and run here; tests/test_reference_shim.py
+ *     checks this file against them in every branch (in-memory and blocked, with and without
+ *     selected loci, soft failures, error text): M.Mt, ReadBlock and extract_geno bit-for-bit,
+ *     a / var(a) / reduced-a to 1e-12.  Their control flow is the real thing; the dense products
+ *     inside are the stand-in's loops, not Eigen's kernels (Eigen is not vendored in the reference);
+ *   - M.Mt is exact integer arithmetic (|entry| <= L < 2^53): any correct implementation, in any
+ *     summation order, produces the same bits;
+ *   - an independent numpy restatement (oracle/np_oracle.py) and a long-double evaluation of
+ *     a / var(a) agree with it (tests/test_oracle.py);
+ *   - results on the shipped demo data are frozen in tests/golden/demo.npz.
+ * What remains unpinned: Eigen's own summation order inside the products (a / var(a) can differ from
+ * a real R run in the last bits), hence the 1e-9 tolerance on those two outputs.
  *
  * Paths cited below are relative to /root/reference/MyPackage/Eagle/.
  * Matrices are column-major doubles, exactly as Eigen::MatrixXd stores them.

@@ -36,6 +36,21 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_REF_SO = os.path.join(_HERE, "_ref", "libeagle_ref.so")
+
+
+def _bind(path):
+    L = C.CDLL(path)
+    dp, lp, ip = C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_int)
+    L.eo_ReadBlock.argtypes = [C.c_char_p, C.c_long, C.c_long, C.c_long, dp]
+    L.eo_calculateMMt.argtypes = [C.c_char_p, C.c_double, C.c_int, dp, C.c_long, lp, dp, ip]
+    L.eo_calculate_a_and_vara.argtypes = [C.c_char_p, dp, C.c_long, dp, dp, C.c_double, lp, dp, dp, dp, ip]
+    L.eo_calculate_reduced_a.argtypes = [C.c_char_p, C.c_double, dp, dp, C.c_double, lp, dp, C.c_long, dp]
+    L.eo_extract_geno.argtypes = [C.c_char_p, C.c_double, C.c_long, lp, ip, ip]
+    L.eo_num_threads.restype = C.c_int
+    if hasattr(L, "ref_last_error"):
+        L.ref_last_error.restype = C.c_char_p
+    return L
 
 
 def lib():
@@ -43,16 +58,29 @@ def lib():
     if _lib is None:
         if not os.path.exists(_SO):
             build()
-        L = C.CDLL(_SO)
-        dp, lp, ip = C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_int)
-        L.eo_ReadBlock.argtypes = [C.c_char_p, C.c_long, C.c_long, C.c_long, dp]
-        L.eo_calculateMMt.argtypes = [C.c_char_p, C.c_double, C.c_int, dp, C.c_long, lp, dp, ip]
-        L.eo_calculate_a_and_vara.argtypes = [C.c_char_p, dp, C.c_long, dp, dp, C.c_double, lp, dp, dp, dp, ip]
-        L.eo_calculate_reduced_a.argtypes = [C.c_char_p, C.c_double, dp, dp, C.c_double, lp, dp, C.c_long, dp]
-        L.eo_extract_geno.argtypes = [C.c_char_p, C.c_double, C.c_long, lp, ip, ip]
-        L.eo_num_threads.restype = C.c_int
-        _lib = L
+        _lib = _bind(_SO)
     return _lib
+
+
+def reference_available() -> bool:
+    """True when oracle/_ref/libeagle_ref.so exists: the reference's OWN sources compiled from
+    /root/reference against the stand-in headers of oracle/refshim (built by oracle/refshim/Makefile)."""
+    return os.path.exists(_REF_SO)
+
+
+class use_reference:
+    """Context manager: route this module's functions to the compiled reference sources."""
+
+    def __enter__(self):
+        global _lib
+        self._saved = _lib
+        _lib = _bind(_REF_SO)
+        return self
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self._saved
+        return False
 
 
 def _d(a):
@@ -61,6 +89,9 @@ def _d(a):
 
 def _check(rc, what):
     if rc:
+        L = lib()
+        if hasattr(L, "ref_last_error") and rc == 1:  # the compiled reference threw (Rcpp::stop -> exception)
+            raise OracleError(f"{what}: {L.ref_last_error().decode('utf-8', 'replace')}")
         raise OracleError(f"{what}: {ERRORS.get(rc, rc)}")
 
 
