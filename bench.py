@@ -262,7 +262,10 @@ def run_gpu(args):
         mark(4)
         device.mmt_finalize(C32, n, out=K)
         mark(5)
-        device.scan_prepare(S, V, ah, n, Wp=Wp, tmp=tmp)
+        if world > 1:
+            device.scan_prepare_sharded(S, V, ah, n, rank, world, Wp=Wp, tmp=tmp)
+        else:
+            device.scan_prepare(S, V, ah, n, Wp=Wp, tmp=tmp)
         mark(6)
         device.scan(storeT, Lg, n, Wp, out_a=oa, out_vara=ov)
         mark(7)
@@ -310,34 +313,45 @@ def run_gpu(args):
         return
 
     stages = dict(zip(STAGES, stage_ms))
-    # scan: symmetric-half algorithm: n(n+1) flops for m^T U m, 2n for the row-dot
-    # bookkeeping, 2n for a = Mt.v; the reference's full T = Mt*W costs 2n(n+1)+2n per marker
-    scan_flops = (1.0 * n * (n + 1) + 4.0 * n) * Lg
+    mode = int(lib.eg_get_scan_mode())
+    k_ms, k_ops = C.c_double(), C.c_double()
+    _lib.check(lib.eg_last_scan_kernel(C.byref(k_ms), C.byref(k_ops)))   # CUDA events around the scan kernel itself
+    k_ms, k_ops = k_ms.value, k_ops.value
+    # reference-equivalent FP64 work of the scan (full T = Mt*W, row-dot): 2n(n+1)+2n flops per marker
     scan_ref_flops = (2.0 * n * (n + 1) + 2.0 * n) * Lg
     syrk_ops = float(Lg) * n * (n + 1)                      # symmetric half, 2 ops per MAC
     dec_bytes = float(n) * (Lg + 1) + float(n) * Lg
-    scan_tf = scan_flops / (stages["scan"] * 1e-3) / 1e12
     syrk_tops = syrk_ops / (stages["syrk"] * 1e-3) / 1e12
     dec_gbs = dec_bytes / (stages["decode"] * 1e-3) / 1e9
     dgemm = ceil.get("dgemm_tflops") or 37.0
     int8_meas = ceil.get("int8_gemm_tops")
-    roofline = {"kernel": "scan_f64_kernel", "bound": "tensor", "achieved": scan_tf, "peak": dgemm, "unit": "TFLOP/s",
-                "frac": scan_tf / dgemm, "traffic": None,
-                "reference_equiv_tflops": scan_ref_flops / (stages["scan"] * 1e-3) / 1e12,
-                "flops_convention": "symmetric half: n(n+1)+4n per marker (reference full product: 2n(n+1)+2n)",
-                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                               "B200 FP64 nominal 37-40 TFLOP/s"}
+    int8_peak = 2.0 * peaks["bf16_tflops"]
+    int8_src = "2 x measured bf16 (no int8 entry in MEASURED_PEAKS.json); nominal 4500"
+    k_rate = k_ops / (k_ms * 1e-3) / 1e12
+    if mode == 1:
+        roofline = {"kernel": "scan_i8_kernel", "bound": "tensor", "achieved": k_rate, "peak": int8_peak,
+                    "unit": "TOP/s (int8)", "frac": k_rate / int8_peak, "traffic": None, "kernel_ms": k_ms,
+                    "ops_convention": "executed int8 ops: 8 slices x symmetric-half contraction, 2 ops per MAC "
+                                      "(DESIGN.md section 4)",
+                    "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
+                    "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas}
+    else:
+        roofline = {"kernel": "scan_f64_kernel", "bound": "tensor", "achieved": k_rate, "peak": dgemm,
+                    "unit": "TFLOP/s (fp64)", "frac": k_rate / dgemm, "traffic": None, "kernel_ms": k_ms,
+                    "ops_convention": "executed FP64 flops of the symmetric-half contraction (DESIGN.md section 4)",
+                    "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 "
+                                   "entry); B200 FP64 nominal 37-40 TFLOP/s"}
     rooflines = {
         "decode_ascii_kernel": {"bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                 "frac": dec_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"]},
         "syrk_i8_kernel": {"bound": "tensor", "achieved": syrk_tops, "unit": "TOP/s (int8, symmetric-half ops)",
                            "full_product_equiv_tops": 2.0 * n * n * Lg / (stages["syrk"] * 1e-3) / 1e12,
-                           "peak": 2.0 * peaks["bf16_tflops"],
-                           "frac": syrk_tops / (2.0 * peaks["bf16_tflops"]),
-                           "peak_source": "2 x measured bf16 (no int8 entry in MEASURED_PEAKS.json); nominal 4500",
+                           "peak": int8_peak, "frac": syrk_tops / int8_peak, "peak_source": int8_src,
                            "cublaslt_int8_gemm_tops_this_run": int8_meas},
-        "scan_f64_kernel": roofline,
+        roofline["kernel"]: roofline,
     }
+    scan_tf = scan_ref_flops / (stages["scan"] * 1e-3) / 1e12
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
@@ -350,10 +364,12 @@ def run_gpu(args):
         "data": "synthetic",
         "config": {"workload": w["name"], "n": n, "L": L, "markers_per_gpu": Lg, "parallelism": f"markers/{world}",
                    "l2": f"inputs larger than L2 ({(dec_bytes + 16.0 * n * n) / 1e9:.1f} GB streamed per step)",
-                   "note": "dtype f64 = the scan; decode is u8, M.Mt is s8 x s8 -> s32 (bit-exact)"},
-        "stage_ms": stages, "mmt_int8_tops": syrk_tops, "decode_gbs": dec_gbs, "scan_tflops": scan_tf,
+                   "note": "dtype f64 = the scan's results (a, var(a)); decode is u8, M.Mt is s8 x s8 -> s32 (bit-exact); "
+                           "var(a) is contracted on int8 slices of the FP64 matrix (exact) or on FP64 DMMA"},
+        "stage_ms": stages, "mmt_int8_tops": syrk_tops, "decode_gbs": dec_gbs,
+        "scan_mode": "int8 slices (tcgen05)" if mode == 1 else "fp64 (DMMA)", "scan_reference_equiv_fp64_tflops": scan_tf,
         "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": 9 * args.steps, "library_ceilings": ceil,
+        "gpu_launches": (12 if mode == 1 else 9) * args.steps, "library_ceilings": ceil,
         "picked_marker": int(res[1]) if not hasattr(res[1], "item") else int(res[1].item()),
     }
     jprint(out)
@@ -412,7 +428,7 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
         device.mmt_finalize(C32, n, out=Kd)
         if rank == 0:
             K_h.copy_(Kd, non_blocking=True)
-        Wp = device.scan_prepare(Sd, Vd, ad, n)
+        Wp = device.scan_prepare_sharded(Sd, Vd, ad, n, rank, world)
         device.scan(storeT, Lg, n, Wp, out_a=oa, out_vara=ov)
         oa_h.copy_(oa, non_blocking=True); ov_h.copy_(ov, non_blocking=True)
         best, idx = device.argmax_tsq(oa, ov)
@@ -439,10 +455,16 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
+    abi_timing = None
+    if world == 1:
+        t8 = (C.c_double * 8)()
+        lib.eg_last_timing(t8, 8)
+        abi_timing = dict(zip(["h2d_decode_ms", "syrk_ms", "finalize_ms", "mmt_d2h_ms", "scan_h2d_ms", "prepare_ms",
+                               "scan_ms", "scan_d2h_ms"], [round(x, 3) for x in t8]))
     h2d = img_bytes + 2 * n * n * 8 + n * 8
     d2h = (n * n * 8 if rank == 0 else 0) + 2 * Lg * 8
     return {"value": L / (ms * 1e-3), "unit": METRIC, "ms_per_step": ms, "steps": ksteps,
-            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "abi_stage_ms": abi_timing,
             "path": "host-level C ABI (eg_store_*) on pinned host buffers" if world == 1 else
                     "pinned host shards -> H2D -> device-level C ABI -> all-reduce -> D2H",
             "timing": "host clock around a synchronised region (max with CUDA events), max over ranks"}

@@ -60,11 +60,16 @@ SIGNATURES = {
     "eg_dev_mmt_finalize": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "eg_scan_wp_elems": (_i64, [_i64]),
     "eg_dev_scan_prepare": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "eg_dev_scan_prepare_cols": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "eg_dev_scan_fold": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "eg_dev_scan": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _lp, _i64, _vp, _vp, _vp]),
     "eg_dev_argmax_tsq": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "eg_dev_gemv_i8": (C.c_int, [_vp, _i64, _i64, _i64, _vp, C.c_double, _vp, _vp]),
     "eg_dev_extract_col": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "eg_dev_synth_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, C.c_uint64, _vp]),
+    "eg_set_scan_mode": (C.c_int, [C.c_int]),
+    "eg_get_scan_mode": (C.c_int, []),
+    "eg_last_scan_kernel": (C.c_int, [_dp, _dp]),
     "eg_last_timing": (C.c_int, [_dp, C.c_int]),
 }
 

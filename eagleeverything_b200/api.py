@@ -198,6 +198,16 @@ class GenotypeStore:
             pass
 
 
+def set_scan_mode(mode):
+    """'f64' / 0: FP64 tensor cores (DMMA).  'i8' / 1: exact int8 slices on the tcgen05 tensor cores."""
+    m = {"f64": 0, "dmma": 0, "i8": 1}.get(mode, mode)
+    _lib.check(_lib.load().eg_set_scan_mode(int(m)))
+
+
+def get_scan_mode():
+    return int(_lib.load().eg_get_scan_mode())
+
+
 def last_timing():
     out = (C.c_double * 8)()
     _lib.check(_lib.load().eg_last_timing(out, 8))

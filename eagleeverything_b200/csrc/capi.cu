@@ -79,6 +79,15 @@ static int ensure_init() {
 }
 
 void syrk_release_cache();
+void scan_i8_release();
+static int g_scan_mode = -1;
+int scan_mode() {
+    if (g_scan_mode < 0) {
+        const char* e = getenv("EAGLE_SCAN_MODE");  // default: exact int8 slices; "f64" / "dmma" / "0" selects DMMA
+        g_scan_mode = (e && (e[0] == 'f' || e[0] == 'd' || e[0] == '0')) ? 0 : 1;
+    }
+    return g_scan_mode;
+}
 int launch_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp,
                 const int64_t* d_zero_rows, int n_zero, double* d_a, double* d_vara, cudaStream_t st);
 
@@ -510,11 +519,42 @@ extern "C" int eg_shutdown(void) {
     cudaDeviceSynchronize();
     eg_cache_clear();
     syrk_release_cache();
+    scan_i8_release();
     if (g_ctx.cublas) cublasDestroy(g_ctx.cublas);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
     if (g_ctx.d_err) cudaFree(g_ctx.d_err);
     g_ctx = Context();
+    return EG_OK;
+}
+
+extern "C" int eg_set_scan_mode(int mode) {
+    if (mode != 0 && mode != 1) return set_error(EG_ERR_ARG, "eg_set_scan_mode: 0 (FP64 DMMA) or 1 (exact int8 slices)");
+    g_scan_mode = mode;
+    return EG_OK;
+}
+extern "C" int eg_get_scan_mode(void) { return scan_mode(); }
+
+namespace eg {
+// CUDA events around the dominant scan kernel of the last eg_dev_scan call (for roofline reporting)
+static cudaEvent_t g_scan_ev[2] = {nullptr, nullptr};
+static double g_scan_ops = 0.0;
+void scan_kernel_mark(int which, cudaStream_t st, double ops) {
+    if (!g_scan_ev[0]) {
+        cudaEventCreate(&g_scan_ev[0]);
+        cudaEventCreate(&g_scan_ev[1]);
+    }
+    cudaEventRecord(g_scan_ev[which], st);
+    if (which == 0) g_scan_ops = ops;
+}
+}  // namespace eg
+extern "C" int eg_last_scan_kernel(double* ms, double* ops) {
+    if (!g_scan_ev[0] || !ms || !ops) return set_error(EG_ERR_ARG, "eg_last_scan_kernel: no scan has run");
+    EG_CUDA(cudaEventSynchronize(g_scan_ev[1]));
+    float f = 0;
+    EG_CUDA(cudaEventElapsedTime(&f, g_scan_ev[0], g_scan_ev[1]));
+    *ms = f;
+    *ops = g_scan_ops;
     return EG_OK;
 }
 
@@ -606,23 +646,36 @@ extern "C" int eg_store_extract_col(const eg_store_t* M, int64_t col, int32_t* o
 }
 
 // ================================================================== device-level: scan pre-products (cuBLAS)
-extern "C" int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a, int64_t n, double* d_tmp,
-                                   double* d_Wp, void* stream) {
-    if (!d_S || !d_V || !d_a || !d_tmp || !d_Wp || n <= 0) return set_error(EG_ERR_ARG, "eg_dev_scan_prepare: bad argument");
+// Columns [col0, col1) of W = S * (V * S) into the packed Wp (ld = Kpad); d_tmp needs n * (col1-col0) doubles.
+extern "C" int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1,
+                                        double* d_tmp, double* d_Wp, void* stream) {
+    if (!d_S || !d_V || !d_tmp || !d_Wp || n <= 0 || col0 < 0 || col1 > n || col0 > col1)
+        return set_error(EG_ERR_ARG, "eg_dev_scan_prepare_cols: bad argument");
+    if (col0 == col1) return EG_OK;
+    EG_TRY(ensure_init());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Kpad = round_up(n, 32), nc = col1 - col0;
+    const double one = 1.0, zero = 0.0;
+    if (cublasSetStream(g_ctx.cublas, st) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasSetStream");
+    // calculate_a_and_vara_rcpp.cpp:97   tmp = dim_reduced_vara * inv_MMt_sqrt      (columns col0..col1)
+    if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)nc, (int)n, &one, d_V, (int)n, d_S + col0 * n,
+                    (int)n, &zero, d_tmp, (int)n) != CUBLAS_STATUS_SUCCESS)
+        return set_error(EG_ERR_CUDA, "cublasDgemm(V*S) failed");
+    // :98   W = inv_MMt_sqrt * tmp, written straight into the packed layout (ld = Kpad)
+    if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)nc, (int)n, &one, d_S, (int)n, d_tmp, (int)n,
+                    &zero, d_Wp + col0 * Kpad, (int)Kpad) != CUBLAS_STATUS_SUCCESS)
+        return set_error(EG_ERR_CUDA, "cublasDgemm(S*tmp) failed");
+    return EG_OK;
+}
+
+// v = S * a into column n of Wp, then fold W into U = diag(W) + strict_upper(W + W^T) (needs ALL columns of W)
+extern "C" int eg_dev_scan_fold(const double* d_S, const double* d_a, int64_t n, double* d_Wp, void* stream) {
+    if (!d_S || !d_a || !d_Wp || n <= 0) return set_error(EG_ERR_ARG, "eg_dev_scan_fold: bad argument");
     EG_TRY(ensure_init());
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t Kpad = round_up(n, 32);
     const double one = 1.0, zero = 0.0;
-    EG_CUDA(cudaMemsetAsync(d_Wp, 0, (size_t)eg_scan_wp_elems(n) * 8, st));
     if (cublasSetStream(g_ctx.cublas, st) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasSetStream");
-    // calculate_a_and_vara_rcpp.cpp:97   tmp = dim_reduced_vara * inv_MMt_sqrt
-    if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_V, (int)n, d_S, (int)n,
-                    &zero, d_tmp, (int)n) != CUBLAS_STATUS_SUCCESS)
-        return set_error(EG_ERR_CUDA, "cublasDgemm(V*S) failed");
-    // :98   W = inv_MMt_sqrt * tmp, written straight into the packed layout (ld = Kpad)
-    if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_S, (int)n, d_tmp, (int)n,
-                    &zero, d_Wp, (int)Kpad) != CUBLAS_STATUS_SUCCESS)
-        return set_error(EG_ERR_CUDA, "cublasDgemm(S*tmp) failed");
     // :90   v = inv_MMt_sqrt * a  -> column n of Wp
     if (cublasDgemv(g_ctx.cublas, CUBLAS_OP_N, (int)n, (int)n, &one, d_S, (int)n, d_a, 1, &zero, d_Wp + n * Kpad, 1) !=
         CUBLAS_STATUS_SUCCESS)
@@ -631,6 +684,15 @@ extern "C" int eg_dev_scan_prepare(const double* d_S, const double* d_V, const d
     const unsigned nb = (unsigned)((n + 31) / 32);
     symmetrize_upper_kernel<<<dim3(nb, nb), 256, 0, st>>>(d_Wp, n, Kpad);
     return check_launch("symmetrize_upper_kernel");
+}
+
+extern "C" int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a, int64_t n, double* d_tmp,
+                                   double* d_Wp, void* stream) {
+    if (!d_S || !d_V || !d_a || !d_tmp || !d_Wp || n <= 0) return set_error(EG_ERR_ARG, "eg_dev_scan_prepare: bad argument");
+    EG_TRY(ensure_init());
+    EG_CUDA(cudaMemsetAsync(d_Wp, 0, (size_t)eg_scan_wp_elems(n) * 8, (cudaStream_t)stream));
+    EG_TRY(eg_dev_scan_prepare_cols(d_S, d_V, n, 0, n, d_tmp, d_Wp, stream));
+    return eg_dev_scan_fold(d_S, d_a, n, d_Wp, stream);
 }
 
 // ================================================================== reference-facing entry points

@@ -232,6 +232,11 @@ extern "C" int64_t eg_scan_wp_elems(int64_t n) {
 }
 
 namespace eg {
+int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp, int64_t Kpad,
+                   const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st);
+void scan_kernel_mark(int which, cudaStream_t st, double ops);
+int scan_mode();  // 0 = FP64 DMMA (scan_f64_kernel), 1 = exact int8 slices (scan_i8_kernel)
+
 __global__ void zero_entries_kernel(double* v, const int64_t* idx, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[idx[i]] = 0.0;
@@ -258,10 +263,13 @@ int launch_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const d
         zero_entries_kernel<<<(n_zero + 127) / 128, 128, 0, st>>>(d_a, d_zero_rows, n_zero);
         EG_TRY(check_launch("zero_entries_kernel"));
     }
+    if (scan_mode() == 1) return launch_scan_i8(d_Mt, L, n, pitch, d_Wp, p.Kpad, d_zero_rows, n_zero, d_vara, st);
     EG_CUDA(cudaFuncSetAttribute(scan_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_BYTES));
     const int64_t cap = (int64_t)num_sms() * SC_CTAS_PER_SM;
     const int64_t grid = p.num_blocks < cap ? p.num_blocks : cap;
+    scan_kernel_mark(0, st, 2.0 * SC_BM * SC_BN * SC_BK * (double)p.total_steps * (double)p.num_blocks);  // executed flops
     scan_f64_kernel<<<(unsigned)grid, SC_THREADS, SC_SMEM_BYTES, st>>>(p);
+    scan_kernel_mark(1, st, 0.0);
     return check_launch("scan_f64_kernel");
 }
 }  // namespace eg

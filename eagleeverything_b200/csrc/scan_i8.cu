@@ -1,0 +1,475 @@
+// K3' -- the variance scan evaluated EXACTLY on the int8 tensor cores (tcgen05.mma.kind::i8).
+//
+// Same quantity as scan_f64.cu (reference src/calculate_a_and_vara_rcpp.cpp:97-112):
+//     vara_j = sum_k ( sum_{i<=k} m_ij U_ik ) m_kj ,   U = diag(W) + strict_upper(W + W^T)
+// The genotypes m are already int8 in {-1,0,1}.  Each column k of the FP64 matrix U is written as
+//     U_ik = 2^(e_k) * sum_{s=0..7} q_s(i,k) * 2^(-6-7s)  +  r ,   q_s in [-64,64] (int8),
+// by repeated round-to-nearest of the exactly computed remainder (|r| <= 2^(e_k-56), i.e. below one
+// ulp of the column's largest entry: the full FP64 significand of U is kept).  Then
+//     P_s(j,k) = sum_i m_ij q_s(i,k)          is an EXACT int32 (|P| <= 64 n), one int8 GEMM per slice,
+//     T'_jk   = 2^(e_k-55) * sum_s P_s 2^(7(7-s))   is recombined exactly except for ONE rounding,
+// which is tighter than the n roundings of an FP64 GEMM accumulation.  8 int8 GEMMs at >3 PFLOP/s
+// replace one FP64 GEMM at ~30 TFLOP/s.
+//
+// Layouts.  A operand: the Mt store (L x n int8, K-major).  B operand: Q, (n/32 groups) x 256 rows x Kp
+// bytes, K-major; row (kk>>2)*32 + s*4 + (kk&3) of group g holds slice s of column k = 32 g + kk, so
+// that one 32-column TMEM load brings all 8 slices of 4 columns to a thread.  Rows i > k and the pad
+// are zero, so the contraction for group g stops at k-block ceil((32g+32)/128).
+//
+// Kernel: same warp-specialised tcgen05 pipeline as syrk_i8.cu (TMA producer, one-thread UMMA issuer
+// M128 N256 K32, double-buffered TMEM, 4 epilogue warps).  Work unit = (128-marker block, group); an
+// epilogue thread owns one marker row (one TMEM lane): it recombines the slices, multiplies by the
+// marker's own genotype bytes and writes ONE double per (marker, group); a second tiny kernel sums
+// the groups in index order.  Fixed order everywhere: identical marker rows give bit-identical
+// results whatever their position, tile or GPU.  Units are ordered in (16 marker blocks x 9 groups)
+// super-tiles and kept in K lock-step by the same phase counters as the SYRK, so a wave shares its
+// operand rows through L2.
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace eg {
+
+constexpr int SI_BM = 128;
+constexpr int SI_BN = 256;
+constexpr int SI_BK = 128;
+constexpr int SI_STAGES = 4;
+constexpr int SI_A_BYTES = SI_BM * SI_BK;
+constexpr int SI_B_BYTES = SI_BN * SI_BK;
+constexpr int SI_STAGE_BYTES = SI_A_BYTES + SI_B_BYTES;
+constexpr int SI_THREADS = 192;
+constexpr int SI_TMEM_COLS = 512;
+constexpr int SI_SLICES = 8;
+constexpr int SI_GCOLS = 32;   // columns of U per group (32 x 8 slices = 256 = one UMMA N)
+constexpr int SI_MSUP = 16;    // super-tile: marker blocks
+constexpr int SI_GSUP = 9;     //             x groups  (~ one wave of 148 CTAs)
+constexpr int SI_PHASE = 16;
+constexpr int SI_LAG = 4;
+constexpr int SI_SMEM_BYTES = SI_STAGES * SI_STAGE_BYTES + 1024 + 256;
+
+struct ScanI8Params {
+    int64_t L, n;
+    int32_t G, MB, KB;          // groups, marker blocks, k-blocks covering n
+    const int8_t* Mt;
+    int64_t pitch;
+    const double* scale;        // [G*32]  2^(e_k - 55), 0 for pad columns
+    double* partial;            // [G][L]
+    const int2* units;          // (mb, g)
+    int64_t nunits;
+    uint32_t* phase_ctr;
+    int32_t phases_per_unit;
+};
+
+__device__ __forceinline__ void si_red_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t si_ld(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int si_kb_end(int g, int KB) {
+    const int kb = (g * SI_GCOLS + SI_GCOLS + SI_BK - 1) / SI_BK;  // rows i <= k of U only
+    return kb < KB ? kb : KB;
+}
+__device__ __forceinline__ double si_s8_to_f64(uint32_t w, int b) {
+    const uint32_t g = (uint32_t)((int32_t)(w << (24 - 8 * b)) >> 24);
+    const uint32_t hi = (g & 0x80000000u) | ((g & 1u) * 0x3FF00000u);
+    return __hiloint2double((int)hi, 0);
+}
+
+__global__ void __launch_bounds__(SI_THREADS, 1)
+scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+               const ScanI8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SI_STAGES * SI_STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + SI_STAGES;
+    uint64_t* tmem_full = bars + 2 * SI_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmapA);
+        ptx::prefetch_tmap(&tmapB);
+        for (int s = 0; s < SI_STAGES; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&tmem_full[a], 1);
+            ptx::mbar_init(&tmem_empty[a], 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<SI_TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (+ K-phase flow control)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int round = 0, known = -1;
+            auto need_of = [&](int gp) -> uint32_t {
+                const int64_t left = p.nunits - (int64_t)(gp / p.phases_per_unit) * gridDim.x;
+                return (uint32_t)(left < (int64_t)gridDim.x ? left : (int64_t)gridDim.x);
+            };
+            for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
+                const int2 un = p.units[u];
+                const int kb1 = si_kb_end(un.y, p.KB);
+                for (int kb = 0; kb < kb1; kb++) {
+                    if (p.phase_ctr && (kb % SI_PHASE) == 0) {
+                        const int gp = round * p.phases_per_unit + kb / SI_PHASE;
+                        if (gp - SI_LAG > known) {
+                            uint32_t v[SI_LAG];
+#pragma unroll
+                            for (int q = 0; q < SI_LAG; q++) v[q] = si_ld(p.phase_ctr + max(gp - 1 - q, 0));
+#pragma unroll
+                            for (int q = SI_LAG - 1; q >= 0; q--)
+                                if (gp - 1 - q >= 0 && gp - 1 - q > known && v[q] >= need_of(gp - 1 - q)) known = gp - 1 - q;
+                            uint32_t spins = 0;
+                            while (gp - SI_LAG > known) {
+                                if (si_ld(p.phase_ctr + gp - SI_LAG) >= need_of(gp - SI_LAG)) known = gp - SI_LAG;
+                                else if (++spins > (1u << 24)) {
+                                    printf("eagle: scan_i8 flow control timed out (block %d phase %d)\n", (int)blockIdx.x, gp);
+                                    __trap();
+                                }
+                            }
+                        }
+                    }
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * SI_STAGE_BYTES;
+                    uint8_t* sB = sA + SI_A_BYTES;
+                    ptx::mbar_expect_tx(&full[stage], SI_STAGE_BYTES);
+                    ptx::tma_load_2d(sA, &tmapA, kb * SI_BK, un.x * SI_BM, &full[stage]);
+                    ptx::tma_load_2d(sB, &tmapB, kb * SI_BK, un.y * SI_BN, &full[stage]);
+                    ptx::tma_load_2d(sB + SI_B_BYTES / 2, &tmapB, kb * SI_BK, un.y * SI_BN + 128, &full[stage]);
+                    if (++stage == SI_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ UMMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_i8(SI_BM, SI_BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            int round = 0;
+            for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
+                const int2 un = p.units[u];
+                const int kb1 = si_kb_end(un.y, p.KB);
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SI_BN);
+                for (int kb = 0; kb < kb1; kb++) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    if (p.phase_ctr && ((kb % SI_PHASE) == SI_PHASE - 1 || kb == kb1 - 1)) {
+                        const int ph = kb / SI_PHASE;
+                        uint32_t* c = p.phase_ctr + (int64_t)round * p.phases_per_unit;
+                        si_red_add(c + ph, 1u);
+                        if (kb == kb1 - 1)
+                            for (int q = ph + 1; q < p.phases_per_unit; q++) si_red_add(c + q, 1u);
+                    }
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + stage * SI_STAGE_BYTES);
+                    const uint64_t a_desc = ptx::make_desc_k_sw128(a_addr);
+                    const uint64_t b_desc = ptx::make_desc_k_sw128(a_addr + SI_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < SI_BK / 32; k++)
+                        ptx::umma_i8(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                     (kb > 0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit(&empty[stage]);
+                    if (++stage == SI_STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: one thread = one marker row
+        const int q4 = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            const int2 un = p.units[u];
+            const int64_t j = (int64_t)un.x * SI_BM + q4 * 32 + lane;
+            const int64_t jc = j < p.L ? j : p.L - 1;
+            // this marker's genotypes at the 32 columns of the group (pad columns are zero in the store)
+            const uint4* mp = reinterpret_cast<const uint4*>(p.Mt + jc * p.pitch + (int64_t)un.y * SI_GCOLS);
+            const uint4 m0 = mp[0], m1 = mp[1];
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const double* sc = p.scale + (int64_t)un.y * SI_GCOLS;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            double sum = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {  // 32 TMEM columns = 8 slices x 4 columns (kk = 4c .. 4c+3)
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_BN + c * 32), v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    // |P_s| <= 64 n, so P*128 + P' fits int32 for n < 260k
+                    const int y01 = (int)v[0 * 4 + e] * 128 + (int)v[1 * 4 + e];
+                    const int y23 = (int)v[2 * 4 + e] * 128 + (int)v[3 * 4 + e];
+                    const int y45 = (int)v[4 * 4 + e] * 128 + (int)v[5 * 4 + e];
+                    const int y67 = (int)v[6 * 4 + e] * 128 + (int)v[7 * 4 + e];
+                    const double hi = fma((double)y01, 16384.0, (double)y23);     // exact (< 2^46)
+                    const double lo = fma((double)y45, 16384.0, (double)y67);     // exact
+                    const double x = fma(hi, 268435456.0, lo);                    // the one rounding
+                    const double t = x * __ldg(sc + c * 4 + e);                   // power-of-two scale: exact
+                    sum = fma(t, si_s8_to_f64(mw[c], e), sum);                    // row-dot with m_kj in {-1,0,1}
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            if (j < p.L) p.partial[(int64_t)un.y * p.L + j] = sum;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<SI_TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------ slicing of U
+// per column: e_k with max_i |U_ik| * 2^(-e_k) in [0.5, 1); scale_k = 2^(e_k - 55)
+__global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
+                                                          int32_t* __restrict__ expo, double* __restrict__ scale,
+                                                          int64_t ncols_pad) {
+    const int64_t k = blockIdx.x;
+    double amax = 0.0;
+    if (k < n)
+        for (int64_t i = threadIdx.x; i <= k; i += 256) amax = fmax(amax, fabs(Wp[i + k * ld]));
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0 && k < ncols_pad) {
+        for (int w = 1; w < 8; w++) amax = fmax(amax, sh[w]);
+        int e = 0;
+        double s = 0.0;
+        if (k < n && amax > 0.0 && amax <= 1.79769313486231570e308) {
+            frexp(amax, &e);
+            s = ldexp(1.0, e - 55);
+        } else if (k < n && amax != amax) {
+            s = amax;  // NaN in U poisons the column, as it would poison the reference's product
+        }
+        expo[k] = e;
+        scale[k] = s;
+    }
+}
+// Q rows for column k = 32 g + kk: g*256 + (kk>>2)*32 + s*4 + (kk&3); thread -> 4 consecutive i
+__global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
+                                                       const int32_t* __restrict__ expo, int8_t* __restrict__ Q,
+                                                       int64_t Kp) {
+    const int64_t k = blockIdx.y;
+    const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= Kp) return;
+    const int64_t g = k / SI_GCOLS;
+    const int kk = (int)(k - g * SI_GCOLS);
+    int8_t* base = Q + (g * SI_BN + (kk >> 2) * 32 + (kk & 3)) * Kp + i0;
+    uint32_t out[SI_SLICES];
+#pragma unroll
+    for (int s = 0; s < SI_SLICES; s++) out[s] = 0;
+    if (k < n) {
+        const int e = expo[k];
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int64_t i = i0 + d;
+            if (i <= k && i < n) {
+                double r = ldexp(Wp[i + k * ld], 6 - e);  // |r| < 64
+#pragma unroll
+                for (int s = 0; s < SI_SLICES; s++) {
+                    const double qd = rint(r);             // in [-64, 64]
+                    out[s] |= ((uint32_t)(int)qd & 0xFFu) << (8 * d);
+                    r = (r - qd) * 128.0;                  // exact: |r - qd| <= 0.5
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < SI_SLICES; s++) *reinterpret_cast<uint32_t*>(base + (int64_t)s * 4 * Kp) = out[s];
+}
+
+// (mb, g) -> position in the super-tile order
+__global__ void si_units_kernel(int2* units, int MB, int G) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)MB * G) return;
+    const int mb = (int)(t % MB), g = (int)(t / MB);
+    const int ms = mb / SI_MSUP, gs = g / SI_GSUP;
+    const int msz = min(SI_MSUP, MB - ms * SI_MSUP);
+    const int64_t u = (int64_t)ms * SI_MSUP * G + (int64_t)gs * SI_GSUP * msz + (int64_t)(g - gs * SI_GSUP) * msz +
+                      (mb - ms * SI_MSUP);
+    units[u] = make_int2(mb, g);
+}
+
+// vara_j = sum over groups in index order; zeroed rows give 0
+__global__ void __launch_bounds__(256) si_reduce_kernel(const double* __restrict__ partial, int64_t L, int G,
+                                                        const int64_t* __restrict__ zero_rows, int n_zero,
+                                                        double* __restrict__ vara) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= L) return;
+    double s = 0.0;
+    for (int g = 0; g < G; g++) s += partial[(int64_t)g * L + j];
+    for (int z = 0; z < n_zero; z++)
+        if (zero_rows[z] == j) s = 0.0;
+    vara[j] = s;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled si_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(f);
+    }
+    return fn;
+}
+static int si_make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int64_t pitch) {
+    PFN_encodeTiled enc = si_encode_fn();
+    if (!enc) return set_error(EG_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {128, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(EG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return EG_OK;
+}
+
+struct ScanI8Workspace {
+    int device = -1;
+    int8_t* Q = nullptr;        size_t q_cap = 0;
+    double* scale = nullptr;    size_t sc_cap = 0;
+    int32_t* expo = nullptr;    size_t expo_cap = 0;
+    double* partial = nullptr;  size_t part_cap = 0;
+    int2* units = nullptr;      size_t unit_cap = 0;  int units_MB = -1, units_G = -1;
+    uint32_t* phase = nullptr;  size_t phase_cap = 0;
+};
+static thread_local ScanI8Workspace g_si;
+
+void scan_kernel_mark(int which, cudaStream_t st, double ops);
+
+void scan_i8_release() {
+    cudaFree(g_si.Q); cudaFree(g_si.scale); cudaFree(g_si.expo); cudaFree(g_si.partial); cudaFree(g_si.units);
+    cudaFree(g_si.phase);
+    g_si = ScanI8Workspace();
+}
+template <class T>
+static int si_grow(T** p, size_t* cap, size_t need, const char* what) {
+    if (need <= *cap && *p) return EG_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (cudaMalloc(p, need * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(EG_ERR_ALLOC, "out of device memory for %s (%zu bytes)", what, need * sizeof(T));
+    }
+    *cap = need;
+    return EG_OK;
+}
+
+// vara for all rows of an Mt store from the folded matrix U (columns 0..n-1 of Wp)
+int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp, int64_t Kpad,
+                   const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st) {
+    int dev = 0;
+    EG_CUDA(cudaGetDevice(&dev));
+    if (g_si.device != dev) {
+        if (g_si.device >= 0) scan_i8_release();
+        g_si.device = dev;
+    }
+    const int G = (int)((n + SI_GCOLS - 1) / SI_GCOLS);
+    const int MB = (int)((L + SI_BM - 1) / SI_BM);
+    const int64_t Kp = round_up(n, 128);
+    const int KB = (int)(Kp / SI_BK);
+    if (pitch < Kp || pitch < (int64_t)G * SI_GCOLS)
+        return set_error(EG_ERR_ARG, "scan_i8: Mt pitch %lld too small for n=%lld", (long long)pitch, (long long)n);
+    EG_TRY(si_grow(&g_si.Q, &g_si.q_cap, (size_t)G * SI_BN * Kp, "sliced U"));
+    EG_TRY(si_grow(&g_si.scale, &g_si.sc_cap, (size_t)G * SI_GCOLS, "column scales"));
+    EG_TRY(si_grow(&g_si.expo, &g_si.expo_cap, (size_t)G * SI_GCOLS, "column exponents"));
+    EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)G * L, "per-group partial sums"));
+    const int64_t nunits = (int64_t)MB * G;
+    if (g_si.units_MB != MB || g_si.units_G != G || !g_si.units) {
+        EG_TRY(si_grow(&g_si.units, &g_si.unit_cap, (size_t)nunits, "unit table"));
+        si_units_kernel<<<(unsigned)((nunits + 255) / 256), 256, 0, st>>>(g_si.units, MB, G);
+        EG_TRY(check_launch("si_units_kernel"));
+        g_si.units_MB = MB;
+        g_si.units_G = G;
+    }
+    // 1. slice U
+    si_colscale_kernel<<<(unsigned)(G * SI_GCOLS), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo, g_si.scale, (int64_t)G * SI_GCOLS);
+    EG_TRY(check_launch("si_colscale_kernel"));
+    si_slice_kernel<<<dim3((unsigned)((Kp / 4 + 255) / 256), (unsigned)(G * SI_GCOLS)), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo,
+                                                                                                   g_si.Q, Kp);
+    EG_TRY(check_launch("si_slice_kernel"));
+    // 2. the int8 contraction with fused recombination + row-dot
+    CUtensorMap tA, tB;
+    EG_TRY(si_make_map(&tA, d_Mt, Kp, L, pitch));
+    EG_TRY(si_make_map(&tB, g_si.Q, Kp, (int64_t)G * SI_BN, Kp));
+    ScanI8Params p;
+    p.L = L; p.n = n; p.G = G; p.MB = MB; p.KB = KB;
+    p.Mt = d_Mt; p.pitch = pitch; p.scale = g_si.scale; p.partial = g_si.partial;
+    p.units = g_si.units; p.nunits = nunits;
+    const int sms = num_sms();
+    const int grid = nunits < sms ? (int)nunits : sms;
+    p.phases_per_unit = (KB + SI_PHASE - 1) / SI_PHASE;
+    const int64_t rounds = (nunits + grid - 1) / grid;
+    const size_t nctr = (size_t)rounds * p.phases_per_unit;
+    const char* env_fc = getenv("EAGLE_SCAN_FLOWCTL");
+    const bool flow = !(env_fc && env_fc[0] == '0') && grid > 1 && nctr < ((size_t)1 << 28);
+    p.phase_ctr = nullptr;
+    if (flow) {
+        EG_TRY(si_grow(&g_si.phase, &g_si.phase_cap, nctr, "flow-control counters"));
+        EG_CUDA(cudaMemsetAsync(g_si.phase, 0, nctr * sizeof(uint32_t), st));
+        p.phase_ctr = g_si.phase;
+    }
+    EG_CUDA(cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SI_THREADS);
+    cfg.dynamicSmemBytes = SI_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = flow ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    double kblocks = 0.0;  // executed int8 ops: 2 * 128 * 256 * 128 per (marker block, k-block of a group)
+    for (int g = 0; g < G; g++) {
+        const int kb = (g * SI_GCOLS + SI_GCOLS + SI_BK - 1) / SI_BK;
+        kblocks += kb < KB ? kb : KB;
+    }
+    scan_kernel_mark(0, st, kblocks * MB * 2.0 * SI_BM * SI_BN * SI_BK);
+    EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel, tA, tB, p));
+    scan_kernel_mark(1, st, 0.0);
+    // 3. groups summed in index order
+    si_reduce_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(g_si.partial, L, G, d_zero_rows, n_zero, d_vara);
+    return check_launch("si_reduce_kernel");
+}
+
+}  // namespace eg

@@ -104,6 +104,28 @@ def scan_prepare(S, V, a, n, Wp=None, tmp=None):
     return Wp
 
 
+def scan_prepare_sharded(S, V, a, n, rank, world, Wp=None, tmp=None):
+    """Pre-products with the columns of W = S (V S) split over the ranks (2*2n^3/world flops each instead of
+    replicated), the blocks exchanged with one broadcast per rank (NCCL), then folded on every rank."""
+    import torch.distributed as dist
+    lib = _lib.load()
+    Kpad = (n + 31) // 32 * 32
+    if Wp is None:
+        Wp = torch.empty(lib.eg_scan_wp_elems(n), dtype=torch.float64, device=S.device)
+    blk = (n + world - 1) // world
+    c0, c1 = min(rank * blk, n), min((rank + 1) * blk, n)
+    if tmp is None:
+        tmp = torch.empty(n * max(blk, 1), dtype=torch.float64, device=S.device)
+    Wp.zero_()
+    _lib.check(lib.eg_dev_scan_prepare_cols(_ptr(S), _ptr(V), n, c0, c1, _ptr(tmp), _ptr(Wp), _stream()))
+    for r in range(world):  # contiguous column blocks of the column-major Wp
+        r0, r1 = min(r * blk, n), min((r + 1) * blk, n)
+        if r1 > r0:
+            dist.broadcast(Wp[r0 * Kpad:r1 * Kpad], src=r)
+    _lib.check(lib.eg_dev_scan_fold(_ptr(S), _ptr(a), n, _ptr(Wp), _stream()))
+    return Wp
+
+
 def scan(storeT, L, n, Wp, zero_rows=(), out_a=None, out_vara=None):
     """K3.  storeT: int8 (L, pitch >= round_up(n+1,128)) holding Mt."""
     lib = _lib.load()

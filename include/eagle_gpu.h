@@ -139,6 +139,13 @@ int eg_dev_mmt_finalize(const int32_t* d_C, int64_t n, int64_t ldc, double* d_ou
 int64_t eg_scan_wp_elems(int64_t n);
 int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a, int64_t n, double* d_tmp,
                         double* d_Wp, void* stream);
+/* The same in two steps, for marker-sharded multi-GPU runs: each rank computes the columns [col0,col1) of W
+ * (d_tmp: n*(col1-col0) doubles; d_Wp zeroed by the caller), the column blocks are exchanged between the
+ * ranks (broadcast / all-gather of contiguous ranges of d_Wp: column c starts at d_Wp + c*round_up(n,32)),
+ * then every rank folds the complete W. */
+int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1, double* d_tmp,
+                             double* d_Wp, void* stream);
+int eg_dev_scan_fold(const double* d_S, const double* d_a, int64_t n, double* d_Wp, void* stream);
 /* K3: a = Mt*v, vara_j = (Mt*W)_j . Mt_j for marker rows of an Mt store (L x n int8, pitch >=
  * round_up(n+1,128)); zero rows get a = vara = 0. */
 int eg_dev_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp,
@@ -157,6 +164,15 @@ int eg_dev_extract_col(const int8_t* d_M, int64_t n, int64_t pitch, int64_t col,
  * Column c is marker col_offset + c, row r is individual row_offset + r of an n_total-individual data set. */
 int eg_dev_synth_ascii(uint8_t* d_img, int64_t rows, int64_t cols, int64_t col_offset, int64_t n_total,
                        int64_t row_offset, uint64_t seed, void* stream);
+
+/* How var(a) is contracted (same result within the stated tolerance, both deterministic):
+ *   1  exact int8 slices of U on the tcgen05 int8 tensor cores, scan_i8.cu -- the default;
+ *   0  FP64 tensor cores (DMMA), scan_f64.cu (also: environment EAGLE_SCAN_MODE=f64). */
+int eg_set_scan_mode(int mode);
+int eg_get_scan_mode(void);
+/* Device time of the dominant kernel of the last eg_dev_scan (scan_i8_kernel or scan_f64_kernel),
+ * measured with CUDA events on its stream, and the arithmetic operations it executed. */
+int eg_last_scan_kernel(double* ms, double* ops);
 
 /* timing of the last host-level call, milliseconds per stage (h2d, decode, syrk, finalize, d2h,
  * prepare, scan); n_out entries written. */

@@ -103,6 +103,33 @@ def test_gemv_matches_float64(dev):
     np.testing.assert_allclose(y, 2.5 * ((G.T.astype(np.float64) - 1) @ x), rtol=1e-12, atol=1e-11)
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["dmma_f64", "tcgen05_i8"])
+def test_scan_modes_agree_at_scale(dev, mode):
+    """n = 3000 (not a multiple of any tile), 40,000 markers: both contractions against torch float64."""
+    device, torch = dev
+    from eagleeverything_b200 import api
+    n, L = 3000, 40000
+    img = device.synth_ascii(L, n, synth.GENO_SEED + 1)       # an Mt.ascii image: L rows of n characters
+    tt, err = device.decode(img, n + 1, L, n)
+    S, V, a = synth.scan_inputs(n, 5)
+    Sd, Vd, ad = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (S, V, a))
+    prev = api.get_scan_mode()
+    api.set_scan_mode(mode)
+    try:
+        Wp = device.scan_prepare(Sd, Vd, ad, n)
+        oa, ov = device.scan(tt, L, n, Wp, zero_rows=[7, 39999])
+        torch.cuda.synchronize()
+    finally:
+        api.set_scan_mode(prev)
+    W = Sd @ (Vd @ Sd)
+    Mr = tt[:, :n].double()
+    ra, rv = Mr @ (Sd @ ad), ((Mr @ W) * Mr).sum(1)
+    ra[[7, 39999]] = 0
+    rv[[7, 39999]] = 0
+    assert ((oa - ra).abs() <= 1e-9 * ra.abs() + 1e-12 * ra.abs().max()).all()
+    assert ((ov - rv).abs() <= 1e-9 * rv.abs() + 1e-12 * rv.abs().max()).all()
+
+
 def test_config2_full_size_properties(dev):
     """BASELINE config 2 (n=2,000 x L=500,000) on one GPU: decode -> M.Mt -> scan, checked by
     properties the domain offers and by an independent torch evaluation on the device."""

@@ -51,6 +51,15 @@ def assert_close(x, ref, cond, n, what=""):
     assert (err[solid] <= RTOL * np.abs(ref[solid])).all(), f"{what}: 1e-9 relative violated on a well-conditioned entry"
 
 
+@pytest.fixture(params=[0, 1], ids=["dmma_f64", "tcgen05_i8"])
+def scan_mode(request):
+    """Every scan parity test runs on both contractions of var(a): FP64 DMMA and exact int8 slices."""
+    prev = api.get_scan_mode()
+    api.set_scan_mode(request.param)
+    yield request.param
+    api.set_scan_mode(prev)
+
+
 def write_pair(tmp_path, G, tag):
     m, mt = str(tmp_path / f"{tag}.M.ascii"), str(tmp_path / f"{tag}.Mt.ascii")
     npo.write_ascii(m, G)
@@ -132,7 +141,7 @@ def test_mmt_split_k_and_many_tiles(tmp_path):
 
 
 # ------------------------------------------------------------------------------- scan
-def test_scan_demo_against_golden(demo):
+def test_scan_demo_against_golden(demo, scan_mode):
     z = demo["z"]
     r = api.calculate_a_and_vara_rcpp(demo["Mt"], [NA], z["it1_S"], z["it1_V"], 8, (demo["L"], demo["n"]), z["it1_hat_a"])
     assert r["a"].shape == (demo["L"], 1) and r["vara"].shape == (demo["L"], 1)
@@ -143,7 +152,7 @@ def test_scan_demo_against_golden(demo):
     assert idx == 2207  # columns 2207 and 2209 are identical: the tie must go to the first
 
 
-def test_scan_synth_with_selected_rows(synth_small):
+def test_scan_synth_with_selected_rows(synth_small, scan_mode):
     s = synth_small
     S, V, a = synth.scan_inputs(s["n"], 3)
     dims = (s["L"], s["n"])
@@ -157,7 +166,7 @@ def test_scan_synth_with_selected_rows(synth_small):
 
 
 @pytest.mark.parametrize("n,L", [(1, 5), (31, 1), (127, 300), (128, 257), (129, 1000), (255, 129), (640, 1500)])
-def test_scan_ragged_sizes(tmp_path, n, L):
+def test_scan_ragged_sizes(tmp_path, n, L, scan_mode):
     G = synth.genotypes(n, L, seed=n + L)
     _, mt = write_pair(tmp_path, G, f"q{n}x{L}")
     S, V, a = synth.scan_inputs(n, n)
@@ -168,7 +177,7 @@ def test_scan_ragged_sizes(tmp_path, n, L):
     assert_close(got["vara"], ref["vara"], cv, n, "vara")
 
 
-def test_scan_identical_and_mirrored_markers_are_bit_identical(tmp_path):
+def test_scan_identical_and_mirrored_markers_are_bit_identical(tmp_path, scan_mode):
     """Tie hazard: duplicates / mirror images anywhere in the file must give
     bit-identical tsq, so that the first index wins exactly as in the reference."""
     n, L = 300, 2000
@@ -206,7 +215,7 @@ def test_reduced_a_and_extract(synth_small):
 
 
 # ------------------------------------------------------------------------------- end to end
-def test_forward_search_matches_oracle(demo):
+def test_forward_search_matches_oracle(demo, scan_mode):
     """Full multi-locus AM() forward search with the GPU library plugged into the restated driver:
     identical selected-QTL sequence, extBIC trace and per-iteration scores."""
     z = demo["z"]
@@ -224,7 +233,7 @@ def test_forward_search_matches_oracle(demo):
     assert r2["selected"] == [] and r2["all_picked"] == [1200]
 
 
-def test_forward_search_synthetic(synth_small):
+def test_forward_search_synthetic(synth_small, scan_mode):
     s = synth_small
     y, qtl = synth.phenotype(s["G"])
     rg = am.AM(api, s["geno"], y, maxit=6)
@@ -234,7 +243,7 @@ def test_forward_search_synthetic(synth_small):
 
 
 # ------------------------------------------------------------------------------- stores / shards
-def test_store_shards_sum_to_full_and_transpose(synth_small):
+def test_store_shards_sum_to_full_and_transpose(synth_small, scan_mode):
     from eagleeverything_b200 import dist as egd
     s = synth_small
     img = synth.ascii_image(s["G"])
