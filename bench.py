@@ -234,8 +234,8 @@ def run_gpu(args):
     V = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g)
     V = (V + V.T) * (0.5 / n ** 0.5); V.diagonal().add_(1.5)
     ah = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
-    pitch_m, pitch_t = device.store_pitch(Lg), device.store_pitch(n)
-    store = torch.empty((n, pitch_m), dtype=torch.int8, device="cuda")
+    pitch_t = device.store_pitch(n)
+    store = torch.empty(((Lg + 127) // 128, n, 128), dtype=torch.int8, device="cuda")  # K-blocked M store
     storeT = torch.empty((Lg, pitch_t), dtype=torch.int8, device="cuda")
     err = torch.zeros(4, dtype=torch.int32, device="cuda")
     C32 = torch.empty((n, n), dtype=torch.int32, device="cuda")
@@ -252,11 +252,11 @@ def run_gpu(args):
             if evs is not None:
                 evs[i].record()
         mark(0)
-        device.decode(img, Lg + 1, n, Lg, out=store, err=err)
+        device.decode_kb(img, Lg + 1, n, Lg, out=store, err=err)
         mark(1)
-        device.transpose(store, n, Lg, out=storeT)
+        device.transpose_kb(store, n, Lg, out=storeT)
         mark(2)
-        device.syrk(store, n, Lg, C32=C32, zero=True)
+        device.syrk_kb(store, n, Lg, C32=C32, zero=True)
         mark(3)
         egd.allreduce_partial_mmt(C32)
         mark(4)
@@ -412,7 +412,7 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
     if world > 1:
         img_d = torch.empty_like(img)
         Sd, Vd, ad = torch.empty_like(S), torch.empty_like(V), torch.empty_like(ah)
-        store = torch.empty((n, device.store_pitch(Lg)), dtype=torch.int8, device="cuda")
+        store = torch.empty(((Lg + 127) // 128, n, 128), dtype=torch.int8, device="cuda")
         storeT = torch.empty((Lg, device.store_pitch(n)), dtype=torch.int8, device="cuda")
         C32 = torch.empty((n, n), dtype=torch.int32, device="cuda")
         Kd = torch.empty((n, n), dtype=torch.float64, device="cuda")
@@ -421,9 +421,9 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
     def step_sharded():
         img_d.copy_(img_h, non_blocking=True)
         Sd.copy_(S_h, non_blocking=True); Vd.copy_(V_h, non_blocking=True); ad.copy_(a_h, non_blocking=True)
-        device.decode(img_d, Lg + 1, n, Lg, out=store)
-        device.transpose(store, n, Lg, out=storeT)
-        device.syrk(store, n, Lg, C32=C32, zero=True)
+        device.decode_kb(img_d, Lg + 1, n, Lg, out=store)
+        device.transpose_kb(store, n, Lg, out=storeT)
+        device.syrk_kb(store, n, Lg, C32=C32, zero=True)
         egd.allreduce_partial_mmt(C32)
         device.mmt_finalize(C32, n, out=Kd)
         if rank == 0:

@@ -54,6 +54,9 @@ SIGNATURES = {
     "eg_store_a_and_vara": (C.c_int, [_vp, _lp, _i64, _dp, _dp, _dp, _dp, _dp]),
     "eg_store_extract_col": (C.c_int, [_vp, _i64, _ip]),
     "eg_dev_decode": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "eg_dev_decode_kb": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "eg_dev_transpose_kb_i8": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
+    "eg_dev_syrk_i8_kb": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "eg_dev_transpose_i8": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "eg_dev_syrk_i8": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "eg_dev_syrk_zero_cols": (C.c_int, [_vp, _i64, _i64, _lp, _i64, _vp, _i64, _vp]),

@@ -18,7 +18,10 @@
 
 struct eg_store {
     int8_t* d = nullptr;
-    int64_t rows = 0, cols = 0, pitch = 0;
+    int64_t rows = 0, cols = 0;
+    int64_t pitch = 0;  // row-major stores (Mt orientation): bytes per row.  0: K-blocked store (M orientation),
+                        // [ceil(cols/128)][rows][128] bytes -- the layout the SYRK streams (syrk_i8.cu)
+    size_t bytes() const { return pitch ? (size_t)rows * (size_t)pitch : (size_t)((cols + 127) / 128) * (size_t)rows * 128; }
 };
 
 namespace eg {
@@ -91,16 +94,24 @@ int scan_mode() {
 int launch_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp,
                 const int64_t* d_zero_rows, int n_zero, double* d_a, double* d_vara, cudaStream_t st);
 
-// RAII device buffer
+// Stream-ordered allocations from the device's default memory pool (release threshold raised in
+// eg_init): multi-GB buffers are recycled between calls instead of going to the driver every time
+// (cudaMalloc + cudaFree of the stores and workspaces cost ~100 ms per forward step at n=10k x L=1M).
+static cudaError_t pool_alloc(void** p, size_t bytes) {
+    return cudaMallocAsync(p, bytes ? bytes : 16, g_ctx.stream);
+}
+static void pool_free(void* p) {
+    if (p) cudaFreeAsync(p, g_ctx.stream);
+}
+
+// RAII device buffer (valid on g_ctx.stream)
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
+    ~DevBuf() { pool_free(p); }
     int alloc(size_t bytes, const char* what) {
-        if (p) cudaFree(p);
+        pool_free(p);
         p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        cudaError_t e = pool_alloc(&p, bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
             p = nullptr;
@@ -149,12 +160,12 @@ static int parse_selected(const double* sel, int64_t nsel, int64_t limit, std::v
 }
 
 // ------------------------------------------------------------------ stores
-static int store_alloc(int64_t rows, int64_t cols, eg_store** out) {
+static int store_alloc(int64_t rows, int64_t cols, bool kblocked, eg_store** out) {
     eg_store* s = new eg_store();
     s->rows = rows;
     s->cols = cols;
-    s->pitch = store_pitch(cols);
-    cudaError_t e = cudaMalloc(&s->d, (size_t)rows * (size_t)s->pitch + 256);
+    s->pitch = kblocked ? 0 : store_pitch(cols);
+    cudaError_t e = pool_alloc((void**)&s->d, s->bytes() + 256);
     if (e != cudaSuccess) {
         cudaGetLastError();
         // evict cached stores (least recently used first) and retry once per eviction
@@ -162,10 +173,11 @@ static int store_alloc(int64_t rows, int64_t cols, eg_store** out) {
             size_t lru = 0;
             for (size_t i = 1; i < g_ctx.cache.size(); i++)
                 if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
-            cudaFree(g_ctx.cache[lru].store->d);
+            pool_free(g_ctx.cache[lru].store->d);
             delete g_ctx.cache[lru].store;
             g_ctx.cache.erase(g_ctx.cache.begin() + lru);
-            e = cudaMalloc(&s->d, (size_t)rows * (size_t)s->pitch + 256);
+            cudaStreamSynchronize(g_ctx.stream);
+            e = pool_alloc((void**)&s->d, s->bytes() + 256);
             if (e != cudaSuccess) cudaGetLastError();
         }
         if (e != cudaSuccess) {
@@ -182,13 +194,13 @@ static int store_alloc(int64_t rows, int64_t cols, eg_store** out) {
 // characters per line.  Row blocks are staged through two device buffers so that the H2D copy of
 // block k+1 overlaps the decode of block k.
 static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t row0, int64_t row1, int64_t col0,
-                            int64_t col1, eg_store** out) {
+                            int64_t col1, bool kblocked, eg_store** out) {
     EG_TRY(ensure_init());
     const int64_t rows = row1 - row0, w = col1 - col0, src_pitch_host = cols_total + 1;
     if (!image || rows <= 0 || w <= 0 || col0 < 0 || col1 > cols_total || row0 < 0)
         return set_error(EG_ERR_ARG, "genotype store: bad image range");
     eg_store* s = nullptr;
-    EG_TRY(store_alloc(rows, w, &s));
+    EG_TRY(store_alloc(rows, w, kblocked, &s));
     const bool full_width = (w == cols_total);
     const int64_t dev_pitch = full_width ? src_pitch_host : round_up(w, 16);
     int64_t block_rows = (int64_t)(256LL << 20) / dev_pitch;
@@ -206,6 +218,9 @@ static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t ro
         cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&decoded[i], cudaEventDisableTiming);
     }
+    // the staging buffers were allocated in g_ctx.stream order: the copy stream must not run ahead of that
+    cudaEventRecord(decoded[0], g_ctx.stream);
+    cudaStreamWaitEvent(g_ctx.copy_stream, decoded[0], 0);
     cudaMemsetAsync(g_ctx.d_err, 0, 4 * sizeof(int32_t), g_ctx.stream);
     double t_h2d = 0, t_dec = 0;
     Timer total(g_ctx.stream);
@@ -229,8 +244,10 @@ static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t ro
         if (rc != EG_OK) break;
         cudaEventRecord(copied[b], g_ctx.copy_stream);
         cudaStreamWaitEvent(g_ctx.stream, copied[b], 0);
-        rc = eg_dev_decode(stg[b].as<uint8_t>(), dev_pitch, (int64_t)block_rows * dev_pitch + 64, nr, w,
-                           s->d + r * s->pitch, s->pitch, g_ctx.d_err, g_ctx.stream);
+        rc = kblocked ? eg_dev_decode_kb(stg[b].as<uint8_t>(), dev_pitch, (int64_t)block_rows * dev_pitch + 64, nr, w, s->d,
+                                         rows, r, g_ctx.d_err, g_ctx.stream)
+                      : eg_dev_decode(stg[b].as<uint8_t>(), dev_pitch, (int64_t)block_rows * dev_pitch + 64, nr, w,
+                                      s->d + r * s->pitch, s->pitch, g_ctx.d_err, g_ctx.stream);
         cudaEventRecord(decoded[b], g_ctx.stream);
     }
     int32_t h_err[4] = {0, 0, 0, 0};
@@ -295,7 +312,7 @@ static int check_image_size(const MappedFile& f, const char* path, int64_t rows,
 }
 
 // cache lookup by (realpath, size, mtime, dims)
-static int cached_store(const char* path, int64_t rows, int64_t cols, eg_store** out) {
+static int cached_store(const char* path, int64_t rows, int64_t cols, bool kblocked, eg_store** out) {
     EG_TRY(ensure_init());
     if (!path) return set_error(EG_ERR_ARG, "null file name");
     if (rows <= 0 || cols <= 0) return set_error(EG_ERR_ARG, "dims must be positive");
@@ -303,8 +320,9 @@ static int cached_store(const char* path, int64_t rows, int64_t cols, eg_store**
     if (stat(path, &st) != 0) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s", path);
     char* rp = realpath(path, nullptr);
     char key[4400];
-    snprintf(key, sizeof(key), "%s|%lld|%lld.%09ld|%lldx%lld", rp ? rp : path, (long long)st.st_size,
-             (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (long long)rows, (long long)cols);
+    snprintf(key, sizeof(key), "%s|%lld|%lld.%09ld|%lldx%lld|%c", rp ? rp : path, (long long)st.st_size,
+             (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (long long)rows, (long long)cols,
+             kblocked ? 'K' : 'R');
     free(rp);
     for (auto& e : g_ctx.cache)
         if (e.key == key) {
@@ -316,14 +334,14 @@ static int cached_store(const char* path, int64_t rows, int64_t cols, eg_store**
     EG_TRY(f.open_ro(path));
     EG_TRY(check_image_size(f, path, rows, cols));
     eg_store* s = nullptr;
-    EG_TRY(store_from_image(f.p, cols, 0, rows, 0, cols, &s));
+    EG_TRY(store_from_image(f.p, cols, 0, rows, 0, cols, kblocked, &s));
     const char* envmax = getenv("EAGLE_GPU_CACHE_ENTRIES");
     const size_t maxe = envmax ? (size_t)atoi(envmax) : 4;
     while (g_ctx.cache.size() >= (maxe ? maxe : 1)) {
         size_t lru = 0;
         for (size_t i = 1; i < g_ctx.cache.size(); i++)
             if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
-        cudaFree(g_ctx.cache[lru].store->d);
+        pool_free(g_ctx.cache[lru].store->d);
         delete g_ctx.cache[lru].store;
         g_ctx.cache.erase(g_ctx.cache.begin() + lru);
     }
@@ -390,7 +408,8 @@ static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols
     EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
     {
         Timer t(st);
-        EG_TRY(eg_dev_syrk_i8(M->d, n, M->cols, M->pitch, C.as<int32_t>(), n, st));
+        EG_TRY(M->pitch ? eg_dev_syrk_i8(M->d, n, M->cols, M->pitch, C.as<int32_t>(), n, st)
+                        : eg_dev_syrk_i8_kb(M->d, n, M->cols, C.as<int32_t>(), n, st));
         g_ctx.timing[1] = t.stop();
     }
     if (!zero_cols.empty())
@@ -412,6 +431,8 @@ static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols
 static int scan_of_store(const eg_store* Mt, const std::vector<int64_t>& zero_rows, const double* S, const double* V,
                          const double* a, double* out_a, double* out_vara) {
     const int64_t L = Mt->rows, n = Mt->cols;
+    if (!Mt->pitch)
+        return set_error(EG_ERR_ARG, "the scan needs an Mt store (markers as rows); transpose the M store first");
     cudaStream_t st = g_ctx.stream;
     DevBuf dS, dV, da, dT, dW, oa, ov;
     EG_TRY(dS.alloc((size_t)n * n * 8, "inv_MMt_sqrt"));
@@ -500,6 +521,12 @@ extern "C" int eg_init(int device) {
     EG_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
     if (cublasCreate(&g_ctx.cublas) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasCreate failed");
     EG_CUDA(cudaMalloc(&g_ctx.d_err, 4 * sizeof(int32_t)));
+    {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        EG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        EG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     g_ctx.device = device;
     g_ctx.ready = true;
     return EG_OK;
@@ -507,10 +534,15 @@ extern "C" int eg_init(int device) {
 
 extern "C" void eg_cache_clear(void) {
     for (auto& e : g_ctx.cache) {
-        cudaFree(e.store->d);
+        pool_free(e.store->d);
         delete e.store;
     }
     g_ctx.cache.clear();
+    if (g_ctx.ready) {  // hand the recycled memory back to the driver
+        cudaStreamSynchronize(g_ctx.stream);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
 }
 
 extern "C" int eg_shutdown(void) {
@@ -568,12 +600,12 @@ extern "C" int eg_last_timing(double* out_ms, int n_out) {
 extern "C" int eg_store_from_host_ascii(const uint8_t* image, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
                                         eg_store_t** out) {
     if (!out) return set_error(EG_ERR_ARG, "null out");
-    return store_from_image(image, cols, 0, rows, col0, col1, out);
+    return store_from_image(image, cols, 0, rows, col0, col1, true, out);  // M orientation: K-blocked
 }
 extern "C" int eg_store_from_host_ascii_rows(const uint8_t* image, int64_t rows, int64_t cols, int64_t row0,
                                              int64_t row1, eg_store_t** out) {
     if (!out || row1 > rows) return set_error(EG_ERR_ARG, "bad row range");
-    return store_from_image(image, cols, row0, row1, 0, cols, out);
+    return store_from_image(image, cols, row0, row1, 0, cols, false, out);  // Mt orientation: row-major
 }
 extern "C" int eg_store_from_file(const char* path, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
                                   eg_store_t** out) {
@@ -581,14 +613,15 @@ extern "C" int eg_store_from_file(const char* path, int64_t rows, int64_t cols, 
     MappedFile f;
     EG_TRY(f.open_ro(path));
     EG_TRY(check_image_size(f, path, rows, cols));
-    return store_from_image(f.p, cols, 0, rows, col0, col1, out);
+    return store_from_image(f.p, cols, 0, rows, col0, col1, true, out);
 }
 extern "C" int eg_store_transpose(const eg_store_t* in, eg_store_t** out) {
     if (!in || !out) return set_error(EG_ERR_ARG, "null argument");
     EG_TRY(ensure_init());
     eg_store* s = nullptr;
-    EG_TRY(store_alloc(in->cols, in->rows, &s));
-    int rc = eg_dev_transpose_i8(in->d, in->rows, in->cols, in->pitch, s->d, s->pitch, g_ctx.stream);
+    EG_TRY(store_alloc(in->cols, in->rows, false, &s));  // the transpose is always a row-major (Mt-type) store
+    int rc = in->pitch ? eg_dev_transpose_i8(in->d, in->rows, in->cols, in->pitch, s->d, s->pitch, g_ctx.stream)
+                       : eg_dev_transpose_kb_i8(in->d, in->rows, in->cols, s->d, s->pitch, g_ctx.stream);
     if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "transpose");
     if (rc != EG_OK) {
         eg_store_free(s);
@@ -599,7 +632,7 @@ extern "C" int eg_store_transpose(const eg_store_t* in, eg_store_t** out) {
 }
 extern "C" int eg_store_free(eg_store_t* s) {
     if (!s) return EG_OK;
-    if (s->d) cudaFree(s->d);
+    pool_free(s->d);
     delete s;
     return EG_OK;
 }
@@ -712,7 +745,7 @@ extern "C" int eg_ReadBlock(const char* asciifname, int64_t start_row, int64_t n
         return set_error(EG_ERR_FORMAT, "ReadBlock: %s has %lld lines, rows [%lld,%lld) requested", asciifname,
                          (long long)nrows_file, (long long)start_row, (long long)(start_row + numrows_in_block));
     eg_store* s = nullptr;
-    EG_TRY(store_from_image(f.p, line, start_row, start_row + numrows_in_block, 0, numcols, &s));
+    EG_TRY(store_from_image(f.p, line, start_row, start_row + numrows_in_block, 0, numcols, false, &s));
     DevBuf d;
     int rc = d.alloc((size_t)numrows_in_block * numcols * 8, "ReadBlock output");
     if (rc == EG_OK) {
@@ -738,7 +771,7 @@ extern "C" int eg_calculateMMt_rcpp(const char* f_name_ascii, double max_memory_
     (void)num_cores;
     if (!dims || !out_MMt) return set_error(EG_ERR_ARG, "calculateMMt_rcpp: null argument");
     eg_store* M = nullptr;
-    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], &M));
+    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], true, &M));
     std::vector<int64_t> z;
     EG_TRY(parse_selected(selected_loci, n_selected_loci, dims[1], z, "calculateMMt_rcpp"));
     if (!quiet) say(message, message_ctx, " M %%*%% t(M) on GPU %d (int8 tensor cores, exact) ", g_ctx.device);
@@ -754,7 +787,7 @@ extern "C" int eg_calculate_a_and_vara_rcpp(const char* f_name_ascii, const doub
     if (!dims || !inv_MMt_sqrt || !dim_reduced_vara || !a || !out_a || !out_vara)
         return set_error(EG_ERR_ARG, "calculate_a_and_vara_rcpp: null argument");
     eg_store* Mt = nullptr;
-    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], &Mt));  // dims of Mt: (L, n)
+    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], false, &Mt));  // dims of Mt: (L, n)
     std::vector<int64_t> z;
     EG_TRY(parse_selected(selected_loci, n_selected_loci, dims[0], z, "calculate_a_and_vara_rcpp"));
     if (!quiet)
@@ -771,7 +804,7 @@ extern "C" int eg_calculate_reduced_a_rcpp(const char* f_name_ascii, double varG
     if (!dims || !P || !y || !out_ar) return set_error(EG_ERR_ARG, "calculate_reduced_a_rcpp: null argument");
     const int64_t n = dims[0], L = dims[1];  // dims of M; the file is Mt.ascii (L lines of n characters)
     eg_store* Mt = nullptr;
-    EG_TRY(cached_store(f_name_ascii, L, n, &Mt));
+    EG_TRY(cached_store(f_name_ascii, L, n, false, &Mt));
     std::vector<int64_t> z;
     EG_TRY(parse_selected(selected_loci, n_selected_loci, L, z, "calculate_reduced_a_rcpp"));
     if (!quiet) say(message, message_ctx, "Inside internal function calculate_reduced_a_rcpp. GPU %d ", g_ctx.device);
@@ -803,6 +836,6 @@ extern "C" int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_
         return set_error(EG_ERR_ARG, "extract_geno_rcpp: locus %lld outside [0, %lld)", (long long)selected_locus,
                          (long long)dims[1]);
     eg_store* M = nullptr;
-    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], &M));
+    EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], true, &M));  // shares the store with calculateMMt_rcpp
     return eg_store_extract_col(M, selected_locus, out);
 }

@@ -28,6 +28,7 @@ struct DecodeParams {
     int64_t rows, cols;
     int8_t* dst;
     int64_t dst_pitch;
+    int64_t kb_rows;          // 0: row-major dst (pitch dst_pitch); else K-blocked dst [col/128][kb_rows][128]
     int32_t* err;
     int32_t rows_per_unit;    // R
     int32_t chunk_bytes;      // CW (multiple of 512)
@@ -47,8 +48,18 @@ struct __align__(16) UnitGeom {
 
 __device__ __forceinline__ UnitGeom unit_geom(const DecodeParams& p, int64_t u, const uint8_t** a0_out) {
     UnitGeom g;
-    int64_t ru = u / p.chunks_per_row;
-    int32_t ch = (int32_t)(u - ru * p.chunks_per_row);
+    int64_t ru;
+    int32_t ch;
+    if (p.kb_rows) {
+        // K-blocked destination: row units fastest, so that CTAs running at the same time write adjacent rows of
+        // the same 128-marker blocks (contiguous memory) instead of 128-byte pieces a whole block apart
+        const int64_t row_units = p.num_units / p.chunks_per_row;
+        ch = (int32_t)(u / row_units);
+        ru = u - (int64_t)ch * row_units;
+    } else {
+        ru = u / p.chunks_per_row;
+        ch = (int32_t)(u - ru * p.chunks_per_row);
+    }
     g.r0 = ru * p.rows_per_unit;
     int64_t left = p.rows - g.r0;
     g.nrows = (int32_t)(left < p.rows_per_unit ? left : p.rows_per_unit);
@@ -163,19 +174,23 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_ascii_kernel(const DecodeP
         int64_t ncol = p.cols - g.c0;                            // valid source bytes per row in this chunk
         const int nvalid_row = ncol >= g.out_bytes ? g.out_bytes : (ncol > 0 ? (int)ncol : 0);
         uint32_t bad_here = 0;
+        // destination of the 16-byte vector at byte vb of this chunk (chunks start at multiples of 128 columns):
+        // row-major  dst + row*pitch + c0 + vb;   K-blocked  dst + (((c0+vb)>>7)*rows + row)*128 + (vb&127)
+        const int64_t kbr = p.kb_rows;
         if (g.nrows == 1) {
-            int8_t* drow = p.dst + g.r0 * p.dst_pitch + g.c0;
+            int8_t* drow = kbr ? p.dst + ((g.c0 >> 7) * kbr + g.r0) * 128 : p.dst + g.r0 * p.dst_pitch + g.c0;
             for (int v = warp * 32 + lane; v < nvec; v += DEC_THREADS) {
                 const int vb = v << 4;
                 int nv = nvalid_row - vb;
                 nv = nv > 16 ? 16 : nv;
                 uint4 out = make_uint4(0, 0, 0, 0);
                 if (nv > 0) out = decode16(sb, g.o0 + (uint32_t)vb, nv, bad_here);
-                *reinterpret_cast<uint4*>(drow + vb) = out;
+                int8_t* d = kbr ? drow + (int64_t)(vb >> 7) * kbr * 128 + (vb & 127) : drow + vb;
+                *reinterpret_cast<uint4*>(d) = out;
             }
         } else {
             for (int rr = warp; rr < g.nrows; rr += DEC_WARPS) {   // one warp per (short) row
-                int8_t* drow = p.dst + (g.r0 + rr) * p.dst_pitch + g.c0;
+                int8_t* drow = kbr ? p.dst + ((g.c0 >> 7) * kbr + g.r0 + rr) * 128 : p.dst + (g.r0 + rr) * p.dst_pitch + g.c0;
                 const uint32_t rbase = g.o0 + (uint32_t)rr * src_pitch32;
                 for (int v = lane; v < nvec; v += 32) {
                     const int vb = v << 4;
@@ -183,7 +198,8 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_ascii_kernel(const DecodeP
                     nv = nv > 16 ? 16 : nv;
                     uint4 out = make_uint4(0, 0, 0, 0);
                     if (nv > 0) out = decode16(sb, rbase + (uint32_t)vb, nv, bad_here);
-                    *reinterpret_cast<uint4*>(drow + vb) = out;
+                    int8_t* d = kbr ? drow + (int64_t)(vb >> 7) * kbr * 128 + (vb & 127) : drow + vb;
+                    *reinterpret_cast<uint4*>(d) = out;
                 }
             }
         }
@@ -200,8 +216,8 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_ascii_kernel(const DecodeP
 
 }  // namespace eg
 
-extern "C" int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_avail, int64_t rows,
-                             int64_t cols, int8_t* d_dst, int64_t dst_pitch, int32_t* d_err, void* stream) {
+static int decode_launch(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_avail, int64_t rows, int64_t cols,
+                         int8_t* d_dst, int64_t dst_pitch, int64_t kb_rows, int32_t* d_err, void* stream) {
     using namespace eg;
     if (!d_src || !d_dst || !d_err || rows < 0 || cols < 0 || src_pitch < cols || dst_pitch < cols ||
         (dst_pitch & 127) || ((uintptr_t)d_dst & 15))
@@ -216,7 +232,7 @@ extern "C" int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t sr
     }
     DecodeParams p;
     p.src = d_src; p.src_pitch = src_pitch; p.rows = rows; p.cols = cols;
-    p.dst = d_dst; p.dst_pitch = dst_pitch; p.err = d_err;
+    p.dst = d_dst; p.dst_pitch = dst_pitch; p.kb_rows = kb_rows; p.err = d_err;
     if (dst_pitch >= 4096 || src_pitch > DEC_SPAN / 2) {
         p.rows_per_unit = 1;
         p.chunk_bytes = DEC_SPAN;
@@ -232,4 +248,19 @@ extern "C" int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t sr
     int64_t grid = p.num_units < (int64_t)num_sms() * 3 ? p.num_units : (int64_t)num_sms() * 3;
     decode_ascii_kernel<<<(unsigned)grid, DEC_THREADS, DEC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
     return check_launch("decode_ascii_kernel");
+}
+
+extern "C" int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_avail, int64_t rows,
+                             int64_t cols, int8_t* d_dst, int64_t dst_pitch, int32_t* d_err, void* stream) {
+    return decode_launch(d_src, src_pitch, src_bytes_avail, rows, cols, d_dst, dst_pitch, 0, d_err, stream);
+}
+
+// K-blocked destination: [ceil(cols/128)][kb_rows][128] bytes; this call fills rows [row0, row0+rows) of it
+// (d_dst points at the start of the whole store).  The tail of the last block is zero-filled.
+extern "C" int eg_dev_decode_kb(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_avail, int64_t rows,
+                                int64_t cols, int8_t* d_dst, int64_t kb_rows, int64_t row0, int32_t* d_err,
+                                void* stream) {
+    if (kb_rows <= 0 || row0 < 0 || row0 + rows > kb_rows) return eg::set_error(EG_ERR_ARG, "eg_dev_decode_kb: bad rows");
+    return decode_launch(d_src, src_pitch, src_bytes_avail, rows, cols, d_dst + row0 * 128, eg::round_up(cols, 128),
+                         kb_rows, d_err, stream);
 }

@@ -14,8 +14,9 @@ namespace eg {
 
 // ------------------------------------------------------------------ transpose (64 x 64 byte tiles)
 constexpr int TR_TILE = 64;
+// in: row-major (in_pitch) when in_kb == 0, else K-blocked [col/128][rows][128]
 __global__ void __launch_bounds__(256) transpose_i8_kernel(const int8_t* __restrict__ in, int64_t rows, int64_t cols,
-                                                           int64_t in_pitch, int8_t* __restrict__ out,
+                                                           int64_t in_pitch, int in_kb, int8_t* __restrict__ out,
                                                            int64_t out_pitch, int64_t tiles_c) {
     __shared__ __align__(16) uint8_t tile[TR_TILE][TR_TILE + 16];
     const int t = threadIdx.x;
@@ -27,8 +28,11 @@ __global__ void __launch_bounds__(256) transpose_i8_kernel(const int8_t* __restr
         {   // load 64 rows x 64 bytes: thread -> (row t/4, 16-byte segment t%4); pitch padding is readable
             const int r = t >> 2, sgm = t & 3;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (r0 + r < rows && c0 + sgm * 16 < in_pitch)
-                v = *reinterpret_cast<const uint4*>(in + (r0 + r) * in_pitch + c0 + sgm * 16);
+            if (r0 + r < rows && c0 + sgm * 16 < in_pitch) {
+                const int64_t c = c0 + sgm * 16;
+                v = in_kb ? *reinterpret_cast<const uint4*>(in + ((c >> 7) * rows + r0 + r) * 128 + (c & 127))
+                          : *reinterpret_cast<const uint4*>(in + (r0 + r) * in_pitch + c);
+            }
             *reinterpret_cast<uint4*>(&tile[r][sgm * 16]) = v;
         }
         __syncthreads();
@@ -81,11 +85,15 @@ __global__ void __launch_bounds__(256) mmt_finalize_kernel(const int32_t* __rest
 }
 
 // ------------------------------------------------------------------ zeroed loci as a rank-k update
+// element (i, c) of an M store: row-major (pitch > 0) or K-blocked (pitch == 0)
+__device__ __forceinline__ int8_t store_at(const int8_t* M, int64_t n, int64_t pitch, int64_t i, int64_t c) {
+    return pitch ? M[i * pitch + c] : M[((c >> 7) * n + i) * 128 + (c & 127)];
+}
 __global__ void gather_cols_kernel(const int8_t* __restrict__ M, int64_t n, int64_t pitch,
                                    const int64_t* __restrict__ cols, int ncols, int8_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (int s = 0; s < ncols; s++) out[i * ncols + s] = M[i * pitch + cols[s]];
+    for (int s = 0; s < ncols; s++) out[i * ncols + s] = store_at(M, n, pitch, i, cols[s]);
 }
 __global__ void __launch_bounds__(256) syrk_zero_cols_kernel(const int8_t* __restrict__ G, int64_t n, int ncols,
                                                              int32_t* __restrict__ C, int64_t ldc) {
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(256) syrk_zero_cols_kernel(const int8_t* __res
 __global__ void extract_col_kernel(const int8_t* __restrict__ M, int64_t n, int64_t pitch, int64_t col,
                                    int32_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int32_t)M[i * pitch + col];
+    if (i < n) out[i] = (int32_t)store_at(M, n, pitch, i, col);
 }
 
 // ------------------------------------------------------------------ tsq argmax
@@ -226,8 +234,8 @@ __global__ void __launch_bounds__(256) gemv_i8_kernel(const int8_t* __restrict__
 
 using namespace eg;
 
-extern "C" int eg_dev_transpose_i8(const int8_t* d_in, int64_t rows, int64_t cols, int64_t in_pitch, int8_t* d_out,
-                                   int64_t out_pitch, void* stream) {
+static int transpose_launch(const int8_t* d_in, int64_t rows, int64_t cols, int64_t in_pitch, int in_kb, int8_t* d_out,
+                            int64_t out_pitch, void* stream) {
     if (!d_in || !d_out || rows < 0 || cols < 0 || (in_pitch & 15) || (out_pitch & 63) || in_pitch < cols ||
         out_pitch < rows)
         return set_error(EG_ERR_ARG, "eg_dev_transpose_i8: bad argument");
@@ -237,9 +245,18 @@ extern "C" int eg_dev_transpose_i8(const int8_t* d_in, int64_t rows, int64_t col
     const int64_t tiles_r = (out_pitch + TR_TILE - 1) / TR_TILE, tiles_c = (cols + TR_TILE - 1) / TR_TILE;
     const int64_t total = tiles_r * tiles_c;
     const int64_t cap = (int64_t)num_sms() * 16;
-    transpose_i8_kernel<<<(unsigned)(total < cap ? total : cap), 256, 0, st>>>(d_in, rows, cols, in_pitch, d_out,
+    transpose_i8_kernel<<<(unsigned)(total < cap ? total : cap), 256, 0, st>>>(d_in, rows, cols, in_pitch, in_kb, d_out,
                                                                               out_pitch, tiles_c);
     return check_launch("transpose_i8_kernel");
+}
+extern "C" int eg_dev_transpose_i8(const int8_t* d_in, int64_t rows, int64_t cols, int64_t in_pitch, int8_t* d_out,
+                                   int64_t out_pitch, void* stream) {
+    return transpose_launch(d_in, rows, cols, in_pitch, 0, d_out, out_pitch, stream);
+}
+// input in the K-blocked layout [ceil(cols/128)][rows][128]
+extern "C" int eg_dev_transpose_kb_i8(const int8_t* d_in_kb, int64_t rows, int64_t cols, int8_t* d_out,
+                                      int64_t out_pitch, void* stream) {
+    return transpose_launch(d_in_kb, rows, cols, round_up(cols, 128), 1, d_out, out_pitch, stream);
 }
 
 extern "C" int eg_dev_mmt_finalize(const int32_t* d_C, int64_t n, int64_t ldc, double* d_out, void* stream) {
@@ -283,7 +300,7 @@ extern "C" int eg_dev_syrk_zero_cols(const int8_t* d_M, int64_t n, int64_t pitch
 
 extern "C" int eg_dev_extract_col(const int8_t* d_M, int64_t n, int64_t pitch, int64_t col, int32_t* d_out,
                                   void* stream) {
-    if (!d_M || !d_out || n <= 0 || col < 0 || col >= pitch)
+    if (!d_M || !d_out || n <= 0 || col < 0 || (pitch && col >= pitch))  // pitch == 0: K-blocked store
         return set_error(EG_ERR_ARG, "eg_dev_extract_col: bad argument");
     extract_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_M, n, pitch, col, d_out);
     return check_launch("extract_col_kernel");

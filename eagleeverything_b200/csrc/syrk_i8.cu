@@ -70,6 +70,9 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     return v;
 }
 
+// KB == false: M row-major, 2-D tensor map {K, rows};  KB == true: M K-blocked [K/128][rows][128],
+// 3-D tensor map {128, rows, K/128} -- one K-block of all rows is a contiguous range of memory.
+template <bool KB>
 __global__ void __launch_bounds__(SY_THREADS, 1)
 syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -143,9 +146,15 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
                     uint8_t* sA = smem + stage * SY_STAGE_BYTES;
                     uint8_t* sB = sA + SY_A_BYTES;
                     ptx::mbar_expect_tx(&full[stage], SY_STAGE_BYTES);
-                    ptx::tma_load_2d(sA, &tmap, kb * SY_BK, t.x * SY_BM, &full[stage]);
-                    ptx::tma_load_2d(sB, &tmap, kb * SY_BK, t.y * SY_BN, &full[stage]);
-                    ptx::tma_load_2d(sB + SY_B_BYTES / 2, &tmap, kb * SY_BK, t.y * SY_BN + 128, &full[stage]);
+                    if (KB) {
+                        ptx::tma_load_3d(sA, &tmap, 0, t.x * SY_BM, kb, &full[stage]);
+                        ptx::tma_load_3d(sB, &tmap, 0, t.y * SY_BN, kb, &full[stage]);
+                        ptx::tma_load_3d(sB + SY_B_BYTES / 2, &tmap, 0, t.y * SY_BN + 128, kb, &full[stage]);
+                    } else {
+                        ptx::tma_load_2d(sA, &tmap, kb * SY_BK, t.x * SY_BM, &full[stage]);
+                        ptx::tma_load_2d(sB, &tmap, kb * SY_BK, t.y * SY_BN, &full[stage]);
+                        ptx::tma_load_2d(sB + SY_B_BYTES / 2, &tmap, kb * SY_BK, t.y * SY_BN + 128, &full[stage]);
+                    }
                     if (++stage == SY_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -301,11 +310,11 @@ void syrk_release_cache() {
 
 }  // namespace eg
 
-extern "C" int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64_t pitch, int32_t* d_C, int64_t ldc,
-                              void* stream) {
+static int syrk_launch(const int8_t* d_M, int64_t n, int64_t kcols, int64_t pitch, bool kblocked, int32_t* d_C,
+                       int64_t ldc, void* stream) {
     using namespace eg;
-    if (!d_M || !d_C || n <= 0 || kcols < 0 || (pitch & 127) || pitch < round_up(kcols, 128) || ldc < n ||
-        ((uintptr_t)d_M & 127))
+    if (!d_M || !d_C || n <= 0 || kcols < 0 || ldc < n || ((uintptr_t)d_M & 127) ||
+        (!kblocked && ((pitch & 127) || pitch < round_up(kcols, 128))))
         return set_error(EG_ERR_ARG, "eg_dev_syrk_i8: bad argument");
     if (kcols == 0) return EG_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -314,13 +323,25 @@ extern "C" int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64
     EG_TRY(build_tiles(n, st));
 
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)round_up(kcols, 128), (cuuint64_t)n};
-    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
-    const cuuint32_t box[2] = {128, 128};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(d_M), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const int64_t kblocks = (kcols + SY_BK - 1) / SY_BK;
+    CUresult r;
+    if (kblocked) {
+        const cuuint64_t gdim[3] = {128, (cuuint64_t)n, (cuuint64_t)kblocks};
+        const cuuint64_t gstride[2] = {128, (cuuint64_t)n * 128};
+        const cuuint32_t box[3] = {128, 128, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(d_M), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gdim[2] = {(cuuint64_t)round_up(kcols, 128), (cuuint64_t)n};
+        const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+        const cuuint32_t box[2] = {128, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(d_M), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) return set_error(EG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
 
     SyrkParams p;
@@ -329,7 +350,7 @@ extern "C" int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64
     p.C = d_C;
     p.tiles = g_tiles.d_tiles;
     p.ntiles = g_tiles.ntiles;
-    p.kblocks_total = (int32_t)((kcols + SY_BK - 1) / SY_BK);
+    p.kblocks_total = (int32_t)kblocks;
     const int sms = num_sms();
     int kchunks = 1;
     const int target = 4 * sms;
@@ -343,7 +364,8 @@ extern "C" int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64
     kchunks = (p.kblocks_total + p.kblocks_per_chunk - 1) / p.kblocks_per_chunk;
     p.nunits = p.ntiles * kchunks;
 
-    EG_CUDA(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+    auto kern = kblocked ? syrk_i8_kernel<true> : syrk_i8_kernel<false>;
+    EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
     const int grid = p.nunits < sms ? p.nunits : sms;
 
     // flow-control counters: one per (round, phase); zeroed on the launch stream
@@ -373,6 +395,16 @@ extern "C" int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64
     attr[0].val.cooperative = flow ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    EG_CUDA(cudaLaunchKernelEx(&cfg, syrk_i8_kernel, tmap, p));
+    EG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, p));
     return check_launch("syrk_i8_kernel");
+}
+
+extern "C" int eg_dev_syrk_i8(const int8_t* d_M, int64_t n, int64_t kcols, int64_t pitch, int32_t* d_C, int64_t ldc,
+                              void* stream) {
+    return syrk_launch(d_M, n, kcols, pitch, false, d_C, ldc, stream);
+}
+// M in the K-blocked layout [ceil(kcols/128)][n][128] (eg_dev_decode_kb): every K step of the contraction reads
+// one contiguous n*128-byte range instead of n rows a whole row pitch apart.
+extern "C" int eg_dev_syrk_i8_kb(const int8_t* d_Mkb, int64_t n, int64_t kcols, int32_t* d_C, int64_t ldc, void* stream) {
+    return syrk_launch(d_Mkb, n, kcols, 0, true, d_C, ldc, stream);
 }

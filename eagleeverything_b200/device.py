@@ -58,6 +58,39 @@ def decode(img, src_pitch, rows, cols, out=None, err=None, src_offset=0):
     return out, err
 
 
+def decode_kb(img, src_pitch, rows, cols, out=None, err=None, src_offset=0):
+    """K1 into the K-blocked layout of M stores: int8 tensor (ceil(cols/128), rows, 128)."""
+    lib = _lib.load()
+    kb = (cols + 127) // 128
+    if out is None:
+        out = torch.empty((kb, rows, 128), dtype=torch.int8, device=img.device)
+    if err is None:
+        err = torch.zeros(4, dtype=torch.int32, device=img.device)
+    _lib.check(lib.eg_dev_decode_kb(C.c_void_p(img.data_ptr() + src_offset), src_pitch, img.numel() - src_offset, rows,
+                                    cols, _ptr(out), rows, 0, _ptr(err), _stream()))
+    return out, err
+
+
+def transpose_kb(store_kb, rows, cols, out=None):
+    """K-blocked M store (ceil(cols/128), rows, 128) -> row-major Mt store (cols, pitch(rows))."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((cols, store_pitch(rows)), dtype=torch.int8, device=store_kb.device)
+    _lib.check(lib.eg_dev_transpose_kb_i8(_ptr(store_kb), rows, cols, _ptr(out), out.stride(0), _stream()))
+    return out
+
+
+def syrk_kb(store_kb, n, kcols, C32=None, zero=True):
+    """K2 on a K-blocked M store."""
+    lib = _lib.load()
+    if C32 is None:
+        C32 = torch.empty((n, n), dtype=torch.int32, device=store_kb.device)
+    if zero:
+        C32.zero_()
+    _lib.check(lib.eg_dev_syrk_i8_kb(_ptr(store_kb), n, kcols, _ptr(C32), C32.stride(0), _stream()))
+    return C32
+
+
 def transpose(store, rows, cols, out=None):
     lib = _lib.load()
     if out is None:
@@ -155,8 +188,8 @@ def gemv_i8(storeT, L, n, x, scale=1.0):
     return y
 
 
-def extract_col(store, n, col):
+def extract_col(store, n, col, kblocked=False):
     lib = _lib.load()
     out = torch.empty(n, dtype=torch.int32, device=store.device)
-    _lib.check(lib.eg_dev_extract_col(_ptr(store), n, store.stride(0), col, _ptr(out), _stream()))
+    _lib.check(lib.eg_dev_extract_col(_ptr(store), n, 0 if kblocked else store.stride(0), col, _ptr(out), _stream()))
     return out

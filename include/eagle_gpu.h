@@ -82,10 +82,16 @@ int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, 
                          const int64_t* dims, int32_t* out);
 
 /* ================================================================ resident genotype stores
- * A store is a decoded genotype matrix held in HBM as int8 in {-1,0,1}: `rows` x `cols`, row
- * pitch `pitch` bytes (multiple of 128, > cols; the tail of every row is zero).  The entry points
- * above keep stores in a cache keyed by (path, size, mtime, dims); these calls manage them
- * explicitly (host buffers in, handles out). */
+ * A store is a decoded genotype matrix held in HBM as int8 in {-1,0,1}, `rows` x `cols`, in one of
+ * two layouts:
+ *   row-major  (Mt orientation: markers as rows; what the scan reads): row pitch `pitch` bytes
+ *              (multiple of 128, > cols; the tail of every row is zero);
+ *   K-blocked  (M orientation: individuals as rows; what M.Mt streams): [ceil(cols/128)][rows][128]
+ *              bytes, i.e. all rows of one 128-marker block are contiguous; eg_store_info reports
+ *              pitch == 0 for it.
+ * eg_store_from_host_ascii / eg_store_from_file build the K-blocked layout, eg_store_from_host_ascii_rows
+ * and eg_store_transpose the row-major one.  The entry points above keep stores in a cache keyed by
+ * (path, size, mtime, dims, layout); these calls manage them explicitly (host buffers in, handles out). */
 typedef struct eg_store eg_store_t;
 
 /* `image` is a byte-exact no-space ASCII file image in host memory (CreateASCIInospace.cpp:119-122):
@@ -122,6 +128,12 @@ int eg_dev_decode(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_ava
                   int8_t* d_dst, int64_t dst_pitch, int32_t* d_err, void* stream);
 int eg_dev_transpose_i8(const int8_t* d_in, int64_t rows, int64_t cols, int64_t in_pitch, int8_t* d_out,
                         int64_t out_pitch, void* stream);
+/* K-blocked variants: the store is [ceil(cols/128)][kb_rows][128] bytes; decode fills rows [row0, row0+rows). */
+int eg_dev_decode_kb(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_avail, int64_t rows, int64_t cols,
+                     int8_t* d_dst, int64_t kb_rows, int64_t row0, int32_t* d_err, void* stream);
+int eg_dev_transpose_kb_i8(const int8_t* d_in_kb, int64_t rows, int64_t cols, int8_t* d_out, int64_t out_pitch,
+                           void* stream);
+int eg_dev_syrk_i8_kb(const int8_t* d_Mkb, int64_t n, int64_t kcols, int32_t* d_C, int64_t ldc, void* stream);
 /* K2: C (int32, n x n row-major, ld = ldc, must be zeroed by the caller) += M * M^T over columns
  * [0, kcols) of M (int8 n x kcols, row pitch multiple of 128 and padded with zeros).  Only entries
  * with col >= row are complete. */
@@ -157,6 +169,7 @@ int eg_dev_argmax_tsq(const double* d_a, const double* d_vara, int64_t L, double
 /* y = scale * Mt * x  (calculate_reduced_a_rcpp.cpp:82-84 second product) */
 int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_x, double scale,
                    double* d_y, void* stream);
+/* pitch == 0 selects the K-blocked layout in the two calls below (and in eg_dev_syrk_zero_cols) */
 int eg_dev_extract_col(const int8_t* d_M, int64_t n, int64_t pitch, int64_t col, int32_t* d_out, void* stream);
 
 /* Bench / test utility: write a synthetic M.ascii image (rows x (cols+1) bytes, Binomial(2,p_j)

@@ -72,6 +72,24 @@ def test_transpose_and_extract(dev):
         assert np.array_equal(c, G[:, cols // 2].astype(np.int32) - 1)
 
 
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 127), (5, 128), (7, 129), (150, 4998), (300, 20001), (4998, 150)])
+def test_kblocked_layout_matches_row_major(dev, rows, cols):
+    """The K-blocked M store ([col/128][row][128]) holds the same genotypes; SYRK and transpose agree."""
+    device, torch = dev
+    G = synth.genotypes(rows, cols, seed=rows * 13 + cols)
+    buf = torch.from_numpy(np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    st, _ = device.decode(buf, cols + 1, rows, cols)
+    kb, err = device.decode_kb(buf, cols + 1, rows, cols)
+    assert err[0].item() == 0
+    nb = (cols + 127) // 128
+    flat = kb.permute(1, 0, 2).reshape(rows, nb * 128)
+    assert torch.equal(flat[:, :cols], st[:, :cols]) and not flat[:, cols:].any()
+    assert torch.equal(torch.triu(device.syrk_kb(kb, rows, cols)), torch.triu(device.syrk(st, rows, cols)))
+    assert torch.equal(device.transpose_kb(kb, rows, cols), device.transpose(st, rows, cols))
+    for c in (0, cols // 2, cols - 1):
+        assert torch.equal(device.extract_col(kb.view(-1), rows, c, kblocked=True), device.extract_col(st, rows, c))
+
+
 def test_argmax_semantics(dev):
     device, torch = dev
     rng = np.random.default_rng(1)
@@ -142,7 +160,9 @@ def test_config2_full_size_properties(dev):
     view = img[: n * (L + 1)].view(n, L + 1)
     assert torch.equal(st[:, :L], (view[:, :L].to(torch.int16) - 49).to(torch.int8))
     assert not st[:, L:].any()
-    C32 = device.syrk(st, n, L)
+    stk, _ = device.decode_kb(img, L + 1, n, L)          # the layout the SYRK streams
+    C32 = device.syrk_kb(stk, n, L)
+    assert torch.equal(torch.triu(C32), torch.triu(device.syrk(st, n, L)))
     K = device.mmt_finalize(C32, n)
     torch.cuda.synchronize()
     assert torch.equal(K, K.T)
@@ -164,7 +184,9 @@ def test_config2_full_size_properties(dev):
     assert torch.equal(torch.triu(Ca + Cb), torch.triu(C32))
     del Ca, Cb, stb
     # scan on the transposed store, against torch float64 on sampled marker rows
-    tt = device.transpose(st, n, L)
+    tt = device.transpose_kb(stk, n, L)
+    assert torch.equal(tt, device.transpose(st, n, L))
+    del stk
     S, V, a = synth.scan_inputs(n)
     Sd, Vd, ad = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (S, V, a))
     Wp = device.scan_prepare(Sd, Vd, ad, n)
