@@ -370,7 +370,9 @@ __global__ void __launch_bounds__(256) i8_to_f64_colmajor_kernel(const int8_t* _
 
 // ------------------------------------------------------------------ W -> U (symmetric half) for the scan
 // In place on the packed Wp (column-major, ld = Kpad): for i < k  U[i][k] = W[i][k] + W[k][i], U[k][i] = 0.
-__global__ void __launch_bounds__(256) symmetrize_upper_kernel(double* __restrict__ Wp, int64_t n, int64_t ld) {
+// w_is_upper != 0: only the upper triangle of W was computed (W known symmetric): U[i][k] = 2 W[i][k].
+__global__ void __launch_bounds__(256) symmetrize_upper_kernel(double* __restrict__ Wp, int64_t n, int64_t ld,
+                                                               int w_is_upper) {
     __shared__ double tile[32][33];
     const int bx = blockIdx.x, by = blockIdx.y;  // tile (rows by*32.., cols bx*32..) with bx >= by
     if (bx < by) return;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(256) symmetrize_upper_kernel(double* __restric
     for (int i = ty; i < 32; i += 8) {
         const int64_t r = r0 + tx, c = c0 + i;  // element (r, c) of the upper tile
         if (r < n && c < n) {
-            if (r < c) Wp[r + c * ld] = Wp[r + c * ld] + tile[tx][i];   // W[r][c] + W[c][r]
+            if (r < c) Wp[r + c * ld] = Wp[r + c * ld] + (w_is_upper ? Wp[r + c * ld] : tile[tx][i]);  // W[r][c] + W[c][r]
             else if (r > c) Wp[r + c * ld] = 0.0;                        // inside a diagonal tile
         }
     }
@@ -395,6 +397,40 @@ __global__ void __launch_bounds__(256) symmetrize_upper_kernel(double* __restric
             const int64_t r = c0 + tx, c = r0 + i;
             if (r < n && c < n) Wp[r + c * ld] = 0.0;  // strictly lower tile
         }
+    }
+}
+
+// max |A_ij| and max |A_ij - A_ji| of a column-major n x n matrix (non-negative doubles order like uint64)
+__global__ void __launch_bounds__(256) symmetry_kernel(const double* __restrict__ A, int64_t n,
+                                                       unsigned long long* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx < by) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)by * 32, c0 = (int64_t)bx * 32;
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = c0 + tx, c = r0 + i;
+        tile[i][tx] = (r < n && c < n) ? A[r + c * n] : 0.0;  // mirrored tile
+    }
+    __syncthreads();
+    double mabs = 0.0, masym = 0.0;
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r0 + tx, c = c0 + i;
+        if (r < n && c < n) {
+            const double a = A[r + c * n], b = tile[tx][i];
+            mabs = fmax(mabs, fmax(fabs(a), fabs(b)));
+            const double d = fabs(a - b);
+            masym = fmax(masym, d == d ? d : 1.0e300);  // NaN counts as asymmetric
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mabs = fmax(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
+        masym = fmax(masym, __shfl_xor_sync(0xffffffffu, masym, o));
+    }
+    if (tx == 0) {
+        atomicMax(out, (unsigned long long)__double_as_longlong(mabs));
+        atomicMax(out + 1, (unsigned long long)__double_as_longlong(masym));
     }
 }
 
@@ -679,9 +715,28 @@ extern "C" int eg_store_extract_col(const eg_store_t* M, int64_t col, int32_t* o
 }
 
 // ================================================================== device-level: scan pre-products (cuBLAS)
+extern "C" int eg_dev_symmetry(const double* d_A, int64_t n, double* max_abs, double* max_asym, void* stream) {
+    if (!d_A || n <= 0 || !max_abs || !max_asym) return set_error(EG_ERR_ARG, "eg_dev_symmetry: bad argument");
+    EG_TRY(ensure_init());
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local unsigned long long* d_out = nullptr;
+    if (!d_out) EG_CUDA(cudaMalloc(&d_out, 2 * sizeof(unsigned long long)));
+    EG_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(unsigned long long), st));
+    const unsigned nb = (unsigned)((n + 31) / 32);
+    symmetry_kernel<<<dim3(nb, nb), 256, 0, st>>>(d_A, n, d_out);
+    EG_TRY(check_launch("symmetry_kernel"));
+    unsigned long long h[2];
+    EG_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+    EG_CUDA(cudaStreamSynchronize(st));
+    memcpy(max_abs, &h[0], 8);
+    memcpy(max_asym, &h[1], 8);
+    return EG_OK;
+}
+
 // Columns [col0, col1) of W = S * (V * S) into the packed Wp (ld = Kpad); d_tmp needs n * (col1-col0) doubles.
+// upper_only != 0: only rows 0 .. col1-1 of those columns are computed (enough when W is symmetric).
 extern "C" int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1,
-                                        double* d_tmp, double* d_Wp, void* stream) {
+                                        int upper_only, double* d_tmp, double* d_Wp, void* stream) {
     if (!d_S || !d_V || !d_tmp || !d_Wp || n <= 0 || col0 < 0 || col1 > n || col0 > col1)
         return set_error(EG_ERR_ARG, "eg_dev_scan_prepare_cols: bad argument");
     if (col0 == col1) return EG_OK;
@@ -695,14 +750,21 @@ extern "C" int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, in
                     (int)n, &zero, d_tmp, (int)n) != CUBLAS_STATUS_SUCCESS)
         return set_error(EG_ERR_CUDA, "cublasDgemm(V*S) failed");
     // :98   W = inv_MMt_sqrt * tmp, written straight into the packed layout (ld = Kpad)
-    if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)nc, (int)n, &one, d_S, (int)n, d_tmp, (int)n,
-                    &zero, d_Wp + col0 * Kpad, (int)Kpad) != CUBLAS_STATUS_SUCCESS)
-        return set_error(EG_ERR_CUDA, "cublasDgemm(S*tmp) failed");
+    const int64_t step = upper_only ? 1024 : nc;
+    for (int64_t b0 = 0; b0 < nc; b0 += step) {
+        const int64_t nb = (b0 + step <= nc) ? step : nc - b0;
+        const int64_t rows = upper_only ? (col0 + b0 + nb) : n;  // rows 0 .. last column of the block
+        if (cublasDgemm(g_ctx.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)rows, (int)nb, (int)n, &one, d_S, (int)n,
+                        d_tmp + b0 * n, (int)n, &zero, d_Wp + (col0 + b0) * Kpad, (int)Kpad) != CUBLAS_STATUS_SUCCESS)
+            return set_error(EG_ERR_CUDA, "cublasDgemm(S*tmp) failed");
+    }
     return EG_OK;
 }
 
-// v = S * a into column n of Wp, then fold W into U = diag(W) + strict_upper(W + W^T) (needs ALL columns of W)
-extern "C" int eg_dev_scan_fold(const double* d_S, const double* d_a, int64_t n, double* d_Wp, void* stream) {
+// v = S * a into column n of Wp, then fold W into U = diag(W) + strict_upper(W + W^T) (needs ALL columns of W;
+// w_is_upper != 0: W holds its upper triangle only and is symmetric, so U = diag + 2 * strict_upper)
+extern "C" int eg_dev_scan_fold(const double* d_S, const double* d_a, int64_t n, int w_is_upper, double* d_Wp,
+                                void* stream) {
     if (!d_S || !d_a || !d_Wp || n <= 0) return set_error(EG_ERR_ARG, "eg_dev_scan_fold: bad argument");
     EG_TRY(ensure_init());
     cudaStream_t st = (cudaStream_t)stream;
@@ -715,17 +777,31 @@ extern "C" int eg_dev_scan_fold(const double* d_S, const double* d_a, int64_t n,
         return set_error(EG_ERR_CUDA, "cublasDgemv(S*a) failed");
     // vara_j = m^T W m only sees the symmetric part of W: fold it into the upper triangle (scan_f64.cu)
     const unsigned nb = (unsigned)((n + 31) / 32);
-    symmetrize_upper_kernel<<<dim3(nb, nb), 256, 0, st>>>(d_Wp, n, Kpad);
+    symmetrize_upper_kernel<<<dim3(nb, nb), 256, 0, st>>>(d_Wp, n, Kpad, w_is_upper);
     return check_launch("symmetrize_upper_kernel");
+}
+
+// S and V symmetric (to 1e-13 of their largest entry; always the case under AM(): chol2inv output and a
+// variance matrix) => W = S V S is symmetric and only its upper triangle is computed (3 n^3 instead of 4 n^3 flops)
+extern "C" int eg_dev_inputs_symmetric(const double* d_S, const double* d_V, int64_t n, int* yes, void* stream) {
+    if (!yes) return set_error(EG_ERR_ARG, "null");
+    double aS, dS, aV, dV;
+    EG_TRY(eg_dev_symmetry(d_S, n, &aS, &dS, stream));
+    EG_TRY(eg_dev_symmetry(d_V, n, &aV, &dV, stream));
+    const char* env = getenv("EAGLE_SCAN_SYMMETRIC");
+    *yes = !(env && env[0] == '0') && dS <= 1e-13 * aS && dV <= 1e-13 * aV;
+    return EG_OK;
 }
 
 extern "C" int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a, int64_t n, double* d_tmp,
                                    double* d_Wp, void* stream) {
     if (!d_S || !d_V || !d_a || !d_tmp || !d_Wp || n <= 0) return set_error(EG_ERR_ARG, "eg_dev_scan_prepare: bad argument");
     EG_TRY(ensure_init());
+    int sym = 0;
+    EG_TRY(eg_dev_inputs_symmetric(d_S, d_V, n, &sym, stream));
     EG_CUDA(cudaMemsetAsync(d_Wp, 0, (size_t)eg_scan_wp_elems(n) * 8, (cudaStream_t)stream));
-    EG_TRY(eg_dev_scan_prepare_cols(d_S, d_V, n, 0, n, d_tmp, d_Wp, stream));
-    return eg_dev_scan_fold(d_S, d_a, n, d_Wp, stream);
+    EG_TRY(eg_dev_scan_prepare_cols(d_S, d_V, n, 0, n, sym, d_tmp, d_Wp, stream));
+    return eg_dev_scan_fold(d_S, d_a, n, sym, d_Wp, stream);
 }
 
 // ================================================================== reference-facing entry points

@@ -138,24 +138,33 @@ def scan_prepare(S, V, a, n, Wp=None, tmp=None):
 
 
 def scan_prepare_sharded(S, V, a, n, rank, world, Wp=None, tmp=None):
-    """Pre-products with the columns of W = S (V S) split over the ranks (2*2n^3/world flops each instead of
-    replicated), the blocks exchanged with one broadcast per rank (NCCL), then folded on every rank."""
+    """Pre-products with the columns of W = S (V S) split over the ranks (instead of replicated), the blocks
+    exchanged with one broadcast per rank (NCCL), then folded on every rank.  With symmetric S, V only the upper
+    triangle of W is computed and the column ranges are cut at equal cost."""
     import torch.distributed as dist
     lib = _lib.load()
     Kpad = (n + 31) // 32 * 32
     if Wp is None:
         Wp = torch.empty(lib.eg_scan_wp_elems(n), dtype=torch.float64, device=S.device)
-    blk = (n + world - 1) // world
-    c0, c1 = min(rank * blk, n), min((rank + 1) * blk, n)
-    if tmp is None:
-        tmp = torch.empty(n * max(blk, 1), dtype=torch.float64, device=S.device)
+    sym = C.c_int(0)
+    _lib.check(lib.eg_dev_inputs_symmetric(_ptr(S), _ptr(V), n, C.byref(sym), _stream()))
+    sym = int(sym.value)
+    if sym:
+        # cost of columns [0,c): n*c (V*S) + c^2/2 (upper part of S*tmp)  ->  equal-cost cuts
+        cuts = [min(n, int(round(n * ((1.0 + 3.0 * r / world) ** 0.5 - 1.0) / 32.0)) * 32) for r in range(world)] + [n]
+    else:
+        blk = (n + world - 1) // world
+        cuts = [min(r * blk, n) for r in range(world)] + [n]
+    c0, c1 = cuts[rank], cuts[rank + 1]
+    need = n * max(max(cuts[r + 1] - cuts[r] for r in range(world)), 1)
+    if tmp is None or tmp.numel() < need:
+        tmp = torch.empty(need, dtype=torch.float64, device=S.device)
     Wp.zero_()
-    _lib.check(lib.eg_dev_scan_prepare_cols(_ptr(S), _ptr(V), n, c0, c1, _ptr(tmp), _ptr(Wp), _stream()))
+    _lib.check(lib.eg_dev_scan_prepare_cols(_ptr(S), _ptr(V), n, c0, c1, sym, _ptr(tmp), _ptr(Wp), _stream()))
     for r in range(world):  # contiguous column blocks of the column-major Wp
-        r0, r1 = min(r * blk, n), min((r + 1) * blk, n)
-        if r1 > r0:
-            dist.broadcast(Wp[r0 * Kpad:r1 * Kpad], src=r)
-    _lib.check(lib.eg_dev_scan_fold(_ptr(S), _ptr(a), n, _ptr(Wp), _stream()))
+        if cuts[r + 1] > cuts[r]:
+            dist.broadcast(Wp[cuts[r] * Kpad:cuts[r + 1] * Kpad], src=r)
+    _lib.check(lib.eg_dev_scan_fold(_ptr(S), _ptr(a), n, sym, _ptr(Wp), _stream()))
     return Wp
 
 

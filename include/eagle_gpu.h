@@ -151,13 +151,17 @@ int eg_dev_mmt_finalize(const int32_t* d_C, int64_t n, int64_t ldc, double* d_ou
 int64_t eg_scan_wp_elems(int64_t n);
 int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a, int64_t n, double* d_tmp,
                         double* d_Wp, void* stream);
-/* The same in two steps, for marker-sharded multi-GPU runs: each rank computes the columns [col0,col1) of W
+/* The same in steps, for marker-sharded multi-GPU runs: each rank computes the columns [col0,col1) of W
  * (d_tmp: n*(col1-col0) doubles; d_Wp zeroed by the caller), the column blocks are exchanged between the
  * ranks (broadcast / all-gather of contiguous ranges of d_Wp: column c starts at d_Wp + c*round_up(n,32)),
- * then every rank folds the complete W. */
-int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1, double* d_tmp,
-                             double* d_Wp, void* stream);
-int eg_dev_scan_fold(const double* d_S, const double* d_a, int64_t n, double* d_Wp, void* stream);
+ * then every rank folds the complete W.  When S and V are symmetric (eg_dev_inputs_symmetric: to 1e-13 of
+ * their largest entry -- always the case under AM()) W is symmetric and `upper_only` / `w_is_upper` restrict
+ * the second product to rows 0..col1-1 (3 n^3 instead of 4 n^3 flops). */
+int eg_dev_symmetry(const double* d_A, int64_t n, double* max_abs, double* max_asym, void* stream);
+int eg_dev_inputs_symmetric(const double* d_S, const double* d_V, int64_t n, int* yes, void* stream);
+int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1,
+                             int upper_only, double* d_tmp, double* d_Wp, void* stream);
+int eg_dev_scan_fold(const double* d_S, const double* d_a, int64_t n, int w_is_upper, double* d_Wp, void* stream);
 /* K3: a = Mt*v, vara_j = (Mt*W)_j . Mt_j for marker rows of an Mt store (L x n int8, pitch >=
  * round_up(n+1,128)); zero rows get a = vara = 0. */
 int eg_dev_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp,

@@ -165,6 +165,22 @@ def test_scan_synth_with_selected_rows(synth_small, scan_mode):
     assert got["a"][3, 0] == 0 and got["vara"][2500, 0] == 0
 
 
+def test_scan_asymmetric_inputs_take_the_general_path(synth_small, scan_mode):
+    """S and V need not be symmetric for the export: the fast path (upper triangle of W only) is guarded by a
+    symmetry check, and the symmetric-half contraction only ever uses W + W^T."""
+    s = synth_small
+    rng = np.random.default_rng(12)
+    n = s["n"]
+    S = rng.standard_normal((n, n)) / np.sqrt(n) + 2 * np.eye(n)
+    V = rng.standard_normal((n, n)) / np.sqrt(n) + 1.5 * np.eye(n)
+    a = rng.standard_normal(n)
+    got = api.calculate_a_and_vara_rcpp(s["Mt"], [NA], S, V, 8, (s["L"], n), a)
+    ref = eo.calculate_a_and_vara_rcpp(s["Mt"], [NA], S, V, 8, (s["L"], n), a)
+    ca, cv = scan_conds(s["G"], S, V, a)
+    assert_close(got["a"], ref["a"], ca, n, "a")
+    assert_close(got["vara"], ref["vara"], cv, n, "vara")
+
+
 @pytest.mark.parametrize("n,L", [(1, 5), (31, 1), (127, 300), (128, 257), (129, 1000), (255, 129), (640, 1500)])
 def test_scan_ragged_sizes(tmp_path, n, L, scan_mode):
     G = synth.genotypes(n, L, seed=n + L)
