@@ -352,6 +352,20 @@ def run_gpu(args):
         roofline["kernel"]: roofline,
     }
     scan_tf = scan_ref_flops / (stages["scan"] * 1e-3) / 1e12
+    # DRAM traffic per launch from the committed `ncu --set full` capture of the same kernel at the same shape
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:  # noqa: BLE001
+        tr = {}
+    for kname, rf in rooflines.items():
+        rec = tr.get(kname)
+        if rec and rec.get("workload") == args.workload and rec.get("n_gpus") == world:
+            rf["traffic"] = rec["dram_bytes_per_launch"]
+            rf["traffic_source"] = rec.get("source")
+            if "tensor_pipe_active_pct" in rec:
+                rf["tensor_pipe_active_pct_ncu"] = rec["tensor_pipe_active_pct"]
+        else:
+            rf.setdefault("traffic", None)
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
