@@ -21,7 +21,7 @@
 // epilogue thread owns one marker row (one TMEM lane): it recombines the slices, multiplies by the
 // marker's own genotype bytes and writes ONE double per (marker, group); a second tiny kernel sums
 // the groups in index order.  Fixed order everywhere: identical marker rows give bit-identical
-// results whatever their position, tile or GPU.  Units are ordered in (16 marker blocks x 9 groups)
+// results whatever their position, tile or GPU.  Units are ordered in (37 marker blocks x 4 groups)
 // super-tiles and kept in K lock-step by the same phase counters as the SYRK, so a wave shares its
 // operand rows through L2.
 #include <cstdlib>
@@ -43,8 +43,8 @@ constexpr int SI_THREADS = 192;
 constexpr int SI_TMEM_COLS = 512;
 constexpr int SI_SLICES = 8;
 constexpr int SI_GCOLS = 32;   // columns of U per group (32 x 8 slices = 256 = one UMMA N)
-constexpr int SI_MSUP = 16;    // super-tile: marker blocks
-constexpr int SI_GSUP = 9;     //             x groups  (~ one wave of 148 CTAs)
+constexpr int SI_MSUP_DEFAULT = 37;  // super-tile: marker blocks (their Mt rows stay L2-resident over the group sweep)
+constexpr int SI_GSUP_DEFAULT = 4;   //             x groups  (~ one wave of 148 CTAs)
 constexpr int SI_PHASE = 16;
 constexpr int SI_LAG = 4;
 constexpr int SI_SMEM_BYTES = SI_STAGES * SI_STAGE_BYTES + 1024 + 256;
@@ -309,14 +309,14 @@ __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict_
 }
 
 // (mb, g) -> position in the super-tile order
-__global__ void si_units_kernel(int2* units, int MB, int G) {
+__global__ void si_units_kernel(int2* units, int MB, int G, int MSUP, int GSUP) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)MB * G) return;
     const int mb = (int)(t % MB), g = (int)(t / MB);
-    const int ms = mb / SI_MSUP, gs = g / SI_GSUP;
-    const int msz = min(SI_MSUP, MB - ms * SI_MSUP);
-    const int64_t u = (int64_t)ms * SI_MSUP * G + (int64_t)gs * SI_GSUP * msz + (int64_t)(g - gs * SI_GSUP) * msz +
-                      (mb - ms * SI_MSUP);
+    const int ms = mb / MSUP, gs = g / GSUP;
+    const int msz = min(MSUP, MB - ms * MSUP);
+    const int64_t u = (int64_t)ms * MSUP * G + (int64_t)gs * GSUP * msz + (int64_t)(g - gs * GSUP) * msz +
+                      (mb - ms * MSUP);
     units[u] = make_int2(mb, g);
 }
 
@@ -368,7 +368,7 @@ struct ScanI8Workspace {
     double* scale = nullptr;    size_t sc_cap = 0;
     int32_t* expo = nullptr;    size_t expo_cap = 0;
     double* partial = nullptr;  size_t part_cap = 0;
-    int2* units = nullptr;      size_t unit_cap = 0;  int units_MB = -1, units_G = -1;
+    int2* units = nullptr;      size_t unit_cap = 0;  int units_MB = -1, units_G = -1, units_shape = -1;
     uint32_t* phase = nullptr;  size_t phase_cap = 0;
 };
 static thread_local ScanI8Workspace g_si;
@@ -414,12 +414,16 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     EG_TRY(si_grow(&g_si.expo, &g_si.expo_cap, (size_t)G * SI_GCOLS, "column exponents"));
     EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)G * L, "per-group partial sums"));
     const int64_t nunits = (int64_t)MB * G;
-    if (g_si.units_MB != MB || g_si.units_G != G || !g_si.units) {
+    int msup = SI_MSUP_DEFAULT, gsup = SI_GSUP_DEFAULT;
+    if (const char* e = getenv("EAGLE_SI_MSUP")) msup = atoi(e) > 0 ? atoi(e) : msup;
+    if (const char* e = getenv("EAGLE_SI_GSUP")) gsup = atoi(e) > 0 ? atoi(e) : gsup;
+    if (g_si.units_MB != MB || g_si.units_G != G || g_si.units_shape != msup * 1000 + gsup || !g_si.units) {
         EG_TRY(si_grow(&g_si.units, &g_si.unit_cap, (size_t)nunits, "unit table"));
-        si_units_kernel<<<(unsigned)((nunits + 255) / 256), 256, 0, st>>>(g_si.units, MB, G);
+        si_units_kernel<<<(unsigned)((nunits + 255) / 256), 256, 0, st>>>(g_si.units, MB, G, msup, gsup);
         EG_TRY(check_launch("si_units_kernel"));
         g_si.units_MB = MB;
         g_si.units_G = G;
+        g_si.units_shape = msup * 1000 + gsup;
     }
     // 1. slice U
     si_colscale_kernel<<<(unsigned)(G * SI_GCOLS), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo, g_si.scale, (int64_t)G * SI_GCOLS);
