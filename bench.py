@@ -331,7 +331,7 @@ def run_gpu(args):
     if mode == 1:
         roofline = {"kernel": "scan_i8_kernel", "bound": "tensor", "achieved": k_rate, "peak": int8_peak,
                     "unit": "TOP/s (int8)", "frac": k_rate / int8_peak, "traffic": None, "kernel_ms": k_ms,
-                    "ops_convention": "executed int8 ops: 8 slices x symmetric-half contraction, 2 ops per MAC "
+                    "ops_convention": "executed int8 ops: 7 balanced-byte slices x symmetric-half contraction, 2 ops per MAC "
                                       "(DESIGN.md section 4)",
                     "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
                     "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas}

@@ -3,21 +3,22 @@
 // Same quantity as scan_f64.cu (reference src/calculate_a_and_vara_rcpp.cpp:97-112):
 //     vara_j = sum_k ( sum_{i<=k} m_ij U_ik ) m_kj ,   U = diag(W) + strict_upper(W + W^T)
 // The genotypes m are already int8 in {-1,0,1}.  Each column k of the FP64 matrix U is written as
-//     U_ik = 2^(e_k) * sum_{s=0..7} q_s(i,k) * 2^(-6-7s)  +  r ,   q_s in [-64,64] (int8),
-// by repeated round-to-nearest of the exactly computed remainder (|r| <= 2^(e_k-56), i.e. below one
-// ulp of the column's largest entry: the full FP64 significand of U is kept).  Then
-//     P_s(j,k) = sum_i m_ij q_s(i,k)          is an EXACT int32 (|P| <= 64 n), one int8 GEMM per slice,
-//     T'_jk   = 2^(e_k-55) * sum_s P_s 2^(7(7-s))   is recombined exactly except for ONE rounding,
-// which is tighter than the n roundings of an FP64 GEMM accumulation.  8 int8 GEMMs at >3 PFLOP/s
+//     U_ik = 2^(e_k-55) * X_ik + r ,   X_ik = rint(U_ik 2^(55-e_k)) ,  |X| <= 127 * 2^48 ,  |r| <= 2^(e_k-56)
+// (below one ulp of the column's largest entry: the full FP64 significand of U is kept), and the
+// integer X in BALANCED base-256 digits,   X = sum_{s=0..6} q_s 256^(6-s) ,  q_s in [-128,127] (int8):
+// seven full bytes carry the 56 bits that eight 7-bit slices used to.  Then
+//     P_s(j,k) = sum_i m_ij q_s(i,k)          is an EXACT int32 (|P| <= 128 n), one int8 GEMM per slice,
+//     T'_jk   = 2^(e_k-55) * sum_s P_s 256^(6-s)   is recombined exactly except for ONE rounding,
+// which is tighter than the n roundings of an FP64 GEMM accumulation.  7 int8 GEMMs at >3 PFLOP/s
 // replace one FP64 GEMM at ~30 TFLOP/s.
 //
-// Layouts.  A operand: the Mt store (L x n int8, K-major).  B operand: Q, (n/32 groups) x 256 rows x Kp
-// bytes, K-major; row (kk>>2)*32 + s*4 + (kk&3) of group g holds slice s of column k = 32 g + kk, so
-// that one 32-column TMEM load brings all 8 slices of 4 columns to a thread.  Rows i > k and the pad
-// are zero, so the contraction for group g stops at k-block ceil((32g+32)/128).
+// Layouts.  A operand: the Mt store (L x n int8, K-major).  B operand: Q, (n/32 groups) x 224 rows x Kp
+// bytes, K-major; row (kk>>2)*28 + s*4 + (kk&3) of group g holds slice s of column k = 32 g + kk, so
+// that one TMEM load of 28 consecutive columns brings all 7 slices of 4 columns to a thread.  Rows
+// i > k and the pad are zero, so the contraction for group g stops at k-block ceil((32g+32)/128).
 //
 // Kernel: same warp-specialised tcgen05 pipeline as syrk_i8.cu (TMA producer, one-thread UMMA issuer
-// M128 N256 K32, double-buffered TMEM, 4 epilogue warps).  Work unit = (128-marker block, group); an
+// M128 N224 K32, double-buffered TMEM, 4 epilogue warps).  Work unit = (128-marker block, group); an
 // epilogue thread owns one marker row (one TMEM lane): it recombines the slices, multiplies by the
 // marker's own genotype bytes and writes ONE double per (marker, group); a second tiny kernel sums
 // the groups in index order.  Fixed order everywhere: identical marker rows give bit-identical
@@ -33,16 +34,18 @@
 namespace eg {
 
 constexpr int SI_BM = 128;
-constexpr int SI_BN = 256;
+constexpr int SI_SLICES = 7;
+constexpr int SI_GCOLS = 32;                  // columns of U per group
+constexpr int SI_BN = SI_GCOLS * SI_SLICES;   // 224 rows of Q per group = one UMMA N
+constexpr int SI_ACC_COLS = 256;              // TMEM columns between the two accumulators
+constexpr int SI_CHUNK = 4 * SI_SLICES;       // TMEM columns of one 4-column chunk
 constexpr int SI_BK = 128;
-constexpr int SI_STAGES = 4;
+constexpr int SI_STAGES = 5;
 constexpr int SI_A_BYTES = SI_BM * SI_BK;
 constexpr int SI_B_BYTES = SI_BN * SI_BK;
 constexpr int SI_STAGE_BYTES = SI_A_BYTES + SI_B_BYTES;
 constexpr int SI_THREADS = 192;
 constexpr int SI_TMEM_COLS = 512;
-constexpr int SI_SLICES = 8;
-constexpr int SI_GCOLS = 32;   // columns of U per group (32 x 8 slices = 256 = one UMMA N)
 constexpr int SI_MSUP_DEFAULT = 37;  // super-tile: marker blocks (their Mt rows stay L2-resident over the group sweep)
 constexpr int SI_GSUP_DEFAULT = 4;   //             x groups  (~ one wave of 148 CTAs)
 constexpr int SI_PHASE = 16;
@@ -151,7 +154,7 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     ptx::mbar_expect_tx(&full[stage], SI_STAGE_BYTES);
                     ptx::tma_load_2d(sA, &tmapA, kb * SI_BK, un.x * SI_BM, &full[stage]);
                     ptx::tma_load_2d(sB, &tmapB, kb * SI_BK, un.y * SI_BN, &full[stage]);
-                    ptx::tma_load_2d(sB + SI_B_BYTES / 2, &tmapB, kb * SI_BK, un.y * SI_BN + 128, &full[stage]);
+                    ptx::tma_load_2d(sB + SI_B_BYTES / 2, &tmapB, kb * SI_BK, un.y * SI_BN + SI_BN / 2, &full[stage]);
                     if (++stage == SI_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -170,7 +173,7 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 const int kb1 = si_kb_end(un.y, p.KB);
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SI_BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SI_ACC_COLS);
                 for (int kb = 0; kb < kb1; kb++) {
                     ptx::mbar_wait(&full[stage], phase);
                     if (p.phase_ctr && ((kb % SI_PHASE) == SI_PHASE - 1 || kb == kb1 - 1)) {
@@ -212,23 +215,29 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
             double sum = 0.0;
+            const bool wide = p.n > 65000;  // P0*256+P1 leaves int32 beyond n = 65280
 #pragma unroll
-            for (int c = 0; c < 8; c++) {  // 32 TMEM columns = 8 slices x 4 columns (kk = 4c .. 4c+3)
+            for (int c = 0; c < 8; c++) {  // 28 TMEM columns = 7 slices x 4 columns (kk = 4c .. 4c+3); 4 more ignored
                 uint32_t v[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_BN + c * 32), v);
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + c * SI_CHUNK), v);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    // |P_s| <= 64 n, so P*128 + P' fits int32 for n < 260k
-                    const int y01 = (int)v[0 * 4 + e] * 128 + (int)v[1 * 4 + e];
-                    const int y23 = (int)v[2 * 4 + e] * 128 + (int)v[3 * 4 + e];
-                    const int y45 = (int)v[4 * 4 + e] * 128 + (int)v[5 * 4 + e];
-                    const int y67 = (int)v[6 * 4 + e] * 128 + (int)v[7 * 4 + e];
-                    const double hi = fma((double)y01, 16384.0, (double)y23);     // exact (< 2^46)
-                    const double lo = fma((double)y45, 16384.0, (double)y67);     // exact
-                    const double x = fma(hi, 268435456.0, lo);                    // the one rounding
-                    const double t = x * __ldg(sc + c * 4 + e);                   // power-of-two scale: exact
-                    sum = fma(t, si_s8_to_f64(mw[c], e), sum);                    // row-dot with m_kj in {-1,0,1}
+                    double y01, y23, y45;
+                    if (!wide) {
+                        y01 = (double)((int)v[0 * 4 + e] * 256 + (int)v[1 * 4 + e]);
+                        y23 = (double)((int)v[2 * 4 + e] * 256 + (int)v[3 * 4 + e]);
+                        y45 = (double)((int)v[4 * 4 + e] * 256 + (int)v[5 * 4 + e]);
+                    } else {
+                        y01 = fma((double)(int)v[0 * 4 + e], 256.0, (double)(int)v[1 * 4 + e]);
+                        y23 = fma((double)(int)v[2 * 4 + e], 256.0, (double)(int)v[3 * 4 + e]);
+                        y45 = fma((double)(int)v[4 * 4 + e], 256.0, (double)(int)v[5 * 4 + e]);
+                    }
+                    const double hi = fma(y01, 65536.0, y23);                      // exact (< 2^48)
+                    const double lo = fma(y45, 256.0, (double)(int)v[6 * 4 + e]);  // exact
+                    const double x = fma(hi, 16777216.0, lo);                      // the one rounding
+                    const double t = x * __ldg(sc + c * 4 + e);                    // power-of-two scale: exact
+                    sum = fma(t, si_s8_to_f64(mw[c], e), sum);                     // row-dot with m_kj in {-1,0,1}
                 }
             }
             ptx::tc_fence_before();
@@ -248,7 +257,8 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ slicing of U
-// per column: e_k with max_i |U_ik| * 2^(-e_k) in [0.5, 1); scale_k = 2^(e_k - 55)
+// per column: e_k with max_i |U_ik| * 2^(-e_k) in [0.5, 127/128) (so that the top digit, carry included,
+// stays <= 127); scale_k = 2^(e_k - 55)
 __global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
                                                           int32_t* __restrict__ expo, double* __restrict__ scale,
                                                           int64_t ncols_pad) {
@@ -266,16 +276,16 @@ __global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restri
         int e = 0;
         double s = 0.0;
         if (k < n && amax > 0.0 && amax <= 1.79769313486231570e308) {
-            frexp(amax, &e);
+            if (frexp(amax, &e) >= 0.9921875) e++;
             s = ldexp(1.0, e - 55);
-        } else if (k < n && amax != amax) {
-            s = amax;  // NaN in U poisons the column, as it would poison the reference's product
+        } else if (k < n && !(amax <= 1.79769313486231570e308)) {
+            s = __longlong_as_double(0x7FF8000000000000LL);  // NaN / Inf in U poisons the column, as in the reference's product
         }
         expo[k] = e;
         scale[k] = s;
     }
 }
-// Q rows for column k = 32 g + kk: g*256 + (kk>>2)*32 + s*4 + (kk&3); thread -> 4 consecutive i
+// Q rows for column k = 32 g + kk: g*224 + (kk>>2)*28 + s*4 + (kk&3); thread -> 4 consecutive i
 __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
                                                        const int32_t* __restrict__ expo, int8_t* __restrict__ Q,
                                                        int64_t Kp) {
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict_
     if (i0 >= Kp) return;
     const int64_t g = k / SI_GCOLS;
     const int kk = (int)(k - g * SI_GCOLS);
-    int8_t* base = Q + (g * SI_BN + (kk >> 2) * 32 + (kk & 3)) * Kp + i0;
+    int8_t* base = Q + (g * SI_BN + (kk >> 2) * SI_CHUNK + (kk & 3)) * Kp + i0;
     uint32_t out[SI_SLICES];
 #pragma unroll
     for (int s = 0; s < SI_SLICES; s++) out[s] = 0;
@@ -294,13 +304,15 @@ __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict_
         for (int d = 0; d < 4; d++) {
             const int64_t i = i0 + d;
             if (i <= k && i < n) {
-                double r = ldexp(Wp[i + k * ld], 6 - e);  // |r| < 64
+                const double xs = ldexp(Wp[i + k * ld], 55 - e);  // |xs| <= 127 * 2^48 (exact scaling)
+                long long X = fabs(xs) < 3.6e16 ? __double2ll_rn(xs) : 0;  // NaN / Inf: the column's scale is NaN
 #pragma unroll
-                for (int s = 0; s < SI_SLICES; s++) {
-                    const double qd = rint(r);             // in [-64, 64]
-                    out[s] |= ((uint32_t)(int)qd & 0xFFu) << (8 * d);
-                    r = (r - qd) * 128.0;                  // exact: |r - qd| <= 0.5
+                for (int s = SI_SLICES - 1; s > 0; s--) {          // balanced digits, least significant first
+                    const int q = (int)(int8_t)(X & 0xFF);
+                    out[s] |= ((uint32_t)q & 0xFFu) << (8 * d);
+                    X = (X - q) >> 8;                              // exact: X - q is a multiple of 256
                 }
+                out[0] |= ((uint32_t)(int)X & 0xFFu) << (8 * d);  // top digit in [-127, 127]
             }
         }
     }
@@ -348,12 +360,12 @@ static PFN_encodeTiled si_encode_fn() {
     }
     return fn;
 }
-static int si_make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int64_t pitch) {
+static int si_make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int64_t pitch, int box_rows) {
     PFN_encodeTiled enc = si_encode_fn();
     if (!enc) return set_error(EG_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
     const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
-    const cuuint32_t box[2] = {128, 128};
+    const cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -433,8 +445,8 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     EG_TRY(check_launch("si_slice_kernel"));
     // 2. the int8 contraction with fused recombination + row-dot
     CUtensorMap tA, tB;
-    EG_TRY(si_make_map(&tA, d_Mt, Kp, L, pitch));
-    EG_TRY(si_make_map(&tB, g_si.Q, Kp, (int64_t)G * SI_BN, Kp));
+    EG_TRY(si_make_map(&tA, d_Mt, Kp, L, pitch, SI_BM));
+    EG_TRY(si_make_map(&tB, g_si.Q, Kp, (int64_t)G * SI_BN, Kp, SI_BN / 2));
     ScanI8Params p;
     p.L = L; p.n = n; p.G = G; p.MB = MB; p.KB = KB;
     p.Mt = d_Mt; p.pitch = pitch; p.scale = g_si.scale; p.partial = g_si.partial;
