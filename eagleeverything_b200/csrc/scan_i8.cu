@@ -83,6 +83,38 @@ __device__ __forceinline__ double si_s8_to_f64(uint32_t w, int b) {
     return __hiloint2double((int)hi, 0);
 }
 
+// One marker row (TMEM lane) of a finished accumulator: recombine the 7 slices of each of the 32 columns,
+// scale, and take the row-dot with the marker's own genotypes at those columns.  Fixed order.
+__device__ __forceinline__ double si_recombine_rowdot(uint32_t taddr, const uint32_t (&mw)[8], const double* __restrict__ sc,
+                                                      bool wide /* P0*256+P1 leaves int32 beyond n = 65280 */) {
+    double sum = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {  // 28 TMEM columns = 7 slices x 4 columns (kk = 4c .. 4c+3); 4 more ignored
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + (uint32_t)(c * SI_CHUNK), v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            double y01, y23, y45;
+            if (!wide) {
+                y01 = (double)((int)v[0 * 4 + e] * 256 + (int)v[1 * 4 + e]);
+                y23 = (double)((int)v[2 * 4 + e] * 256 + (int)v[3 * 4 + e]);
+                y45 = (double)((int)v[4 * 4 + e] * 256 + (int)v[5 * 4 + e]);
+            } else {
+                y01 = fma((double)(int)v[0 * 4 + e], 256.0, (double)(int)v[1 * 4 + e]);
+                y23 = fma((double)(int)v[2 * 4 + e], 256.0, (double)(int)v[3 * 4 + e]);
+                y45 = fma((double)(int)v[4 * 4 + e], 256.0, (double)(int)v[5 * 4 + e]);
+            }
+            const double hi = fma(y01, 65536.0, y23);                      // exact (< 2^48)
+            const double lo = fma(y45, 256.0, (double)(int)v[6 * 4 + e]);  // exact
+            const double x = fma(hi, 16777216.0, lo);                      // the one rounding
+            const double t = x * __ldg(sc + c * 4 + e);                    // power-of-two scale: exact
+            sum = fma(t, si_s8_to_f64(mw[c], e), sum);                     // row-dot with m_kj in {-1,0,1}
+        }
+    }
+    return sum;
+}
+
 __global__ void __launch_bounds__(SI_THREADS, 1)
 scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const ScanI8Params p) {
@@ -214,32 +246,8 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const double* sc = p.scale + (int64_t)un.y * SI_GCOLS;
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
-            double sum = 0.0;
-            const bool wide = p.n > 65000;  // P0*256+P1 leaves int32 beyond n = 65280
-#pragma unroll
-            for (int c = 0; c < 8; c++) {  // 28 TMEM columns = 7 slices x 4 columns (kk = 4c .. 4c+3); 4 more ignored
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + c * SI_CHUNK), v);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    double y01, y23, y45;
-                    if (!wide) {
-                        y01 = (double)((int)v[0 * 4 + e] * 256 + (int)v[1 * 4 + e]);
-                        y23 = (double)((int)v[2 * 4 + e] * 256 + (int)v[3 * 4 + e]);
-                        y45 = (double)((int)v[4 * 4 + e] * 256 + (int)v[5 * 4 + e]);
-                    } else {
-                        y01 = fma((double)(int)v[0 * 4 + e], 256.0, (double)(int)v[1 * 4 + e]);
-                        y23 = fma((double)(int)v[2 * 4 + e], 256.0, (double)(int)v[3 * 4 + e]);
-                        y45 = fma((double)(int)v[4 * 4 + e], 256.0, (double)(int)v[5 * 4 + e]);
-                    }
-                    const double hi = fma(y01, 65536.0, y23);                      // exact (< 2^48)
-                    const double lo = fma(y45, 256.0, (double)(int)v[6 * 4 + e]);  // exact
-                    const double x = fma(hi, 16777216.0, lo);                      // the one rounding
-                    const double t = x * __ldg(sc + c * 4 + e);                    // power-of-two scale: exact
-                    sum = fma(t, si_s8_to_f64(mw[c], e), sum);                     // row-dot with m_kj in {-1,0,1}
-                }
-            }
+            const double sum = si_recombine_rowdot(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS), mw,
+                                                   sc, p.n > 65000);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
@@ -253,6 +261,174 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<SI_TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------ CTA-pair version (EAGLE_SI_PAIR=1)
+// Two CTAs of one TPC share a 256-marker x 224 tile: tcgen05.mma.cta_group::2, M = 256.  Each CTA stages its own
+// 128 marker rows (A) and only HALF of the slice rows (B, 112 of 224), so a k-block costs 30 KB of shared-memory
+// fill per SM instead of 44 KB.  Measured at n=10k (profiles/r1f_scan_sustained.txt): same throughput as the
+// single-CTA kernel (70.6 vs 70.2 ms per 250k markers, both at the 1 kW power cap, where a cuBLASLt int8 GEMM
+// sustains LESS than either), so the simpler kernel stays the default and this one is kept selectable.
+// Barrier protocol: full[s] lives in the leader (rank 0) and collects the bytes of both CTAs' TMA loads; the
+// leader's UMMA thread frees a stage / publishes an accumulator in BOTH CTAs with a multicast commit; the epilogue
+// warps of both CTAs release an accumulator by arriving on the leader's tmem_empty (count 8).
+constexpr int SP_STAGES = 7;
+constexpr int SP_MSUP_DEFAULT = 18;  // super-tile in units of 256-marker blocks x groups (see SI_MSUP_DEFAULT)
+constexpr int SP_GSUP_DEFAULT = 4;
+constexpr int SP_A_BYTES = SI_BM * SI_BK;               // 128 marker rows
+constexpr int SP_B_BYTES = (SI_BN / 2) * SI_BK;         // 112 slice rows
+constexpr int SP_STAGE_BYTES = SP_A_BYTES + SP_B_BYTES; // 30 KB
+constexpr int SP_SMEM_BYTES = SP_STAGES * SP_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(SI_THREADS, 1)
+scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                    const ScanI8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_STAGES * SP_STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + SP_STAGES;
+    uint64_t* tmem_full = bars + 2 * SP_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int64_t cid = ptx::cluster_id_x();
+    const int64_t ncl = gridDim.x / 2;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmapA);
+        ptx::prefetch_tmap(&tmapB);
+        for (int s = 0; s < SP_STAGES; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&tmem_full[a], 1);
+            ptx::mbar_init(&tmem_empty[a], 8);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc_pair<SI_TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (flow control in the leader)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int round = 0, known = -1;
+            auto need_of = [&](int gp) -> uint32_t {
+                const int64_t left = p.nunits - (int64_t)(gp / p.phases_per_unit) * ncl;
+                return (uint32_t)(left < ncl ? left : ncl);
+            };
+            for (int64_t u = cid; u < p.nunits; u += ncl, round++) {
+                const int2 un = p.units[u];
+                const int kb1 = si_kb_end(un.y, p.KB);
+                for (int kb = 0; kb < kb1; kb++) {
+                    if (rank == 0 && p.phase_ctr && (kb % SI_PHASE) == 0) {
+                        const int gp = round * p.phases_per_unit + kb / SI_PHASE;
+                        if (gp - SI_LAG > known) {
+                            uint32_t v[SI_LAG];
+#pragma unroll
+                            for (int q = 0; q < SI_LAG; q++) v[q] = si_ld(p.phase_ctr + max(gp - 1 - q, 0));
+#pragma unroll
+                            for (int q = SI_LAG - 1; q >= 0; q--)
+                                if (gp - 1 - q >= 0 && gp - 1 - q > known && v[q] >= need_of(gp - 1 - q)) known = gp - 1 - q;
+                            uint32_t spins = 0;
+                            while (gp - SI_LAG > known) {
+                                if (si_ld(p.phase_ctr + gp - SI_LAG) >= need_of(gp - SI_LAG)) known = gp - SI_LAG;
+                                else if (++spins > (1u << 24)) {
+                                    printf("eagle: scan_i8 (pair) flow control timed out (cluster %d phase %d)\n", (int)cid, gp);
+                                    __trap();
+                                }
+                            }
+                        }
+                    }
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * SP_STAGE_BYTES;
+                    uint8_t* sB = sA + SP_A_BYTES;
+                    const uint32_t lead_full = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+                    if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * SP_STAGE_BYTES);
+                    ptx::tma_load_2d_pair(sA, &tmapA, kb * SI_BK, un.x * (2 * SI_BM) + (int)rank * SI_BM, lead_full);
+                    ptx::tma_load_2d_pair(sB, &tmapB, kb * SI_BK, un.y * SI_BN + (int)rank * (SI_BN / 2), lead_full);
+                    if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ UMMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_i8(2 * SI_BM, SI_BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            int round = 0;
+            for (int64_t u = cid; u < p.nunits; u += ncl, round++) {
+                const int2 un = p.units[u];
+                const int kb1 = si_kb_end(un.y, p.KB);
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SI_ACC_COLS);
+                for (int kb = 0; kb < kb1; kb++) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    if (p.phase_ctr && ((kb % SI_PHASE) == SI_PHASE - 1 || kb == kb1 - 1)) {
+                        const int ph = kb / SI_PHASE;
+                        uint32_t* c = p.phase_ctr + (int64_t)round * p.phases_per_unit;
+                        si_red_add(c + ph, 1u);
+                        if (kb == kb1 - 1)
+                            for (int q = ph + 1; q < p.phases_per_unit; q++) si_red_add(c + q, 1u);
+                    }
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + stage * SP_STAGE_BYTES);
+                    const uint64_t a_desc = ptx::make_desc_k_sw128(a_addr);
+                    const uint64_t b_desc = ptx::make_desc_k_sw128(a_addr + SP_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < SI_BK / 32; k++)
+                        ptx::umma_i8_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                          (kb > 0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit_pair(&empty[stage], 3);
+                    if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit_pair(&tmem_full[acc], 3);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: one thread = one marker row
+        const int q4 = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t u = cid; u < p.nunits; u += ncl) {
+            const int2 un = p.units[u];
+            const int64_t j = (int64_t)un.x * (2 * SI_BM) + (int64_t)rank * SI_BM + q4 * 32 + lane;
+            const int64_t jc = j < p.L ? j : p.L - 1;
+            const uint4* mp = reinterpret_cast<const uint4*>(p.Mt + jc * p.pitch + (int64_t)un.y * SI_GCOLS);
+            const uint4 m0 = mp[0], m1 = mp[1];
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const double* sc = p.scale + (int64_t)un.y * SI_GCOLS;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            const double sum = si_recombine_rowdot(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS), mw,
+                                                   sc, p.n > 65000);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
+            if (j < p.L) p.partial[(int64_t)un.y * p.L + j] = sum;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // no CTA leaves while its peer can still signal it or read its shared memory
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_pair<SI_TMEM_COLS>(tmem_base);
     }
 }
 
@@ -416,7 +592,10 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
         g_si.device = dev;
     }
     const int G = (int)((n + SI_GCOLS - 1) / SI_GCOLS);
-    const int MB = (int)((L + SI_BM - 1) / SI_BM);
+    const char* env_pair = getenv("EAGLE_SI_PAIR");
+    const bool pair = env_pair && env_pair[0] == '1';      // CTA pairs (cta_group::2): opt-in, see the kernel's header
+    const int rows_per_unit = pair ? 2 * SI_BM : SI_BM;
+    const int MB = (int)((L + rows_per_unit - 1) / rows_per_unit);
     const int64_t Kp = round_up(n, 128);
     const int KB = (int)(Kp / SI_BK);
     if (pitch < Kp || pitch < (int64_t)G * SI_GCOLS)
@@ -426,16 +605,17 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     EG_TRY(si_grow(&g_si.expo, &g_si.expo_cap, (size_t)G * SI_GCOLS, "column exponents"));
     EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)G * L, "per-group partial sums"));
     const int64_t nunits = (int64_t)MB * G;
-    int msup = SI_MSUP_DEFAULT, gsup = SI_GSUP_DEFAULT;
+    int msup = pair ? SP_MSUP_DEFAULT : SI_MSUP_DEFAULT, gsup = pair ? SP_GSUP_DEFAULT : SI_GSUP_DEFAULT;
     if (const char* e = getenv("EAGLE_SI_MSUP")) msup = atoi(e) > 0 ? atoi(e) : msup;
     if (const char* e = getenv("EAGLE_SI_GSUP")) gsup = atoi(e) > 0 ? atoi(e) : gsup;
-    if (g_si.units_MB != MB || g_si.units_G != G || g_si.units_shape != msup * 1000 + gsup || !g_si.units) {
+    const int shape_key = (pair ? 1000000 : 0) + msup * 1000 + gsup;
+    if (g_si.units_MB != MB || g_si.units_G != G || g_si.units_shape != shape_key || !g_si.units) {
         EG_TRY(si_grow(&g_si.units, &g_si.unit_cap, (size_t)nunits, "unit table"));
         si_units_kernel<<<(unsigned)((nunits + 255) / 256), 256, 0, st>>>(g_si.units, MB, G, msup, gsup);
         EG_TRY(check_launch("si_units_kernel"));
         g_si.units_MB = MB;
         g_si.units_G = G;
-        g_si.units_shape = msup * 1000 + gsup;
+        g_si.units_shape = shape_key;
     }
     // 1. slice U
     si_colscale_kernel<<<(unsigned)(G * SI_GCOLS), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo, g_si.scale, (int64_t)G * SI_GCOLS);
@@ -452,36 +632,44 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     p.Mt = d_Mt; p.pitch = pitch; p.scale = g_si.scale; p.partial = g_si.partial;
     p.units = g_si.units; p.nunits = nunits;
     const int sms = num_sms();
-    const int grid = nunits < sms ? (int)nunits : sms;
+    const int workers_max = pair ? sms / 2 : sms;          // CTAs, or CTA pairs
+    const int workers = nunits < workers_max ? (int)nunits : workers_max;
     p.phases_per_unit = (KB + SI_PHASE - 1) / SI_PHASE;
-    const int64_t rounds = (nunits + grid - 1) / grid;
+    const int64_t rounds = (nunits + workers - 1) / workers;
     const size_t nctr = (size_t)rounds * p.phases_per_unit;
     const char* env_fc = getenv("EAGLE_SCAN_FLOWCTL");
-    const bool flow = !(env_fc && env_fc[0] == '0') && grid > 1 && nctr < ((size_t)1 << 28);
+    const bool flow = !(env_fc && env_fc[0] == '0') && workers > 1 && nctr < ((size_t)1 << 28);
     p.phase_ctr = nullptr;
     if (flow) {
         EG_TRY(si_grow(&g_si.phase, &g_si.phase_cap, nctr, "flow-control counters"));
         EG_CUDA(cudaMemsetAsync(g_si.phase, 0, nctr * sizeof(uint32_t), st));
         p.phase_ctr = g_si.phase;
     }
-    EG_CUDA(cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM_BYTES));
+    const int smem_bytes = pair ? SP_SMEM_BYTES : SI_SMEM_BYTES;
+    if (pair) EG_CUDA(cudaFuncSetAttribute(scan_i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else EG_CUDA(cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
+    cfg.gridDim = dim3((unsigned)(pair ? 2 * workers : workers));
     cfg.blockDim = dim3(SI_THREADS);
-    cfg.dynamicSmemBytes = SI_SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;           // co-residency: the flow control spins on other CTAs
     attr[0].val.cooperative = flow ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    double kblocks = 0.0;  // executed int8 ops: 2 * 128 * 256 * 128 per (marker block, k-block of a group)
+    cfg.numAttrs = pair ? 2 : 1;
+    double kblocks = 0.0;  // executed int8 ops: 2 * rows * 224 * 128 per (marker block, k-block of a group)
     for (int g = 0; g < G; g++) {
         const int kb = (g * SI_GCOLS + SI_GCOLS + SI_BK - 1) / SI_BK;
         kblocks += kb < KB ? kb : KB;
     }
-    scan_kernel_mark(0, st, kblocks * MB * 2.0 * SI_BM * SI_BN * SI_BK);
-    EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel, tA, tB, p));
+    scan_kernel_mark(0, st, kblocks * MB * 2.0 * rows_per_unit * SI_BN * SI_BK);
+    if (pair) EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_pair_kernel, tA, tB, p));
+    else EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel, tA, tB, p));
     scan_kernel_mark(1, st, 0.0);
     // 3. groups summed in index order
     si_reduce_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(g_si.partial, L, G, d_zero_rows, n_zero, d_vara);
