@@ -83,6 +83,9 @@ static int ensure_init() {
 
 void syrk_release_cache();
 void scan_i8_release();
+void prep_i8_release();
+int launch_prepare_i8(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1, double* d_tmp,
+                      double* d_Wp, int64_t Kpad, cudaStream_t st, bool* done);
 static int g_scan_mode = -1;
 int scan_mode() {
     if (g_scan_mode < 0) {
@@ -588,6 +591,7 @@ extern "C" int eg_shutdown(void) {
     eg_cache_clear();
     syrk_release_cache();
     scan_i8_release();
+    prep_i8_release();
     if (g_ctx.cublas) cublasDestroy(g_ctx.cublas);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
@@ -743,6 +747,14 @@ extern "C" int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, in
     EG_TRY(ensure_init());
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t Kpad = round_up(n, 32), nc = col1 - col0;
+    // symmetric inputs: both products on the int8 tensor cores (prep_i8.cu) unless EAGLE_PREP_MODE=f64 or the
+    // digit slices do not fit in memory
+    const char* env_pm = getenv("EAGLE_PREP_MODE");
+    if (upper_only && !(env_pm && env_pm[0] == 'f')) {
+        bool done = false;
+        EG_TRY(launch_prepare_i8(d_S, d_V, n, col0, col1, d_tmp, d_Wp, Kpad, st, &done));
+        if (done) return EG_OK;
+    }
     const double one = 1.0, zero = 0.0;
     if (cublasSetStream(g_ctx.cublas, st) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasSetStream");
     // calculate_a_and_vara_rcpp.cpp:97   tmp = dim_reduced_vara * inv_MMt_sqrt      (columns col0..col1)

@@ -44,7 +44,7 @@ constexpr int SI_STAGES = 5;
 constexpr int SI_A_BYTES = SI_BM * SI_BK;
 constexpr int SI_B_BYTES = SI_BN * SI_BK;
 constexpr int SI_STAGE_BYTES = SI_A_BYTES + SI_B_BYTES;
-constexpr int SI_THREADS = 192;
+constexpr int SI_THREADS = 320;        // TMA warp, UMMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int SI_TMEM_COLS = 512;
 constexpr int SI_MSUP_DEFAULT = 37;  // super-tile: marker blocks (their Mt rows stay L2-resident over the group sweep)
 constexpr int SI_GSUP_DEFAULT = 4;   //             x groups  (~ one wave of 148 CTAs)
@@ -58,7 +58,7 @@ struct ScanI8Params {
     const int8_t* Mt;
     int64_t pitch;
     const double* scale;        // [G*32]  2^(e_k - 55), 0 for pad columns
-    double* partial;            // [G][L]
+    double* partial;            // [2 G][L]: (group, column half) x marker
     const int2* units;          // (mb, g)
     int64_t nunits;
     uint32_t* phase_ctr;
@@ -83,36 +83,48 @@ __device__ __forceinline__ double si_s8_to_f64(uint32_t w, int b) {
     return __hiloint2double((int)hi, 0);
 }
 
-// One marker row (TMEM lane) of a finished accumulator: recombine the 7 slices of each of the 32 columns,
-// scale, and take the row-dot with the marker's own genotypes at those columns.  Fixed order.
-__device__ __forceinline__ double si_recombine_rowdot(uint32_t taddr, const uint32_t (&mw)[8], const double* __restrict__ sc,
+// int32 -> double without I2F.F64 (the conversion unit retires only a few results per clock per SM): 2^52 + 2^31 + x
+// is exactly representable with x in the low mantissa word.
+__device__ __forceinline__ double si_i2d(int x) {
+    return __hiloint2double(0x43300000, x ^ (int)0x80000000) - 4503601774854144.0;
+}
+
+// One marker row (TMEM lane) of a finished accumulator, 16 of the group's 32 columns (the warp's half): recombine
+// the 7 slices of each column, scale, and take the row-dot with the marker's own genotypes at those columns.
+// Four independent running sums (one per column position in a chunk) combined at the end: fixed order.
+// Measured (EG_SI_PROFILE): ~6,000 clk per unit whatever the arithmetic (9 FP64 operations per column or 2 plus
+// integer normalisation): the 114 KB of TMEM reads per unit, competing with the MMAs for the TMEM port, set the
+// pace.  Units with fewer than ~14 k-blocks are therefore epilogue-bound (3 % of the time at n = 10k).
+__device__ __forceinline__ double si_recombine_rowdot(uint32_t taddr, const uint32_t (&mw)[4], const double* __restrict__ sc,
                                                       bool wide /* P0*256+P1 leaves int32 beyond n = 65280 */) {
-    double sum = 0.0;
+    double sum[4] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t v4[4][32];
 #pragma unroll
-    for (int c = 0; c < 8; c++) {  // 28 TMEM columns = 7 slices x 4 columns (kk = 4c .. 4c+3); 4 more ignored
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + (uint32_t)(c * SI_CHUNK), v);
-        ptx::tmem_ld_wait();
+    for (int c = 0; c < 4; c++) ptx::tmem_ld_32x28(taddr + (uint32_t)(c * SI_CHUNK), v4[c]);  // all 112 columns in flight
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {  // 28 TMEM columns = 7 slices x 4 columns (kk = 4c .. 4c+3)
+        uint32_t(&v)[32] = v4[c];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             double y01, y23, y45;
             if (!wide) {
-                y01 = (double)((int)v[0 * 4 + e] * 256 + (int)v[1 * 4 + e]);
-                y23 = (double)((int)v[2 * 4 + e] * 256 + (int)v[3 * 4 + e]);
-                y45 = (double)((int)v[4 * 4 + e] * 256 + (int)v[5 * 4 + e]);
+                y01 = si_i2d((int)v[0 * 4 + e] * 256 + (int)v[1 * 4 + e]);
+                y23 = si_i2d((int)v[2 * 4 + e] * 256 + (int)v[3 * 4 + e]);
+                y45 = si_i2d((int)v[4 * 4 + e] * 256 + (int)v[5 * 4 + e]);
             } else {
-                y01 = fma((double)(int)v[0 * 4 + e], 256.0, (double)(int)v[1 * 4 + e]);
-                y23 = fma((double)(int)v[2 * 4 + e], 256.0, (double)(int)v[3 * 4 + e]);
-                y45 = fma((double)(int)v[4 * 4 + e], 256.0, (double)(int)v[5 * 4 + e]);
+                y01 = fma(si_i2d((int)v[0 * 4 + e]), 256.0, si_i2d((int)v[1 * 4 + e]));
+                y23 = fma(si_i2d((int)v[2 * 4 + e]), 256.0, si_i2d((int)v[3 * 4 + e]));
+                y45 = fma(si_i2d((int)v[4 * 4 + e]), 256.0, si_i2d((int)v[5 * 4 + e]));
             }
             const double hi = fma(y01, 65536.0, y23);                      // exact (< 2^48)
-            const double lo = fma(y45, 256.0, (double)(int)v[6 * 4 + e]);  // exact
+            const double lo = fma(y45, 256.0, si_i2d((int)v[6 * 4 + e]));  // exact
             const double x = fma(hi, 16777216.0, lo);                      // the one rounding
             const double t = x * __ldg(sc + c * 4 + e);                    // power-of-two scale: exact
-            sum = fma(t, si_s8_to_f64(mw[c], e), sum);                     // row-dot with m_kj in {-1,0,1}
+            sum[e] = fma(t, si_s8_to_f64(mw[c], e), sum[e]);               // row-dot with m_kj in {-1,0,1}
         }
     }
-    return sum;
+    return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
 __global__ void __launch_bounds__(SI_THREADS, 1)
@@ -137,7 +149,7 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 4);
+            ptx::mbar_init(&tmem_empty[a], 8);
         }
         ptx::fence_mbar_init();
     }
@@ -200,14 +212,30 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             int acc = 0;
             uint32_t acc_phase = 0;
             int round = 0;
+#ifdef EG_SI_PROFILE
+            long long t_acc = 0, t_full = 0, t_all = clock64(), nkb = 0;
+#endif
             for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
                 const int2 un = p.units[u];
                 const int kb1 = si_kb_end(un.y, p.KB);
+#ifdef EG_SI_PROFILE
+                long long t0 = clock64();
+#endif
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+#ifdef EG_SI_PROFILE
+                t_acc += clock64() - t0;
+                nkb += kb1;
+#endif
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SI_ACC_COLS);
                 for (int kb = 0; kb < kb1; kb++) {
+#ifdef EG_SI_PROFILE
+                    t0 = clock64();
+#endif
                     ptx::mbar_wait(&full[stage], phase);
+#ifdef EG_SI_PROFILE
+                    t_full += clock64() - t0;
+#endif
                     if (p.phase_ctr && ((kb % SI_PHASE) == SI_PHASE - 1 || kb == kb1 - 1)) {
                         const int ph = kb / SI_PHASE;
                         uint32_t* c = p.phase_ctr + (int64_t)round * p.phases_per_unit;
@@ -229,31 +257,64 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 ptx::umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+#ifdef EG_SI_PROFILE
+            if (blockIdx.x == 7)
+                printf("si profile (MMA thread, block 7): total %lld clk, units %d, k-blocks %lld (x448 = %lld clk of MMA), waiting "
+                       "for a free accumulator %lld, for operands %lld\n",
+                       clock64() - t_all, round, nkb, nkb * 448, t_acc, t_full);
+#endif
         }
     } else {
         // ------------------------------------------------------------ epilogue: one thread = one marker row
-        const int q4 = warp & 3;
+        const int q4 = warp & 3;          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2; // which 16 of the group's 32 columns
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-            const int2 un = p.units[u];
+#ifdef EG_SI_PROFILE
+        long long e_wait = 0, e_work = 0;
+#endif
+        // this marker's genotypes at the 32 columns of the group (pad columns are zero in the store); the unit
+        // table entry and these bytes are fetched one unit ahead, off the critical path of a short unit
+        auto fetch = [&](int64_t u, int2& un, uint4& m0) {
+            un = p.units[u];
             const int64_t j = (int64_t)un.x * SI_BM + q4 * 32 + lane;
-            const int64_t jc = j < p.L ? j : p.L - 1;
-            // this marker's genotypes at the 32 columns of the group (pad columns are zero in the store)
-            const uint4* mp = reinterpret_cast<const uint4*>(p.Mt + jc * p.pitch + (int64_t)un.y * SI_GCOLS);
-            const uint4 m0 = mp[0], m1 = mp[1];
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-            const double* sc = p.scale + (int64_t)un.y * SI_GCOLS;
+            m0 = *reinterpret_cast<const uint4*>(p.Mt + (j < p.L ? j : p.L - 1) * p.pitch + (int64_t)un.y * SI_GCOLS + half * 16);
+        };
+        int2 un_n = make_int2(0, 0);
+        uint4 m0_n = make_uint4(0, 0, 0, 0);
+        if ((int64_t)blockIdx.x < p.nunits) fetch(blockIdx.x, un_n, m0_n);
+        for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            const int2 un = un_n;
+            const uint4 m0 = m0_n;
+            if (u + gridDim.x < p.nunits) fetch(u + gridDim.x, un_n, m0_n);
+            const int64_t j = (int64_t)un.x * SI_BM + q4 * 32 + lane;
+            const uint32_t mw[4] = {m0.x, m0.y, m0.z, m0.w};
+            const double* sc = p.scale + (int64_t)un.y * SI_GCOLS + half * 16;
+#ifdef EG_SI_PROFILE
+            long long t0 = clock64();
+#endif
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
+#ifdef EG_SI_PROFILE
+            e_wait += clock64() - t0;
+            t0 = clock64();
+#endif
             ptx::tc_fence_after();
-            const double sum = si_recombine_rowdot(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS), mw,
-                                                   sc, p.n > 65000);
+            const double sum = si_recombine_rowdot(
+                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SI_CHUNK), mw, sc, p.n > 65000);
             ptx::tc_fence_before();
             __syncwarp();
+#ifdef EG_SI_PROFILE
+            e_work += clock64() - t0;
+#endif
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-            if (j < p.L) p.partial[(int64_t)un.y * p.L + j] = sum;
+            if (j < p.L) p.partial[((int64_t)un.y * 2 + half) * p.L + j] = sum;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+#ifdef EG_SI_PROFILE
+        if (blockIdx.x == 7 && warp == 2 && lane == 0)
+            printf("si profile (epilogue warp 2, block 7): waiting for a full accumulator %lld clk, recombining %lld clk\n", e_wait,
+                   e_work);
+#endif
     }
 
     ptx::tc_fence_before();
@@ -306,7 +367,7 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 8);
+            ptx::mbar_init(&tmem_empty[a], 16);
         }
         ptx::fence_mbar_init();
     }
@@ -401,25 +462,33 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
     } else {
         // ------------------------------------------------------------ epilogue: one thread = one marker row
-        const int q4 = warp & 3;
+        const int q4 = warp & 3;          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2; // which 16 of the group's 32 columns
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int64_t u = cid; u < p.nunits; u += ncl) {
-            const int2 un = p.units[u];
+        auto fetch = [&](int64_t u, int2& un, uint4& m0) {
+            un = p.units[u];
             const int64_t j = (int64_t)un.x * (2 * SI_BM) + (int64_t)rank * SI_BM + q4 * 32 + lane;
-            const int64_t jc = j < p.L ? j : p.L - 1;
-            const uint4* mp = reinterpret_cast<const uint4*>(p.Mt + jc * p.pitch + (int64_t)un.y * SI_GCOLS);
-            const uint4 m0 = mp[0], m1 = mp[1];
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-            const double* sc = p.scale + (int64_t)un.y * SI_GCOLS;
+            m0 = *reinterpret_cast<const uint4*>(p.Mt + (j < p.L ? j : p.L - 1) * p.pitch + (int64_t)un.y * SI_GCOLS + half * 16);
+        };
+        int2 un_n = make_int2(0, 0);
+        uint4 m0_n = make_uint4(0, 0, 0, 0);
+        if (cid < p.nunits) fetch(cid, un_n, m0_n);
+        for (int64_t u = cid; u < p.nunits; u += ncl) {
+            const int2 un = un_n;
+            const uint4 m0 = m0_n;
+            if (u + ncl < p.nunits) fetch(u + ncl, un_n, m0_n);
+            const int64_t j = (int64_t)un.x * (2 * SI_BM) + (int64_t)rank * SI_BM + q4 * 32 + lane;
+            const uint32_t mw[4] = {m0.x, m0.y, m0.z, m0.w};
+            const double* sc = p.scale + (int64_t)un.y * SI_GCOLS + half * 16;
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
-            const double sum = si_recombine_rowdot(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS), mw,
-                                                   sc, p.n > 65000);
+            const double sum = si_recombine_rowdot(
+                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SI_CHUNK), mw, sc, p.n > 65000);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
-            if (j < p.L) p.partial[(int64_t)un.y * p.L + j] = sum;
+            if (j < p.L) p.partial[((int64_t)un.y * 2 + half) * p.L + j] = sum;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -508,7 +577,7 @@ __global__ void si_units_kernel(int2* units, int MB, int G, int MSUP, int GSUP) 
     units[u] = make_int2(mb, g);
 }
 
-// vara_j = sum over groups in index order; zeroed rows give 0
+// vara_j = sum over (group, column half) in index order; zeroed rows give 0
 __global__ void __launch_bounds__(256) si_reduce_kernel(const double* __restrict__ partial, int64_t L, int G,
                                                         const int64_t* __restrict__ zero_rows, int n_zero,
                                                         double* __restrict__ vara) {
@@ -603,7 +672,7 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     EG_TRY(si_grow(&g_si.Q, &g_si.q_cap, (size_t)G * SI_BN * Kp, "sliced U"));
     EG_TRY(si_grow(&g_si.scale, &g_si.sc_cap, (size_t)G * SI_GCOLS, "column scales"));
     EG_TRY(si_grow(&g_si.expo, &g_si.expo_cap, (size_t)G * SI_GCOLS, "column exponents"));
-    EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)G * L, "per-group partial sums"));
+    EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)2 * G * L, "per-group partial sums"));
     const int64_t nunits = (int64_t)MB * G;
     int msup = pair ? SP_MSUP_DEFAULT : SI_MSUP_DEFAULT, gsup = pair ? SP_GSUP_DEFAULT : SI_GSUP_DEFAULT;
     if (const char* e = getenv("EAGLE_SI_MSUP")) msup = atoi(e) > 0 ? atoi(e) : msup;
@@ -672,7 +741,7 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     else EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel, tA, tB, p));
     scan_kernel_mark(1, st, 0.0);
     // 3. groups summed in index order
-    si_reduce_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(g_si.partial, L, G, d_zero_rows, n_zero, d_vara);
+    si_reduce_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(g_si.partial, L, 2 * G, d_zero_rows, n_zero, d_vara);
     return check_launch("si_reduce_kernel");
 }
 

@@ -121,6 +121,53 @@ def test_gemv_matches_float64(dev):
     np.testing.assert_allclose(y, 2.5 * ((G.T.astype(np.float64) - 1) @ x), rtol=1e-12, atol=1e-11)
 
 
+@pytest.mark.parametrize("n,cuts", [(777, [0, 777]), (1500, [0, 416, 1500]), (2048, [0, 2048])])
+def test_preproducts_int8_slices_match_float64(dev, n, cuts, monkeypatch):
+    """W = S (V S) on the int8 tensor cores (prep_i8.cu) against the cuBLAS FP64 path and torch float64:
+    badly scaled symmetric inputs (per-column exponents), ragged n, column shards, run-to-run identical."""
+    import ctypes as C
+    device, torch = dev
+    from eagleeverything_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+
+    def sym(shift):
+        A = rng.standard_normal((n, n)); A = (A + A.T) / np.sqrt(n) + shift * np.eye(n)
+        d = 2.0 ** rng.integers(-12, 13, n)
+        return A * d[:, None] * d[None, :]
+    S, V = sym(2.0), sym(1.5)
+    Sd, Vd = torch.from_numpy(S).cuda(), torch.from_numpy(V).cuda()
+    Kpad = (n + 31) // 32 * 32
+    tmp = torch.empty(n * n, dtype=torch.float64, device="cuda")
+
+    def run(mode):
+        monkeypatch.setenv("EAGLE_PREP_MODE", mode)
+        Wp = torch.zeros(lib.eg_scan_wp_elems(n), dtype=torch.float64, device="cuda")
+        for c0, c1 in zip(cuts[:-1], cuts[1:]):
+            _lib.check(lib.eg_dev_scan_prepare_cols(C.c_void_p(Sd.data_ptr()), C.c_void_p(Vd.data_ptr()), n, c0, c1, 1,
+                                                    C.c_void_p(tmp.data_ptr()), C.c_void_p(Wp.data_ptr()), None))
+        torch.cuda.synchronize()
+        return Wp[: Kpad * n].view(n, Kpad).T[:n, :]     # column-major content -> W[i, j]
+    Wi, Wi2, Wf = run("i8"), run("i8"), run("f64")
+    assert torch.equal(torch.triu(Wi), torch.triu(Wi2))
+    X = Vd @ Sd
+    ref = Sd @ X
+    eps = np.finfo(np.float64).eps
+    # FP64 GEMM: componentwise bound.  Digit slices: the residual is relative to (row max) x (column max) of each
+    # product, 2^-56 per operand entry and 6 * 2^-56 for the dropped levels, n terms
+    comp = 4 * n * eps * (Sd.abs() @ (Vd.abs() @ Sd.abs()))
+    rmax = lambda A: A.abs().max(dim=1).values
+    cmax = lambda A: A.abs().max(dim=0).values
+    norm1 = torch.outer(rmax(Vd), cmax(Sd))                  # error scale of X = V S
+    normw = 8 * n * 2.0 ** -56 * (torch.outer(rmax(Sd), cmax(X)) + Sd.abs() @ norm1)
+    assert (torch.triu(Wf - ref).abs() <= torch.triu(comp)).all()
+    assert (torch.triu(Wi - ref).abs() <= torch.triu(comp + normw)).all()
+    # typical (not worst-case) behaviour: the integer path is about as close to the FP64 GEMM as two FP64 GEMMs
+    # with different summation orders are to each other
+    rel = (torch.triu(Wi - Wf).abs() / comp).max().item()
+    assert rel < 2.0, rel
+
+
 @pytest.mark.parametrize("mode", [0, 1], ids=["dmma_f64", "tcgen05_i8"])
 def test_scan_modes_agree_at_scale(dev, mode):
     """n = 3000 (not a multiple of any tile), 40,000 markers: both contractions against torch float64."""
