@@ -75,6 +75,8 @@ SIGNATURES = {
     "eg_set_scan_mode": (C.c_int, [C.c_int]),
     "eg_get_scan_mode": (C.c_int, []),
     "eg_last_scan_kernel": (C.c_int, [_dp, _dp]),
+    "eg_last_prep_kernels": (C.c_int, [_dp, _dp]),
+    "eg_launch_count": (C.c_longlong, []),
     "eg_last_timing": (C.c_int, [_dp, C.c_int]),
 }
 

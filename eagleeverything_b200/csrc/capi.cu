@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -44,7 +45,11 @@ int check_cuda(cudaError_t e, const char* what) {
     }
     return set_error(EG_ERR_CUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
 }
-int check_launch(const char* kernel) { return check_cuda(cudaGetLastError(), kernel); }
+static std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py reports the count)
+int check_launch(const char* kernel) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_cuda(cudaGetLastError(), kernel);
+}
 
 // ------------------------------------------------------------------ context
 struct CacheEntry {
@@ -627,6 +632,17 @@ extern "C" int eg_last_scan_kernel(double* ms, double* ops) {
     EG_CUDA(cudaEventElapsedTime(&f, g_scan_ev[0], g_scan_ev[1]));
     *ms = f;
     *ops = g_scan_ops;
+    return EG_OK;
+}
+
+extern "C" long long eg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+namespace eg {
+void prep_kernel_times(double* ms, double* ops);
+}
+extern "C" int eg_last_prep_kernels(double* ms, double* ops) {
+    if (!ms || !ops) return set_error(EG_ERR_ARG, "eg_last_prep_kernels: null");
+    prep_kernel_times(ms, ops);
     return EG_OK;
 }
 

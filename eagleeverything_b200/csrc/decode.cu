@@ -10,6 +10,8 @@
 // copy (cp.async.bulk, completion on an mbarrier, 4-stage ring of 16 KB per CTA, 3 CTAs per SM); warps then read aligned
 // 16-byte vectors, realign them with funnel shifts (the misalignment is warp-uniform), subtract
 // '1' bytewise, validate and emit aligned 16-byte stores into the padded int8 matrix.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -214,6 +216,132 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_ascii_kernel(const DecodeP
     }
 }
 
+// ------------------------------------------------------------------ K-blocked destination, long rows
+// The K-blocked M store [col/128][rows][128] wants, per 128-marker block, the 128-byte pieces of ADJACENT rows next
+// to each other.  The row-chunk kernel above writes one row's 16 KB as 128 pieces 128*rows bytes apart (measured at
+// n = 10k: 71 % of the copy bandwidth, against 79 % at n = 2k).  Here a unit is 16 rows x 1 KB of columns: sixteen
+// ~1 KB bulk copies in (one per row, each 16-byte aligned on its own), eight 2 KB contiguous ranges out.  A
+// producer warp (lanes = rows) and 8 consumer warps are decoupled by full/empty mbarriers: no block-wide barrier.
+constexpr int DK_ROWS = 16;
+constexpr int DK_CW = 1024;                          // source bytes per row per unit (8 marker blocks)
+constexpr int DK_SUB = DK_CW + 64;                   // 16 B head slack + 32 B over-read slack, 64-B multiple
+constexpr int DK_STAGE_BYTES = DK_ROWS * DK_SUB;     // 17,408
+constexpr int DK_STAGES = 4;
+constexpr int DK_THREADS = 288;                      // 8 consumer warps + 1 producer warp
+constexpr int DK_SMEM_BYTES = DK_STAGES * DK_STAGE_BYTES + 1024;
+
+struct __align__(16) DkGeom {
+    int64_t r0, c0;
+    int32_t nrows, out_bytes;
+    uint32_t o0[DK_ROWS];
+};
+
+__global__ void __launch_bounds__(DK_THREADS) decode_kb_kernel(const DecodeParams p) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint8_t* stage0 = dsm;
+    DkGeom* geom = reinterpret_cast<DkGeom*>(dsm + DK_STAGES * DK_STAGE_BYTES);                 // [DK_STAGES] x 96 B
+    uint64_t* full = reinterpret_cast<uint64_t*>(dsm + DK_STAGES * DK_STAGE_BYTES + 512);        // [DK_STAGES]
+    uint64_t* empty = full + DK_STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < DK_STAGES; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 8);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t row_units = (p.rows + DK_ROWS - 1) / DK_ROWS;
+    const int64_t first_unit = blockIdx.x, stride = gridDim.x;
+    const int64_t my_units = p.num_units > first_unit ? (p.num_units - first_unit + stride - 1) / stride : 0;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------ producer: lane r stages row r of the unit
+        for (int64_t i = 0; i < my_units; i++) {
+            const int s = (int)(i % DK_STAGES);
+            ptx::mbar_wait(&empty[s], (uint32_t)(((i / DK_STAGES) & 1) ^ 1));
+            const int64_t u = first_unit + i * stride;
+            const int64_t ch = u / row_units, ru = u - ch * row_units;   // row groups fastest: neighbours write neighbours
+            const int64_t r0 = ru * DK_ROWS, c0 = ch * DK_CW;
+            const int64_t left = p.rows - r0;
+            const int nrows = (int)(left < DK_ROWS ? left : DK_ROWS);
+            int64_t cend = c0 + DK_CW;
+            if (cend > p.cols) cend = p.cols;
+            uint32_t bytes = 0, o0 = 0;
+            const uint8_t* a0 = nullptr;
+            if (lane < nrows && cend > c0) {
+                const uintptr_t fa = (uintptr_t)(p.src + (r0 + lane) * p.src_pitch + c0);
+                const uintptr_t la = (uintptr_t)(p.src + (r0 + lane) * p.src_pitch + cend);
+                const uintptr_t b0 = fa & ~(uintptr_t)15, b1 = (la + 15) & ~(uintptr_t)15;
+                a0 = (const uint8_t*)b0;
+                o0 = (uint32_t)(fa - b0);
+                bytes = (uint32_t)(b1 - b0);
+            }
+            if (lane < DK_ROWS) geom[s].o0[lane] = o0;
+            if (lane == 0) {
+                geom[s].r0 = r0;
+                geom[s].c0 = c0;
+                geom[s].nrows = nrows;
+                const int64_t ob = p.dst_pitch - c0;
+                geom[s].out_bytes = (int32_t)(ob < DK_CW ? ob : DK_CW);
+            }
+            uint32_t total = bytes;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            __syncwarp();
+            if (lane == 0) {
+                if (total) ptx::mbar_expect_tx(&full[s], total);
+                else ptx::mbar_arrive(&full[s]);
+            }
+            __syncwarp();
+            if (bytes) ptx::bulk_g2s(stage0 + s * DK_STAGE_BYTES + lane * DK_SUB, a0, bytes, &full[s]);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers: warp w decodes rows w and w + 8
+    uint32_t bad = 0;
+    for (int64_t i = 0; i < my_units; i++) {
+        const int s = (int)(i % DK_STAGES);
+        ptx::mbar_wait(&full[s], (uint32_t)((i / DK_STAGES) & 1));
+        const DkGeom& g = geom[s];
+        const int64_t r0 = g.r0, c0 = g.c0;
+        const int nrows = g.nrows, nvec = g.out_bytes >> 4;
+        const int64_t ncol = p.cols - c0;
+        const int nvalid_row = ncol >= g.out_bytes ? g.out_bytes : (ncol > 0 ? (int)ncol : 0);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int rr = warp + 8 * h;
+            if (rr < nrows) {
+                const uint8_t* sb = stage0 + s * DK_STAGE_BYTES + rr * DK_SUB;
+                const uint32_t o0 = g.o0[rr];
+                int8_t* drow = p.dst + ((c0 >> 7) * p.kb_rows + r0 + rr) * 128;
+                uint32_t bad_here = 0;
+                for (int v = lane; v < nvec; v += 32) {
+                    const int vb = v << 4;
+                    int nv = nvalid_row - vb;
+                    nv = nv > 16 ? 16 : nv;
+                    uint4 out = make_uint4(0, 0, 0, 0);
+                    if (nv > 0) out = decode16(sb, o0 + (uint32_t)vb, nv, bad_here);
+                    *reinterpret_cast<uint4*>(drow + (int64_t)(vb >> 7) * p.kb_rows * 128 + (vb & 127)) = out;
+                }
+                if (__any_sync(0xffffffffu, bad_here != 0) && !bad) {
+                    bad = 1;
+                    if (lane == 0 && atomicExch(&p.err[0], 1) == 0) {  // first reporter records (row, chunk column)
+                        p.err[1] = (int32_t)((r0 + rr) & 0x7FFFFFFF);
+                        p.err[2] = (int32_t)(c0 & 0x7FFFFFFF);
+                        p.err[3] = (int32_t)((r0 + rr) >> 31);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    }
+}
+
 }  // namespace eg
 
 static int decode_launch(const uint8_t* d_src, int64_t src_pitch, int64_t src_bytes_avail, int64_t rows, int64_t cols,
@@ -233,6 +361,18 @@ static int decode_launch(const uint8_t* d_src, int64_t src_pitch, int64_t src_by
     DecodeParams p;
     p.src = d_src; p.src_pitch = src_pitch; p.rows = rows; p.cols = cols;
     p.dst = d_dst; p.dst_pitch = dst_pitch; p.kb_rows = kb_rows; p.err = d_err;
+    const char* env_dk = getenv("EAGLE_DECODE_KB_TILES");
+    if (kb_rows && dst_pitch >= 4096 && !(env_dk && env_dk[0] == '0')) {
+        // K-blocked destination, long rows: 16-row x 1 KB units (decode_kb_kernel)
+        p.rows_per_unit = DK_ROWS;
+        p.chunk_bytes = DK_CW;
+        p.chunks_per_row = (int32_t)((dst_pitch + DK_CW - 1) / DK_CW);
+        p.num_units = ((rows + DK_ROWS - 1) / DK_ROWS) * p.chunks_per_row;
+        EG_CUDA(cudaFuncSetAttribute(decode_kb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DK_SMEM_BYTES));
+        const int64_t cap = (int64_t)num_sms() * 3;
+        decode_kb_kernel<<<(unsigned)(p.num_units < cap ? p.num_units : cap), DK_THREADS, DK_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+        return check_launch("decode_kb_kernel");
+    }
     if (dst_pitch >= 4096 || src_pitch > DEC_SPAN / 2) {
         p.rows_per_unit = 1;
         p.chunk_bytes = DEC_SPAN;

@@ -355,6 +355,20 @@ struct PrepWorkspace {
 };
 static thread_local PrepWorkspace g_pi;
 
+// CUDA events around the two prep_i8_kernel launches of the last launch_prepare_i8 (roofline reporting)
+static cudaEvent_t g_pi_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static double g_pi_ops = 0.0;
+static int g_pi_marks = 0;
+void prep_kernel_times(double* ms, double* ops) {
+    *ms = 0.0;
+    *ops = g_pi_ops;
+    for (int i = 0; i + 1 < g_pi_marks; i += 2) {
+        float f = 0.f;
+        if (cudaEventSynchronize(g_pi_ev[i + 1]) == cudaSuccess && cudaEventElapsedTime(&f, g_pi_ev[i], g_pi_ev[i + 1]) == cudaSuccess)
+            *ms += f;
+    }
+}
+
 void prep_i8_release() {
     cudaFree(g_pi.qS); cudaFree(g_pi.qV); cudaFree(g_pi.qX); cudaFree(g_pi.sc); cudaFree(g_pi.ex); cudaFree(g_pi.tiles); cudaFree(g_pi.phase);
     g_pi = PrepWorkspace();
@@ -463,7 +477,17 @@ static int pi_product(const int8_t* qL, int64_t lrows, const double* sL, int64_t
     attr[0].val.cooperative = flow ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (!g_pi_ev[0])
+        for (int i = 0; i < 4; i++) cudaEventCreate(&g_pi_ev[i]);
+    if (g_pi_marks <= 2) {
+        cudaEventRecord(g_pi_ev[g_pi_marks], st);
+        g_pi_ops += (double)p.ntiles * nt * p.KB * 2.0 * PI_BM * PI_BN * PI_BK;  // executed int8 ops
+    }
     EG_CUDA(cudaLaunchKernelEx(&cfg, prep_i8_kernel, tL, tR, p));
+    if (g_pi_marks <= 2) {
+        cudaEventRecord(g_pi_ev[g_pi_marks + 1], st);
+        g_pi_marks += 2;
+    }
     return check_launch("prep_i8_kernel");
 }
 
@@ -473,6 +497,8 @@ static int pi_product(const int8_t* qL, int64_t lrows, const double* sL, int64_t
 int launch_prepare_i8(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1, double* d_tmp,
                       double* d_Wp, int64_t Kpad, cudaStream_t st, bool* done) {
     *done = false;
+    g_pi_marks = 0;
+    g_pi_ops = 0.0;
     int dev = 0;
     EG_CUDA(cudaGetDevice(&dev));
     if (g_pi.device != dev) {

@@ -739,6 +739,7 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     scan_kernel_mark(0, st, kblocks * MB * 2.0 * rows_per_unit * SI_BN * SI_BK);
     if (pair) EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_pair_kernel, tA, tB, p));
     else EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel, tA, tB, p));
+    EG_TRY(check_launch("scan_i8_kernel"));
     scan_kernel_mark(1, st, 0.0);
     // 3. groups summed in index order
     si_reduce_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(g_si.partial, L, 2 * G, d_zero_rows, n_zero, d_vara);

@@ -191,6 +191,12 @@ int eg_get_scan_mode(void);
  * measured with CUDA events on its stream, and the arithmetic operations it executed. */
 int eg_last_scan_kernel(double* ms, double* ops);
 
+/* Device time (CUDA events) and executed int8 operations of the prep_i8_kernel launches of the last
+ * eg_dev_scan_prepare / eg_dev_scan_prepare_cols; ms = 0 when the cuBLAS path ran. */
+int eg_last_prep_kernels(double* ms, double* ops);
+/* Kernels launched by this library in this process so far (bench.py reports the difference over its timed region). */
+long long eg_launch_count(void);
+
 /* timing of the last host-level call, milliseconds per stage (h2d, decode, syrk, finalize, d2h,
  * prepare, scan); n_out entries written. */
 int eg_last_timing(double* out_ms, int n_out);
