@@ -765,8 +765,11 @@ extern "C" int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, in
     const int64_t Kpad = round_up(n, 32), nc = col1 - col0;
     // symmetric inputs: both products on the int8 tensor cores (prep_i8.cu) unless EAGLE_PREP_MODE=f64 or the
     // digit slices do not fit in memory
+    // (below n ~ 3000 the fixed costs of slicing and of the 7 level passes outweigh the faster products: auto = by n;
+    // EAGLE_PREP_MODE=i8 / f64 forces a path)
     const char* env_pm = getenv("EAGLE_PREP_MODE");
-    if (upper_only && !(env_pm && env_pm[0] == 'f')) {
+    const bool want_i8 = env_pm && env_pm[0] == 'i' ? true : (env_pm && env_pm[0] == 'f' ? false : n >= 3072);
+    if (upper_only && want_i8) {
         bool done = false;
         EG_TRY(launch_prepare_i8(d_S, d_V, n, col0, col1, d_tmp, d_Wp, Kpad, st, &done));
         if (done) return EG_OK;

@@ -195,6 +195,32 @@ def test_scan_modes_agree_at_scale(dev, mode):
     assert ((ov - rv).abs() <= 1e-9 * rv.abs() + 1e-12 * rv.abs().max()).all()
 
 
+def test_scan_at_config5_width(dev):
+    """n = 20,000 individuals (BASELINE config 5's width) x 3,000 markers: beyond n = 18,724 a level of the sliced
+    pre-products no longer fits one int32 accumulation and is split; checked against torch float64 on the device."""
+    device, torch = dev
+    n, L = 20000, 3000
+    img = device.synth_ascii(L, n, synth.GENO_SEED + 3)
+    tt, err = device.decode(img, n + 1, L, n)
+    assert err[0].item() == 0
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    S = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g); S = (S + S.T) * (0.5 / n ** 0.5); S.diagonal().add_(2.0)
+    V = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g); V = (V + V.T) * (0.5 / n ** 0.5); V.diagonal().add_(1.5)
+    a = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    Wp = device.scan_prepare(S, V, a, n)
+    oa, ov = device.scan(tt, L, n, Wp)
+    torch.cuda.synchronize()
+    del Wp
+    X = V @ S
+    del V
+    W = S @ X
+    del X
+    Mr = tt[:, :n].double()
+    ra, rv = Mr @ (S @ a), ((Mr @ W) * Mr).sum(1)
+    assert ((oa - ra).abs() <= 1e-9 * ra.abs() + 1e-12 * ra.abs().max()).all()
+    assert ((ov - rv).abs() <= 1e-9 * rv.abs() + 1e-12 * rv.abs().max()).all()
+
+
 def test_config2_full_size_properties(dev):
     """BASELINE config 2 (n=2,000 x L=500,000) on one GPU: decode -> M.Mt -> scan, checked by
     properties the domain offers and by an independent torch evaluation on the device."""
