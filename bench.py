@@ -322,6 +322,8 @@ def run_gpu(args):
     clocks = sampler.stop() if sampler else None
     ms_total = t0.elapsed_time(t1)
     stage_ms = [sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)) / args.steps for i in range(8)]
+    if os.environ.get("EAGLE_BENCH_DEBUG"):
+        print(f"[rank {rank}] stage_ms " + " ".join(f"{a}={b:.2f}" for a, b in zip(STAGES, stage_ms)), file=sys.stderr, flush=True)
     if world > 1:
         tt = torch.tensor([ms_total] + stage_ms, dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -278,3 +278,67 @@ def test_config2_full_size_properties(dev):
     best, idx = device.argmax_tsq(oa, ov)
     tsq = oa * oa / ov
     assert best.item() == tsq.max().item() and idx.item() == int((tsq == tsq.max()).nonzero()[0].item())
+
+
+def test_config3_full_size_properties(dev):
+    """BASELINE config 3 (n=10,000 x L=1,000,000) on one GPU, the shape bench.py times: decode -> M.Mt -> scan,
+    checked through size-independent properties and spot checks recomputed independently with torch
+    (64 M.Mt rows, 1,024 markers' a / var(a))."""
+    device, torch = dev
+    n, L = 10000, 1000000
+    img = device.synth_ascii(n, L, synth.GENO_SEED)
+    kb, err = device.decode_kb(img, L + 1, n, L)
+    assert err[0].item() == 0
+    rng = np.random.default_rng(3)
+    rows = np.sort(rng.choice(n, 64, replace=False))
+    rows_t = torch.from_numpy(rows).cuda()
+    view = img[: n * (L + 1)].view(n, L + 1)
+    Mrows = kb[:, rows_t, :].permute(1, 0, 2).reshape(64, -1)           # 64 decoded rows out of the K-blocked store
+    assert torch.equal(Mrows[:, :L], (view[rows_t, :L].to(torch.int16) - 49).to(torch.int8))
+    assert not Mrows[:, L:].any()
+    del view
+    C32 = device.syrk_kb(kb, n, L)
+    K = device.mmt_finalize(C32, n)
+    torch.cuda.synchronize()
+    assert torch.equal(K, K.T)
+    # trace = number of non-heterozygous genotypes (exact integer)
+    nz = sum(int((kb[b0:b0 + 512] != 0).sum().item()) for b0 in range(0, kb.shape[0], 512))
+    assert K.diagonal().sum().item() == float(nz)
+    # 64 rows of M.Mt recomputed with fp32 GEMMs that are exact per 32,768-marker chunk (|partial| < 2^24)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = torch.zeros((64, n), dtype=torch.float64, device="cuda")
+    for b0 in range(0, kb.shape[0], 256):
+        blk = kb[b0:b0 + 256]                                              # [256][n][128]
+        full = blk.permute(1, 0, 2).reshape(n, -1).float()
+        ref += (full[rows_t] @ full.T).double()
+    assert torch.equal(K[rows_t], ref)
+    del ref, full, blk
+    # linearity over marker shards (what the multi-GPU all-reduce relies on): two halves, 128-aligned cut
+    hb = kb.shape[0] // 2
+    Ca = device.syrk_kb(kb[:hb].contiguous(), n, hb * 128)
+    Cb = device.syrk_kb(kb[hb:].contiguous(), n, L - hb * 128)
+    assert torch.equal(torch.triu(Ca + Cb), torch.triu(C32))
+    del Ca, Cb, C32, K
+    tt = device.transpose_kb(kb, n, L)
+    mk = torch.from_numpy(np.sort(rng.choice(L, 1024, replace=False))).cuda()
+    cols = kb.permute(1, 0, 2).reshape(n, -1)[:, mk]                     # the same markers, read as columns of M
+    assert torch.equal(tt[mk, :n], cols.T.contiguous())
+    assert not tt[:, n:].any()
+    del kb, img, cols
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    S = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g); S = (S + S.T) * (0.5 / n ** 0.5); S.diagonal().add_(2.0)
+    V = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g); V = (V + V.T) * (0.5 / n ** 0.5); V.diagonal().add_(1.5)
+    a = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    Wp = device.scan_prepare(S, V, a, n)
+    oa, ov = device.scan(tt, L, n, Wp)
+    torch.cuda.synchronize()
+    W = S @ (V @ S)
+    Mr = tt[mk, :n].double()
+    ra, rv = Mr @ (S @ a), ((Mr @ W) * Mr).sum(1)
+    tol = 1e-9
+    assert ((oa[mk] - ra).abs() <= tol * torch.maximum(ra.abs(), tol * ra.abs().max())).all()
+    assert ((ov[mk] - rv).abs() <= tol * torch.maximum(rv.abs(), tol * rv.abs().max())).all()
+    assert bool((ov > 0).all())                                           # W is positive definite here
+    best, idx = device.argmax_tsq(oa, ov)
+    tsq = oa * oa / ov
+    assert best.item() == tsq.max().item() and idx.item() == int((tsq == tsq.max()).nonzero()[0].item())
