@@ -408,24 +408,37 @@ __global__ void __launch_bounds__(256) symmetrize_upper_kernel(double* __restric
     }
 }
 
-// max |A_ij| and max |A_ij - A_ji| of a column-major n x n matrix (non-negative doubles order like uint64)
+// max |A_ij| and max |A_ij - A_ji| of a column-major n x n matrix (non-negative doubles order like uint64).
+// 64 x 64 tiles, 16 independent 8-byte loads per thread and phase (the 32 x 32 version ran at 0.9 TB/s).
 __global__ void __launch_bounds__(256) symmetry_kernel(const double* __restrict__ A, int64_t n,
                                                        unsigned long long* __restrict__ out) {
-    __shared__ double tile[32][33];
+    __shared__ double tile[64][65];
     const int bx = blockIdx.x, by = blockIdx.y;
     if (bx < by) return;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t r0 = (int64_t)by * 32, c0 = (int64_t)bx * 32;
-    for (int i = ty; i < 32; i += 8) {
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+    const int64_t r0 = (int64_t)by * 64, c0 = (int64_t)bx * 64;
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {  // mirrored tile: element (c0 + tx, r0 + i), first index fastest (coalesced)
+        const int i = ty + 4 * k;
         const int64_t r = c0 + tx, c = r0 + i;
-        tile[i][tx] = (r < n && c < n) ? A[r + c * n] : 0.0;  // mirrored tile
+        v[k] = (r < n && c < n) ? A[r + c * n] : 0.0;
     }
+#pragma unroll
+    for (int k = 0; k < 16; k++) tile[ty + 4 * k][tx] = v[k];
     __syncthreads();
-    double mabs = 0.0, masym = 0.0;
-    for (int i = ty; i < 32; i += 8) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int i = ty + 4 * k;
         const int64_t r = r0 + tx, c = c0 + i;
-        if (r < n && c < n) {
-            const double a = A[r + c * n], b = tile[tx][i];
+        v[k] = (r < n && c < n) ? A[r + c * n] : 0.0;
+    }
+    double mabs = 0.0, masym = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int i = ty + 4 * k;
+        if (r0 + tx < n && c0 + i < n) {
+            const double a = v[k], b = tile[tx][i];
             mabs = fmax(mabs, fmax(fabs(a), fabs(b)));
             const double d = fabs(a - b);
             masym = fmax(masym, d == d ? d : 1.0e300);  // NaN counts as asymmetric
@@ -436,7 +449,7 @@ __global__ void __launch_bounds__(256) symmetry_kernel(const double* __restrict_
         mabs = fmax(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
         masym = fmax(masym, __shfl_xor_sync(0xffffffffu, masym, o));
     }
-    if (tx == 0) {
+    if ((threadIdx.x & 31) == 0) {
         atomicMax(out, (unsigned long long)__double_as_longlong(mabs));
         atomicMax(out + 1, (unsigned long long)__double_as_longlong(masym));
     }
@@ -742,7 +755,7 @@ extern "C" int eg_dev_symmetry(const double* d_A, int64_t n, double* max_abs, do
     static thread_local unsigned long long* d_out = nullptr;
     if (!d_out) EG_CUDA(cudaMalloc(&d_out, 2 * sizeof(unsigned long long)));
     EG_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(unsigned long long), st));
-    const unsigned nb = (unsigned)((n + 31) / 32);
+    const unsigned nb = (unsigned)((n + 63) / 64);
     symmetry_kernel<<<dim3(nb, nb), 256, 0, st>>>(d_A, n, d_out);
     EG_TRY(check_launch("symmetry_kernel"));
     unsigned long long h[2];

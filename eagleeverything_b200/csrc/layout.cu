@@ -292,6 +292,131 @@ __global__ void __launch_bounds__(256) transpose_kb128_kernel(const int8_t* __re
     }
 }
 
+// ------------------------------------------------------------------ y = alpha * Mt * x, exact on the integer pipe
+// FP64 FMAs outside the tensor cores retire a few per clock per SM on B200: the FP64 kernel above spends 5 ms on
+// the 10^10 FMAs of config 3 where reading Mt takes 1.7 ms.  Same digit scheme as scan_i8.cu instead: x is written
+// as 2^(e-55) * sum_s q_s 256^(6-s) with 7 balanced int8 digits (|residual| <= 2^(e-56), e from max |x|), the seven
+// integer dot products  A_s(j) = sum_i m_ji q_s(i)  are exact (DP4A, int32) in any order, and they are recombined
+// with ONE rounding.  Identical rows give bit-identical results wherever they sit.
+constexpr int GD_KW = 4096;           // words (4 genotypes each) of x digits staged per pass: 7 x 16 KB of shared memory
+constexpr int GD_ROWS_PER_WARP = 8;
+constexpr int GD_SMEM_BYTES = 7 * GD_KW * 4;
+
+__global__ void __launch_bounds__(1024) gv_slice_kernel(const double* __restrict__ x, int64_t n, int64_t Kw,
+                                                        uint32_t* __restrict__ xs, double* __restrict__ xscale) {
+    __shared__ unsigned long long sh[32];
+    __shared__ int s_e;
+    unsigned long long m = 0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(x[i]) & 0x7FFFFFFFFFFFFFFFull;
+        m = b > m ? b : m;   // |x| bit patterns order like integers; NaN > Inf > finite
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; w++) m = sh[w] > m ? sh[w] : m;
+        int e = 0;
+        double sc = 0.0;
+        if (m >= 0x7FF0000000000000ull) sc = __longlong_as_double(0x7FF8000000000000LL);  // NaN / Inf in x poisons y
+        else if (m) {
+            if (frexp(__longlong_as_double((long long)m), &e) >= 0.9921875) e++;
+            sc = ldexp(1.0, e - 55);
+        }
+        s_e = e;
+        *xscale = sc;
+    }
+    __syncthreads();
+    const int e = s_e;
+    for (int64_t w = threadIdx.x; w < Kw; w += 1024) {
+        uint32_t out[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int64_t i = 4 * w + d;
+            if (i < n) {
+                const double v = ldexp(x[i], 55 - e);
+                long long X = fabs(v) < 3.6e16 ? __double2ll_rn(v) : 0;
+#pragma unroll
+                for (int sidx = 6; sidx > 0; sidx--) {
+                    const int q = (int)(int8_t)(X & 0xFF);
+                    out[sidx] |= ((uint32_t)q & 0xFFu) << (8 * d);
+                    X = (X - q) >> 8;
+                }
+                out[0] |= ((uint32_t)(int)X & 0xFFu) << (8 * d);
+            }
+        }
+#pragma unroll
+        for (int sidx = 0; sidx < 7; sidx++) xs[sidx * Kw + w] = out[sidx];
+    }
+}
+
+__global__ void __launch_bounds__(256) gemv_i8_dp4a_kernel(const int8_t* __restrict__ Mt, int64_t L, int64_t pitch,
+                                                           const uint32_t* __restrict__ xs, int64_t Kw,
+                                                           const double* __restrict__ xscale, double alpha,
+                                                           double* __restrict__ y) {
+    extern __shared__ __align__(16) uint32_t sx[];  // [7][GD_KW]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t groups = (L + 8 * GD_ROWS_PER_WARP - 1) / (8 * GD_ROWS_PER_WARP);
+    const double sc = *xscale;
+    int64_t staged = -1;
+    for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+        const int64_t row0 = (grp * 8 + warp) * GD_ROWS_PER_WARP;
+        int acc[GD_ROWS_PER_WARP][7];
+#pragma unroll
+        for (int r = 0; r < GD_ROWS_PER_WARP; r++)
+#pragma unroll
+            for (int q = 0; q < 7; q++) acc[r][q] = 0;
+        for (int64_t k0 = 0; k0 < Kw; k0 += GD_KW) {
+            const int kw = (int)(Kw - k0 < GD_KW ? Kw - k0 : GD_KW);
+            if (staged != k0) {   // one pass when the whole of x fits (n <= 16384): staged once per CTA
+                __syncthreads();
+                for (int q = 0; q < 7; q++)
+                    for (int w = threadIdx.x; w < kw; w += 256) sx[q * GD_KW + w] = xs[q * Kw + k0 + w];
+                __syncthreads();
+                staged = k0;
+            }
+            for (int w4 = lane; w4 < (kw >> 2); w4 += 32) {  // 16 genotypes per lane and row: 4 KB per warp in flight
+                uint4 m[GD_ROWS_PER_WARP];
+#pragma unroll
+                for (int r = 0; r < GD_ROWS_PER_WARP; r++) {
+                    const int64_t row = row0 + r < L ? row0 + r : L - 1;
+                    m[r] = *reinterpret_cast<const uint4*>(Mt + row * pitch + 4 * k0 + 16 * (int64_t)w4);
+                }
+#pragma unroll
+                for (int q = 0; q < 7; q++) {
+                    const uint4 d = *reinterpret_cast<const uint4*>(&sx[q * GD_KW + 4 * w4]);
+#pragma unroll
+                    for (int r = 0; r < GD_ROWS_PER_WARP; r++) {
+                        int a = acc[r][q];
+                        a = __dp4a((int)m[r].x, (int)d.x, a);
+                        a = __dp4a((int)m[r].y, (int)d.y, a);
+                        a = __dp4a((int)m[r].z, (int)d.z, a);
+                        a = __dp4a((int)m[r].w, (int)d.w, a);
+                        acc[r][q] = a;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < GD_ROWS_PER_WARP; r++) {
+#pragma unroll
+            for (int q = 0; q < 7; q++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], o);  // exact: any order
+            if (lane == r && row0 + r < L) {
+                const long long hi = (((long long)acc[r][0] * 256 + acc[r][1]) * 256 + acc[r][2]) * 256 + acc[r][3];
+                const long long lo = ((long long)acc[r][4] * 256 + acc[r][5]) * 256 + acc[r][6];
+                const double v = fma((double)hi, 16777216.0, (double)lo);  // the one rounding of the recombination
+                y[row0 + r] = alpha * (v * sc);                             // power-of-two scale: exact
+            }
+        }
+    }
+}
+
 }  // namespace eg
 
 using namespace eg;
@@ -400,9 +525,37 @@ extern "C" int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t 
                               double scale, double* d_y, void* stream) {
     if (!d_Mt || !d_x || !d_y || L <= 0 || n <= 0 || (pitch & 15) || pitch < n)
         return set_error(EG_ERR_ARG, "eg_dev_gemv_i8: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* env = getenv("EAGLE_GEMV_MODE");
+    if (!(env && env[0] == 'f')) {
+        // exact integer evaluation (DP4A); workspace: 7 digit planes of x + its scale
+        static thread_local uint32_t* d_xs = nullptr;
+        static thread_local size_t xs_cap = 0;
+        static thread_local int xs_dev = -1;
+        int dev = 0;
+        EG_CUDA(cudaGetDevice(&dev));
+        const int64_t Kw = round_up(n, 16) / 4;
+        const size_t need = (size_t)7 * Kw + 2;
+        if (xs_dev != dev || need > xs_cap) {
+            if (d_xs && xs_dev == dev) cudaFree(d_xs);
+            d_xs = nullptr;
+            EG_CUDA(cudaMalloc(&d_xs, need * sizeof(uint32_t)));
+            xs_cap = need;
+            xs_dev = dev;
+        }
+        double* d_scale = reinterpret_cast<double*>(d_xs + (((size_t)7 * Kw + 1) & ~(size_t)1));
+        gv_slice_kernel<<<1, 1024, 0, st>>>(d_x, n, Kw, d_xs, d_scale);
+        EG_TRY(check_launch("gv_slice_kernel"));
+        EG_CUDA(cudaFuncSetAttribute(gemv_i8_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GD_SMEM_BYTES));
+        const int64_t groups = (L + 8 * GD_ROWS_PER_WARP - 1) / (8 * GD_ROWS_PER_WARP);
+        const int64_t capb = (int64_t)num_sms() * 2;
+        gemv_i8_dp4a_kernel<<<(unsigned)(groups < capb ? groups : capb), 256, GD_SMEM_BYTES, st>>>(d_Mt, L, pitch, d_xs, Kw,
+                                                                                               d_scale, scale, d_y);
+        return check_launch("gemv_i8_dp4a_kernel");
+    }
     int64_t nb = (L + GV_ROWS_PER_BLOCK - 1) / GV_ROWS_PER_BLOCK;
     const int64_t cap = (int64_t)num_sms() * 6;
     if (nb > cap) nb = cap;
-    gemv_i8_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(d_Mt, L, n, pitch, d_x, scale, d_y);
+    gemv_i8_kernel<<<(unsigned)nb, 256, 0, st>>>(d_Mt, L, n, pitch, d_x, scale, d_y);
     return check_launch("gemv_i8_kernel");
 }

@@ -56,11 +56,11 @@ def global_argmax(best: torch.Tensor, idx_local: torch.Tensor, marker_offset: in
     gidx = torch.where(idx_local >= 0, idx_local + marker_offset, idx_local)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         w = dist.get_world_size(group)
-        bests = [torch.empty_like(best) for _ in range(w)]
-        idxs = [torch.empty_like(gidx) for _ in range(w)]
-        dist.all_gather(bests, best, group=group)
-        dist.all_gather(idxs, gidx, group=group)
-        return combine_argmax(torch.cat(bests).cpu(), torch.cat(idxs).cpu())
+        mine = torch.cat([best.reshape(1).view(torch.int64), gidx.reshape(1).to(torch.int64)])  # (tsq bits, index)
+        allr = torch.empty(2 * w, dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(allr, mine, group=group)                                   # ONE collective, one D2H
+        allr = allr.cpu().view(w, 2)
+        return combine_argmax(allr[:, 0].contiguous().view(torch.float64), allr[:, 1].contiguous())
     return combine_argmax(best.cpu(), gidx.cpu())
 
 
