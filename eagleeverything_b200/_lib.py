@@ -74,6 +74,16 @@ SIGNATURES = {
     "eg_dev_synth_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, C.c_uint64, _vp]),
     "eg_set_scan_mode": (C.c_int, [C.c_int]),
     "eg_get_scan_mode": (C.c_int, []),
+    "eg_calculateMMt_sqrt_and_sqrtinv": (C.c_int, [_dp, _i64, C.c_int, MESSAGE_FN, _vp, _dp, _dp, C.POINTER(C.c_int)]),
+    "eg_calculateH": (C.c_int, [_dp, _i64, C.c_double, C.c_double, MESSAGE_FN, _vp, _dp, C.POINTER(C.c_int)]),
+    "eg_calculateP": (C.c_int, [_dp, _dp, _i64, C.c_int, _dp]),
+    "eg_calculate_reduced_a": (C.c_int, [C.c_double, _dp, _dp, _dp, _i64, _dp]),
+    "eg_calculate_reduced_vara": (C.c_int, [_dp, _i64, C.c_int, C.c_double, C.c_double, _dp, _dp]),
+    "eg_dev_sqrt_and_sqrtinv": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(C.c_int), _dp, _vp]),
+    "eg_dev_calculateH": (C.c_int, [_vp, _i64, C.c_double, C.c_double, _vp, _vp]),
+    "eg_dev_calculateP": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),
+    "eg_dev_calculate_reduced_a": (C.c_int, [C.c_double, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "eg_dev_calculate_reduced_vara": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _i64, _vp, _vp, _vp, _vp]),
     "eg_last_scan_kernel": (C.c_int, [_dp, _dp]),
     "eg_last_prep_kernels": (C.c_int, [_dp, _dp]),
     "eg_launch_count": (C.c_longlong, []),

@@ -198,6 +198,79 @@ class GenotypeStore:
             pass
 
 
+# ----------------------------------------------------------------------------- SURVEY.md section 8(f) rank 1
+# The n x n algebra between two scans: R functions of the same names (R/calculateMMt_sqrt_and_sqrtinv.R,
+# R/calculateH.R, R/calculateP.R, R/calculate_reduced_a.R, R/calculate_reduced_vara.R), same argument order;
+# `ngpu` is accepted and ignored as in the reference's current R code.
+def _f(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def calculateMMt_sqrt_and_sqrtinv(MMt, checkres=True, quiet=True, ngpu=0, message=None):
+    """-> dict(sqrt_MMt=..., inverse_sqrt_MMt=...), or None after the reference's messages when MMt is not
+    positive definite (calculateMMt_sqrt_and_sqrtinv.R:14-21)."""
+    lib = _lib.require_gpu()
+    K = _f(MMt)
+    n = K.shape[0]
+    sq, inv = np.empty((n, n), order="F"), np.empty((n, n), order="F")
+    ok = C.c_int(0)
+    cb, keep = _msg(message)
+    _lib.check(lib.eg_calculateMMt_sqrt_and_sqrtinv(_d(K), n, int(bool(checkres)), cb, None, _d(sq), _d(inv), C.byref(ok)))
+    return dict(sqrt_MMt=sq, inverse_sqrt_MMt=inv) if ok.value else None
+
+
+def calculateH(MMt, varE, varG, message=None):
+    """H = varE * I + varG * MMt (calculateH.R:36); None with the reference's message for a negative variance."""
+    lib = _lib.require_gpu()
+    K = _f(MMt)
+    n = K.shape[0]
+    H = np.empty((n, n), order="F")
+    ok = C.c_int(0)
+    cb, keep = _msg(message)
+    _lib.check(lib.eg_calculateH(_d(K), n, float(varE), float(varG), cb, None, _d(H), C.byref(ok)))
+    return H if ok.value else None
+
+
+def calculateP(H, X, ngpu=0, message=None):
+    """P = Hinv - Hinv X (X' Hinv X)^-1 X' Hinv (calculateP.R:27-28)."""
+    lib = _lib.require_gpu()
+    Hf, Xf = _f(H), _f(np.asarray(X, dtype=np.float64).reshape(np.asarray(H).shape[0], -1))
+    if Hf.shape[0] != Xf.shape[0]:
+        if message:
+            message(" The number of rows in H and X are not the same.")
+        return None
+    n, q = Xf.shape
+    P = np.empty((n, n), order="F")
+    _lib.check(lib.eg_calculateP(_d(Hf), _d(Xf), n, q, _d(P)))
+    return P
+
+
+def calculate_reduced_a(varG, P, MMtsqrt, y, quiet=True, message=None):
+    """varG * MMtsqrt %*% P %*% y (calculate_reduced_a.R:31) -> (n, 1)."""
+    lib = _lib.require_gpu()
+    Pf, Sf = _f(P), _f(MMtsqrt)
+    yv = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    n = Pf.shape[0]
+    if n != yv.size:
+        if message:
+            message(" Error:  there is a problem with the  dimensions of  P, and/or the vector y.")
+        return None
+    out = np.empty(n)
+    _lib.check(lib.eg_calculate_reduced_a(float(varG), _d(Pf), _d(Sf), _d(yv), n, _d(out)))
+    return out.reshape(n, 1)
+
+
+def calculate_reduced_vara(X, varE, varG, invMMt, MMtsqrt, quiet=True, message=None):
+    """calculate_reduced_vara.R:21-35 (invMMt only gives the dimension there)."""
+    lib = _lib.require_gpu()
+    Sf = _f(MMtsqrt)
+    n = Sf.shape[0]
+    Xf = _f(np.asarray(X, dtype=np.float64).reshape(n, -1))
+    V = np.empty((n, n), order="F")
+    _lib.check(lib.eg_calculate_reduced_vara(_d(Xf), n, Xf.shape[1], float(varE), float(varG), _d(Sf), _d(V)))
+    return V
+
+
 def set_scan_mode(mode):
     """'f64' / 0: FP64 tensor cores (DMMA).  'i8' / 1: exact int8 slices on the tcgen05 tensor cores."""
     m = {"f64": 0, "dmma": 0, "i8": 1}.get(mode, mode)

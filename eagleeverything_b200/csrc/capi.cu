@@ -86,8 +86,14 @@ static int ensure_init() {
     return eg_init(env ? atoi(env) : 0);
 }
 
+// accessors for the other translation units of the library (algebra.cu)
+int ensure_init_pub() { return ensure_init(); }
+cudaStream_t ctx_stream() { return g_ctx.stream; }
+cublasHandle_t ctx_cublas() { return g_ctx.cublas; }
+
 void syrk_release_cache();
 void scan_i8_release();
+void algebra_release();
 void prep_i8_release();
 int launch_prepare_i8(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1, double* d_tmp,
                       double* d_Wp, int64_t Kpad, cudaStream_t st, bool* done);
@@ -610,6 +616,7 @@ extern "C" int eg_shutdown(void) {
     syrk_release_cache();
     scan_i8_release();
     prep_i8_release();
+    algebra_release();
     if (g_ctx.cublas) cublasDestroy(g_ctx.cublas);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);

@@ -92,3 +92,45 @@ Eigen::VectorXi extract_geno_rcpp(Rcpp::CharacterVector f_name_ascii, double max
     check(eg_extract_geno_rcpp(fname.c_str(), max_memory_in_Gbytes, selected_locus, d.data(), column_of_genos.data()));
     return column_of_genos;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// the n x n algebra between two scans.  These are NEW exports (the
+// reference does this work in R: R/calculateMMt_sqrt_and_sqrtinv.R:26-31, R/calculateH.R:36, R/calculateP.R:27-28,
+// R/calculate_reduced_a.R:31, R/calculate_reduced_vara.R:21-35).  Each R function keeps its name, arguments,
+// checks and messages and replaces only its arithmetic by one call, e.g. in calculateP.R:
+//     P <- calculateP_gpu(H, X)            instead of lines 27-28
+// so AM() and find_qtl() stay untouched.
+// ---------------------------------------------------------------------------------------------------
+
+// [[Rcpp::export]]
+Rcpp::List calculateMMt_sqrt_and_sqrtinv_gpu(Eigen::Map<Eigen::MatrixXd> MMt, bool checkres, Rcpp::Function message) {
+    const long n = MMt.rows();
+    Eigen::MatrixXd sq(n, n), inv(n, n);
+    int ok = 0;
+    check(eg_calculateMMt_sqrt_and_sqrtinv(MMt.data(), n, checkres, r_message, &message, sq.data(), inv.data(), &ok));
+    if (!ok) return R_NilValue;  // the messages of calculateMMt_sqrt_and_sqrtinv.R:15-21 were already emitted
+    return Rcpp::List::create(Rcpp::Named("sqrt_MMt") = sq, Rcpp::Named("inverse_sqrt_MMt") = inv);
+}
+
+// [[Rcpp::export]]
+Eigen::MatrixXd calculateP_gpu(Eigen::Map<Eigen::MatrixXd> H, Eigen::Map<Eigen::MatrixXd> X) {
+    Eigen::MatrixXd P(H.rows(), H.rows());
+    check(eg_calculateP(H.data(), X.data(), H.rows(), (int)X.cols(), P.data()));
+    return P;
+}
+
+// [[Rcpp::export]]
+Eigen::MatrixXd calculate_reduced_a_gpu(double varG, Eigen::Map<Eigen::MatrixXd> P, Eigen::Map<Eigen::MatrixXd> MMtsqrt,
+                                        Eigen::Map<Eigen::MatrixXd> y) {
+    Eigen::MatrixXd a(P.rows(), 1);
+    check(eg_calculate_reduced_a(varG, P.data(), MMtsqrt.data(), y.data(), P.rows(), a.data()));
+    return a;
+}
+
+// [[Rcpp::export]]
+Eigen::MatrixXd calculate_reduced_vara_gpu(Eigen::Map<Eigen::MatrixXd> X, double varE, double varG,
+                                           Eigen::Map<Eigen::MatrixXd> MMtsqrt) {
+    Eigen::MatrixXd V(MMtsqrt.rows(), MMtsqrt.rows());
+    check(eg_calculate_reduced_vara(X.data(), MMtsqrt.rows(), (int)X.cols(), varE, varG, MMtsqrt.data(), V.data()));
+    return V;
+}

@@ -182,6 +182,33 @@ int eg_dev_extract_col(const int8_t* d_M, int64_t n, int64_t pitch, int64_t col,
 int eg_dev_synth_ascii(uint8_t* d_img, int64_t rows, int64_t cols, int64_t col_offset, int64_t n_total,
                        int64_t row_offset, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * the n x n FP64 algebra between two scans (base-R LAPACK/BLAS in the
+ * reference).  Matrices are n x n column-major doubles as R holds them; X is n x q.  csrc/algebra.cu.
+ * ------------------------------------------------------------------------------------------------ */
+/* R/calculateMMt_sqrt_and_sqrtinv.R:1-52.  *ok = 0 after the reference's messages when MMt is not positive
+ * definite (R returns NULL); an asymmetric MMt is an error as in matrixcalc::is.positive.definite. */
+int eg_calculateMMt_sqrt_and_sqrtinv(const double* MMt, int64_t n, int checkres, eg_message_fn message, void* message_ctx,
+                                     double* out_sqrt, double* out_invsqrt, int* ok);
+/* R/calculateH.R:1-38: H = varE I + varG MMt; *ok = 0 with the reference's message for a negative variance. */
+int eg_calculateH(const double* MMt, int64_t n, double varE, double varG, eg_message_fn message, void* message_ctx,
+                  double* out_H, int* ok);
+/* R/calculateP.R:1-32 */
+int eg_calculateP(const double* H, const double* X, int64_t n, int q, double* out_P);
+/* R/calculate_reduced_a.R:1-35: varG * MMtsqrt %*% P %*% y */
+int eg_calculate_reduced_a(double varG, const double* P, const double* MMtsqrt, const double* y, int64_t n, double* out_a);
+/* R/calculate_reduced_vara.R:1-38 (invMMt is only used for its dimension there: pass n) */
+int eg_calculate_reduced_vara(const double* X, int64_t n, int q, double varE, double varG, const double* MMtsqrt, double* out_V);
+/* device-level forms (device pointers, caller-provided scratch; see csrc/algebra.cu for the sizes) */
+int eg_dev_sqrt_and_sqrtinv(const double* d_K, int64_t n, double* d_sqrt, double* d_invsqrt, double* d_tmp, int* not_pd,
+                            double* trace_check, void* stream);
+int eg_dev_calculateH(const double* d_K, int64_t n, double varE, double varG, double* d_H, void* stream);
+int eg_dev_calculateP(const double* d_H, const double* d_X, int64_t n, int q, double* d_P, double* d_small, void* stream);
+int eg_dev_calculate_reduced_a(double varG, const double* d_P, const double* d_sqrt, const double* d_y, int64_t n,
+                               double* d_tmp_n, double* d_out, void* stream);
+int eg_dev_calculate_reduced_vara(const double* d_X, int q, double varE, double varG, const double* d_sqrt, int64_t n,
+                                  double* d_V, double* d_D, double* d_small, void* stream);
+
 /* How var(a) is contracted (same result within the stated tolerance, both deterministic):
  *   1  exact int8 slices of U on the tcgen05 int8 tensor cores, scan_i8.cu -- the default;
  *   0  FP64 tensor cores (DMMA), scan_f64.cu (also: environment EAGLE_SCAN_MODE=f64). */

@@ -1,0 +1,94 @@
+"""GPU parity of the n x n algebra between two scans against the oracle's
+restatements of the R functions (oracle/am_driver.py, which follow R/calculateMMt_sqrt_and_sqrtinv.R,
+calculateH.R, calculateP.R, calculate_reduced_a.R, calculate_reduced_vara.R line by line).
+
+Tolerance: 1e-9 of the largest entry of each result (these are LAPACK-shaped FP64 computations whose
+operation order differs between libraries; the scan that consumes them is held to 1e-9)."""
+import numpy as np
+import pytest
+
+from eagleeverything_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, tol=1e-9):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() <= tol * np.abs(b).max()
+
+
+@pytest.fixture(scope="module", params=[(150, 1), (333, 3), (1000, 2)], ids=["n150q1", "n333q3", "n1000q2"])
+def problem(request):
+    n, q = request.param
+    rng = np.random.default_rng(n)
+    G = synth.genotypes(n, 4 * n, seed=n).astype(np.float64) - 1.0
+    MMt = G @ G.T
+    K = MMt / MMt.max() + 0.95 * np.eye(n)                     # calcMMt.R:13
+    X = np.column_stack([np.ones(n)] + [rng.integers(-1, 2, n).astype(float) for _ in range(q - 1)])
+    y = rng.standard_normal(n) + 0.5 * G[:, 7]
+    return dict(n=n, q=q, K=K, X=X, y=y, ve=0.7, vg=1.3)
+
+
+def test_sqrt_and_sqrtinv(problem):
+    from eagleeverything_b200 import api
+    from oracle import am_driver as am
+    K = problem["K"]
+    res = api.calculateMMt_sqrt_and_sqrtinv(K)
+    sq, inv = am.calculateMMt_sqrt_and_sqrtinv(K)
+    assert close(res["sqrt_MMt"], sq) and close(res["inverse_sqrt_MMt"], inv)
+    assert np.array_equal(res["inverse_sqrt_MMt"], res["inverse_sqrt_MMt"].T)          # chol2inv returns a mirrored triangle
+    assert close(res["sqrt_MMt"] @ res["sqrt_MMt"], K) and close(res["sqrt_MMt"] @ res["inverse_sqrt_MMt"], np.eye(len(K)))
+
+
+def test_not_positive_definite_and_asymmetric(problem):
+    from eagleeverything_b200 import _lib, api
+    K = problem["K"].copy()
+    K[1, :] = K[0, :]; K[:, 1] = K[:, 0]; K[1, 1] = K[0, 0]      # two identical individuals: singular
+    said = []
+    assert api.calculateMMt_sqrt_and_sqrtinv(K, message=said.append) is None
+    assert "not positive definite" in said[0] and "terminated with errors" in said[-1]
+    K2 = problem["K"].copy()
+    K2[0, 1] += 1e-12
+    with pytest.raises(_lib.EagleGpuError, match="not a symmetric matrix"):
+        api.calculateMMt_sqrt_and_sqrtinv(K2)
+
+
+def test_H_P_reduced_a_reduced_vara(problem):
+    from eagleeverything_b200 import api
+    from oracle import am_driver as am
+    K, X, y, ve, vg = (problem[k] for k in ("K", "X", "y", "ve", "vg"))
+    H = api.calculateH(K, ve, vg)
+    assert np.array_equal(H, am.calculateH(K, ve, vg))
+    said = []
+    assert api.calculateH(K, -1.0, vg, message=said.append) is None and "VarE cannot be negative" in said[0]
+    P = api.calculateP(H, X)
+    Pref = am.calculateP(H, X)
+    assert close(P, Pref)
+    assert np.abs(P @ X).max() <= 1e-9 * np.abs(P).max() * np.abs(X).max() * len(K)   # P annihilates the fixed effects
+    sq, _ = am.calculateMMt_sqrt_and_sqrtinv(K)
+    a = api.calculate_reduced_a(vg, Pref, sq, y)
+    assert a.shape == (len(K), 1) and close(a.reshape(-1), am.calculate_reduced_a(vg, Pref, sq, y))
+    V = api.calculate_reduced_vara(X, ve, vg, K, sq)
+    assert close(V, am.calculate_reduced_vara(X, ve, vg, K, sq))
+
+
+def test_scan_inputs_chain_picks_the_same_locus(problem):
+    """find_qtl.R:5-45 end to end: GPU algebra -> GPU scan against oracle algebra -> oracle scan."""
+    from eagleeverything_b200 import api
+    from oracle import am_driver as am
+    from oracle import np_oracle as npo
+    K, X, y, ve, vg, n = (problem[k] for k in ("K", "X", "y", "ve", "vg", "n"))
+    H = api.calculateH(K, ve, vg)
+    P = api.calculateP(H, X)
+    r = api.calculateMMt_sqrt_and_sqrtinv(K)
+    hat_a = api.calculate_reduced_a(vg, P, r["sqrt_MMt"], y)
+    V = api.calculate_reduced_vara(X, ve, vg, K, r["sqrt_MMt"])
+    S0, V0, a0 = am.scan_inputs(K, K, X, y, ve, vg)
+    assert close(r["inverse_sqrt_MMt"], S0) and close(V, V0) and close(hat_a.reshape(-1), np.asarray(a0).reshape(-1))
+    G = synth.genotypes(n, 2000, seed=n + 1)
+    Mt = (G.T.astype(np.float64) - 1.0)
+    def scan(S, Vv, a):
+        W = S @ (Vv @ S)
+        aa = Mt @ (S @ np.asarray(a).reshape(-1))
+        return am.pick_locus(aa, np.einsum("ij,jk,ik->i", Mt, W, Mt))[0]
+    assert scan(r["inverse_sqrt_MMt"], V, hat_a) == scan(S0, V0, a0)
