@@ -253,8 +253,17 @@ def calcMMt(backend, geno, availmemGb, ncpu, selected_loci):
     return MMt / MMt.max() + np.diag(np.full(MMt.shape[0], 0.95))
 
 
-def scan_inputs(MMt, invMMt, X, y, ve, vg):
-    """find_qtl.R:5-45: everything the scan export consumes (S = K^-1/2, V, a_hat)."""
+def scan_inputs(MMt, invMMt, X, y, ve, vg, algebra=None):
+    """find_qtl.R:5-45: everything the scan export consumes (S = K^-1/2, V, a_hat).
+    `algebra`: an object exposing the five R-named functions (eagleeverything_b200.api, so that a test can drive
+    the device implementation through the same loop); default: the restatements in this module."""
+    if algebra is not None:
+        H = algebra.calculateH(MMt, ve, vg)
+        P = algebra.calculateP(H, X)
+        r = algebra.calculateMMt_sqrt_and_sqrtinv(MMt)
+        sq, sqinv = r["sqrt_MMt"], r["inverse_sqrt_MMt"]
+        hat_a = np.asarray(algebra.calculate_reduced_a(vg, P, sq, y)).reshape(-1)
+        return sqinv, algebra.calculate_reduced_vara(X, ve, vg, invMMt, sq), hat_a
     H = calculateH(MMt, ve, vg)
     P = calculateP(H, X)
     sq, sqinv = calculateMMt_sqrt_and_sqrtinv(MMt)
@@ -271,8 +280,8 @@ def pick_locus(a, vara):
     return int(np.flatnonzero(tsq == mx)[0]) + 1, tsq
 
 
-def find_qtl(backend, geno, availmemGb, selected_loci, MMt, invMMt, ve, vg, X, y, trace=None):
-    S, V, hat_a = scan_inputs(MMt, invMMt, X, y, ve, vg)
+def find_qtl(backend, geno, availmemGb, selected_loci, MMt, invMMt, ve, vg, X, y, trace=None, algebra=None):
+    S, V, hat_a = scan_inputs(MMt, invMMt, X, y, ve, vg, algebra)
     n, L = geno["dim_of_ascii_M"]
     sel = np.asarray(selected_loci, dtype=np.float64)
     if not np.any(np.isnan(sel)):  # calculate_a_and_vara.R:23 (never true under AM(): AM.R:260)
@@ -292,7 +301,7 @@ def calc_extBIC(y, X, MMt, L):
     return BIC + 2 * lchoose(L, X.shape[1] - 1)
 
 
-def AM(backend, geno, y, X0=None, availmemGb=8, ncpu=1, maxit=20, keep_trace=False):
+def AM(backend, geno, y, X0=None, availmemGb=8, ncpu=1, maxit=20, keep_trace=False, algebra=None):
     """AM.R:260, 395-504.  geno = dict(asciifileM, asciifileMt, dim_of_ascii_M=(n, L));
     y = trait vector (no NAs); X0 = design matrix before marker effects (default: intercept).
     Returns dict(selected=[1-based loci], extBIC=[...], trace=[per-iteration scan inputs/outputs])."""
@@ -317,7 +326,7 @@ def AM(backend, geno, y, X0=None, availmemGb=8, ncpu=1, maxit=20, keep_trace=Fal
         extBIC.append(calc_extBIC(y, X, MMt, L))         # AM.R:436
         if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) == len(extBIC) - 1:  # AM.R:448
             new_selected_locus = find_qtl(backend, geno, availmemGb, selected_loci, MMt, invMMt,
-                                          vc["ve"], vc["vg"], X, y, trace)
+                                          vc["ve"], vc["vg"], X, y, trace, algebra)
             selected_loci.append(new_selected_locus)     # AM.R:455
         else:
             cont = False

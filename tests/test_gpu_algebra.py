@@ -92,3 +92,19 @@ def test_scan_inputs_chain_picks_the_same_locus(problem):
         aa = Mt @ (S @ np.asarray(a).reshape(-1))
         return am.pick_locus(aa, np.einsum("ij,jk,ik->i", Mt, W, Mt))[0]
     assert scan(r["inverse_sqrt_MMt"], V, hat_a) == scan(S0, V0, a0)
+
+
+def test_forward_search_with_device_algebra(demo, synth_small):
+    """The restated AM() loop with BOTH the hot path and the n x n algebra on the device: the selected-QTL sequence
+    and the extBIC trace of the shipped demo data (golden) and of a synthetic set."""
+    from eagleeverything_b200 import api
+    from oracle import am_driver as am
+    from oracle import eagle_oracle as eo
+    z = demo["z"]
+    r = am.AM(api, demo["geno"], z["trait1"], algebra=api)
+    assert r["selected"] == list(z["am1_selected"]) and r["all_picked"] == list(z["am1_all_picked"])
+    np.testing.assert_allclose(r["extBIC"], z["am1_extBIC"], rtol=1e-9)
+    y, _ = synth.phenotype(synth_small["G"])
+    rg = am.AM(api, synth_small["geno"], y, maxit=6, algebra=api)
+    ro = am.AM(eo, synth_small["geno"], y, maxit=6)
+    assert rg["all_picked"] == ro["all_picked"] and rg["selected"] == ro["selected"]
