@@ -79,6 +79,10 @@ SIGNATURES = {
     "eg_calculateP": (C.c_int, [_dp, _dp, _i64, C.c_int, _dp]),
     "eg_calculate_reduced_a": (C.c_int, [C.c_double, _dp, _dp, _dp, _i64, _dp]),
     "eg_calculate_reduced_vara": (C.c_int, [_dp, _i64, C.c_int, C.c_double, C.c_double, _dp, _dp]),
+    "eg_emma_eigen_L_wo_Z": (C.c_int, [_dp, _i64, _dp, _dp]),
+    "eg_emma_eigen_R_wo_Z": (C.c_int, [_dp, _dp, _i64, C.c_int, _dp, _dp]),
+    "eg_dev_eigen_sym": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "eg_dev_emma_SKS": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp]),
     "eg_dev_sqrt_and_sqrtinv": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(C.c_int), _dp, _vp]),
     "eg_dev_calculateH": (C.c_int, [_vp, _i64, C.c_double, C.c_double, _vp, _vp]),
     "eg_dev_calculateP": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),

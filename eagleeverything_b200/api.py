@@ -271,6 +271,30 @@ def calculate_reduced_vara(X, varE, varG, invMMt, MMtsqrt, quiet=True, message=N
     return V
 
 
+def emma_eigen_L_wo_Z(K, ngpu=0, vectors=True):
+    """emma.eigen.L.wo.Z (emma_eigen_L_wo_Z.R:9): eigen(K, symmetric=TRUE) -> dict(values (decreasing), vectors)."""
+    lib = _lib.require_gpu()
+    Kf = _f(K)
+    n = Kf.shape[0]
+    w = np.empty(n)
+    U = np.empty((n, n), order="F") if vectors else None
+    _lib.check(lib.eg_emma_eigen_L_wo_Z(_d(Kf), n, _d(w), _d(U) if vectors else None))
+    return dict(values=w, vectors=U)
+
+
+def emma_eigen_R_wo_Z(K, X, ngpu=0):
+    """emma.eigen.R.wo.Z (emma_eigen_R_wo_Z.R:4-20) -> dict(values (n-q), vectors (n x (n-q)))."""
+    lib = _lib.require_gpu()
+    Kf = _f(K)
+    n = Kf.shape[0]
+    Xf = _f(np.asarray(X, dtype=np.float64).reshape(n, -1))
+    q = Xf.shape[1]
+    w = np.empty(n - q)
+    U = np.empty((n, n - q), order="F")
+    _lib.check(lib.eg_emma_eigen_R_wo_Z(_d(Kf), _d(Xf), n, q, _d(w), _d(U)))
+    return dict(values=w, vectors=U)
+
+
 def set_scan_mode(mode):
     """'f64' / 0: FP64 tensor cores (DMMA).  'i8' / 1: exact int8 slices on the tcgen05 tensor cores."""
     m = {"f64": 0, "dmma": 0, "i8": 1}.get(mode, mode)

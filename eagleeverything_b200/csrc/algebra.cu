@@ -120,6 +120,26 @@ __global__ void pd_screen_kernel(const double* __restrict__ w, int64_t n, double
     if (bad) atomicExch(not_pd, 1);
 }
 
+// eigen(): LAPACK returns ascending eigenvalues, R descending: reverse values and the columns of the vectors in place
+__global__ void __launch_bounds__(256) reverse_cols_kernel(double* __restrict__ U, double* __restrict__ w, int64_t n) {
+    const int64_t j = blockIdx.y;  // 0 .. n/2 - 1
+    const int64_t jj = n - 1 - j;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double a = U[i + j * n], b = U[i + jj * n];
+        U[i + j * n] = b;
+        U[i + jj * n] = a;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double a = w[j], b = w[jj];
+        w[j] = b;
+        w[jj] = a;
+    }
+}
+__global__ void __launch_bounds__(256) add_scalar_kernel(double* __restrict__ v, int64_t n, double c) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) v[i] += c;
+}
+
 static dim3 grid_cols(int64_t n) { return dim3((unsigned)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64), (unsigned)n); }
 
 // A (n x n, SPD, column-major) -> its inverse, full symmetric, in place: chol2inv(chol(A))
@@ -300,6 +320,50 @@ extern "C" int eg_dev_calculate_reduced_vara(const double* d_X, int q, double va
     return EG_OK;
 }
 
+// eigen(A, symmetric = TRUE) as R returns it: values in DEcreasing order, vectors in the columns of d_A (in place; only
+// the lower triangle of A is read).  d_values: n doubles.
+extern "C" int eg_dev_eigen_sym(double* d_A, int64_t n, double* d_values, void* stream) {
+    if (!d_A || !d_values || n <= 0 || n > 46000) return set_error(EG_ERR_ARG, "eg_dev_eigen_sym: bad argument");
+    EG_TRY(ensure_init_pub());
+    cudaStream_t st = (cudaStream_t)stream;
+    EG_TRY(alg_init(st));
+    int lw = 0;
+    EG_SOLVER(cusolverDnDsyevd_bufferSize(g_alg.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, d_A, (int)n,
+                                          d_values, &lw));
+    EG_TRY(alg_work((size_t)lw));
+    EG_SOLVER(cusolverDnDsyevd(g_alg.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, d_A, (int)n, d_values,
+                               g_alg.work, lw, g_alg.d_info));
+    EG_TRY(alg_info("dsyevd", st));
+    if (n > 1) {
+        reverse_cols_kernel<<<dim3((unsigned)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64), (unsigned)(n / 2)), 256, 0, st>>>(d_A, d_values, n);
+        EG_TRY(check_launch("reverse_cols_kernel"));
+    }
+    return EG_OK;
+}
+
+// d_out = S (K + I) S with S = I - X (X^T X)^-1 X^T   (R/emma_eigen_R_wo_Z.R:7-13).  d_tmp: n*n, d_small: 2*n*q + 2*q*q.
+extern "C" int eg_dev_emma_SKS(const double* d_K, const double* d_X, int64_t n, int q, double* d_out, double* d_tmp,
+                               double* d_small, void* stream) {
+    if (!d_K || !d_X || !d_out || !d_tmp || !d_small || n <= 0 || q <= 0) return set_error(EG_ERR_ARG, "eg_dev_emma_SKS: bad argument");
+    EG_TRY(ensure_init_pub());
+    cudaStream_t st = (cudaStream_t)stream;
+    EG_TRY(alg_init(st));
+    const double one = 1.0, zero = 0.0, minus = -1.0;
+    double *B = d_small, *XtX = B + (size_t)n * q, *Xi = XtX + (size_t)q * q;
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_T, CUBLAS_OP_N, q, q, (int)n, &one, d_X, (int)n, d_X, (int)n, &zero, XtX, q));
+    EG_TRY(small_inverse(XtX, q, Xi, st, "solve(crossprod(X, X))"));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, q, q, &one, d_X, (int)n, Xi, q, &zero, B, (int)n));
+    // S in d_out:  I - B X^T
+    EG_CUDA(cudaMemsetAsync(d_tmp, 0, (size_t)n * n * 8, st));
+    axpby_eye_kernel<<<grid_cols(n), 256, 0, st>>>(d_tmp, n, 0.0, 1.0, d_out);
+    EG_TRY(check_launch("axpby_eye_kernel"));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)n, q, &minus, B, (int)n, d_X, (int)n, &one, d_out, (int)n));
+    // d_tmp = K + I;  then (S (K+I)) S with S kept in d_out until the last product
+    axpby_eye_kernel<<<grid_cols(n), 256, 0, st>>>(d_K, n, 1.0, 1.0, d_tmp);
+    EG_TRY(check_launch("axpby_eye_kernel"));
+    return EG_OK;
+}
+
 // ================================================================== host level (what an R-facing glue binds)
 namespace {
 struct HostDev {
@@ -416,4 +480,39 @@ extern "C" int eg_calculate_reduced_vara(const double* X, int64_t n, int q, doub
     EG_TRY(up(dX.p, X, (size_t)n * q, st)); EG_TRY(up(dS.p, MMtsqrt, nn, st));
     EG_TRY(eg_dev_calculate_reduced_vara(dX.p, q, varE, varG, dS.p, n, dV.p, dD.p, dW.p, st));
     return down(out_V, dV.p, nn, st);
+}
+
+// R/emma_eigen_L_wo_Z.R:9  eigen(K, symmetric = TRUE): values (decreasing) and, when out_vectors is not NULL, vectors
+extern "C" int eg_emma_eigen_L_wo_Z(const double* K, int64_t n, double* out_values, double* out_vectors) {
+    if (!K || !out_values || n <= 0) return set_error(EG_ERR_ARG, "emma.eigen.L.wo.Z: bad argument");
+    EG_TRY(ensure_init_pub());
+    cudaStream_t st = ctx_stream();
+    const size_t nn = (size_t)n * n;
+    HostDev A, w;
+    EG_TRY(A.alloc(nn, "K")); EG_TRY(w.alloc((size_t)n, "eigenvalues"));
+    EG_TRY(up(A.p, K, nn, st));
+    EG_TRY(eg_dev_eigen_sym(A.p, n, w.p, st));
+    EG_TRY(down(out_values, w.p, (size_t)n, st));
+    return out_vectors ? down(out_vectors, A.p, nn, st) : EG_OK;
+}
+
+// R/emma_eigen_R_wo_Z.R:4-20: eigen(S (K + I) S); values[1:(n-q)] - 1 and the first n-q vectors (n x (n-q), column-major)
+extern "C" int eg_emma_eigen_R_wo_Z(const double* K, const double* X, int64_t n, int q, double* out_values, double* out_vectors) {
+    if (!K || !X || !out_values || !out_vectors || n <= 0 || q <= 0 || q >= n) return set_error(EG_ERR_ARG, "emma.eigen.R.wo.Z: bad argument");
+    EG_TRY(ensure_init_pub());
+    cudaStream_t st = ctx_stream();
+    const size_t nn = (size_t)n * n;
+    HostDev dK, dX, S, T, M, sm, w;
+    EG_TRY(dK.alloc(nn, "K")); EG_TRY(dX.alloc((size_t)n * q, "X")); EG_TRY(S.alloc(nn, "S")); EG_TRY(T.alloc(nn, "K + I"));
+    EG_TRY(M.alloc(nn, "S (K + I) S")); EG_TRY(sm.alloc(2 * (size_t)n * q + 2 * (size_t)q * q, "scratch")); EG_TRY(w.alloc((size_t)n, "eigenvalues"));
+    EG_TRY(up(dK.p, K, nn, st)); EG_TRY(up(dX.p, X, (size_t)n * q, st));
+    EG_TRY(eg_dev_emma_SKS(dK.p, dX.p, n, q, S.p, T.p, sm.p, st));   // S, and K + I in T
+    const double one = 1.0, zero = 0.0;
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, S.p, (int)n, T.p, (int)n, &zero, M.p, (int)n));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, M.p, (int)n, S.p, (int)n, &zero, T.p, (int)n));
+    EG_TRY(eg_dev_eigen_sym(T.p, n, w.p, st));
+    add_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.p, n - q, -1.0);
+    EG_TRY(check_launch("add_scalar_kernel"));
+    EG_TRY(down(out_values, w.p, (size_t)(n - q), st));
+    return down(out_vectors, T.p, (size_t)n * (size_t)(n - q), st);
 }

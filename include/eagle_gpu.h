@@ -199,7 +199,16 @@ int eg_calculateP(const double* H, const double* X, int64_t n, int q, double* ou
 int eg_calculate_reduced_a(double varG, const double* P, const double* MMtsqrt, const double* y, int64_t n, double* out_a);
 /* R/calculate_reduced_vara.R:1-38 (invMMt is only used for its dimension there: pass n) */
 int eg_calculate_reduced_vara(const double* X, int64_t n, int q, double varE, double varG, const double* MMtsqrt, double* out_V);
+/* EMMA's eigendecompositions (the rcppMagmaSYEVD hooks the reference left commented out):
+ * R/emma_eigen_L_wo_Z.R:9 -- eigen(K, symmetric=TRUE), values decreasing; out_vectors may be NULL;
+ * R/emma_eigen_R_wo_Z.R:4-20 -- eigen(S (K+I) S): values[1:(n-q)] - 1 and the first n-q vectors (n x (n-q)).
+ * Eigenvectors are determined up to sign (and up to rotation inside a repeated eigenvalue), as in LAPACK. */
+int eg_emma_eigen_L_wo_Z(const double* K, int64_t n, double* out_values, double* out_vectors);
+int eg_emma_eigen_R_wo_Z(const double* K, const double* X, int64_t n, int q, double* out_values, double* out_vectors);
 /* device-level forms (device pointers, caller-provided scratch; see csrc/algebra.cu for the sizes) */
+int eg_dev_eigen_sym(double* d_A, int64_t n, double* d_values, void* stream);
+int eg_dev_emma_SKS(const double* d_K, const double* d_X, int64_t n, int q, double* d_out, double* d_tmp, double* d_small,
+                    void* stream);
 int eg_dev_sqrt_and_sqrtinv(const double* d_K, int64_t n, double* d_sqrt, double* d_invsqrt, double* d_tmp, int* not_pd,
                             double* trace_check, void* stream);
 int eg_dev_calculateH(const double* d_K, int64_t n, double varE, double varG, double* d_H, void* stream);

@@ -32,6 +32,7 @@ t["H"] = timed("calculateH", lambda: _lib.check(lib.eg_dev_calculateH(vp(K), n, 
 t["P"] = timed("calculateP", lambda: _lib.check(lib.eg_dev_calculateP(vp(H), vp(X), n, q, vp(P), vp(small), None)))
 t["a"] = timed("calculate_reduced_a", lambda: _lib.check(lib.eg_dev_calculate_reduced_a(vg, vp(P), vp(sq), vp(y), n, vp(t_n), vp(a), None)))
 t["V"] = timed("calculate_reduced_vara", lambda: _lib.check(lib.eg_dev_calculate_reduced_vara(vp(X), q, ve, vg, vp(sq), n, vp(V), vp(D), vp(small), None)))
+t["eigen"] = timed("eigen(K, symmetric=TRUE)", lambda: (tmp.copy_(K.view(-1)), _lib.check(lib.eg_dev_eigen_sym(vp(tmp), n, vp(t_n.new_empty(n)), None))))
 print(f"per iteration (H + P + a + V): {t['H'] + t['P'] + t['a'] + t['V']:.1f} ms; first iteration adds {t['sqrt_and_sqrtinv']:.1f} ms")
 Km = sq.view(n, n) @ sq.view(n, n)
 print("check: |sqrt^2 - K|_max / |K|_max =", ((Km - K).abs().max() / K.abs().max()).item())

@@ -108,3 +108,24 @@ def test_forward_search_with_device_algebra(demo, synth_small):
     rg = am.AM(api, synth_small["geno"], y, maxit=6, algebra=api)
     ro = am.AM(eo, synth_small["geno"], y, maxit=6)
     assert rg["all_picked"] == ro["all_picked"] and rg["selected"] == ro["selected"]
+
+
+def test_emma_eigendecompositions(problem):
+    """emma.eigen.L.wo.Z / emma.eigen.R.wo.Z: eigenvalues to 1e-9; eigenvectors are compared through what EMMA
+    uses them for -- eta^2 = (U' y)^2 -- and as projectors, both invariant to the sign LAPACK happens to pick."""
+    from eagleeverything_b200 import api
+    from oracle import am_driver as am
+    K, X, y, n, q = (problem[k] for k in ("K", "X", "y", "n", "q"))
+    rl = api.emma_eigen_L_wo_Z(K)
+    xi, Uo = am.r_eigen_sym(K)
+    assert close(rl["values"], xi) and np.all(np.diff(rl["values"]) <= 0)
+    assert close(rl["vectors"] @ np.diag(rl["values"]) @ rl["vectors"].T, K)
+    assert close(api.emma_eigen_L_wo_Z(K, vectors=False)["values"], xi)
+    rr = api.emma_eigen_R_wo_Z(K, X)
+    lam, U = am.emma_eigen_R_wo_Z(K, X)
+    assert rr["values"].shape == (n - q,) and rr["vectors"].shape == (n, n - q)
+    assert close(rr["values"], lam)
+    assert np.abs(np.abs(np.sum(rr["vectors"] * U, axis=0)) - 1.0).max() < 1e-6       # same vectors up to sign
+    eg, eo_ = (rr["vectors"].T @ y) ** 2, (U.T @ y) ** 2
+    assert np.abs(eg - eo_).max() <= 1e-7 * eo_.max()
+    assert np.abs(rr["vectors"].T @ X).max() < 1e-8 * n                                # orthogonal to the fixed effects
