@@ -501,35 +501,68 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
 
     fn = step_host_abi if world == 1 else step_sharded
     ksteps = max(1, min(args.steps, args.e2e_steps))
-    fn()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(ksteps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    # the host-level ABI synchronises internally on its own streams, so the host clock around the
-    # synchronised region is the honest end-to-end figure; report the device-event figure beside it
-    ms = max(wall_ms, e0.elapsed_time(e1)) / ksteps
-    if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = tt.item()
+
+    def time_host(f):
+        f()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(ksteps):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        # the host-level ABI synchronises internally on its own streams, so the host clock around the
+        # synchronised region is the honest end-to-end figure; report the device-event figure beside it
+        return max(wall_ms, e0.elapsed_time(e1)) / ksteps
+
+    ms = time_host(fn)
     abi_timing = None
     if world == 1:
         t8 = (C.c_double * 8)()
         lib.eg_last_timing(t8, 8)
         abi_timing = dict(zip(["h2d_decode_ms", "syrk_ms", "finalize_ms", "mmt_d2h_ms", "scan_h2d_ms", "prepare_ms",
                                "scan_ms", "scan_d2h_ms"], [round(x, 3) for x in t8]))
+    packed = None
+    if world == 1:
+        # the same step from the packed 2-bit container: 4x fewer bytes over PCIe
+        try:
+            wpr = int(lib.eg_packed_words_per_row(Lg))
+            kb = torch.empty(((Lg + 127) // 128, n, 128), dtype=torch.int8, device="cuda")
+            device.decode_kb(img, Lg + 1, n, Lg, out=kb)
+            wd = torch.empty((n, wpr), dtype=torch.int64, device="cuda")
+            _lib.check(lib.eg_dev_pack_2bit(vp(kb.data_ptr()), n, Lg, 0, vp(wd.data_ptr()), None))
+            words_h = torch.empty((n, wpr), dtype=torch.int64, pin_memory=True); words_h.copy_(wd)
+            del kb, wd
+            torch.cuda.synchronize()
+
+            def step_host_packed():
+                h, ht = vp(), vp()
+                _lib.check(lib.eg_store_from_host_packed(vp(words_h.data_ptr()), n, Lg, 1, C.byref(h)))
+                _lib.check(lib.eg_store_mmt(h, None, 0, dp(K_h)))
+                _lib.check(lib.eg_store_transpose(h, C.byref(ht)))
+                _lib.check(lib.eg_store_a_and_vara(ht, None, 0, dp(S_h), dp(V_h), dp(a_h), dp(oa_h), dp(ov_h)))
+                lib.eg_store_free(h); lib.eg_store_free(ht)
+                tsq = oa_h * oa_h / ov_h
+                return int(torch.argmax(torch.nan_to_num(tsq, nan=-1.0)))
+            pms = time_host(step_host_packed)
+            packed = {"value": L / (pms * 1e-3), "unit": METRIC, "ms_per_step": pms,
+                      "h2d_bytes_per_step": int(n * wpr * 8 + 2 * n * n * 8 + n * 8), "picked_marker": step_host_packed(),
+                      "container": "2-bit packed genotypes (RcppFunctions.cpp.gpu:224-345 layout) instead of the ASCII image"}
+        except Exception as ex:  # noqa: BLE001
+            packed = {"value": None, "note": f"{type(ex).__name__}: {ex}"}
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
     h2d = img_bytes + 2 * n * n * 8 + n * 8
     d2h = (n * n * 8 if rank == 0 else 0) + 2 * Lg * 8
     return {"value": L / (ms * 1e-3), "unit": METRIC, "ms_per_step": ms, "steps": ksteps,
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "abi_stage_ms": abi_timing,
+            "from_packed_container": packed,
             "path": "host-level C ABI (eg_store_*) on pinned host buffers" if world == 1 else
                     "pinned host shards -> H2D -> device-level C ABI -> all-reduce -> D2H",
             "timing": "host clock around a synchronised region (max with CUDA events), max over ranks"}

@@ -47,6 +47,11 @@ SIGNATURES = {
     "eg_store_from_host_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
     "eg_store_from_host_ascii_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
     "eg_store_from_file": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
+    "eg_packed_words_per_row": (C.c_int64, [_i64]),
+    "eg_store_from_host_packed": (C.c_int, [_vp, _i64, _i64, C.c_int, C.POINTER(_vp)]),
+    "eg_store_to_host_packed": (C.c_int, [_vp, _vp]),
+    "eg_dev_pack_2bit": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "eg_dev_unpack_2bit": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "eg_store_transpose": (C.c_int, [_vp, C.POINTER(_vp)]),
     "eg_store_free": (C.c_int, [_vp]),
     "eg_store_info": (C.c_int, [_vp, _lp, _lp, _lp, C.POINTER(_vp)]),

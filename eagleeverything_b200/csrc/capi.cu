@@ -683,6 +683,71 @@ extern "C" int eg_store_from_host_ascii_rows(const uint8_t* image, int64_t rows,
     if (!out || row1 > rows) return set_error(EG_ERR_ARG, "bad row range");
     return store_from_image(image, cols, row0, row1, 0, cols, false, out);  // Mt orientation: row-major
 }
+// ------------------------------------------------------------------ packed 2-bit container (pack2.cu)
+// Host words in, K-blocked (M orientation) or row-major (Mt orientation) store out: H2D of rows*wpr*8 bytes in two
+// row blocks overlapped with the unpack kernel.
+extern "C" int eg_store_from_host_packed(const uint64_t* words, int64_t rows, int64_t cols, int kblocked, eg_store_t** out) {
+    if (!words || !out || rows <= 0 || cols <= 0) return set_error(EG_ERR_ARG, "eg_store_from_host_packed: bad argument");
+    EG_TRY(ensure_init());
+    const int64_t wpr = eg_packed_words_per_row(cols);
+    if (kblocked) {
+        // K-blocked stores interleave the rows: unpack after the whole (4x smaller) image has landed
+        eg_store* s = nullptr;
+        EG_TRY(store_alloc(rows, cols, true, &s));
+        DevBuf w;
+        int rc = w.alloc((size_t)rows * wpr * 8, "packed genotype words");
+        Timer total(g_ctx.stream);
+        if (rc == EG_OK) rc = check_cuda(cudaMemcpyAsync(w.p, words, (size_t)rows * wpr * 8, cudaMemcpyHostToDevice, g_ctx.stream), "H2D of the packed genotypes");
+        if (rc == EG_OK) rc = check_cuda(cudaMemsetAsync(g_ctx.d_err, 0, 4 * sizeof(int32_t), g_ctx.stream), "memset");
+        if (rc == EG_OK) rc = eg_dev_unpack_2bit(w.as<uint64_t>(), rows, cols, s->d, 0, g_ctx.d_err, g_ctx.stream);
+        int32_t h_err[4] = {0, 0, 0, 0};
+        if (rc == EG_OK) rc = check_cuda(cudaMemcpyAsync(h_err, g_ctx.d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream), "status D2H");
+        if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "unpack");
+        g_ctx.timing[0] = total.stop();
+        if (rc == EG_OK && h_err[0])
+            rc = set_error(EG_ERR_FORMAT, "packed genotype container: code 3 or stray bits near row %lld, column %lld",
+                           (long long)(((int64_t)h_err[3] << 31) | h_err[1]), (long long)h_err[2]);
+        if (rc != EG_OK) {
+            eg_store_free(s);
+            return rc;
+        }
+        *out = s;
+        return EG_OK;
+    }
+    eg_store* s = nullptr;
+    EG_TRY(store_alloc(rows, cols, false, &s));
+    DevBuf w;
+    int rc = w.alloc((size_t)rows * wpr * 8, "packed genotype words");
+    Timer total(g_ctx.stream);
+    if (rc == EG_OK) rc = check_cuda(cudaMemcpyAsync(w.p, words, (size_t)rows * wpr * 8, cudaMemcpyHostToDevice, g_ctx.stream), "H2D of the packed genotypes");
+    if (rc == EG_OK) rc = check_cuda(cudaMemsetAsync(g_ctx.d_err, 0, 4 * sizeof(int32_t), g_ctx.stream), "memset");
+    if (rc == EG_OK) rc = eg_dev_unpack_2bit(w.as<uint64_t>(), rows, cols, s->d, s->pitch, g_ctx.d_err, g_ctx.stream);
+    int32_t h_err[4] = {0, 0, 0, 0};
+    if (rc == EG_OK) rc = check_cuda(cudaMemcpyAsync(h_err, g_ctx.d_err, sizeof(h_err), cudaMemcpyDeviceToHost, g_ctx.stream), "status D2H");
+    if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "unpack");
+    g_ctx.timing[0] = total.stop();
+    if (rc == EG_OK && h_err[0])
+        rc = set_error(EG_ERR_FORMAT, "packed genotype container: code 3 or stray bits near row %lld, column %lld",
+                       (long long)(((int64_t)h_err[3] << 31) | h_err[1]), (long long)h_err[2]);
+    if (rc != EG_OK) {
+        eg_store_free(s);
+        return rc;
+    }
+    *out = s;
+    return EG_OK;
+}
+// store -> host words (rows * eg_packed_words_per_row(cols) uint64): what an ingest step writes to disk once
+extern "C" int eg_store_to_host_packed(const eg_store_t* s, uint64_t* out_words) {
+    if (!s || !out_words) return set_error(EG_ERR_ARG, "eg_store_to_host_packed: bad argument");
+    EG_TRY(ensure_init());
+    const int64_t wpr = eg_packed_words_per_row(s->cols);
+    DevBuf w;
+    EG_TRY(w.alloc((size_t)s->rows * wpr * 8, "packed genotype words"));
+    EG_TRY(eg_dev_pack_2bit(s->d, s->rows, s->cols, s->pitch, w.as<uint64_t>(), g_ctx.stream));
+    EG_CUDA(cudaMemcpyAsync(out_words, w.p, (size_t)s->rows * wpr * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    return check_cuda(cudaStreamSynchronize(g_ctx.stream), "pack D2H");
+}
+
 extern "C" int eg_store_from_file(const char* path, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
                                   eg_store_t** out) {
     if (!out || !path) return set_error(EG_ERR_ARG, "null argument");

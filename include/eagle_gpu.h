@@ -104,6 +104,15 @@ int eg_store_from_file(const char* path, int64_t rows, int64_t cols, int64_t col
 int eg_store_from_host_ascii_rows(const uint8_t* image, int64_t rows, int64_t cols, int64_t row0, int64_t row1,
                                   eg_store_t** out);
 int eg_store_transpose(const eg_store_t* in, eg_store_t** out); /* replaces createMt_ASCII_rcpp.cpp:99 on device */
+/* the packed 2-bit container of the pre-CRAN code (RcppFunctions.cpp.gpu:224-345,
+ * CreatePackedBinary): per row ceil(cols/32) little-endian uint64, genotype k in bits 2(k%32).. of word k/32, codes 0/1/2
+ * as in the ASCII file.  4x fewer bytes over PCIe / from disk than the ASCII image.  csrc/pack2.cu. */
+int64_t eg_packed_words_per_row(int64_t cols);
+int eg_store_from_host_packed(const uint64_t* words, int64_t rows, int64_t cols, int kblocked, eg_store_t** out);
+int eg_store_to_host_packed(const eg_store_t* s, uint64_t* out_words);
+int eg_dev_pack_2bit(const int8_t* d_store, int64_t rows, int64_t cols, int64_t pitch, uint64_t* d_words, void* stream);
+int eg_dev_unpack_2bit(const uint64_t* d_words, int64_t rows, int64_t cols, int8_t* d_store, int64_t pitch, int32_t* d_err,
+                       void* stream);
 int eg_store_free(eg_store_t* s);
 int eg_store_info(const eg_store_t* s, int64_t* rows, int64_t* cols, int64_t* pitch, void** device_ptr);
 

@@ -146,3 +146,28 @@ def a_and_vara_longdouble(Mt_int8, S, V, a, rows):
         out_a.append(m @ v)
         out_v.append((m @ W) @ m)
     return np.array(out_a, dtype=ld), np.array(out_v, dtype=ld)
+
+
+# ----------------------------------------------------------------------------- packed 2-bit container
+def pack_2bit(G):
+    """MyPackage/RcppFunctions.cpp.gpu:224-345 (CreatePackedBinary), restated: G holds the file's codes 0/1/2
+    (rows x cols).  Each row becomes ceil(cols/32) unsigned 64-bit words, genotype k in bits 2(k%32), 2(k%32)+1 of
+    word k//32 (bit 2k' set for AB = 1, bit 2k'+1 for BB = 2, :316-326); a row starts on a fresh word (:304-306,
+    :329-333) and unused bits stay 0 (packed.reset())."""
+    G = np.asarray(G)
+    rows, cols = G.shape
+    wpr = (cols + 31) // 32
+    P = np.zeros((rows, wpr * 32), dtype=np.uint64)
+    P[:, :cols] = G.astype(np.uint64)
+    P = P.reshape(rows, wpr, 32)
+    shifts = (2 * np.arange(32, dtype=np.uint64))[None, None, :]
+    return np.bitwise_or.reduce(P << shifts, axis=2)
+
+
+def unpack_2bit(words, cols):
+    """Inverse of pack_2bit -> codes 0/1/2/3 (rows x cols)."""
+    words = np.asarray(words, dtype=np.uint64)
+    rows, wpr = words.shape
+    shifts = (2 * np.arange(32, dtype=np.uint64))[None, None, :]
+    codes = ((words[:, :, None] >> shifts) & np.uint64(3)).reshape(rows, wpr * 32)
+    return codes[:, :cols].astype(np.uint8)

@@ -1,0 +1,80 @@
+"""The packed 2-bit genotype container (format of the reference's pre-CRAN
+CreatePackedBinary, MyPackage/RcppFunctions.cpp.gpu:224-345) against the oracle's restatement: bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from eagleeverything_b200 import synth
+
+
+def test_oracle_pack_roundtrip_and_known_bits():
+    from oracle import np_oracle as npo
+    G = np.array([[0, 1, 2, 2, 1], [2, 2, 2, 0, 0]], dtype=np.uint8)
+    W = npo.pack_2bit(G)
+    assert W.shape == (2, 1) and W.dtype == np.uint64
+    # row 0: codes 0,1,2,2,1 -> bits (LSB first) 00 10 01 01 10  = 0b01_10_10_01_00
+    assert int(W[0, 0]) == 0b0110100100 and int(W[1, 0]) == 0b0000101010
+    for rows, cols in [(3, 1), (2, 31), (2, 32), (5, 33), (4, 1000)]:
+        G = synth.genotypes(rows, cols, seed=cols)
+        assert np.array_equal(npo.unpack_2bit(npo.pack_2bit(G), cols), G)
+        assert npo.pack_2bit(G).shape == (rows, (cols + 31) // 32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 31), (7, 32), (5, 33), (64, 127), (200, 128), (129, 1000), (300, 5000)])
+def test_pack_unpack_bit_exact(rows, cols):
+    import torch
+    from eagleeverything_b200 import _lib, device
+    from oracle import np_oracle as npo
+    lib = device.init(0)
+    G = synth.genotypes(rows, cols, seed=rows * 7 + cols)
+    ref_words = npo.pack_2bit(G)
+    buf = torch.from_numpy(np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    st, _ = device.decode(buf, cols + 1, rows, cols)              # row-major store
+    kb, _ = device.decode_kb(buf, cols + 1, rows, cols)           # K-blocked store
+    wpr = int(lib.eg_packed_words_per_row(cols))
+    assert wpr == ref_words.shape[1]
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    for store, pitch in ((st, st.stride(0)), (kb, 0)):
+        words = torch.full((rows, wpr), -1, dtype=torch.int64, device="cuda")
+        _lib.check(lib.eg_dev_pack_2bit(vp(store), rows, cols, pitch, vp(words), None))
+        assert np.array_equal(words.cpu().numpy().view(np.uint64), ref_words)
+    dwords = torch.from_numpy(ref_words.view(np.int64)).cuda()
+    err = torch.zeros(4, dtype=torch.int32, device="cuda")
+    out = torch.full_like(st, 5)
+    _lib.check(lib.eg_dev_unpack_2bit(vp(dwords), rows, cols, vp(out), out.stride(0), vp(err), None))
+    assert err[0].item() == 0 and torch.equal(out, st)            # including the zero pad of every row
+    outk = torch.full_like(kb, 5)
+    _lib.check(lib.eg_dev_unpack_2bit(vp(dwords), rows, cols, vp(outk), 0, vp(err), None))
+    assert err[0].item() == 0 and torch.equal(outk, kb)
+
+
+@pytest.mark.gpu
+def test_packed_store_host_api_and_bad_code(tmp_path):
+    """Host-level path: packed words -> store -> M.Mt equals the ASCII path bit for bit; a code 3 is refused."""
+    import torch
+    from eagleeverything_b200 import _lib, device
+    from oracle import np_oracle as npo
+    lib = device.init(0)
+    n, L = 150, 3001
+    G = synth.genotypes(n, L, seed=3)
+    img = np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])
+    words = np.ascontiguousarray(npo.pack_2bit(G))
+    h1, h2 = C.c_void_p(), C.c_void_p()
+    _lib.check(lib.eg_store_from_host_ascii(img.ctypes.data_as(C.c_void_p), n, L, 0, L, C.byref(h1)))
+    _lib.check(lib.eg_store_from_host_packed(words.ctypes.data_as(C.c_void_p), n, L, 1, C.byref(h2)))
+    K1, K2 = np.empty((n, n), order="F"), np.empty((n, n), order="F")
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    _lib.check(lib.eg_store_mmt(h1, None, 0, dp(K1)))
+    _lib.check(lib.eg_store_mmt(h2, None, 0, dp(K2)))
+    assert np.array_equal(K1, K2)
+    back = np.empty_like(words)
+    _lib.check(lib.eg_store_to_host_packed(h1, back.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(back, words)
+    lib.eg_store_free(h1); lib.eg_store_free(h2)
+    bad = words.copy()
+    bad[17, 5] |= np.uint64(3) << np.uint64(10)
+    h3 = C.c_void_p()
+    rc = lib.eg_store_from_host_packed(bad.ctypes.data_as(C.c_void_p), n, L, 0, C.byref(h3))
+    assert rc == _lib.EG_ERR_FORMAT and b"row 17" in lib.eg_last_error()
