@@ -47,6 +47,9 @@ SIGNATURES = {
     "eg_store_from_host_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
     "eg_store_from_host_ascii_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
     "eg_store_from_file": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
+    "eg_store_drop_individuals": (C.c_int, [_vp, _lp, _i64, C.c_int, C.POINTER(_vp)]),
+    "eg_dev_gather_rows": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "eg_dev_gather_cols": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
     "eg_packed_words_per_row": (C.c_int64, [_i64]),
     "eg_store_from_host_packed": (C.c_int, [_vp, _i64, _i64, C.c_int, C.POINTER(_vp)]),
     "eg_store_to_host_packed": (C.c_int, [_vp, _vp]),

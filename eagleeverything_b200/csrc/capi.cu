@@ -748,6 +748,48 @@ extern "C" int eg_store_to_host_packed(const eg_store_t* s, uint64_t* out_words)
     return check_cuda(cudaStreamSynchronize(g_ctx.stream), "pack D2H");
 }
 
+// ------------------------------------------------------------------ ReshapeM on resident stores
+// Drops the individuals `idx` (0-based, any order, duplicates ignored): rows of an M store (individuals_are_rows != 0)
+// or columns of an Mt store.  reference: src/ReshapeM_rcpp.cpp:59-109 (which rewrites both ASCII files).
+extern "C" int eg_store_drop_individuals(const eg_store_t* in, const int64_t* idx, int64_t k, int individuals_are_rows,
+                                         eg_store_t** out) {
+    if (!in || !out || k < 0 || (k > 0 && !idx)) return set_error(EG_ERR_ARG, "eg_store_drop_individuals: bad argument");
+    EG_TRY(ensure_init());
+    const int64_t n_in = individuals_are_rows ? in->rows : in->cols;
+    std::vector<char> drop((size_t)n_in, 0);
+    for (int64_t i = 0; i < k; i++) {
+        if (idx[i] < 0 || idx[i] >= n_in)
+            return set_error(EG_ERR_ARG, "ReshapeM: individual %lld is outside 0..%lld", (long long)idx[i], (long long)n_in - 1);
+        drop[(size_t)idx[i]] = 1;
+    }
+    std::vector<int64_t> map;
+    for (int64_t i = 0; i < n_in; i++)
+        if (!drop[(size_t)i]) map.push_back(i);
+    if (map.empty()) return set_error(EG_ERR_ARG, "ReshapeM: no individual left");
+    if (!individuals_are_rows && in->pitch == 0)
+        return set_error(EG_ERR_ARG, "ReshapeM: dropping columns needs a row-major (Mt orientation) store");
+    DevBuf dm;
+    EG_TRY(dm.alloc(map.size() * sizeof(int64_t), "ReshapeM index map"));
+    EG_CUDA(cudaMemcpyAsync(dm.p, map.data(), map.size() * sizeof(int64_t), cudaMemcpyHostToDevice, g_ctx.stream));
+    eg_store* s = nullptr;
+    const int64_t n_out = (int64_t)map.size();
+    int rc;
+    if (individuals_are_rows) {
+        EG_TRY(store_alloc(n_out, in->cols, in->pitch == 0, &s));
+        rc = eg_dev_gather_rows(in->d, in->rows, in->cols, in->pitch, dm.as<int64_t>(), n_out, s->d, s->pitch, g_ctx.stream);
+    } else {
+        EG_TRY(store_alloc(in->rows, n_out, false, &s));
+        rc = eg_dev_gather_cols(in->d, in->rows, in->pitch, dm.as<int64_t>(), n_out, s->d, s->pitch, g_ctx.stream);
+    }
+    if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "ReshapeM gather");  // `map` goes out of scope
+    if (rc != EG_OK) {
+        eg_store_free(s);
+        return rc;
+    }
+    *out = s;
+    return EG_OK;
+}
+
 extern "C" int eg_store_from_file(const char* path, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
                                   eg_store_t** out) {
     if (!out || !path) return set_error(EG_ERR_ARG, "null argument");

@@ -417,6 +417,41 @@ __global__ void __launch_bounds__(256) gemv_i8_dp4a_kernel(const int8_t* __restr
     }
 }
 
+// ------------------------------------------------------------------ ReshapeM as a device row / column mask
+// (reference: src/ReshapeM_rcpp.cpp:59-109 rewrites M.ascii without the rows of individuals whose trait is NA and
+// Mt.ascii without the matching columns).  map[new] = old index of the individuals that stay.
+// rows: one thread = one 16-byte vector of an output row; both layouts (pitch == 0: K-blocked [c/128][rows][128])
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int8_t* __restrict__ in, int64_t in_rows, int64_t in_pitch,
+                                                          const int64_t* __restrict__ map, int64_t out_rows, int64_t out_pitch,
+                                                          int64_t vec_per_row, int8_t* __restrict__ out) {
+    const int64_t total = out_rows * vec_per_row;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        int64_t r, v;
+        if (in_pitch) { r = t / vec_per_row; v = t - r * vec_per_row; }
+        else { r = (t >> 3) % out_rows; v = ((t >> 3) / out_rows) * 8 + (t & 7); }  // 8 vectors = one 128-byte line
+        const int64_t c = 16 * v, ro = map[r];
+        const int64_t src = in_pitch ? ro * in_pitch + c : ((c >> 7) * in_rows + ro) * 128 + (c & 127);
+        const int64_t dst = out_pitch ? r * out_pitch + c : ((c >> 7) * out_rows + r) * 128 + (c & 127);
+        *reinterpret_cast<uint4*>(out + dst) = *reinterpret_cast<const uint4*>(in + src);
+    }
+}
+// columns of a row-major store (Mt: columns = individuals): one thread = 4 output bytes; the output pad is zero
+__global__ void __launch_bounds__(256) gather_cols_kernel(const int8_t* __restrict__ in, int64_t rows, int64_t in_pitch,
+                                                          const int64_t* __restrict__ map, int64_t out_cols, int64_t out_pitch,
+                                                          int8_t* __restrict__ out) {
+    const int64_t wpr = out_pitch / 4, total = rows * wpr;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int64_t r = t / wpr, w = t - r * wpr;
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int64_t c = 4 * w + b;
+            if (c < out_cols) v |= (uint32_t)(uint8_t)in[r * in_pitch + map[c]] << (8 * b);
+        }
+        *reinterpret_cast<uint32_t*>(out + r * out_pitch + 4 * w) = v;
+    }
+}
+
 }  // namespace eg
 
 using namespace eg;
@@ -559,3 +594,27 @@ extern "C" int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t 
     gemv_i8_kernel<<<(unsigned)nb, 256, 0, st>>>(d_Mt, L, n, pitch, d_x, scale, d_y);
     return check_launch("gemv_i8_kernel");
 }
+
+// in/out: stores of the given geometry (pitch 0 = K-blocked); d_map: kept individuals, new index -> old index
+extern "C" int eg_dev_gather_rows(const int8_t* d_in, int64_t in_rows, int64_t cols, int64_t in_pitch, const int64_t* d_map,
+                                  int64_t out_rows, int8_t* d_out, int64_t out_pitch, void* stream) {
+    if (!d_in || !d_out || !d_map || out_rows <= 0 || cols <= 0 || (in_pitch == 0) != (out_pitch == 0) || (in_pitch & 15) ||
+        (out_pitch & 15) || (in_pitch && out_pitch > in_pitch))
+        return set_error(EG_ERR_ARG, "eg_dev_gather_rows: bad argument");
+    const int64_t vec = in_pitch ? out_pitch / 16 : round_up(cols, 128) / 16, total = out_rows * vec;
+    const int64_t cap = (int64_t)num_sms() * 32, nb = (total + 255) / 256;
+    gather_rows_kernel<<<(unsigned)(nb < cap ? nb : cap), 256, 0, (cudaStream_t)stream>>>(d_in, in_rows, in_pitch, d_map, out_rows,
+                                                                                       out_pitch, vec, d_out);
+    return check_launch("gather_rows_kernel");
+}
+extern "C" int eg_dev_gather_cols(const int8_t* d_in, int64_t rows, int64_t in_pitch, const int64_t* d_map, int64_t out_cols,
+                                  int8_t* d_out, int64_t out_pitch, void* stream) {
+    if (!d_in || !d_out || !d_map || rows <= 0 || out_cols <= 0 || (out_pitch & 3) || out_pitch < out_cols || in_pitch <= 0)
+        return set_error(EG_ERR_ARG, "eg_dev_gather_cols: bad argument");
+    const int64_t total = rows * (out_pitch / 4);
+    const int64_t cap = (int64_t)num_sms() * 32, nb = (total + 255) / 256;
+    gather_cols_kernel<<<(unsigned)(nb < cap ? nb : cap), 256, 0, (cudaStream_t)stream>>>(d_in, rows, in_pitch, d_map, out_cols,
+                                                                                       out_pitch, d_out);
+    return check_launch("gather_cols_kernel");
+}
+

@@ -107,6 +107,14 @@ int eg_store_transpose(const eg_store_t* in, eg_store_t** out); /* replaces crea
 /* the packed 2-bit container of the pre-CRAN code (RcppFunctions.cpp.gpu:224-345,
  * CreatePackedBinary): per row ceil(cols/32) little-endian uint64, genotype k in bits 2(k%32).. of word k/32, codes 0/1/2
  * as in the ASCII file.  4x fewer bytes over PCIe / from disk than the ASCII image.  csrc/pack2.cu. */
+/* SURVEY.md section 8(f) rank 3 (half of it): ReshapeM as a device mask instead of rewriting both ASCII files
+ * (src/ReshapeM_rcpp.cpp:59-109).  idx: 0-based individuals to drop -- rows of an M store (individuals_are_rows != 0) or
+ * columns of a row-major Mt store. */
+int eg_store_drop_individuals(const eg_store_t* in, const int64_t* idx, int64_t k, int individuals_are_rows, eg_store_t** out);
+int eg_dev_gather_rows(const int8_t* d_in, int64_t in_rows, int64_t cols, int64_t in_pitch, const int64_t* d_map, int64_t out_rows,
+                       int8_t* d_out, int64_t out_pitch, void* stream);
+int eg_dev_gather_cols(const int8_t* d_in, int64_t rows, int64_t in_pitch, const int64_t* d_map, int64_t out_cols, int8_t* d_out,
+                       int64_t out_pitch, void* stream);
 int64_t eg_packed_words_per_row(int64_t cols);
 int eg_store_from_host_packed(const uint64_t* words, int64_t rows, int64_t cols, int kblocked, eg_store_t** out);
 int eg_store_to_host_packed(const eg_store_t* s, uint64_t* out_words);

@@ -78,3 +78,44 @@ def test_packed_store_host_api_and_bad_code(tmp_path):
     h3 = C.c_void_p()
     rc = lib.eg_store_from_host_packed(bad.ctypes.data_as(C.c_void_p), n, L, 0, C.byref(h3))
     assert rc == _lib.EG_ERR_FORMAT and b"row 17" in lib.eg_last_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,L,drop", [(150, 3001, [149, 77, 3, 0]), (40, 130, [5]), (257, 500, list(range(256, 0, -2)))])
+def test_reshapeM_as_a_device_mask(n, L, drop):
+    """ReshapeM_rcpp.cpp:59-109 on resident stores: M without the rows, Mt without the columns of the dropped
+    individuals -- the scan inputs built from them equal those of freshly written reduced files."""
+    import torch
+    from eagleeverything_b200 import _lib, device
+    lib = device.init(0)
+    G = synth.genotypes(n, L, seed=n + L)
+    keep = np.array([i for i in range(n) if i not in set(drop)])
+    img = np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])
+    imgT = np.concatenate([synth.ascii_image(np.ascontiguousarray(G.T)).reshape(-1), np.zeros(64, np.uint8)])
+    hM, hT, hM2, hT2 = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _lib.check(lib.eg_store_from_host_ascii(img.ctypes.data_as(C.c_void_p), n, L, 0, L, C.byref(hM)))
+    _lib.check(lib.eg_store_from_host_ascii_rows(imgT.ctypes.data_as(C.c_void_p), L, n, 0, L, C.byref(hT)))
+    idx = (C.c_int64 * len(drop))(*drop)
+    _lib.check(lib.eg_store_drop_individuals(hM, idx, len(drop), 1, C.byref(hM2)))
+    _lib.check(lib.eg_store_drop_individuals(hT, idx, len(drop), 0, C.byref(hT2)))
+
+    def dump(h):
+        r, c, p, ptr = C.c_int64(), C.c_int64(), C.c_int64(), C.c_void_p()
+        _lib.check(lib.eg_store_info(h, C.byref(r), C.byref(c), C.byref(p), C.byref(ptr)))
+        return r.value, c.value, p.value
+    nk = len(keep)
+    assert dump(hM2)[:2] == (nk, L) and dump(hT2)[:2] == (L, nk)
+    # M.Mt of the masked store == M.Mt of the reduced genotypes (exact integers)
+    K = np.empty((nk, nk), order="F")
+    _lib.check(lib.eg_store_mmt(hM2, None, 0, K.ctypes.data_as(C.POINTER(C.c_double))))
+    Mk = G[keep].astype(np.float64) - 1
+    assert np.array_equal(K, Mk @ Mk.T)
+    # the masked Mt store == transpose of the masked M store
+    hT3 = C.c_void_p()
+    _lib.check(lib.eg_store_transpose(hM2, C.byref(hT3)))
+    words = lambda h, r, c: (lambda w: (_lib.check(lib.eg_store_to_host_packed(h, w.ctypes.data_as(C.c_void_p))), w)[1])(np.empty((r, (c + 31) // 32), np.uint64))
+    assert np.array_equal(words(hT2, L, nk), words(hT3, L, nk))
+    bad = (C.c_int64 * 1)(n)
+    assert lib.eg_store_drop_individuals(hM, bad, 1, 1, C.byref(C.c_void_p())) == _lib.EG_ERR_ARG
+    for h in (hM, hT, hM2, hT2, hT3):
+        lib.eg_store_free(h)
