@@ -30,6 +30,10 @@ if ROOT not in sys.path:
 WORKLOADS = {
     "c2": dict(n=2000, L=500000, name="config 2: synthetic n=2,000 x L=500,000, single trait, one forward step"),
     "c3": dict(n=10000, L=1000000, name="config 3 shape: synthetic n=10,000 x L=1,000,000, one forward step"),
+    # multi-GPU shapes (marker-sharded; they do not fit one GPU next to their n x n workspaces)
+    "c5": dict(n=20000, L=2000000, name="config 5 shape: synthetic n=20,000 x L=2,000,000, one forward step (Z and the "
+                                        "covariates only enter the R-side EMMA / design matrix, not this path)"),
+    "c4": dict(n=50000, L=600000, name="config 4 shape: synthetic n=50,000 x L=600,000, one forward step"),
 }
 METRIC = "markers/s"
 GENO_SEED = 20261018
@@ -332,7 +336,12 @@ def run_gpu(args):
     value = L / (ms_step * 1e-3)
 
     # ---------------- end to end with host buffers (H2D of the image / S / V / a, D2H of K, a, vara)
-    e2e = run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img, S, V, ah)
+    if args.no_e2e:
+        e2e = {"value": None, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "skipped (--no-e2e)"}
+    else:
+        del store, storeT, C32, K, Wp, tmp, oa, ov
+        torch.cuda.empty_cache()
+        e2e = run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img, S, V, ah)
 
     if rank != 0:
         if world > 1:
@@ -578,6 +587,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (shapes that leave no room for its copies)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
