@@ -42,6 +42,7 @@ constexpr int PI_SMEM_BYTES = PI_STAGES * PI_STAGE_BYTES + 1024 + 256;
 // K lock-step (same soft barrier as syrk_i8.cu, finer grain): one (p, q) term of a wave touches ~50 MB of operand
 // rows, the running FP64 tiles another ~38 MB, and without the throttle the CTAs drift apart until neither stays
 // in L2 (measured at n = 10k: 196 GB of DRAM reads, L2 hit 41 %, DRAM-bound at 43 % tensor pipe).
+constexpr int PI_SROWS = 12;  // tile rows per super-row of the tile order (a wave = PI_SROWS x ~12 tiles)     (EAGLE_PREP_SROWS)
 constexpr int PI_PHASE = 8;   // k-blocks per phase                                                   (EAGLE_PREP_PHASE)
 constexpr int PI_LAG = 4;     // phases a producer may run ahead of the slowest CTA of its wave, <= 8  (EAGLE_PREP_LAG)
 
@@ -404,9 +405,11 @@ static int pi_product(const int8_t* qL, int64_t lrows, const double* sL, int64_t
     // tiles ordered in compact blocks of 12 tile rows so that a wave of CTAs shares its operand rows through L2
     const int TM = (int)((M + PI_BM - 1) / PI_BM), TN = (int)((N + PI_BN - 1) / PI_BN);
     std::vector<int2> h;
-    for (int sr = 0; sr < TM; sr += 12)
+    int srows = PI_SROWS;
+    if (const char* e = getenv("EAGLE_PREP_SROWS")) srows = atoi(e) > 0 ? atoi(e) : srows;
+    for (int sr = 0; sr < TM; sr += srows)
         for (int tj = 0; tj < TN; tj++)
-            for (int ti = sr; ti < TM && ti < sr + 12; ti++) {
+            for (int ti = sr; ti < TM && ti < sr + srows; ti++) {
                 if (upper_only && (int64_t)(tj + 1) * PI_BN - 1 + diag_shift < (int64_t)ti * PI_BM) continue;
                 h.push_back(make_int2(ti, tj));
             }

@@ -51,13 +51,20 @@ def assert_close(x, ref, cond, n, what=""):
     assert (err[solid] <= RTOL * np.abs(ref[solid])).all(), f"{what}: 1e-9 relative violated on a well-conditioned entry"
 
 
-@pytest.fixture(params=[0, 1], ids=["dmma_f64", "tcgen05_i8"])
+@pytest.fixture(params=[0, 1, 2], ids=["dmma_f64", "tcgen05_i8", "tcgen05_i8_cta_pair"])
 def scan_mode(request):
-    """Every scan parity test runs on both contractions of var(a): FP64 DMMA and exact int8 slices."""
+    """Every scan parity test runs on all contractions of var(a): FP64 DMMA, exact int8 digit slices, and the
+    CTA-pair (cta_group::2) variant of the latter."""
     prev = api.get_scan_mode()
-    api.set_scan_mode(request.param)
+    prev_pair = os.environ.get("EAGLE_SI_PAIR")
+    api.set_scan_mode(min(request.param, 1))
+    os.environ["EAGLE_SI_PAIR"] = "1" if request.param == 2 else "0"
     yield request.param
     api.set_scan_mode(prev)
+    if prev_pair is None:
+        os.environ.pop("EAGLE_SI_PAIR", None)
+    else:
+        os.environ["EAGLE_SI_PAIR"] = prev_pair
 
 
 def write_pair(tmp_path, G, tag):
@@ -191,6 +198,42 @@ def test_scan_ragged_sizes(tmp_path, n, L, scan_mode):
     ca, cv = scan_conds(G, S, V, a)
     assert_close(got["a"], ref["a"], ca, n, "a")
     assert_close(got["vara"], ref["vara"], cv, n, "vara")
+
+
+def test_scan_digit_slices_against_extended_precision(tmp_path):
+    """The int8 digit-slice contraction claims one rounding per entry of T = Mt U plus the FP64 row-dot: against an
+    80-bit evaluation of the same quantity it must be at least as close as the FP64 restatement is, on inputs with
+    columns of very different scale and heavy cancellation."""
+    n, L = 257, 400
+    G = synth.genotypes(n, L, seed=5)
+    _, mt = write_pair(tmp_path, G, "xp")
+    rng = np.random.default_rng(4)
+    d = 2.0 ** rng.integers(-20, 21, n)
+    A = rng.standard_normal((n, n))
+    S = ((A + A.T) / np.sqrt(n) + 2 * np.eye(n)) * d[:, None] * d[None, :]
+    B = rng.standard_normal((n, n))
+    V = (B + B.T) / np.sqrt(n) - 0.5 * np.eye(n)                   # indefinite: var(a) sums cancel
+    a = rng.standard_normal(n)
+    prev = api.get_scan_mode()
+    api.set_scan_mode(1)
+    try:
+        got = api.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
+    finally:
+        api.set_scan_mode(prev)
+    ld = np.longdouble
+    Ml = (G.T.astype(ld) - 1)
+    Wl = S.astype(ld) @ (V.astype(ld) @ S.astype(ld))
+    vx = np.einsum("ij,ij->i", Ml @ Wl, Ml)
+    ax = Ml @ (S.astype(ld) @ a.astype(ld))
+    ref64 = npo.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
+    _, cv = scan_conds(G, S, V, a)
+    e_gpu = np.abs(got["vara"].reshape(-1).astype(ld) - vx).astype(np.float64) / cv
+    e_f64 = np.abs(ref64["vara"].reshape(-1).astype(ld) - vx).astype(np.float64) / cv
+    assert e_gpu.max() <= 8 * EPS * n                                # a few ulps of the sum of absolute terms
+    assert e_gpu.max() <= 4 * max(e_f64.max(), EPS)
+    ea = np.abs(got["a"].reshape(-1).astype(ld) - ax).astype(np.float64)
+    ca, _ = scan_conds(G, S, V, a)
+    assert (ea <= 8 * EPS * n * ca).all()
 
 
 def test_scan_identical_and_mirrored_markers_are_bit_identical(tmp_path, scan_mode):
