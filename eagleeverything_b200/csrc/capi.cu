@@ -23,6 +23,9 @@ struct eg_store {
     int64_t pitch = 0;  // row-major stores (Mt orientation): bytes per row.  0: K-blocked store (M orientation),
                         // [ceil(cols/128)][rows][128] bytes -- the layout the SYRK streams (syrk_i8.cu)
     size_t bytes() const { return pitch ? (size_t)rows * (size_t)pitch : (size_t)((cols + 127) / 128) * (size_t)rows * 128; }
+    // M stores uploaded from a host image: rows x rows int32, M * M^T over all columns of the store, accumulated chunk
+    // by chunk UNDER the host-to-device copy (store_from_image); eg_store_mmt then only finalizes.  nullptr otherwise.
+    int32_t* C32 = nullptr;
 };
 
 namespace eg {
@@ -187,6 +190,7 @@ static int store_alloc(int64_t rows, int64_t cols, bool kblocked, eg_store** out
             size_t lru = 0;
             for (size_t i = 1; i < g_ctx.cache.size(); i++)
                 if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
+            pool_free(g_ctx.cache[lru].store->C32);
             pool_free(g_ctx.cache[lru].store->d);
             delete g_ctx.cache[lru].store;
             g_ctx.cache.erase(g_ctx.cache.begin() + lru);
@@ -204,6 +208,83 @@ static int store_alloc(int64_t rows, int64_t cols, bool kblocked, eg_store** out
     return EG_OK;
 }
 
+// K-blocked (M orientation) stores: the image is uploaded in COLUMN chunks (2-D copies, ~256 MB each, two staging
+// buffers); every chunk is decoded into its 128-marker blocks and its contribution to M * M^T is accumulated right
+// away (int32, exact, order-free), so that decode and the whole SYRK hide under the PCIe transfer -- at config 3 the
+// upload takes 181 ms and the SYRK 34.  The product stays with the store (eg_store::C32).
+static int store_from_image_kb(const uint8_t* image, int64_t src_pitch_host, int64_t row0, int64_t rows, int64_t col0,
+                               int64_t w, eg_store* s, eg_store** out) {
+    int64_t cw = ((int64_t)(256LL << 20) / rows) / 128 * 128;
+    if (cw < 128) cw = 128;
+    if (cw > round_up(w, 128)) cw = round_up(w, 128);
+    const int64_t nchunks = (w + cw - 1) / cw;
+    DevBuf stg[2], errs;
+    cudaEvent_t copied[2], decoded[2];
+    int rc = EG_OK;
+    for (int i = 0; i < 2 && rc == EG_OK; i++) rc = stg[i].alloc((size_t)rows * cw + 64, "ASCII staging");
+    if (rc == EG_OK) rc = errs.alloc((size_t)nchunks * 4 * sizeof(int32_t), "decode status");
+    bool eager = rc == EG_OK && rows >= 2;
+    if (eager && pool_alloc((void**)&s->C32, (size_t)rows * rows * sizeof(int32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        s->C32 = nullptr;   // no room for the product: upload only
+        eager = false;
+    }
+    if (rc != EG_OK) {
+        eg_store_free(s);
+        return rc;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&decoded[i], cudaEventDisableTiming);
+    }
+    cudaMemsetAsync(errs.p, 0, (size_t)nchunks * 4 * sizeof(int32_t), g_ctx.stream);
+    if (eager) cudaMemsetAsync(s->C32, 0, (size_t)rows * rows * sizeof(int32_t), g_ctx.stream);
+    cudaEventRecord(decoded[0], g_ctx.stream);
+    cudaStreamWaitEvent(g_ctx.copy_stream, decoded[0], 0);  // staging buffers were allocated in g_ctx.stream order
+    Timer total(g_ctx.stream);
+    for (int64_t k = 0; k < nchunks && rc == EG_OK; k++) {
+        const int b = (int)(k & 1);
+        const int64_t c = k * cw, wk = (c + cw <= w) ? cw : w - c;
+        if (k >= 2) cudaStreamWaitEvent(g_ctx.copy_stream, decoded[b], 0);
+        const uint8_t* src = image + row0 * src_pitch_host + col0 + c;
+        rc = check_cuda(cudaMemcpy2DAsync(stg[b].p, cw, src, src_pitch_host, wk, rows, cudaMemcpyHostToDevice, g_ctx.copy_stream),
+                        "H2D copy of the ASCII genotype image");
+        if (rc != EG_OK) break;
+        cudaEventRecord(copied[b], g_ctx.copy_stream);
+        cudaStreamWaitEvent(g_ctx.stream, copied[b], 0);
+        int8_t* blocks = s->d + (c / 128) * rows * 128;     // first 128-marker block of this chunk
+        rc = eg_dev_decode_kb(stg[b].as<uint8_t>(), cw, (int64_t)rows * cw + 64, rows, wk, blocks, rows, 0,
+                              errs.as<int32_t>() + 4 * k, g_ctx.stream);
+        cudaEventRecord(decoded[b], g_ctx.stream);
+        if (rc == EG_OK && eager) rc = eg_dev_syrk_i8_kb(blocks, rows, wk, s->C32, rows, g_ctx.stream);
+    }
+    std::vector<int32_t> h_err((size_t)nchunks * 4, 0);
+    if (rc == EG_OK)
+        rc = check_cuda(cudaMemcpyAsync(h_err.data(), errs.p, h_err.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream),
+                        "decode status D2H");
+    if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "genotype decode");
+    cudaStreamSynchronize(g_ctx.copy_stream);
+    g_ctx.timing[0] = total.stop();  // H2D + decode + M.Mt (overlapped)
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(copied[i]);
+        cudaEventDestroy(decoded[i]);
+    }
+    for (int64_t k = 0; k < nchunks && rc == EG_OK; k++)
+        if (h_err[4 * k]) {
+            const int64_t brow = ((int64_t)h_err[4 * k + 3] << 31) | (int64_t)h_err[4 * k + 1];
+            rc = set_error(EG_ERR_FORMAT,
+                           "genotype file is not in no-space ASCII format: byte outside {'0','1','2'} near row %lld, column %lld "
+                           "(wrong dims / line pitch?)",
+                           (long long)(row0 + brow), (long long)(col0 + k * cw + h_err[4 * k + 2]));
+        }
+    if (rc != EG_OK) {
+        eg_store_free(s);
+        return rc;
+    }
+    *out = s;
+    return EG_OK;
+}
+
 // Host ASCII image -> store.  Rows [row0,row1), columns [col0,col1) of an image with `cols_total`
 // characters per line.  Row blocks are staged through two device buffers so that the H2D copy of
 // block k+1 overlaps the decode of block k.
@@ -215,6 +296,15 @@ static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t ro
         return set_error(EG_ERR_ARG, "genotype store: bad image range");
     eg_store* s = nullptr;
     EG_TRY(store_alloc(rows, w, kblocked, &s));
+    if (kblocked) {
+        // column-chunk pipeline with the M.Mt accumulation under the copy: for page-locked images (2-D copies out of
+        // pageable / mmap'ed memory are staged by the driver and slower than the row-block path below)
+        const char* env = getenv("EAGLE_EAGER_MMT");
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, image) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned && !(env && env[0] == '0')) return store_from_image_kb(image, src_pitch_host, row0, rows, col0, w, s, out);
+    }
     const bool full_width = (w == cols_total);
     const int64_t dev_pitch = full_width ? src_pitch_host : round_up(w, 16);
     int64_t block_rows = (int64_t)(256LL << 20) / dev_pitch;
@@ -355,6 +445,7 @@ static int cached_store(const char* path, int64_t rows, int64_t cols, bool kbloc
         size_t lru = 0;
         for (size_t i = 1; i < g_ctx.cache.size(); i++)
             if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
+        pool_free(g_ctx.cache[lru].store->C32);
         pool_free(g_ctx.cache[lru].store->d);
         delete g_ctx.cache[lru].store;
         g_ctx.cache.erase(g_ctx.cache.begin() + lru);
@@ -468,8 +559,11 @@ static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols
     EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
     EG_TRY(D.alloc((size_t)n * n * sizeof(double), "MMt output"));
     cudaStream_t st = g_ctx.stream;
-    EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
-    {
+    if (M->C32) {  // accumulated under the upload (store_from_image_kb): keep it intact for later calls
+        EG_CUDA(cudaMemcpyAsync(C.p, M->C32, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        g_ctx.timing[1] = 0.0;
+    } else {
+        EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
         Timer t(st);
         EG_TRY(M->pitch ? eg_dev_syrk_i8(M->d, n, M->cols, M->pitch, C.as<int32_t>(), n, st)
                         : eg_dev_syrk_i8_kb(M->d, n, M->cols, C.as<int32_t>(), n, st));
@@ -597,6 +691,7 @@ extern "C" int eg_init(int device) {
 
 extern "C" void eg_cache_clear(void) {
     for (auto& e : g_ctx.cache) {
+        pool_free(e.store->C32);
         pool_free(e.store->d);
         delete e.store;
     }
@@ -815,6 +910,7 @@ extern "C" int eg_store_transpose(const eg_store_t* in, eg_store_t** out) {
 }
 extern "C" int eg_store_free(eg_store_t* s) {
     if (!s) return EG_OK;
+    pool_free(s->C32);
     pool_free(s->d);
     delete s;
     return EG_OK;

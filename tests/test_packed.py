@@ -119,3 +119,39 @@ def test_reshapeM_as_a_device_mask(n, L, drop):
     assert lib.eg_store_drop_individuals(hM, bad, 1, 1, C.byref(C.c_void_p())) == _lib.EG_ERR_ARG
     for h in (hM, hT, hM2, hT2, hT3):
         lib.eg_store_free(h)
+
+
+@pytest.mark.gpu
+def test_pinned_upload_accumulates_mmt_under_the_copy():
+    """eg_store_from_host_ascii on a page-locked image uploads in column chunks and accumulates M.Mt on the way
+    (eg_store::C32): same store bytes and same product as the pageable row-block path, selected loci included,
+    and a bad byte is still located."""
+    import torch
+    from eagleeverything_b200 import _lib, device
+    lib = device.init(0)
+    n, L = 300, 70001                                   # several chunks would need rows*cw > 256 MB: force via many rows? no: 1 chunk
+    G = synth.genotypes(n, L, seed=8)
+    img_np = np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])
+    pinned = torch.from_numpy(img_np.copy()).pin_memory()
+    hP, hU = C.c_void_p(), C.c_void_p()
+    _lib.check(lib.eg_store_from_host_ascii(C.c_void_p(pinned.data_ptr()), n, L, 0, L, C.byref(hP)))
+    _lib.check(lib.eg_store_from_host_ascii(img_np.ctypes.data_as(C.c_void_p), n, L, 0, L, C.byref(hU)))
+    wpr = (L + 31) // 32
+    wP, wU = np.empty((n, wpr), np.uint64), np.empty((n, wpr), np.uint64)
+    _lib.check(lib.eg_store_to_host_packed(hP, wP.ctypes.data_as(C.c_void_p)))
+    _lib.check(lib.eg_store_to_host_packed(hU, wU.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(wP, wU)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    M = G.astype(np.float64) - 1
+    for zero in ([], [5, 69999, 123]):
+        z = (C.c_int64 * max(1, len(zero)))(*zero) if zero else None
+        KP, KU = np.empty((n, n), order="F"), np.empty((n, n), order="F")
+        _lib.check(lib.eg_store_mmt(hP, z, len(zero), dp(KP)))
+        _lib.check(lib.eg_store_mmt(hU, z, len(zero), dp(KU)))
+        Mz = M.copy(); Mz[:, zero] = 0
+        assert np.array_equal(KP, KU) and np.array_equal(KP, Mz @ Mz.T)
+    lib.eg_store_free(hP); lib.eg_store_free(hU)
+    pinned[13 * (L + 1) + 40000] = ord("7")
+    h = C.c_void_p()
+    rc = lib.eg_store_from_host_ascii(C.c_void_p(pinned.data_ptr()), n, L, 0, L, C.byref(h))
+    assert rc == _lib.EG_ERR_FORMAT and b"row 13" in lib.eg_last_error()
