@@ -507,24 +507,32 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 __global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
                                                           int32_t* __restrict__ expo, double* __restrict__ scale,
                                                           int64_t ncols_pad) {
+    // |x| bit patterns order like unsigned integers and NaN > Inf > finite: an integer max finds the column's largest
+    // magnitude AND lets a NaN / Inf through (fmax would drop a NaN and turn a poisoned column into zeros)
     const int64_t k = blockIdx.x;
-    double amax = 0.0;
+    unsigned long long m = 0;
     if (k < n)
-        for (int64_t i = threadIdx.x; i <= k; i += 256) amax = fmax(amax, fabs(Wp[i + k * ld]));
-    __shared__ double sh[8];
+        for (int64_t i = threadIdx.x; i <= k; i += 256) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(Wp[i + k * ld]) & 0x7FFFFFFFFFFFFFFFull;
+            m = b > m ? b : m;
+        }
+    __shared__ unsigned long long sh[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0 && k < ncols_pad) {
-        for (int w = 1; w < 8; w++) amax = fmax(amax, sh[w]);
+        for (int w = 1; w < 8; w++) m = sh[w] > m ? sh[w] : m;
         int e = 0;
         double s = 0.0;
-        if (k < n && amax > 0.0 && amax <= 1.79769313486231570e308) {
-            if (frexp(amax, &e) >= 0.9921875) e++;
-            s = ldexp(1.0, e - 55);
-        } else if (k < n && !(amax <= 1.79769313486231570e308)) {
+        if (k < n && m >= 0x7FF0000000000000ull) {
             s = __longlong_as_double(0x7FF8000000000000LL);  // NaN / Inf in U poisons the column, as in the reference's product
+        } else if (k < n && m) {
+            if (frexp(__longlong_as_double((long long)m), &e) >= 0.9921875) e++;
+            s = ldexp(1.0, e - 55);
         }
         expo[k] = e;
         scale[k] = s;

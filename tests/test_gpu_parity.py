@@ -200,6 +200,51 @@ def test_scan_ragged_sizes(tmp_path, n, L, scan_mode):
     assert_close(got["vara"], ref["vara"], cv, n, "vara")
 
 
+@pytest.mark.parametrize("n,L", [(1, 7), (2, 64), (33, 100), (129, 300), (257, 129)])
+def test_tiny_shapes_on_the_forced_digit_slice_paths(tmp_path, n, L, monkeypatch):
+    """Far below the sizes where they are chosen automatically: pre-products, scan and GEMV all on int8 digit slices."""
+    monkeypatch.setenv("EAGLE_PREP_MODE", "i8")
+    monkeypatch.setenv("EAGLE_GEMV_MODE", "i8")
+    G = synth.genotypes(n, L, seed=3 * n + L)
+    _, mt = write_pair(tmp_path, G, f"t{n}x{L}")
+    S, V, a = synth.scan_inputs(n, n + 1)
+    prev = api.get_scan_mode()
+    api.set_scan_mode(1)
+    try:
+        got = api.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
+    finally:
+        api.set_scan_mode(prev)
+    ref = npo.calculate_a_and_vara_rcpp(mt, [NA], S, V, 8, (L, n), a)
+    ca, cv = scan_conds(G, S, V, a)
+    assert_close(got["a"], ref["a"], ca, n, "a")
+    assert_close(got["vara"], ref["vara"], cv, n, "vara")
+
+
+@pytest.mark.parametrize("prep", ["i8", "f64"])
+def test_non_finite_inputs_poison_instead_of_passing_silently(synth_small, prep, scan_mode, monkeypatch):
+    """A NaN / Inf in S, V or a_hat reaches every marker in the reference's FP64 products (0 * NaN = NaN).  No path,
+    integer or floating, may turn it into a finite number: every marker comes back non-finite, as from the oracle.
+    (An fmax-based column maximum once dropped the NaNs and returned zeros.)"""
+    monkeypatch.setenv("EAGLE_PREP_MODE", prep)
+    s = synth_small
+    S, V, a = synth.scan_inputs(s["n"], 2)
+    dims = (s["L"], s["n"])
+    for which, val in (("V", np.nan), ("S", np.inf), ("a", np.nan)):
+        S2, V2, a2 = S.copy(), V.copy(), a.copy()
+        if which == "V":
+            V2[5, 7] = V2[7, 5] = val
+        elif which == "S":
+            S2[11, 3] = S2[3, 11] = val
+        else:
+            a2[9] = val
+        got = api.calculate_a_and_vara_rcpp(s["Mt"], [NA], S2, V2, 8, dims, a2)
+        ref = eo.calculate_a_and_vara_rcpp(s["Mt"], [NA], S2, V2, 8, dims, a2)
+        key = "a" if which == "a" else "vara"
+        rbad = ~np.isfinite(ref[key].reshape(-1))
+        gbad = ~np.isfinite(got[key].reshape(-1))
+        assert rbad.all() and gbad.all(), (which, int(rbad.sum()), int(gbad.sum()))
+
+
 def test_scan_digit_slices_against_extended_precision(tmp_path):
     """The int8 digit-slice contraction claims one rounding per entry of T = Mt U plus the FP64 row-dot: against an
     80-bit evaluation of the same quantity it must be at least as close as the FP64 restatement is, on inputs with
