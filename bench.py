@@ -443,6 +443,12 @@ def run_gpu(args):
         "stage_ms": stages, "mmt_int8_tops": syrk_tops, "decode_gbs": dec_gbs,
         "scan_mode": "int8 slices (tcgen05)" if mode == 1 else "fp64 (DMMA)", "scan_reference_equiv_fp64_tflops": scan_tf,
         "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "allreduce": (None if world == 1 else {
+            "bytes": 4 * n * n, "ms": stages["allreduce"],
+            "algbw_gbs": 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
+            "busbw_gbs": 2.0 * (world - 1) / world * 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
+            "note": "NCCL int32 sum of the n x n partial M.Mt; measured reference on this pool: 725 GB/s bus bandwidth "
+                    "for an 8-rank all-reduce at 1 GiB (B200_PROFILING.md)"}),
         "gpu_launches": launches, "library_ceilings": ceil,
         "picked_marker": int(res[1]) if not hasattr(res[1], "item") else int(res[1].item()),
     }

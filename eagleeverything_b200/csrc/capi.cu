@@ -326,7 +326,7 @@ static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t ro
     cudaEventRecord(decoded[0], g_ctx.stream);
     cudaStreamWaitEvent(g_ctx.copy_stream, decoded[0], 0);
     cudaMemsetAsync(g_ctx.d_err, 0, 4 * sizeof(int32_t), g_ctx.stream);
-    double t_h2d = 0, t_dec = 0;
+    double t_h2d = 0;
     Timer total(g_ctx.stream);
     int k = 0;
     for (int64_t r = 0; r < rows && rc == EG_OK; r += block_rows, k++) {
@@ -361,7 +361,6 @@ static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t ro
     if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "genotype decode");
     cudaStreamSynchronize(g_ctx.copy_stream);
     t_h2d = total.stop();
-    (void)t_dec;
     g_ctx.timing[0] = t_h2d;  // H2D + decode (overlapped)
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(copied[i]);
