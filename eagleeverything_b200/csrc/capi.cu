@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) i8_to_f64_colmajor_kernel(const int8_t* _
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int64_t c = c0 + i, r = r0 + tx;
-        if (r < rows && c < cols) out[r + c * rows] = (double)tile[tx][i];
+        if (r < rows && c < cols) out[r + c * rows] = -(double)tile[tx][i];  // stores hold the negated value (decode.cu)
     }
 }
 

@@ -1,4 +1,11 @@
-// K1 -- packed no-space ASCII genotypes -> int8 in {-1,0,1}.
+// K1 -- packed no-space ASCII genotypes -> int8 store.
+//
+// STORE ENCODING.  The reference decodes a character c to  c - '0' - 1  (AA = -1, AB = 0, BB = +1).  Every quantity
+// on the path is invariant under a global sign flip of M (M M^T, m^T W m) or flips with it (a = Mt v), so the stores
+// hold the NEGATED value  1 - (c - '0')  (AA = +1 = 0x01, AB = 0, BB = -1 = 0xFF) and the few consumers that see the
+// sign (GEMV, ReadBlock, extract_geno) flip it back.  Reason: power.  AA is the most frequent class in genotype data,
+// and -1 = 0xFF in most operand bytes costs the int8 tensor cores ~15 % of their throughput under the 1 kW cap
+// (scripts/microbench/int8_encoding_power.py: cuBLASLt int8 sustains 2.25 POP/s with AA = 0xFF, 2.59 with AA = 0x01).
 //
 // Replaces the character loop of ReadBlock (reference: src/ReadBlock.cpp:47-58,
 // value = line[ii] - '0' - 1) for the file format written by CreateASCIInospace.cpp:119-122:
@@ -117,7 +124,7 @@ __device__ __forceinline__ uint4 decode16(const uint8_t* sb, uint32_t soff, int 
     for (int k = 0; k < 4; k++) {
         const uint32_t d = x[k] ^ 0x30303030u;                         // '0','1','2' -> 0,1,2
         uint32_t b = (d & 0xFCFCFCFCu) | ((d & (d >> 1)) & 0x01010101u);  // any byte > 2
-        uint32_t v = ((d | 0x80808080u) - 0x01010101u) ^ 0x80808080u;  // bytewise d - 1, no inter-byte borrow
+        uint32_t v = (0x81818181u - d) ^ 0x80808080u;                  // bytewise 1 - d (store encoding), no inter-byte borrow
         if (nvalid < 16) {
             const int nvk = nvalid - 4 * k;
             const uint32_t m = nvk >= 4 ? 0xFFFFFFFFu : (nvk > 0 ? ((1u << (8 * nvk)) - 1u) : 0u);

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) syrk_zero_cols_kernel(const int8_t* __res
 __global__ void extract_col_kernel(const int8_t* __restrict__ M, int64_t n, int64_t pitch, int64_t col,
                                    int32_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int32_t)store_at(M, n, pitch, i, col);
+    if (i < n) out[i] = -(int32_t)store_at(M, n, pitch, i, col);  // stores hold the negated value (decode.cu)
 }
 
 // ------------------------------------------------------------------ tsq argmax
@@ -561,6 +561,7 @@ extern "C" int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t 
     if (!d_Mt || !d_x || !d_y || L <= 0 || n <= 0 || (pitch & 15) || pitch < n)
         return set_error(EG_ERR_ARG, "eg_dev_gemv_i8: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    scale = -scale;  // the store holds the negated genotype values (decode.cu): y = scale * (M_true x)
     const char* env = getenv("EAGLE_GEMV_MODE");
     if (!(env && env[0] == 'f')) {
         // exact integer evaluation (DP4A); workspace: 7 digit planes of x + its scale

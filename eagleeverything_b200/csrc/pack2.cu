@@ -18,13 +18,14 @@ __device__ __forceinline__ int64_t store_off(int64_t r, int64_t c, int64_t rows,
     return pitch ? r * pitch + c : ((c >> 7) * rows + r) * 128 + (c & 127);
 }
 
-// 16 int8 genotypes in {-1,0,1} -> 32 bits of 2-bit codes (value + 1)
+// 16 store bytes (1 - code) -> 32 bits of 2-bit codes
 __device__ __forceinline__ uint32_t pack16(uint4 v) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t out = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const uint32_t c = (((w[k] & 0x7F7F7F7Fu) + 0x01010101u) ^ (w[k] & 0x80808080u)) & 0x03030303u;  // bytewise + 1, no carries
+        // store byte +1 / 0 / -1 (= 1 - code, decode.cu) -> code 0 / 1 / 2: bit 1 = sign, bit 0 = !(low bit)
+        const uint32_t c = ((w[k] >> 6) & 0x02020202u) | (~w[k] & 0x01010101u);
         const uint32_t p = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;  // the four 2-bit codes into one byte
         out |= p << (8 * k);
     }
@@ -38,7 +39,7 @@ __device__ __forceinline__ uint4 unpack16(uint32_t bits, uint32_t& bad) {
     for (int k = 0; k < 4; k++) {
         const uint32_t b = (bits >> (8 * k)) & 0xFFu;
         const uint32_t c = (b & 3u) | ((b & 0xCu) << 6) | ((b & 0x30u) << 12) | ((b & 0xC0u) << 18);  // one code per byte
-        w[k] = ((c | 0x80808080u) - 0x01010101u) ^ 0x80808080u;                                     // bytewise - 1
+        w[k] = (0x81818181u - c) ^ 0x80808080u;                                                     // bytewise 1 - code
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }

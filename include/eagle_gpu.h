@@ -82,7 +82,9 @@ int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, 
                          const int64_t* dims, int32_t* out);
 
 /* ================================================================ resident genotype stores
- * A store is a decoded genotype matrix held in HBM as int8 in {-1,0,1}, `rows` x `cols`, in one of
+ * A store is a decoded genotype matrix held in HBM as int8, `rows` x `cols`, holding the NEGATED reference value
+ * 1 - code (AA = +1, AB = 0, BB = -1; csrc/decode.cu explains why: power); every entry point that returns genotypes or
+ * signed projections undoes the sign.  It is laid out in one of
  * two layouts:
  *   row-major  (Mt orientation: markers as rows; what the scan reads): row pitch `pitch` bytes
  *              (multiple of 128, > cols; the tail of every row is zero);

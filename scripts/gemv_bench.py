@@ -22,6 +22,6 @@ for mode in ("i8", "f64"):
     ms = timed(lambda: device.gemv_i8(tt, L, n, x, 1.5))
     res[mode] = device.gemv_i8(tt, L, n, x, 1.5)
     print(f"gemv {mode}: {ms:.3f} ms  ({L * tt.stride(0) / ms / 1e6:.0f} GB/s of store)", flush=True)
-ref = 1.5 * (tt[:4096, :n].double() @ x)
+ref = -1.5 * (tt[:4096, :n].double() @ x)   # the store holds the negated genotype values
 for mode in res:
     print(mode, "max rel err vs torch on 4096 rows:", ((res[mode][:4096] - ref).abs() / ref.abs().clamp_min(1e-6)).max().item())

@@ -40,7 +40,7 @@ def test_decode_bit_exact_all_alignments(dev, rows, cols):
         torch.cuda.synchronize()
         o = out.cpu().numpy()
         assert err.cpu().numpy()[0] == 0
-        assert np.array_equal(o[:, :cols], G.astype(np.int8) - 1)
+        assert np.array_equal(o[:, :cols], 1 - G.astype(np.int8))      # store encoding: 1 - code (decode.cu)
         assert not o[:, cols:].any(), "row padding must be zero"
 
 
@@ -51,7 +51,7 @@ def test_decode_column_shard_and_bad_byte(dev):
     img_np = synth.ascii_image(G).reshape(-1).copy()
     buf = torch.from_numpy(np.concatenate([img_np, np.zeros(64, np.uint8)])).cuda()
     out, err = device.decode(buf, cols + 1, rows, 1111, src_offset=777)  # columns [777, 1888)
-    assert np.array_equal(out.cpu().numpy()[:, :1111], G[:, 777:1888].astype(np.int8) - 1) and err[0].item() == 0
+    assert np.array_equal(out.cpu().numpy()[:, :1111], 1 - G[:, 777:1888].astype(np.int8)) and err[0].item() == 0
     img_np[13 * (cols + 1) + 4000] = ord("3")
     buf = torch.from_numpy(np.concatenate([img_np, np.zeros(64, np.uint8)])).cuda()
     out, err = device.decode(buf, cols + 1, rows, cols)
@@ -67,7 +67,7 @@ def test_transpose_and_extract(dev):
         st, _ = device.decode(buf, cols + 1, rows, cols)
         tt = device.transpose(st, rows, cols)
         t = tt.cpu().numpy()
-        assert np.array_equal(t[:, :rows], (G.astype(np.int8) - 1).T) and not t[:, rows:].any()
+        assert np.array_equal(t[:, :rows], (1 - G.astype(np.int8)).T) and not t[:, rows:].any()
         c = device.extract_col(st, rows, cols // 2).cpu().numpy()
         assert np.array_equal(c, G[:, cols // 2].astype(np.int32) - 1)
 
@@ -187,7 +187,7 @@ def test_scan_modes_agree_at_scale(dev, mode):
     finally:
         api.set_scan_mode(prev)
     W = Sd @ (Vd @ Sd)
-    Mr = tt[:, :n].double()
+    Mr = -tt[:, :n].double()   # the reference's genotype values: the store holds their negation
     ra, rv = Mr @ (Sd @ ad), ((Mr @ W) * Mr).sum(1)
     ra[[7, 39999]] = 0
     rv[[7, 39999]] = 0
@@ -215,7 +215,7 @@ def test_scan_at_config5_width(dev):
     del V
     W = S @ X
     del X
-    Mr = tt[:, :n].double()
+    Mr = -tt[:, :n].double()   # the reference's genotype values: the store holds their negation
     ra, rv = Mr @ (S @ a), ((Mr @ W) * Mr).sum(1)
     assert ((oa - ra).abs() <= 1e-9 * ra.abs() + 1e-12 * ra.abs().max()).all()
     assert ((ov - rv).abs() <= 1e-9 * rv.abs() + 1e-12 * rv.abs().max()).all()
@@ -231,7 +231,7 @@ def test_config2_full_size_properties(dev):
     assert err[0].item() == 0
     # decode == image - '1' (torch elementwise as the independent checker)
     view = img[: n * (L + 1)].view(n, L + 1)
-    assert torch.equal(st[:, :L], (view[:, :L].to(torch.int16) - 49).to(torch.int8))
+    assert torch.equal(st[:, :L], (49 - view[:, :L].to(torch.int16)).to(torch.int8))
     assert not st[:, L:].any()
     stk, _ = device.decode_kb(img, L + 1, n, L)          # the layout the SYRK streams
     C32 = device.syrk_kb(stk, n, L)
@@ -268,7 +268,7 @@ def test_config2_full_size_properties(dev):
     W = Sd @ (Vd @ Sd)      # S, V symmetric: row-major view == column-major content
     v = Sd @ ad
     rows = torch.from_numpy(np.random.default_rng(0).choice(L, 4096, replace=False)).cuda()
-    Mr = tt[rows, :n].double()
+    Mr = -tt[rows, :n].double()
     ra = Mr @ v
     rv = ((Mr @ W) * Mr).sum(1)
     tol = 1e-9
@@ -294,7 +294,7 @@ def test_config3_full_size_properties(dev):
     rows_t = torch.from_numpy(rows).cuda()
     view = img[: n * (L + 1)].view(n, L + 1)
     Mrows = kb[:, rows_t, :].permute(1, 0, 2).reshape(64, -1)           # 64 decoded rows out of the K-blocked store
-    assert torch.equal(Mrows[:, :L], (view[rows_t, :L].to(torch.int16) - 49).to(torch.int8))
+    assert torch.equal(Mrows[:, :L], (49 - view[rows_t, :L].to(torch.int16)).to(torch.int8))
     assert not Mrows[:, L:].any()
     del view
     C32 = device.syrk_kb(kb, n, L)
@@ -333,7 +333,7 @@ def test_config3_full_size_properties(dev):
     oa, ov = device.scan(tt, L, n, Wp)
     torch.cuda.synchronize()
     W = S @ (V @ S)
-    Mr = tt[mk, :n].double()
+    Mr = -tt[mk, :n].double()
     ra, rv = Mr @ (S @ a), ((Mr @ W) * Mr).sum(1)
     tol = 1e-9
     assert ((oa[mk] - ra).abs() <= tol * torch.maximum(ra.abs(), tol * ra.abs().max())).all()
