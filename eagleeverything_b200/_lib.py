@@ -44,6 +44,15 @@ SIGNATURES = {
     "eg_calculate_reduced_a_rcpp": (C.c_int, [C.c_char_p, C.c_double, _dp, _dp, C.c_double, _lp, _dp, _i64, C.c_int,
                                               MESSAGE_FN, _vp, _dp]),
     "eg_extract_geno_rcpp": (C.c_int, [C.c_char_p, C.c_double, _i64, _lp, _ip]),
+    "eg_createM_ASCII_rcpp": (C.c_int, [C.c_char_p] * 6 + [C.c_double, _lp, C.c_int, MESSAGE_FN, _vp, C.c_char_p,
+                                        C.POINTER(C.c_int)]),
+    "eg_createMt_ASCII_rcpp": (C.c_int, [C.c_char_p] * 3 + [C.c_double, _lp, C.c_int, MESSAGE_FN, _vp]),
+    "eg_tokenise_chunks": (_i64, [_i64]),
+    "eg_tokenise_chunk_bytes": (_i64, []),
+    "eg_dev_tokenise_scan": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "eg_dev_tokenise_emit": (C.c_int, [_vp, _i64, _vp, _i64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _vp, _i64,
+                                       _vp, _vp]),
+    "eg_dev_encode_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "eg_store_from_host_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
     "eg_store_from_host_ascii_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
     "eg_store_from_file": (C.c_int, [C.c_char_p, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),

@@ -107,6 +107,27 @@ def extract_geno_rcpp(f_name_ascii, max_memory_in_Gbytes, selected_locus, dims):
     return out
 
 
+def createM_ASCII_rcpp(f_name, f_name_ascii, type, AA, AB, BB, max_memory_in_Gbytes, dims, quiet=True, message=None,
+                       missing="NA"):
+    """createM_ASCII_rcpp.cpp:19-106 (text files: CreateASCIInospace.cpp:17-164, tokenised on the device).
+    dims = (rows, columns) of the text file.  -> bool, the reference's return value."""
+    lib = _lib.require_gpu()
+    cb, keep = _msg(message)
+    ok = C.c_int(0)
+    _lib.check(lib.eg_createM_ASCII_rcpp(os.fsencode(f_name), os.fsencode(f_name_ascii), str(type).encode(), str(AA).encode(),
+                                         str(AB).encode(), str(BB).encode(), float(max_memory_in_Gbytes), _dims(dims),
+                                         int(bool(quiet)), cb, None, str(missing).encode(), C.byref(ok)))
+    return bool(ok.value)
+
+
+def createMt_ASCII_rcpp(f_name, f_name_ascii, type, max_memory_in_Gbytes, dims, quiet=True, message=None):
+    """createMt_ASCII_rcpp.cpp:15-245: f_name = M.ascii with dims = (n, L); writes Mt.ascii to f_name_ascii."""
+    lib = _lib.require_gpu()
+    cb, keep = _msg(message)
+    _lib.check(lib.eg_createMt_ASCII_rcpp(os.fsencode(f_name), os.fsencode(f_name_ascii), str(type).encode(),
+                                          float(max_memory_in_Gbytes), _dims(dims), int(bool(quiet)), cb, None))
+
+
 # ------------------------------------------------------------------ resident stores (host buffers in, handles out)
 class GenotypeStore:
     """A decoded int8 genotype matrix resident in HBM (eg_store_t)."""

@@ -414,30 +414,20 @@ static int check_image_size(const MappedFile& f, const char* path, int64_t rows,
     return EG_OK;
 }
 
-// cache lookup by (realpath, size, mtime, dims)
-static int cached_store(const char* path, int64_t rows, int64_t cols, bool kblocked, eg_store** out) {
-    EG_TRY(ensure_init());
-    if (!path) return set_error(EG_ERR_ARG, "null file name");
-    if (rows <= 0 || cols <= 0) return set_error(EG_ERR_ARG, "dims must be positive");
+// cache key: (realpath, size, mtime, dims, layout)
+static int cache_key(const char* path, int64_t rows, int64_t cols, bool kblocked, std::string& key) {
     struct stat st;
     if (stat(path, &st) != 0) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s", path);
     char* rp = realpath(path, nullptr);
-    char key[4400];
-    snprintf(key, sizeof(key), "%s|%lld|%lld.%09ld|%lldx%lld|%c", rp ? rp : path, (long long)st.st_size,
+    char buf[4400];
+    snprintf(buf, sizeof(buf), "%s|%lld|%lld.%09ld|%lldx%lld|%c", rp ? rp : path, (long long)st.st_size,
              (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (long long)rows, (long long)cols,
              kblocked ? 'K' : 'R');
     free(rp);
-    for (auto& e : g_ctx.cache)
-        if (e.key == key) {
-            e.stamp = ++g_ctx.clock;
-            *out = e.store;
-            return EG_OK;
-        }
-    MappedFile f;
-    EG_TRY(f.open_ro(path));
-    EG_TRY(check_image_size(f, path, rows, cols));
-    eg_store* s = nullptr;
-    EG_TRY(store_from_image(f.p, cols, 0, rows, 0, cols, kblocked, &s));
+    key = buf;
+    return EG_OK;
+}
+static void cache_insert(const std::string& key, eg_store* s) {
     const char* envmax = getenv("EAGLE_GPU_CACHE_ENTRIES");
     const size_t maxe = envmax ? (size_t)atoi(envmax) : 4;
     while (g_ctx.cache.size() >= (maxe ? maxe : 1)) {
@@ -450,6 +440,25 @@ static int cached_store(const char* path, int64_t rows, int64_t cols, bool kbloc
         g_ctx.cache.erase(g_ctx.cache.begin() + lru);
     }
     g_ctx.cache.push_back({key, s, ++g_ctx.clock});
+}
+static int cached_store(const char* path, int64_t rows, int64_t cols, bool kblocked, eg_store** out) {
+    EG_TRY(ensure_init());
+    if (!path) return set_error(EG_ERR_ARG, "null file name");
+    if (rows <= 0 || cols <= 0) return set_error(EG_ERR_ARG, "dims must be positive");
+    std::string key;
+    EG_TRY(cache_key(path, rows, cols, kblocked, key));
+    for (auto& e : g_ctx.cache)
+        if (e.key == key) {
+            e.stamp = ++g_ctx.clock;
+            *out = e.store;
+            return EG_OK;
+        }
+    MappedFile f;
+    EG_TRY(f.open_ro(path));
+    EG_TRY(check_image_size(f, path, rows, cols));
+    eg_store* s = nullptr;
+    EG_TRY(store_from_image(f.p, cols, 0, rows, 0, cols, kblocked, &s));
+    cache_insert(key, s);
     *out = s;
     return EG_OK;
 }
@@ -1167,4 +1176,304 @@ extern "C" int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_
     eg_store* M = nullptr;
     EG_TRY(cached_store(f_name_ascii, dims[0], dims[1], true, &M));  // shares the store with calculateMMt_rcpp
     return eg_store_extract_col(M, selected_locus, out);
+}
+
+// ================================================================== ingest: SURVEY.md section 8(f) rank 3 (csrc/ingest.cu)
+namespace eg {
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    int ensure(size_t n, const char* what) {
+        if (n <= cap) return EG_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMallocHost(&p, n) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return set_error(EG_ERR_ALLOC, "out of page-locked host memory allocating %zu bytes for %s", n, what);
+        }
+        cap = n;
+        return EG_OK;
+    }
+};
+struct OutFile {
+    FILE* f = nullptr;
+    ~OutFile() {
+        if (f) fclose(f);
+    }
+};
+static bool host_ws(uint8_t b) { return b == ' ' || (b >= 9 && b <= 13); }
+// read-only view of a whole file; an empty file is a valid (zero-row) input here
+struct TextFile {
+    int fd = -1;
+    const uint8_t* p = nullptr;
+    size_t size = 0;
+    ~TextFile() {
+        if (p) munmap(const_cast<uint8_t*>(p), size);
+        if (fd >= 0) close(fd);
+    }
+    bool open_ro(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
+        size = (size_t)st.st_size;
+        if (size == 0) return true;
+        void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        p = static_cast<const uint8_t*>(m);
+        madvise(m, size, MADV_SEQUENTIAL);
+        return true;
+    }
+};
+
+// CreateASCIInospace(fname, asciifname, dims, AA, AB, BB, quiet, message, missing)   src/CreateASCIInospace.cpp:17-164
+// The text is tokenised on the device in pieces of whole lines; *ok mirrors the reference's bool.
+static int create_ascii_nospace(const char* fname, const char* asciifname, const int64_t* dims, const char* AA, const char* AB,
+                                const char* BB, int quiet, eg_message_fn message, void* mctx, const char* missing, int* ok) {
+    *ok = 0;
+    const int64_t L = dims[1];
+    if (L <= 0) return set_error(EG_ERR_ARG, "CreateASCIInospace: dims[1] must be positive");
+    EG_TRY(ensure_init());
+    TextFile in;
+    if (!in.open_ro(fname)) {
+        say(message, mctx, "ERROR: Text file could not be opened with filename  %s\n", fname);  // :39-41
+        return EG_OK;
+    }
+    OutFile outf;
+    outf.f = fopen(asciifname, "wb");
+    if (!outf.f) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s for writing", asciifname);
+    if (!quiet) {  // :45-50
+        say(message, mctx, "%s", "");
+        say(message, mctx, " Reading text File  ");
+        say(message, mctx, "%s", "");
+        say(message, mctx, " Loading file ");
+    }
+    const char* envp = getenv("EAGLE_INGEST_PIECE_BYTES");
+    int64_t piece_max = envp ? atoll(envp) : (256LL << 20);
+    if (piece_max < 64) piece_max = 64;
+    cudaStream_t st = g_ctx.stream;
+    DevBuf dtext, dout, dcounts, dprefix, derr;
+    PinnedBuf hout;
+    EG_TRY(derr.alloc(sizeof(uint64_t), "tokeniser status"));
+    size_t text_cap = 0, out_cap = 0, chunk_cap = 0;
+    int64_t rows_done = 0;
+    size_t off = 0;
+    while (off < in.size) {
+        // a piece = whole lines: cut after the last '\n' inside the window, or extend to the end of a longer line
+        size_t end = off + (size_t)piece_max < in.size ? off + (size_t)piece_max : in.size;
+        if (end < in.size) {
+            const void* nlp = memrchr(in.p + off, '\n', end - off);
+            if (nlp) end = (size_t)((const uint8_t*)nlp - in.p) + 1;
+            else {
+                const void* nx = memchr(in.p + end, '\n', in.size - end);
+                end = nx ? (size_t)((const uint8_t*)nx - in.p) + 1 : in.size;
+            }
+        }
+        const int64_t nb = (int64_t)(end - off);
+        const uint8_t* piece = in.p + off;
+        const int64_t nch = eg_tokenise_chunks(nb);
+        if ((size_t)nb + 64 > text_cap) {
+            text_cap = (size_t)nb + 64;
+            EG_TRY(dtext.alloc(text_cap, "text piece"));
+        }
+        if ((size_t)nch > chunk_cap) {
+            chunk_cap = (size_t)nch;
+            EG_TRY(dcounts.alloc(chunk_cap * 2 * sizeof(uint32_t), "tokeniser counts"));
+            EG_TRY(dprefix.alloc((chunk_cap + 1) * 2 * sizeof(int64_t), "tokeniser prefix"));
+        }
+        EG_CUDA(cudaMemcpyAsync(dtext.p, piece, (size_t)nb, cudaMemcpyHostToDevice, st));
+        EG_TRY(eg_dev_tokenise_scan(dtext.as<uint8_t>(), nb, dcounts.as<uint32_t>(), dprefix.as<int64_t>(), st));
+        int64_t totals[2] = {0, 0};
+        EG_CUDA(cudaMemcpyAsync(totals, dprefix.as<int64_t>() + 2 * nch, sizeof(totals), cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        const int64_t lines = totals[1] + (piece[nb - 1] != '\n' ? 1 : 0);
+        const size_t out_bytes = (size_t)lines * (size_t)(L + 1);
+        if (out_bytes + 16 > out_cap) {
+            out_cap = out_bytes + 16;
+            EG_TRY(dout.alloc(out_cap, "no-space ASCII rows"));
+        }
+        EG_TRY(hout.ensure(out_bytes + 16, "no-space ASCII rows"));
+        uint64_t h_err = UINT64_MAX;
+        EG_CUDA(cudaMemcpyAsync(derr.p, &h_err, sizeof(h_err), cudaMemcpyHostToDevice, st));
+        EG_TRY(eg_dev_tokenise_emit(dtext.as<uint8_t>(), nb, dprefix.as<int64_t>(), L, AA, AB, BB, missing, dout.as<uint8_t>(), lines,
+                                    derr.as<uint64_t>(), st));
+        EG_CUDA(cudaMemcpyAsync(&h_err, derr.p, sizeof(h_err), cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        int64_t good_rows = lines;
+        if (h_err != UINT64_MAX) {
+            // first error event of the piece: recover its row and what the reference would have printed
+            const int64_t pos = (int64_t)h_err, cb = eg_tokenise_chunk_bytes();
+            const int64_t ch = (pos >= nb ? nb - 1 : pos) / cb;
+            int64_t pre[2];
+            EG_CUDA(cudaMemcpyAsync(pre, dprefix.as<int64_t>() + 2 * ch, sizeof(pre), cudaMemcpyDeviceToHost, st));
+            EG_CUDA(cudaStreamSynchronize(st));
+            int64_t toks = pre[0], row = pre[1];
+            for (int64_t q = ch * cb; q < pos; q++) {
+                if (piece[q] == '\n') row++;
+                else if (!host_ws(piece[q]) && (q == 0 || host_ws(piece[q - 1]))) toks++;
+            }
+            good_rows = row;
+            const long long row1 = (long long)(rows_done + row + 1);
+            if (pos >= nb || piece[pos] == '\n') {  // :108-116
+                say(message, mctx, "\n");
+                say(message, mctx, "Error:  Marker text file contains an unequal number of columns per row.  ");
+                say(message, mctx, "        The error has occurred at row %lld which contains %lld but ", row1, (long long)(toks - row * L));
+                say(message, mctx, "        it should contain %lld columns of data. ", (long long)L);
+                say(message, mctx, "\n");
+                say(message, mctx, " ReadMarkerData has terminated with errors");
+            } else {  // :94-104
+                int64_t e = pos;
+                while (e < nb && !host_ws(piece[e])) e++;
+                std::string token((const char*)piece + pos, (size_t)(e - pos));
+                if (AB && strcmp(AB, "NA") == 0)
+                    say(message, mctx, "\n Marker file contains marker genotypes that are different to AA=%s BB=%s", AA, BB);
+                else
+                    say(message, mctx, "\n Marker file contains marker genotypes that are different to AA=%s AB=%s BB=%s", AA, AB, BB);
+                say(message, mctx, " For example , %s in row %lld", token.c_str(), row1);
+                say(message, mctx, "\n ReadMarker has terminated with errors\n");
+            }
+        }
+        // rows before the first error are complete (the reference has written them by then, too)
+        const size_t wbytes = (size_t)good_rows * (size_t)(L + 1);
+        if (wbytes) {
+            EG_CUDA(cudaMemcpyAsync(hout.p, dout.p, wbytes, cudaMemcpyDeviceToHost, st));
+            EG_CUDA(cudaStreamSynchronize(st));
+            if (fwrite(hout.p, 1, wbytes, outf.f) != wbytes) return set_error(EG_ERR_OPEN, "short write to %s", asciifname);
+        }
+        if (h_err != UINT64_MAX) return EG_OK;  // *ok stays 0
+        rows_done += lines;
+        off = end;
+    }
+    if (fflush(outf.f) != 0) return set_error(EG_ERR_OPEN, "short write to %s", asciifname);
+    {   // :129-157  echo of the first lines (printed whatever `quiet` says)
+        const int nrowsp = dims[0] < 5 ? (int)dims[0] : 5, ncolsp = L < 12 ? (int)L : 12;
+        say(message, mctx, " First %d lines and %d columns of the marker text  file. ", nrowsp, ncolsp);
+        size_t q = 0;
+        std::string tmp;
+        for (int r = 0; r < nrowsp && q < in.size; r++) {
+            const void* nlp = memchr(in.p + q, '\n', in.size - q);
+            const size_t e = nlp ? (size_t)((const uint8_t*)nlp - in.p) : in.size;
+            std::string rowline;
+            size_t c = q;
+            for (int i = 0; i < ncolsp; i++) {
+                while (c < e && host_ws(in.p[c])) c++;
+                size_t t0 = c;
+                while (c < e && !host_ws(in.p[c])) c++;
+                if (c > t0) tmp.assign((const char*)in.p + t0, c - t0);  // a failed extraction leaves tmp as it was
+                rowline += tmp;
+                rowline += " ";
+            }
+            say(message, mctx, "%s", rowline.c_str());
+            q = e + 1;
+        }
+    }
+    *ok = 1;
+    return EG_OK;
+}
+}  // namespace eg
+
+extern "C" int eg_createM_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const char* type, const char* AA, const char* AB,
+                                     const char* BB, double max_memory_in_Gbytes, const int64_t* dims, int quiet,
+                                     eg_message_fn message, void* message_ctx, const char* missing, int* ok) {
+    (void)max_memory_in_Gbytes;  // both branches of the reference call the same line-by-line routine (createM_ASCII_rcpp.cpp:88-96)
+    if (!f_name || !f_name_ascii || !type || !AA || !AB || !BB || !missing || !dims || !ok)
+        return set_error(EG_ERR_ARG, "createM_ASCII_rcpp: null argument");
+    if (strcmp(type, "PLINK") == 0)
+        return set_error(EG_ERR_ARG, "createM_ASCII_rcpp: PLINK ped files are converted by the package's own CPU routine "
+                                     "(CreateASCIInospace_PLINK); only text files are tokenised on the GPU");
+    if (!quiet) say(message, message_ctx, " A text file is being assumed as the input data file type. ");  // :85-86
+    return create_ascii_nospace(f_name, f_name_ascii, dims, AA, AB, BB, quiet, message, message_ctx, missing, ok);
+}
+
+// createMt_ASCII_rcpp(f_name, f_name_ascii, type, max_memory_in_Gbytes, dims, quiet, message)   src/createMt_ASCII_rcpp.cpp:15-245
+// f_name = M.ascii (dims = (n, L)), f_name_ascii = Mt.ascii to be written.  Decode -> transpose -> encode on the device; both
+// resident stores stay in the path cache, so the calculateMMt_rcpp / calculate_a_and_vara_rcpp calls that follow do not
+// upload anything.
+extern "C" int eg_createMt_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const char* type, double max_memory_in_Gbytes,
+                                      const int64_t* dims, int quiet, eg_message_fn message, void* message_ctx) {
+    (void)quiet;
+    if (!f_name || !f_name_ascii || !type || !dims) return set_error(EG_ERR_ARG, "createMt_ASCII_rcpp: null argument");
+    const int64_t n = dims[0], L = dims[1];
+    EG_TRY(ensure_init());
+    {   // the reference's Rcpp::stop text (:72-75)
+        struct stat stt;
+        if (stat(f_name, &stt) != 0) return set_error(EG_ERR_OPEN, "\n\nERROR: Could not open  %s\n\n\n", f_name);
+    }
+    eg_store* M = nullptr;
+    EG_TRY(cached_store(f_name, n, L, true, &M));
+    eg_store* Mt = nullptr;
+    EG_TRY(eg_store_transpose(M, &Mt));
+    OutFile outf;
+    outf.f = fopen(f_name_ascii, "wb");
+    int rc = outf.f ? EG_OK : set_error(EG_ERR_OPEN, "ERROR: Could not open  %s for writing", f_name_ascii);
+    // encode in row blocks of ~256 MB, two page-locked buffers: the D2H of block k runs while block k-1 is written
+    const int64_t line = n + 1;
+    int64_t block_rows = (256LL << 20) / line;
+    if (block_rows < 1) block_rows = 1;
+    if (block_rows > L) block_rows = L;
+    DevBuf denc[2];
+    PinnedBuf henc[2];
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2 && rc == EG_OK; i++) {
+        rc = denc[i].alloc((size_t)block_rows * line + 16, "ASCII rows");
+        if (rc == EG_OK) rc = henc[i].ensure((size_t)block_rows * line + 16, "ASCII rows");
+        if (rc == EG_OK) rc = check_cuda(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    int64_t pending_rows[2] = {0, 0};
+    int k = 0;
+    for (int64_t r = 0; rc == EG_OK && r < L; r += block_rows, k++) {
+        const int b = k & 1;
+        const int64_t nr = r + block_rows <= L ? block_rows : L - r;
+        rc = eg_dev_encode_ascii(Mt->d, Mt->pitch, n, r, nr, denc[b].as<uint8_t>(), g_ctx.stream);
+        if (rc == EG_OK)
+            rc = check_cuda(cudaMemcpyAsync(henc[b].p, denc[b].p, (size_t)nr * line, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H of Mt.ascii rows");
+        if (rc == EG_OK) rc = check_cuda(cudaEventRecord(done[b], g_ctx.stream), "cudaEventRecord");
+        pending_rows[b] = nr;
+        if (rc == EG_OK && k >= 1) {  // write the previous block while this one is in flight
+            const int pb = b ^ 1;
+            rc = check_cuda(cudaEventSynchronize(done[pb]), "Mt.ascii rows");
+            const size_t wb = (size_t)pending_rows[pb] * line;
+            if (rc == EG_OK && fwrite(henc[pb].p, 1, wb, outf.f) != wb) rc = set_error(EG_ERR_OPEN, "short write to %s", f_name_ascii);
+            pending_rows[pb] = 0;
+        }
+    }
+    if (rc == EG_OK && k >= 1) {
+        const int pb = (k - 1) & 1;
+        rc = check_cuda(cudaEventSynchronize(done[pb]), "Mt.ascii rows");
+        const size_t wb = (size_t)pending_rows[pb] * line;
+        if (rc == EG_OK && fwrite(henc[pb].p, 1, wb, outf.f) != wb) rc = set_error(EG_ERR_OPEN, "short write to %s", f_name_ascii);
+    }
+    cudaStreamSynchronize(g_ctx.stream);
+    for (int i = 0; i < 2; i++)
+        if (done[i]) cudaEventDestroy(done[i]);
+    if (outf.f) {
+        if (fclose(outf.f) != 0 && rc == EG_OK) rc = set_error(EG_ERR_OPEN, "short write to %s", f_name_ascii);
+        outf.f = nullptr;
+    }
+    if (rc != EG_OK) {
+        eg_store_free(Mt);
+        return rc;
+    }
+    {   // the Mt store now corresponds to the file just written: keep it for calculate_a_and_vara_rcpp
+        std::string key;
+        if (cache_key(f_name_ascii, L, n, false, key) == EG_OK) cache_insert(key, Mt);
+        else eg_store_free(Mt);
+    }
+    // :224-243  summary (printed whatever `quiet` says); bits_in_int/8 == 3 in the reference's integer arithmetic
+    const double mem_bytes = 3.5 * (double)n * (double)L * 3.0;
+    say(message, message_ctx, "\n\n                    Summary of Marker File  ");
+    say(message, message_ctx, "                   ~~~~~~~~~~~~~~~~~~~~~~~~   ");
+    say(message, message_ctx, " File type:                   %s", type);
+    say(message, message_ctx, " Reformatted ASCII file name:  %s", f_name);
+    say(message, message_ctx, " Number of individuals:        %lld", (long long)n);
+    say(message, message_ctx, " Number of loci:               %lld", (long long)L);
+    say(message, message_ctx, " File size (gigabytes):       %.15g", mem_bytes / 1000000000);
+    say(message, message_ctx, " Available memory (gigabytes): %.15g", max_memory_in_Gbytes);
+    say(message, message_ctx, "\n\n");
+    say(message, message_ctx, " The marker file has been Uploaded");
+    return EG_OK;
 }

@@ -81,6 +81,25 @@ int eg_calculate_reduced_a_rcpp(const char* f_name_ascii, double varG, const dou
 int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, int64_t selected_locus,
                          const int64_t* dims, int32_t* out);
 
+/* ---------------------------------------------------------------- ingest
+ * createM_ASCII_rcpp(f_name, f_name_ascii, type, AA, AB, BB, max_memory_in_Gbytes, dims, quiet, message, missing)
+ *                                                  src/createM_ASCII_rcpp.cpp:19-106, src/CreateASCIInospace.cpp:17-164
+ * Whitespace-separated genotype text -> the no-space ASCII file, tokenised on the device (csrc/ingest.cu).  *ok is the
+ * reference's bool: 0 after the reference's messages for an unreadable input, a token that is none of BB / AB / AA /
+ * missing, or a row whose token count is not dims[1] (rows before the offending one have been written, as in the
+ * reference).  type "PLINK" is refused with EG_ERR_ARG: ped files stay with the package's CPU routine. */
+int eg_createM_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const char* type, const char* AA, const char* AB,
+                          const char* BB, double max_memory_in_Gbytes, const int64_t* dims, int quiet,
+                          eg_message_fn message, void* message_ctx, const char* missing, int* ok);
+/* createMt_ASCII_rcpp(f_name, f_name_ascii, type, max_memory_in_Gbytes, dims, quiet, message)
+ *                                                                          src/createMt_ASCII_rcpp.cpp:15-245
+ * f_name = M.ascii with dims = (n, L); writes its transpose Mt.ascii (L lines of n characters) to f_name_ascii: decode,
+ * transpose and re-encode on the device.  Both stores stay resident under their file names, so the calculateMMt_rcpp /
+ * calculate_a_and_vara_rcpp calls that follow upload nothing.  A missing input is EG_ERR_OPEN with the reference's
+ * Rcpp::stop text. */
+int eg_createMt_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const char* type, double max_memory_in_Gbytes,
+                           const int64_t* dims, int quiet, eg_message_fn message, void* message_ctx);
+
 /* ================================================================ resident genotype stores
  * A store is a decoded genotype matrix held in HBM as int8, `rows` x `cols`, holding the NEGATED reference value
  * 1 - code (AA = +1, AB = 0, BB = -1; csrc/decode.cu explains why: power); every entry point that returns genotypes or
@@ -194,6 +213,23 @@ int eg_dev_gemv_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
                    double* d_y, void* stream);
 /* pitch == 0 selects the K-blocked layout in the two calls below (and in eg_dev_syrk_zero_cols) */
 int eg_dev_extract_col(const int8_t* d_M, int64_t n, int64_t pitch, int64_t col, int32_t* d_out, void* stream);
+
+/* Tokeniser of CreateASCIInospace.cpp:67-125 on a text resident in HBM.  d_text: nbytes of text at a 16-byte aligned
+ * address, readable for 32 bytes beyond nbytes.  Work is cut into eg_tokenise_chunks(nbytes) chunks of
+ * eg_tokenise_chunk_bytes() bytes.  _scan: d_counts = 2 * chunks uint32 of scratch; d_prefix = 2 * (chunks + 1) int64:
+ * (tokens, '\n' bytes) before each chunk, the last pair = totals.  _emit: d_out = out_rows * (cols + 1) bytes; *d_err_pos
+ * (set to UINT64_MAX by the caller) receives the smallest byte position of an error event: the start of a token that is
+ * none of the codes, or the '\n' (nbytes for an unterminated last line) that closes a row without exactly `cols` tokens. */
+int64_t eg_tokenise_chunks(int64_t nbytes);
+int64_t eg_tokenise_chunk_bytes(void);
+int eg_dev_tokenise_scan(const uint8_t* d_text, int64_t nbytes, uint32_t* d_counts, int64_t* d_prefix, void* stream);
+int eg_dev_tokenise_emit(const uint8_t* d_text, int64_t nbytes, const int64_t* d_prefix, int64_t cols, const char* AA,
+                         const char* AB, const char* BB, const char* missing, uint8_t* d_out, int64_t out_rows,
+                         uint64_t* d_err_pos, void* stream);
+/* Rows [row0, row0 + nrows) of a row-major int8 store as no-space ASCII ('0' + code, '\n' after each row):
+ * nrows * (cols + 1) bytes at d_out (16-byte aligned).  The writer of createMt_ASCII_rcpp.cpp:104-118. */
+int eg_dev_encode_ascii(const int8_t* d_store, int64_t pitch, int64_t cols, int64_t row0, int64_t nrows, uint8_t* d_out,
+                        void* stream);
 
 /* Bench / test utility: write a synthetic M.ascii image (rows x (cols+1) bytes, Binomial(2,p_j)
  * genotypes from a counter-based hash; same bytes as eagleeverything_b200/synth.py) into device memory.

@@ -396,6 +396,211 @@ int eo_extract_geno(const char *f_name_ascii, double max_memory_in_Gbytes, long 
     return rc;
 }
 
+/* ------------------------------------------------------------------ */
+/* ingest: createM_ASCII_rcpp (text files) and createMt_ASCII_rcpp     */
+/* ------------------------------------------------------------------ */
+/* message(...) calls are collected into msgbuf, separated by 0x1e; R's message() pastes its arguments
+ * without separators. */
+#include <stdarg.h>
+static void eo_msg(char *buf, long cap, const char *fmt, ...)
+{
+    if (!buf || cap <= 0) return;
+    size_t used = strlen(buf);
+    if (used && used + 1 < (size_t)cap) { buf[used++] = '\x1e'; buf[used] = 0; }
+    if (used + 1 >= (size_t)cap) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf + used, (size_t)cap - used, fmt, ap);
+    va_end(ap);
+}
+/* what operator>> (std::string) skips: isspace in the "C" locale */
+static int eo_isspace(int c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+/* CreateASCIInospace (src/CreateASCIInospace.cpp:17-164).  dims = (rows, columns) of the text file. */
+static int eo_CreateASCIInospace(const char *fname, const char *asciifname, const long *dims, const char *AA,
+                                 const char *AB, const char *BB, int quiet, const char *missing, char *msgbuf,
+                                 long msgcap, int *ok)
+{
+    *ok = 0;
+    FILE *in = fopen(fname, "r");
+    if (!in) { /* :38-41 */
+        eo_msg(msgbuf, msgcap, "ERROR: Text file could not be opened with filename  %s\n", fname);
+        return EO_OK;
+    }
+    FILE *out = fopen(asciifname, "w"); /* :43 */
+    if (!out) { fclose(in); return EO_ERR_OPEN; }
+    if (!quiet) { /* :44-50 */
+        eo_msg(msgbuf, msgcap, "%s", "");
+        eo_msg(msgbuf, msgcap, " Reading text File  ");
+        eo_msg(msgbuf, msgcap, "%s", "");
+        eo_msg(msgbuf, msgcap, " Loading file ");
+    }
+    char *rowinfile = (char *)malloc((size_t)dims[1] + 1); /* :58-63 */
+    char *line = NULL;
+    size_t cap = 0;
+    ssize_t len;
+    long counter = 0;
+    int rc = EO_OK, failed = 0;
+    if (!rowinfile) { fclose(in); fclose(out); return EO_ERR_ALLOC; }
+    memset(rowinfile, '0', (size_t)dims[1]);
+    while (!failed && (len = getline(&line, &cap, in)) >= 0) { /* :67 */
+        if (len > 0 && line[len - 1] == '\n') len--;
+        long i = 0, number_of_columns = 0;
+        ssize_t p = 0;
+        for (;;) { /* :79  while (streamA >> token) */
+            while (p < len && eo_isspace((unsigned char)line[p])) p++;
+            if (p >= len) break;
+            ssize_t t0 = p;
+            while (p < len && !eo_isspace((unsigned char)line[p])) p++;
+            size_t tl = (size_t)(p - t0);
+            const char *tok = line + t0;
+            number_of_columns++;
+            char code;
+#define EO_TOKEQ(s) (strlen(s) == tl && memcmp(tok, (s), tl) == 0)
+            if (EO_TOKEQ(BB)) code = '2';            /* :84 */
+            else if (EO_TOKEQ(AB)) code = '1';       /* :86 */
+            else if (EO_TOKEQ(AA)) code = '0';       /* :88 */
+            else if (EO_TOKEQ(missing)) code = '1';  /* :90-92 missing -> het */
+            else {                                   /* :93-105 */
+                if (strcmp(AB, "NA") == 0)
+                    eo_msg(msgbuf, msgcap, "\n Marker file contains marker genotypes that are different to AA=%s BB=%s", AA, BB);
+                else
+                    eo_msg(msgbuf, msgcap, "\n Marker file contains marker genotypes that are different to AA=%s AB=%s BB=%s", AA, AB, BB);
+                eo_msg(msgbuf, msgcap, " For example , %.*s in row %ld", (int)tl, tok, counter + 1);
+                eo_msg(msgbuf, msgcap, "\n ReadMarker has terminated with errors\n");
+                failed = 1;
+                break;
+            }
+#undef EO_TOKEQ
+            if (i < dims[1]) rowinfile[i] = code; /* the reference writes out of bounds for i >= dims[1] (:85) */
+            i++;
+        }
+        if (failed) break;
+        if (number_of_columns != dims[1]) { /* :108-116 */
+            eo_msg(msgbuf, msgcap, "\n");
+            eo_msg(msgbuf, msgcap, "Error:  Marker text file contains an unequal number of columns per row.  ");
+            eo_msg(msgbuf, msgcap, "        The error has occurred at row %ld which contains %ld but ", counter + 1, number_of_columns);
+            eo_msg(msgbuf, msgcap, "        it should contain %ld columns of data. ", dims[1]);
+            eo_msg(msgbuf, msgcap, "\n");
+            eo_msg(msgbuf, msgcap, " ReadMarkerData has terminated with errors");
+            failed = 1;
+            break;
+        }
+        fwrite(rowinfile, 1, (size_t)number_of_columns, out); /* :118-121 */
+        fputc('\n', out);
+        counter++;
+    }
+    if (!failed) { /* :129-157 echo of the first lines */
+        int nrowsp = dims[0] < 5 ? (int)dims[0] : 5, ncolsp = dims[1] < 12 ? (int)dims[1] : 12;
+        eo_msg(msgbuf, msgcap, " First %d lines and %d columns of the marker text  file. ", nrowsp, ncolsp);
+        rewind(in);
+        char tmp[256] = "";
+        long c2 = 0;
+        while (c2 < nrowsp && (len = getline(&line, &cap, in)) >= 0) {
+            if (len > 0 && line[len - 1] == '\n') len--;
+            char rowline[4096] = "";
+            ssize_t p = 0;
+            for (int i = 0; i < ncolsp; i++) {
+                while (p < len && eo_isspace((unsigned char)line[p])) p++;
+                ssize_t t0 = p;
+                while (p < len && !eo_isspace((unsigned char)line[p])) p++;
+                if (p > t0) snprintf(tmp, sizeof(tmp), "%.*s", (int)(p - t0), line + t0); /* failed >> keeps tmp */
+                strncat(rowline, tmp, sizeof(rowline) - strlen(rowline) - 2);
+                strcat(rowline, " ");
+            }
+            eo_msg(msgbuf, msgcap, "%s", rowline);
+            c2++;
+        }
+        *ok = 1;
+    }
+    free(line); free(rowinfile);
+    fclose(in); fclose(out);
+    return rc;
+}
+
+/* createM_ASCII_rcpp (src/createM_ASCII_rcpp.cpp:19-106), text files only: type "PLINK" (CreateASCIInospace_PLINK.cpp) is
+ * not restated here, the compiled reference (oracle/_ref) covers it. */
+int eo_createM_ASCII(const char *f_name, const char *f_name_ascii, const char *type, const char *AA, const char *AB,
+                     const char *BB, double max_memory_in_Gbytes, const long *dims, int quiet, const char *missing,
+                     char *msgbuf, long msgcap, int *ok)
+{
+    (void)max_memory_in_Gbytes; /* :88-96: both branches call the same routine */
+    if (msgbuf && msgcap > 0) msgbuf[0] = 0;
+    if (strcmp(type, "PLINK") == 0) return EO_ERR_SOFT;
+    if (!quiet) eo_msg(msgbuf, msgcap, " A text file is being assumed as the input data file type. "); /* :85-86 */
+    return eo_CreateASCIInospace(f_name, f_name_ascii, dims, AA, AB, BB, quiet, missing, msgbuf, msgcap, ok);
+}
+
+/* createMt_ASCII_rcpp (src/createMt_ASCII_rcpp.cpp:15-245).  dims = (n, L) of M.ascii.  Both situations (:66-122 in
+ * memory, :123-218 column blocks) write the same bytes: line c of the output is column c of the input. */
+int eo_createMt_ASCII(const char *f_name, const char *f_name_ascii, const char *type, double max_memory_in_Gbytes,
+                      const long *dims, int quiet, char *msgbuf, long msgcap)
+{
+    const long n = dims[0], L = dims[1];
+    if (msgbuf && msgcap > 0) msgbuf[0] = 0;
+    const double max_mem_in_bytes = max_memory_in_Gbytes * 1000000000; /* :43-44 */
+    const double mem_bytes = 3.5 * n * L * (31 / 8);                   /* :50  bits_in_int = 31, integer division */
+    FILE *in = fopen(f_name, "r");
+    if (!in) return EO_ERR_OPEN; /* :72-75, :150-153 */
+    FILE *out = fopen(f_name_ascii, "w");
+    if (!out) { fclose(in); return EO_ERR_OPEN; }
+    long ncols_block = L, n_blocks = 1;
+    if (!(mem_bytes < max_mem_in_bytes)) { /* :123-141 */
+        if (!quiet) {
+            eo_msg(msgbuf, msgcap, " A block transpose is being performed due to lack of memory.  ");
+            eo_msg(msgbuf, msgcap, " Memory parameter availmemGb is set to %ggigabytes", max_memory_in_Gbytes);
+            eo_msg(msgbuf, msgcap, " If possible, increase availmemGb parameter. ");
+        }
+        ncols_block = (long)(max_mem_in_bytes * 1.0 / (3.5 * n * (31 / 8.0)));
+        if (ncols_block <= 0) { fclose(in); fclose(out); return EO_ERR_BLOCK0; }
+        n_blocks = L / ncols_block;
+        if (L % ncols_block != 0) n_blocks++;
+        if (!quiet) {
+            eo_msg(msgbuf, msgcap, " Block Transpose of ASCII genotype file beginning ... ");
+            eo_msg(msgbuf, msgcap, "  Due to marker data exceeding memory, data being processed in blocks. Number of blocks being processed is %ld", n_blocks);
+        }
+    }
+    char *M = (char *)malloc((size_t)n * (size_t)ncols_block), *row = (char *)malloc((size_t)n + 1);
+    char *line = NULL;
+    size_t cap = 0;
+    int rc = (M && row) ? EO_OK : EO_ERR_ALLOC;
+    for (long b = 0; b < n_blocks && !rc; b++) {
+        if (n_blocks > 1 || !(mem_bytes < max_mem_in_bytes)) {
+            if (!quiet) eo_msg(msgbuf, msgcap, " Processing block ... %ld of a total number of blocks of %ld", b, n_blocks);
+            if (!quiet) eo_msg(msgbuf, msgcap, "\n\n");
+        }
+        long start_val = b * ncols_block, end_val = (b + 1) * ncols_block;
+        if (end_val > L) end_val = L;
+        long nc = end_val - start_val;
+        rewind(in);
+        for (long r = 0; r < n && !rc; r++) {
+            ssize_t len = getline(&line, &cap, in);
+            if (len < 0 || len < end_val) { rc = EO_ERR_SHORT; break; }
+            memcpy(M + (size_t)r * nc, line + start_val, (size_t)nc);
+        }
+        for (long c = 0; c < nc && !rc; c++) {
+            for (long r = 0; r < n; r++) row[r] = M[(size_t)r * nc + c];
+            row[n] = '\n';
+            fwrite(row, 1, (size_t)n + 1, out);
+        }
+    }
+    free(line); free(M); free(row);
+    fclose(in); fclose(out);
+    if (rc) return rc;
+    /* :224-243 */
+    eo_msg(msgbuf, msgcap, "\n\n                    Summary of Marker File  ");
+    eo_msg(msgbuf, msgcap, "                   ~~~~~~~~~~~~~~~~~~~~~~~~   ");
+    eo_msg(msgbuf, msgcap, " File type:                   %s", type);
+    eo_msg(msgbuf, msgcap, " Reformatted ASCII file name:  %s", f_name);
+    eo_msg(msgbuf, msgcap, " Number of individuals:        %ld", n);
+    eo_msg(msgbuf, msgcap, " Number of loci:               %ld", L);
+    eo_msg(msgbuf, msgcap, " File size (gigabytes):       %g", mem_bytes / 1000000000);
+    eo_msg(msgbuf, msgcap, " Available memory (gigabytes): %g", max_memory_in_Gbytes);
+    eo_msg(msgbuf, msgcap, "\n\n");
+    eo_msg(msgbuf, msgcap, " The marker file has been Uploaded");
+    return EO_OK;
+}
+
 int eo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -47,6 +47,8 @@ def _bind(path):
     L.eo_calculate_a_and_vara.argtypes = [C.c_char_p, dp, C.c_long, dp, dp, C.c_double, lp, dp, dp, dp, ip]
     L.eo_calculate_reduced_a.argtypes = [C.c_char_p, C.c_double, dp, dp, C.c_double, lp, dp, C.c_long, dp]
     L.eo_extract_geno.argtypes = [C.c_char_p, C.c_double, C.c_long, lp, ip, ip]
+    L.eo_createM_ASCII.argtypes = [C.c_char_p] * 6 + [C.c_double, lp, C.c_int, C.c_char_p, C.c_char_p, C.c_long, ip]
+    L.eo_createMt_ASCII.argtypes = [C.c_char_p] * 3 + [C.c_double, lp, C.c_int, C.c_char_p, C.c_long]
     L.eo_num_threads.restype = C.c_int
     if hasattr(L, "ref_last_error"):
         L.ref_last_error.restype = C.c_char_p
@@ -173,6 +175,31 @@ def extract_geno_rcpp(f_name_ascii, max_memory_in_Gbytes, selected_locus, dims, 
                                  _dims(dims), out.ctypes.data_as(C.POINTER(C.c_int)), C.byref(br)),
            "extract_geno_rcpp")
     return (out, br.value) if return_branch else out
+
+
+def _messages(buf):
+    raw = buf.value.decode("utf-8", "replace")
+    return raw.split("\x1e") if raw else []
+
+
+def createM_ASCII_rcpp(f_name, f_name_ascii, type, AA, AB, BB, max_memory_in_Gbytes, dims, quiet, missing):
+    """createM_ASCII_rcpp.cpp:19-106 + CreateASCIInospace.cpp:17-164 (text files; PLINK only through the compiled
+    reference).  -> (ok, [message, ...]); the no-space ASCII file is written to f_name_ascii."""
+    buf = C.create_string_buffer(1 << 16)
+    ok = C.c_int(0)
+    e = lambda x: x.encode() if isinstance(x, str) else os.fsencode(x)
+    _check(lib().eo_createM_ASCII(os.fsencode(f_name), os.fsencode(f_name_ascii), e(type), e(AA), e(AB), e(BB),
+                                  float(max_memory_in_Gbytes), _dims(dims), int(bool(quiet)), e(missing), buf, len(buf),
+                                  C.byref(ok)), "createM_ASCII_rcpp")
+    return bool(ok.value), _messages(buf)
+
+
+def createMt_ASCII_rcpp(f_name, f_name_ascii, type, max_memory_in_Gbytes, dims, quiet):
+    """createMt_ASCII_rcpp.cpp:15-245.  dims = (n, L) of M.ascii (f_name); writes Mt.ascii to f_name_ascii. -> messages."""
+    buf = C.create_string_buffer(1 << 16)
+    _check(lib().eo_createMt_ASCII(os.fsencode(f_name), os.fsencode(f_name_ascii), type.encode(), float(max_memory_in_Gbytes),
+                                   _dims(dims), int(bool(quiet)), buf, len(buf)), "createMt_ASCII_rcpp")
+    return _messages(buf)
 
 
 def num_threads() -> int:

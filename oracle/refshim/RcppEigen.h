@@ -1,8 +1,9 @@
 // Stand-in for <RcppEigen.h> -- TEST INFRASTRUCTURE ONLY (oracle/refshim).
 //
 // Lets the REFERENCE'S OWN hot-path sources (ReadBlock.cpp, calculateMMt_rcpp.cpp,
-// calculate_a_and_vara_rcpp.cpp, calculate_reduced_a_rcpp.cpp, extract_geno_rcpp.cpp under
-// /root/reference/MyPackage/Eagle/src) compile unmodified, from where they lie, without R, Rcpp or
+// calculate_a_and_vara_rcpp.cpp, calculate_reduced_a_rcpp.cpp, extract_geno_rcpp.cpp, and the ingest
+// routines createM_ASCII_rcpp.cpp, CreateASCIInospace.cpp, CreateASCIInospace_PLINK.cpp,
+// createMt_ASCII_rcpp.cpp under /root/reference/MyPackage/Eagle/src) compile unmodified, from where they lie, without R, Rcpp or
 // Eigen (none of which exist in this image).  Only the small part of the two libraries' API that
 // those five files use is provided, with eager evaluation and straightforward loops.  What runs is
 // therefore the reference's own control flow -- file parsing, memory tests, row blocking, the
@@ -15,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <limits>
 #include <map>
 #include <sstream>
@@ -38,6 +40,26 @@ class VectorXi {
     long size() const { return (long)v_.size(); }
     int* data() { return v_.data(); }
     std::vector<int> v_;
+};
+
+// integer matrix of createMt_ASCII_rcpp.cpp:79-99 (element access and transpose only)
+class MatrixXi {
+  public:
+    MatrixXi() : r_(0), c_(0) {}
+    MatrixXi(long r, long c) : r_(r), c_(c), d_((size_t)r * (size_t)c, 0) {}
+    long rows() const { return r_; }
+    long cols() const { return c_; }
+    int& operator()(long r, long c) { return d_[(size_t)r + (size_t)c * r_]; }
+    int operator()(long r, long c) const { return d_[(size_t)r + (size_t)c * r_]; }
+    MatrixXi transpose() const {
+        MatrixXi t(c_, r_);
+        for (long j = 0; j < c_; j++)
+            for (long i = 0; i < r_; i++) t(j, i) = (*this)(i, j);
+        return t;
+    }
+  private:
+    long r_, c_;
+    std::vector<int> d_;
 };
 
 class MatrixXd {
@@ -162,6 +184,8 @@ class CharacterVector {
     std::string s_;
 };
 template <class T> T as(const CharacterVector& c) { return T(c.s_); }
+inline std::ostream& operator<<(std::ostream& os, const CharacterVector& c) { return os << c.s_; }
+static std::ostream Rcout(nullptr);  // progress output of the ingest routines: discarded
 
 class NumericVector {
   public:

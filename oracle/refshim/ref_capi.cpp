@@ -19,7 +19,24 @@ Eigen::MatrixXd calculate_reduced_a_rcpp(Rcpp::CharacterVector f_name_ascii, dou
 Eigen::VectorXi extract_geno_rcpp(Rcpp::CharacterVector f_name_ascii, double max_memory_in_Gbytes,
                                   long selected_locus, std::vector<long> dims);
 
+bool createM_ASCII_rcpp(Rcpp::CharacterVector f_name, Rcpp::CharacterVector f_name_ascii, Rcpp::CharacterVector type,
+                        std::string AA, std::string AB, std::string BB, double max_memory_in_Gbytes, std::vector<long> dims,
+                        bool quiet, Rcpp::Function message, std::string missing);
+void createMt_ASCII_rcpp(Rcpp::CharacterVector f_name, Rcpp::CharacterVector f_name_ascii, Rcpp::CharacterVector type,
+                         double max_memory_in_Gbytes, std::vector<long> dims, bool quiet, Rcpp::Function message);
+
 static thread_local std::string g_what;
+// messages joined with the ASCII record separator into a caller-provided buffer
+static void join_msgs(const std::vector<std::string>& msgs, char* buf, long cap) {
+    if (!buf || cap <= 0) return;
+    std::string all;
+    for (size_t i = 0; i < msgs.size(); i++) {
+        if (i) all += '\x1e';
+        all += msgs[i];
+    }
+    if ((long)all.size() >= cap) all.resize(cap - 1);
+    std::memcpy(buf, all.c_str(), all.size() + 1);
+}
 #define GUARD(...)                                                           \
     try { __VA_ARGS__; return 0; }                                           \
     catch (const std::exception& e) { g_what = e.what(); return 1; }         \
@@ -88,6 +105,25 @@ int eo_extract_geno(const char* f, double mem, long locus, const long* dims, int
         Eigen::VectorXi v = extract_geno_rcpp(f, mem, locus, std::vector<long>{dims[0], dims[1]});
         std::memcpy(out, v.data(), sizeof(int) * (size_t)v.size());
         if (branch) *branch = (mem > ((double)dims[0] * dims[1] * sizeof(double)) / 1000000000.0) ? 0 : 1;
+    })
+}
+
+int eo_createM_ASCII(const char* f, const char* fascii, const char* type, const char* AA, const char* AB, const char* BB,
+                     double mem, const long* dims, int quiet, const char* missing, char* msgbuf, long msgcap, int* ok) {
+    GUARD({
+        std::vector<std::string> msgs;
+        *ok = createM_ASCII_rcpp(f, fascii, type, AA, AB, BB, mem, std::vector<long>{dims[0], dims[1]}, quiet != 0,
+                                 Rcpp::Function(&msgs), missing) ? 1 : 0;
+        join_msgs(msgs, msgbuf, msgcap);
+    })
+}
+
+int eo_createMt_ASCII(const char* f, const char* fascii, const char* type, double mem, const long* dims, int quiet,
+                      char* msgbuf, long msgcap) {
+    GUARD({
+        std::vector<std::string> msgs;
+        createMt_ASCII_rcpp(f, fascii, type, mem, std::vector<long>{dims[0], dims[1]}, quiet != 0, Rcpp::Function(&msgs));
+        join_msgs(msgs, msgbuf, msgcap);
     })
 }
 
