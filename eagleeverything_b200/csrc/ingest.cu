@@ -11,9 +11,10 @@
 // tokens, so two prefix sums over the bytes -- token starts and newlines -- place every token:
 //   tok_count_kernel   token starts and newlines per 32 KB chunk
 //   tok_scan_kernel    exclusive prefix over the chunks (one CTA; 64-bit)
-//   tok_emit_kernel    per chunk: the same masks again, a CTA-wide scan per 4 KB step, then every token start classifies
-//                      its token and stores one byte at row*(L+1)+col, and every newline checks "tokens so far ==
-//                      (row+1)*L" and stores the '\n'.
+//   tok_emit_kernel    per chunk: the same masks again and a CTA-wide scan per 4 KB step; every token start classifies
+//                      its token, every newline checks "tokens so far == (row+1)*L", and both emit one byte.  The output
+//                      offset row*(L+1)+col equals (tokens before) + (newlines before): the output is a stream
+//                      compaction of the events, staged in shared memory and written as aligned 16-byte vectors.
 // Errors are events with a byte position (start of the offending token / the newline that ends the short or long
 // row); the smallest position is kept with one atomicMin, which is the event the reference's sequential loop meets
 // first.  The host turns it into the reference's message (row number, token text or column count).
@@ -38,21 +39,22 @@ struct TokCodes {  // order of comparison in the reference: BB, AB, AA, missing 
     uint8_t s[4][16];
     int32_t len[4];
     uint8_t out[4];
-    int32_t all_single;  // every non-empty code is one character
 };
 
 __device__ __forceinline__ bool is_ws(uint32_t b) { return b == 0x20u || (b - 9u) <= 4u; }  // isspace in the C locale
 
+// 0xFF / 0x00 per byte -> one bit per byte
+__device__ __forceinline__ uint32_t byte_flags(uint32_t m) { return ((m & 0x08040201u) * 0x01010101u) >> 24; }
 // masks over the 16 bytes at p0: whitespace (bytes at or beyond nbytes count as whitespace) and '\n'
 __device__ __forceinline__ void byte_masks(const uint4& v, int64_t p0, int64_t nbytes, uint32_t& ws, uint32_t& nl) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     ws = 0;
     nl = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-        ws |= (is_ws(b) ? 1u : 0u) << i;
-        nl |= (b == 0x0Au ? 1u : 0u) << i;
+    for (int k = 0; k < 4; k++) {
+        const uint32_t sp = __vcmpeq4(w[k], 0x20202020u) | (__vcmpgeu4(w[k], 0x09090909u) & __vcmpleu4(w[k], 0x0D0D0D0Du));
+        ws |= byte_flags(sp) << (4 * k);
+        nl |= byte_flags(__vcmpeq4(w[k], 0x0A0A0A0Au)) << (4 * k);
     }
     const int64_t left = nbytes - p0;
     if (left < 16) {
@@ -148,9 +150,9 @@ __global__ void __launch_bounds__(1024) tok_scan_kernel(const uint32_t* __restri
     if (threadIdx.x < 2) prefix[2 * nchunks + threadIdx.x] = carry[threadIdx.x];
 }
 
-// which code the token starting at p is: index into TokCodes, or -1
-__device__ __forceinline__ int classify_token(const uint8_t* __restrict__ text, int64_t p, int64_t nbytes, const TokCodes& c) {
-#pragma unroll
+// which code the token starting at p is: index into TokCodes (a copy in shared memory), or -1.  Deliberately not inlined:
+// sixteen unrolled copies of it made the kernel 37,000 instructions long and instruction-fetch bound.
+__device__ __noinline__ int classify_token(const uint8_t* __restrict__ text, int64_t p, int64_t nbytes, const TokCodes& c) {
     for (int k = 0; k < 4; k++) {
         const int len = c.len[k];
         if (len == 0 || p + len > nbytes) continue;
@@ -161,13 +163,24 @@ __device__ __forceinline__ int classify_token(const uint8_t* __restrict__ text, 
     return -1;
 }
 
+// The output is a stream compaction of the events: a token start writes its code, a '\n' writes '\n', and the byte goes
+// to offset (tokens before) + (newlines before) -- as long as every earlier row holds exactly L tokens that IS
+// row * (L + 1) + column.  Each 4 KB step stages its bytes in shared memory and writes them out as aligned 16-byte vectors.
+// One-character tokens (the usual 0/1/2 or A/H/B files) are classified from registers against the one-character codes;
+// longer tokens (e.g. the missing-value string "NA") go through classify_token.
 __global__ void __launch_bounds__(TK_THREADS) tok_emit_kernel(const uint8_t* __restrict__ text, int64_t nbytes, int64_t nchunks,
-                                                              const int64_t* __restrict__ prefix, int64_t L, const TokCodes codes,
-                                                              uint8_t* __restrict__ out, int64_t out_rows,
+                                                              const int64_t* __restrict__ prefix, int64_t L, const TokCodes codes_param,
+                                                              uint8_t* __restrict__ out, int64_t out_bytes,
                                                               unsigned long long* __restrict__ err_pos) {
     __shared__ uint32_t wsum[TK_THREADS / 32];
+    __shared__ TokCodes codes;  // dynamic indexing of a kernel parameter would put it on every thread's stack
+    if (threadIdx.x < sizeof(TokCodes) / 4) reinterpret_cast<uint32_t*>(&codes)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&codes_param)[threadIdx.x];
+    __syncthreads();
+    const uint32_t c1[4] = {codes.s[0][0], codes.s[1][0], codes.s[2][0], codes.s[3][0]};
+    const uint32_t o1[4] = {codes.out[0], codes.out[1], codes.out[2], codes.out[3]};
+    const bool has[4] = {codes.len[0] == 1, codes.len[1] == 1, codes.len[2] == 1, codes.len[3] == 1};
+    __shared__ __align__(16) uint8_t stage[TK_STEP + 32];  // at most one event per text byte
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t pitch = L + 1;
     for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         int64_t base_tok = prefix[2 * ch], base_nl = prefix[2 * ch + 1];
         for (int s = 0; s < TK_STEPS; s++) {
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(TK_THREADS) tok_emit_kernel(const uint8_t* __r
                 const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += u;
             }
-            __syncthreads();  // wsum of the previous step has been read
+            __syncthreads();  // wsum and stage of the previous step have been read
             if (lane == 31) wsum[warp] = inc;
             __syncthreads();
             uint32_t before = inc - mine, total = 0;
@@ -198,44 +211,69 @@ __global__ void __launch_bounds__(TK_THREADS) tok_emit_kernel(const uint8_t* __r
                 if (w < warp) before += x;
                 total += x;
             }
-            int64_t t = base_tok + (before >> 16);     // tokens that start before this thread's bytes
-            int64_t r = base_nl + (before & 0xFFFFu);  // newlines before them = row of the first byte
+            uint32_t tl = before >> 16, rl = before & 0xFFFFu;  // tokens / newlines of this step before this thread's bytes
+            uint32_t e = tl + rl;                               // = its first slot in the stage
             // does the byte after this vector end a token that starts at byte 15?
             const bool single15 = (ts & 0x8000u) && (p0 + 16 >= nbytes || is_ws(text[p0 + 16]));
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            uint32_t ev = ts | nl;
-            while (ev) {
-                const int i = __ffs(ev) - 1;
-                ev &= ev - 1;
-                const int64_t p = p0 + i;
-                if ((nl >> i) & 1u) {
-                    if (t != (r + 1) * L) atomicMin(err_pos, (unsigned long long)p);
-                    if (r < out_rows) out[r * pitch + L] = '\n';
-                    r++;
-                } else {
-                    int k;
-                    const bool single = (i < 15) ? ((ws >> (i + 1)) & 1u) : single15;
-                    if (codes.all_single) {
-                        k = -1;
+            if (ts | nl) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if ((nl >> i) & 1u) {
+                        if (base_tok + tl != (base_nl + rl + 1) * L) atomicMin(err_pos, (unsigned long long)(p0 + i));
+                        stage[e++] = '\n';
+                        rl++;
+                    } else if ((ts >> i) & 1u) {
+                        uint32_t ob = 0;  // 0: none of the codes
+                        const bool single = (i < 15) ? ((ws >> (i + 1)) & 1u) : single15;
                         if (single) {
                             const uint32_t b = (w4[i >> 2] >> (8 * (i & 3))) & 0xFFu;
 #pragma unroll
                             for (int q = 3; q >= 0; q--)
-                                if (codes.len[q] && b == codes.s[q][0]) k = q;  // the first match in BB, AB, AA, missing order wins
+                                if (has[q] && b == c1[q]) ob = o1[q];  // first match in BB, AB, AA, missing order wins
+                        } else {
+                            const int k = classify_token(text, p0 + i, nbytes, codes);
+                            if (k >= 0) ob = codes.out[k];
                         }
-                    } else {
-                        k = classify_token(text, p, nbytes, codes);
+                        if (!ob) atomicMin(err_pos, (unsigned long long)(p0 + i));
+                        stage[e++] = ob ? (uint8_t)ob : (uint8_t)'?';
+                        tl++;
                     }
-                    if (k < 0) atomicMin(err_pos, (unsigned long long)p);
-                    const int64_t col = t - r * L;
-                    if (k >= 0 && col >= 0 && col < L && r < out_rows) out[r * pitch + col] = codes.out[k];
-                    t++;
                 }
             }
             // a last line without '\n' is a row too (getline returns it): the thread that holds the last byte closes it
-            if (p0 < nbytes && nbytes <= p0 + 16 && text[nbytes - 1] != '\n') {
-                if (t != (r + 1) * L) atomicMin(err_pos, (unsigned long long)nbytes);
-                if (r < out_rows) out[r * pitch + L] = '\n';
+            const bool closes = p0 < nbytes && nbytes <= p0 + 16 && text[nbytes - 1] != '\n';
+            if (closes) {
+                if (base_tok + tl != (base_nl + rl + 1) * L) atomicMin(err_pos, (unsigned long long)nbytes);
+                stage[e++] = '\n';  // e == all events of the step here: nothing follows the last byte
+            }
+            __syncthreads();
+            // copy-out: stage[0, nev) -> out[o0, o0 + nev), as 16-byte vectors aligned in `out`
+            const int64_t o0 = base_tok + base_nl;
+            const uint32_t tot_ev = (total >> 16) + (total & 0xFFFFu);
+            const int64_t last_pos = ch * TK_CHUNK + (int64_t)s * TK_STEP + TK_STEP;  // the closing thread is in this step?
+            const uint32_t nev = tot_ev + ((nbytes <= last_pos && text[nbytes - 1] != '\n') ? 1u : 0u);
+            const uint32_t head = (uint32_t)((16 - (o0 & 15)) & 15);  // bytes before the first aligned vector
+            for (uint32_t j = threadIdx.x; j < head && j < nev; j += TK_THREADS)
+                if (o0 + j < out_bytes) out[o0 + j] = stage[j];
+            if (nev > head) {
+                const uint32_t nvec = (nev - head) >> 4, tail0 = head + (nvec << 4);
+                const uint32_t sh = (head & 3u) * 8u;
+                const uint32_t* st32 = reinterpret_cast<const uint32_t*>(stage);
+                for (uint32_t j = threadIdx.x; j < nvec; j += TK_THREADS) {
+                    const uint32_t so = head + (j << 4);  // stage offset of this vector: so & 3 == head & 3
+                    const uint32_t* q = st32 + (so >> 2);
+                    const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+                    const uint4 x = make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh),
+                                               __funnelshift_r(a3, a4, sh));
+                    const int64_t oo = o0 + so;
+                    if (oo + 16 <= out_bytes) *reinterpret_cast<uint4*>(out + oo) = x;
+                    else
+                        for (int b = 0; b < 16; b++)
+                            if (oo + b < out_bytes) out[oo + b] = stage[so + b];
+                }
+                for (uint32_t j = tail0 + threadIdx.x; j < nev; j += TK_THREADS)
+                    if (o0 + j < out_bytes) out[o0 + j] = stage[j];
             }
             base_tok += (total >> 16);
             base_nl += (total & 0xFFFFu);
@@ -283,7 +321,6 @@ static int fill_codes(TokCodes& c, const char* AA, const char* AB, const char* B
     const char* s[4] = {BB, AB, AA, missing};
     const uint8_t o[4] = {'2', '1', '0', '1'};
     memset(&c, 0, sizeof(c));
-    c.all_single = 1;
     for (int k = 0; k < 4; k++) {
         const size_t len = s[k] ? strlen(s[k]) : 0;
         if (len > TK_MAXLEN) return set_error(EG_ERR_ARG, "genotype code \"%s\" is longer than %d characters", s[k], TK_MAXLEN);
@@ -292,7 +329,6 @@ static int fill_codes(TokCodes& c, const char* AA, const char* AB, const char* B
         memcpy(c.s[k], s[k] ? s[k] : "", len);
         c.len[k] = (int32_t)len;
         c.out[k] = o[k];
-        if (len > 1) c.all_single = 0;
     }
     return EG_OK;
 }
@@ -327,7 +363,7 @@ extern "C" int eg_dev_tokenise_emit(const uint8_t* d_text, int64_t nbytes, const
     EG_TRY(fill_codes(codes, AA, AB, BB, missing));
     const int64_t nch = eg_tokenise_chunks(nbytes), cap = (int64_t)num_sms() * 8;
     tok_emit_kernel<<<(unsigned)(nch < cap ? nch : cap), TK_THREADS, 0, (cudaStream_t)stream>>>(
-        d_text, nbytes, nch, d_prefix, cols, codes, d_out, out_rows, reinterpret_cast<unsigned long long*>(d_err_pos));
+        d_text, nbytes, nch, d_prefix, cols, codes, d_out, out_rows * (cols + 1), reinterpret_cast<unsigned long long*>(d_err_pos));
     return check_launch("tok_emit_kernel");
 }
 
