@@ -52,6 +52,8 @@ SIGNATURES = {
     "eg_dev_tokenise_scan": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "eg_dev_tokenise_emit": (C.c_int, [_vp, _i64, _vp, _i64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _vp, _i64,
                                        _vp, _vp]),
+    "eg_dev_ped_alleles": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "eg_dev_ped_genotypes": (C.c_int, [_vp, _i64, _i64, C.c_int, _i64, _vp, _vp, _vp, _vp]),
     "eg_dev_encode_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "eg_store_from_host_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),
     "eg_store_from_host_ascii_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp)]),

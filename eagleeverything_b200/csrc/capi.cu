@@ -561,7 +561,10 @@ __global__ void __launch_bounds__(256) symmetry_kernel(const double* __restrict_
 }
 
 // ------------------------------------------------------------------ compute helpers on stores
-static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols, double* out_host) {
+// keep_product: cache the int32 product with the store (stores of the path cache: calculateMMt_rcpp is called again by
+// SummaryAM with other selected loci, R/summary_am.R:142 -- the repeat then costs a copy, the rank-k correction and the
+// finalize pass instead of a second contraction)
+static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols, double* out_host, bool keep_product = false) {
     const int64_t n = M->rows;
     DevBuf C, D;
     EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
@@ -576,6 +579,15 @@ static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols
         EG_TRY(M->pitch ? eg_dev_syrk_i8(M->d, n, M->cols, M->pitch, C.as<int32_t>(), n, st)
                         : eg_dev_syrk_i8_kb(M->d, n, M->cols, C.as<int32_t>(), n, st));
         g_ctx.timing[1] = t.stop();
+        if (keep_product) {
+            int32_t* keep = nullptr;
+            if (pool_alloc((void**)&keep, (size_t)n * n * sizeof(int32_t)) == cudaSuccess) {
+                EG_CUDA(cudaMemcpyAsync(keep, C.p, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                const_cast<eg_store*>(M)->C32 = keep;
+            } else {
+                cudaGetLastError();  // no room: contract again next time
+            }
+        }
     }
     if (!zero_cols.empty())
         EG_TRY(eg_dev_syrk_zero_cols(M->d, n, M->pitch, zero_cols.data(), (int64_t)zero_cols.size(), C.as<int32_t>(), n, st));
@@ -1113,7 +1125,7 @@ extern "C" int eg_calculateMMt_rcpp(const char* f_name_ascii, double max_memory_
     std::vector<int64_t> z;
     EG_TRY(parse_selected(selected_loci, n_selected_loci, dims[1], z, "calculateMMt_rcpp"));
     if (!quiet) say(message, message_ctx, " M %%*%% t(M) on GPU %d (int8 tensor cores, exact) ", g_ctx.device);
-    return mmt_of_store(M, z, out_MMt);
+    return mmt_of_store(M, z, out_MMt, true);
 }
 
 extern "C" int eg_calculate_a_and_vara_rcpp(const char* f_name_ascii, const double* selected_loci,
@@ -1229,6 +1241,8 @@ struct TextFile {
         return true;
     }
 };
+
+static void echo_first_lines(const TextFile& in, int nrowsp, int ncolsp, eg_message_fn message, void* mctx);
 
 // CreateASCIInospace(fname, asciifname, dims, AA, AB, BB, quiet, message, missing)   src/CreateASCIInospace.cpp:17-164
 // The text is tokenised on the device in pieces of whole lines; *ok mirrors the reference's bool.
@@ -1352,25 +1366,172 @@ static int create_ascii_nospace(const char* fname, const char* asciifname, const
     {   // :129-157  echo of the first lines (printed whatever `quiet` says)
         const int nrowsp = dims[0] < 5 ? (int)dims[0] : 5, ncolsp = L < 12 ? (int)L : 12;
         say(message, mctx, " First %d lines and %d columns of the marker text  file. ", nrowsp, ncolsp);
-        size_t q = 0;
-        std::string tmp;
-        for (int r = 0; r < nrowsp && q < in.size; r++) {
-            const void* nlp = memchr(in.p + q, '\n', in.size - q);
-            const size_t e = nlp ? (size_t)((const uint8_t*)nlp - in.p) : in.size;
-            std::string rowline;
-            size_t c = q;
-            for (int i = 0; i < ncolsp; i++) {
-                while (c < e && host_ws(in.p[c])) c++;
-                size_t t0 = c;
-                while (c < e && !host_ws(in.p[c])) c++;
-                if (c > t0) tmp.assign((const char*)in.p + t0, c - t0);  // a failed extraction leaves tmp as it was
-                rowline += tmp;
-                rowline += " ";
-            }
-            say(message, mctx, "%s", rowline.c_str());
-            q = e + 1;
-        }
+        echo_first_lines(in, nrowsp, ncolsp, message, mctx);
     }
+    *ok = 1;
+    return EG_OK;
+}
+
+// echo of the first lines of the input (CreateASCIInospace.cpp:129-157, CreateASCIInospace_PLINK.cpp:203-236)
+static void echo_first_lines(const TextFile& in, int nrowsp, int ncolsp, eg_message_fn message, void* mctx) {
+    size_t q = 0;
+    std::string tmp;
+    for (int r = 0; r < nrowsp && q < in.size; r++) {
+        const void* nlp = memchr(in.p + q, '\n', in.size - q);
+        const size_t e = nlp ? (size_t)((const uint8_t*)nlp - in.p) : in.size;
+        std::string rowline;
+        size_t c = q;
+        for (int i = 0; i < ncolsp; i++) {
+            while (c < e && host_ws(in.p[c])) c++;
+            size_t t0 = c;
+            while (c < e && !host_ws(in.p[c])) c++;
+            if (c > t0) tmp.assign((const char*)in.p + t0, c - t0);  // a failed extraction leaves tmp as it was
+            rowline += tmp;
+            rowline += " ";
+        }
+        say(message, mctx, "%s", rowline.c_str());
+        q = e + 1;
+    }
+}
+
+// CreateASCIInospace_PLINK(fname, asciifname, dims, quiet, message)            src/CreateASCIInospace_PLINK.cpp:16-248
+// dims = (rows, 6 + 2 * nsnp) of the ped file.  Allele tokens must be single characters (the reference reads the alleles
+// character by character, :88-93, and silently misreads anything else; here that is EG_ERR_FORMAT).
+static int create_ascii_nospace_plink(const char* fname, const char* asciifname, const int64_t* dims, int quiet,
+                                      eg_message_fn message, void* mctx, int* ok) {
+    (void)quiet;
+    *ok = 0;
+    const int64_t ncols = dims[1], nsnp = (ncols - 6) / 2;
+    if (ncols < 8 || ((ncols - 6) & 1)) return set_error(EG_ERR_ARG, "CreateASCIInospace_PLINK: dims[1] must be 6 + 2 * (number of SNPs)");
+    EG_TRY(ensure_init());
+    TextFile in;
+    if (!in.open_ro(fname)) {  // :38-42
+        say(message, mctx, "ERROR: PLINK ped file could not be opened with filename  %s", fname);
+        say(message, mctx, "ERROR: ReadMarkerData has terminated with errors.  ");
+        return EG_OK;
+    }
+    OutFile outf;
+    outf.f = fopen(asciifname, "wb");
+    if (!outf.f) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s for writing", asciifname);
+    const char* envp = getenv("EAGLE_INGEST_PIECE_BYTES");
+    int64_t piece_max = envp ? atoll(envp) : (256LL << 20);
+    if (piece_max < 64) piece_max = 64;
+    cudaStream_t st = g_ctx.stream;
+    DevBuf dtext, dall, dout, dcounts, dprefix, dstat, dstate;
+    PinnedBuf hout;
+    EG_TRY(dstat.alloc(3 * sizeof(uint64_t), "ped status"));
+    EG_TRY(dstate.alloc((size_t)nsnp * 2, "allele state"));
+    size_t text_cap = 0, rows_cap = 0, chunk_cap = 0;
+    int64_t rows_done = 0;
+    bool warned = false;
+    size_t off = 0;
+    while (off < in.size) {
+        size_t end = off + (size_t)piece_max < in.size ? off + (size_t)piece_max : in.size;
+        if (end < in.size) {
+            const void* nlp = memrchr(in.p + off, '\n', end - off);
+            if (nlp) end = (size_t)((const uint8_t*)nlp - in.p) + 1;
+            else {
+                const void* nx = memchr(in.p + end, '\n', in.size - end);
+                end = nx ? (size_t)((const uint8_t*)nx - in.p) + 1 : in.size;
+            }
+        }
+        const int64_t nb = (int64_t)(end - off);
+        const uint8_t* piece = in.p + off;
+        const int64_t nch = eg_tokenise_chunks(nb);
+        if ((size_t)nb + 64 > text_cap) {
+            text_cap = (size_t)nb + 64;
+            EG_TRY(dtext.alloc(text_cap, "ped piece"));
+        }
+        if ((size_t)nch > chunk_cap) {
+            chunk_cap = (size_t)nch;
+            EG_TRY(dcounts.alloc(chunk_cap * 2 * sizeof(uint32_t), "tokeniser counts"));
+            EG_TRY(dprefix.alloc((chunk_cap + 1) * 2 * sizeof(int64_t), "tokeniser prefix"));
+        }
+        EG_CUDA(cudaMemcpyAsync(dtext.p, piece, (size_t)nb, cudaMemcpyHostToDevice, st));
+        EG_TRY(eg_dev_tokenise_scan(dtext.as<uint8_t>(), nb, dcounts.as<uint32_t>(), dprefix.as<int64_t>(), st));
+        int64_t totals[2] = {0, 0};
+        EG_CUDA(cudaMemcpyAsync(totals, dprefix.as<int64_t>() + 2 * nch, sizeof(totals), cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        const int64_t lines = totals[1] + (piece[nb - 1] != '\n' ? 1 : 0);
+        if ((size_t)lines > rows_cap) {
+            rows_cap = (size_t)lines;
+            EG_TRY(dall.alloc(rows_cap * (size_t)nsnp * 2 + 16, "allele characters"));
+            EG_TRY(dout.alloc(rows_cap * (size_t)(nsnp + 1) + 16, "no-space ASCII rows"));
+        }
+        EG_TRY(hout.ensure((size_t)lines * (size_t)(nsnp + 1) + 16, "no-space ASCII rows"));
+        uint64_t h_stat[3] = {UINT64_MAX, UINT64_MAX, UINT64_MAX};  // stage-1 error position, third-allele key, missing key
+        EG_CUDA(cudaMemcpyAsync(dstat.p, h_stat, sizeof(h_stat), cudaMemcpyHostToDevice, st));
+        EG_TRY(eg_dev_ped_alleles(dtext.as<uint8_t>(), nb, dprefix.as<int64_t>(), ncols, dall.as<uint8_t>(), lines, dstat.as<uint64_t>(), st));
+        EG_CUDA(cudaMemcpyAsync(h_stat, dstat.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        int64_t good_rows = lines, bad_cols = -1;
+        if (h_stat[0] != UINT64_MAX) {  // rows before the offending line are still processed, as in the reference
+            const int64_t pos = (int64_t)h_stat[0], cb = eg_tokenise_chunk_bytes();
+            const int64_t ch = (pos >= nb ? nb - 1 : pos) / cb;
+            int64_t pre[2];
+            EG_CUDA(cudaMemcpyAsync(pre, dprefix.as<int64_t>() + 2 * ch, sizeof(pre), cudaMemcpyDeviceToHost, st));
+            EG_CUDA(cudaStreamSynchronize(st));
+            int64_t toks = pre[0], row = pre[1];
+            for (int64_t q = ch * cb; q < pos; q++) {
+                if (piece[q] == '\n') row++;
+                else if (!host_ws(piece[q]) && (q == 0 || host_ws(piece[q - 1]))) toks++;
+            }
+            if (!(pos >= nb || piece[pos] == '\n')) {
+                int64_t e = pos;
+                while (e < nb && !host_ws(piece[e])) e++;
+                return set_error(EG_ERR_FORMAT, "PLINK ped file: allele \"%.*s\" in row %lld is not a single character", (int)(e - pos),
+                                 (const char*)piece + pos, (long long)(rows_done + row + 1));
+            }
+            good_rows = row;
+            bad_cols = toks - row * ncols;
+        }
+        EG_TRY(eg_dev_ped_genotypes(dall.as<uint8_t>(), good_rows, nsnp, rows_done == 0 ? 1 : 0, rows_done, dstate.as<uint8_t>(),
+                                    dout.as<uint8_t>(), dstat.as<uint64_t>() + 1, st));
+        EG_CUDA(cudaMemcpyAsync(h_stat + 1, dstat.as<uint64_t>() + 1, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        const bool third = h_stat[1] != UINT64_MAX;
+        if (!warned && h_stat[2] != UINT64_MAX && (!third || h_stat[2] < h_stat[1])) {  // :119-129, printed once
+            warned = true;
+            say(message, mctx, "\n");
+            say(message, mctx, " Warning:  PLINK file contains missing alleles (i.e. 0 or - ) ");
+            say(message, mctx, "           These missing genotypes should be imputed before running Eagle.");
+            say(message, mctx, "           As an approximation, AMpus has set these missing genotypes to heterozygotes. ");
+            say(message, mctx, "           Since Eagle assumes an additive model, heterozygote genotypes do not contribute to the estimation of ");
+            say(message, mctx, "           the additive effects.  ");
+            say(message, mctx, "\n");
+        }
+        if (third) good_rows = (int64_t)(h_stat[1] / (uint64_t)nsnp) - rows_done;
+        const size_t wbytes = (size_t)good_rows * (size_t)(nsnp + 1);
+        if (wbytes) {
+            EG_CUDA(cudaMemcpyAsync(hout.p, dout.p, wbytes, cudaMemcpyDeviceToHost, st));
+            EG_CUDA(cudaStreamSynchronize(st));
+            if (fwrite(hout.p, 1, wbytes, outf.f) != wbytes) return set_error(EG_ERR_OPEN, "short write to %s", asciifname);
+        }
+        if (third) {  // :161-167
+            say(message, mctx, "\n");
+            say(message, mctx, "Error:  PLINK file cannot contain more than two alleles at a locus.");
+            say(message, mctx, "        The error has occurred at snp locus %lld for individual %lld", (long long)(h_stat[1] % (uint64_t)nsnp) + 1,
+                (long long)(h_stat[1] / (uint64_t)nsnp) + 1);
+            say(message, mctx, "\n");
+            say(message, mctx, " ReadMarkerData has terminated with errors");
+            return EG_OK;
+        }
+        if (bad_cols >= 0) {  // :69-76
+            say(message, mctx, "\n");
+            say(message, mctx, "Error:  PLINK file contains an unequal number of columns per row.  ");
+            say(message, mctx, "        The error has occurred at row %lld which contains %lld but ", (long long)(rows_done + good_rows + 1), (long long)bad_cols);
+            say(message, mctx, "        it should contain %lld columns of data. ", (long long)ncols);
+            say(message, mctx, "\n");
+            say(message, mctx, " ReadMarkerData has terminated with errors");
+            return EG_OK;
+        }
+        rows_done += lines;
+        off = end;
+    }
+    if (fflush(outf.f) != 0) return set_error(EG_ERR_OPEN, "short write to %s", asciifname);
+    const int nrowsp = dims[0] < 5 ? (int)dims[0] : 5, ncolsp = ncols < 25 ? (int)ncols : 24;  // :209-214
+    say(message, mctx, " First %d lines and %d columns of the PLINK ped file. ", nrowsp, ncolsp);
+    echo_first_lines(in, nrowsp, ncolsp, message, mctx);
     *ok = 1;
     return EG_OK;
 }
@@ -1382,9 +1543,8 @@ extern "C" int eg_createM_ASCII_rcpp(const char* f_name, const char* f_name_asci
     (void)max_memory_in_Gbytes;  // both branches of the reference call the same line-by-line routine (createM_ASCII_rcpp.cpp:88-96)
     if (!f_name || !f_name_ascii || !type || !AA || !AB || !BB || !missing || !dims || !ok)
         return set_error(EG_ERR_ARG, "createM_ASCII_rcpp: null argument");
-    if (strcmp(type, "PLINK") == 0)
-        return set_error(EG_ERR_ARG, "createM_ASCII_rcpp: PLINK ped files are converted by the package's own CPU routine "
-                                     "(CreateASCIInospace_PLINK); only text files are tokenised on the GPU");
+    if (strcmp(type, "PLINK") == 0)  // :71-78
+        return create_ascii_nospace_plink(f_name, f_name_ascii, dims, quiet, message, message_ctx, ok);
     if (!quiet) say(message, message_ctx, " A text file is being assumed as the input data file type. ");  // :85-86
     return create_ascii_nospace(f_name, f_name_ascii, dims, AA, AB, BB, quiet, message, message_ctx, missing, ok);
 }

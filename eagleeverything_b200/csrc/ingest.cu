@@ -281,6 +281,128 @@ __global__ void __launch_bounds__(TK_THREADS) tok_emit_kernel(const uint8_t* __r
     }
 }
 
+// ------------------------------------------------------------------ PLINK ped files (src/CreateASCIInospace_PLINK.cpp:16-248)
+// A ped line is 6 leading fields and two allele characters per SNP.  The reference checks the token count of the line
+// against dims[1] (:64-76), skips six tokens and then reads dims[1] - 6 single non-blank CHARACTERS (:88-93); with
+// one-character allele tokens -- the only kind it reads correctly -- character k of the line is token 6 + k.  Stage 1
+// (ped_emit_kernel, the tokeniser's scans again) therefore gathers token 6 + k of every row into a dense rows x 2*nsnp
+// byte matrix, offset (tokens before) - 6 * (newlines before + 1), and reports the first line with a wrong token count
+// or a multi-character allele token.  Stage 2 (ped_genotype_kernel) is the reference's per-SNP state machine (:99-196):
+// the two alleles seen so far are per-column state carried down the rows, so one thread owns one SNP and walks the rows
+// (reads and writes coalesced across the threads of a warp); columns are independent, and the sequential loop's first
+// error is the smallest (row, snp) key.
+__global__ void __launch_bounds__(TK_THREADS) ped_emit_kernel(const uint8_t* __restrict__ text, int64_t nbytes, int64_t nchunks,
+                                                              const int64_t* __restrict__ prefix, int64_t ncols, uint8_t* __restrict__ out,
+                                                              int64_t out_rows, unsigned long long* __restrict__ err_pos) {
+    __shared__ uint32_t wsum[TK_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t width = ncols - 6;
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        int64_t base_tok = prefix[2 * ch], base_nl = prefix[2 * ch + 1];
+        for (int s = 0; s < TK_STEPS; s++) {
+            const int64_t p0 = ch * TK_CHUNK + (int64_t)s * TK_STEP + threadIdx.x * 16;
+            if (ch * TK_CHUNK + (int64_t)s * TK_STEP >= nbytes) break;  // CTA-uniform
+            uint4 v = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+            uint32_t ws = 0xFFFFu, nl = 0, ts = 0;
+            if (p0 < nbytes) {
+                v = *reinterpret_cast<const uint4*>(text + p0);
+                byte_masks(v, p0, nbytes, ws, nl);
+                ts = token_starts(ws, text, p0);
+            }
+            const uint32_t mine = ((uint32_t)__popc(ts) << 16) | (uint32_t)__popc(nl);
+            uint32_t inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            __syncthreads();
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            uint32_t before = inc - mine, total = 0;
+#pragma unroll
+            for (int w = 0; w < TK_THREADS / 32; w++) {
+                const uint32_t x = wsum[w];
+                if (w < warp) before += x;
+                total += x;
+            }
+            int64_t t = base_tok + (before >> 16), r = base_nl + (before & 0xFFFFu);
+            const bool single15 = (ts & 0x8000u) && (p0 + 16 >= nbytes || is_ws(text[p0 + 16]));
+            const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            uint32_t ev = ts | nl;
+            while (ev) {
+                const int i = __ffs(ev) - 1;
+                ev &= ev - 1;
+                if ((nl >> i) & 1u) {
+                    if (t != (r + 1) * ncols) atomicMin(err_pos, (unsigned long long)(p0 + i));
+                    r++;
+                } else {
+                    const int64_t col = t - r * ncols;
+                    if (col >= 6 && col < ncols && r < out_rows) {
+                        const bool single = (i < 15) ? ((ws >> (i + 1)) & 1u) : single15;
+                        if (!single) atomicMin(err_pos, (unsigned long long)(p0 + i));
+                        out[r * width + (col - 6)] = (uint8_t)(((i < 8 ? lo : hi) >> (8 * (i & 7))) & 0xFFu);
+                    }
+                    t++;
+                }
+            }
+            if (p0 < nbytes && nbytes <= p0 + 16 && text[nbytes - 1] != '\n') {
+                if (t != (r + 1) * ncols) atomicMin(err_pos, (unsigned long long)nbytes);
+            }
+            base_tok += (total >> 16);
+            base_nl += (total & 0xFFFFu);
+        }
+    }
+}
+
+// alleles: rows x 2*nsnp characters.  state: 2*nsnp bytes (alleles0, alleles1 per SNP), carried between pieces of a file.
+// keys[0]: smallest (row_base + row) * nsnp + snp with a third allele; keys[1]: the same for the first missing allele.
+__global__ void __launch_bounds__(256) ped_genotype_kernel(const uint8_t* __restrict__ alleles, int64_t rows, int64_t nsnp,
+                                                           int first_piece, int64_t row_base, uint8_t* __restrict__ state,
+                                                           uint8_t* __restrict__ out, unsigned long long* __restrict__ keys) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nsnp; i += (int64_t)gridDim.x * 256) {
+        uint8_t a0 = 'I', a1 = 'I';
+        if (!first_piece) { a0 = state[2 * i]; a1 = state[2 * i + 1]; }
+        bool warned = false;
+        for (int64_t r = 0; r < rows; r++) {
+            const uchar2 ab = *reinterpret_cast<const uchar2*>(alleles + (r * nsnp + i) * 2);
+            uint8_t a = ab.x, b = ab.y;
+            const bool miss = a == '0' || b == '0' || a == '-' || b == '-';
+            if (first_piece && r == 0) {  // :99-111
+                a0 = miss ? (uint8_t)'I' : a;
+                a1 = miss ? (uint8_t)'I' : b;
+            }
+            if (miss) {  // :118-133
+                if (!warned) atomicMin(&keys[1], (unsigned long long)((row_base + r) * nsnp + i));
+                warned = true;
+                a = b = 'I';
+            }
+            bool bad = false;
+#pragma unroll
+            for (int j = 1; j >= 0; --j) {  // :137-172, second allele first
+                const uint8_t x = j ? b : a;
+                if (x != a0 && x != a1 && x != 'I') {
+                    if (a0 == 'I') a0 = x;
+                    else if (a1 == 'I') a1 = x;
+                    else if (a0 == a1) a1 = x;
+                    else bad = true;
+                }
+                if (bad) break;
+            }
+            if (bad) {
+                atomicMin(&keys[0], (unsigned long long)((row_base + r) * nsnp + i));
+                break;
+            }
+            uint8_t g = '1';  // :177-190
+            if (a != 'I' && b != 'I' && a == b) g = (a == a0) ? '0' : '2';
+            out[r * (nsnp + 1) + i] = g;
+            if (i == 0) out[r * (nsnp + 1) + nsnp] = '\n';
+        }
+        state[2 * i] = a0;
+        state[2 * i + 1] = a1;
+    }
+}
+
 // ------------------------------------------------------------------ store -> no-space ASCII rows
 // rows [row0, row0 + nrows) of a row-major store; out: nrows * (cols + 1) bytes, 16-byte aligned base.
 __global__ void __launch_bounds__(256) encode_ascii_kernel(const int8_t* __restrict__ store, int64_t pitch, int64_t cols, int64_t row0,
@@ -376,4 +498,31 @@ extern "C" int eg_dev_encode_ascii(const int8_t* d_store, int64_t pitch, int64_t
     const int64_t nvec = (nrows * (cols + 1) + 15) / 16, nb = (nvec + 255) / 256, cap = (int64_t)num_sms() * 16;
     encode_ascii_kernel<<<(unsigned)(nb < cap ? nb : cap), 256, 0, (cudaStream_t)stream>>>(d_store, pitch, cols, row0, nrows, d_out);
     return check_launch("encode_ascii_kernel");
+}
+
+// PLINK ped, stage 1: token 6 + k of every line -> d_alleles[row * (ncols - 6) + k] (ncols = 6 + 2 * nsnp tokens per line).
+// d_prefix from eg_dev_tokenise_scan.  *d_err_pos as in eg_dev_tokenise_emit: the '\n' closing a line whose token count is
+// not ncols, or the start of an allele token longer than one character.
+extern "C" int eg_dev_ped_alleles(const uint8_t* d_text, int64_t nbytes, const int64_t* d_prefix, int64_t ncols, uint8_t* d_alleles,
+                                  int64_t out_rows, uint64_t* d_err_pos, void* stream) {
+    if (!d_text || !d_prefix || !d_alleles || !d_err_pos || nbytes <= 0 || ncols <= 6 || ((ncols - 6) & 1) || out_rows < 0 ||
+        ((uintptr_t)d_text & 15))
+        return set_error(EG_ERR_ARG, "eg_dev_ped_alleles: bad argument");
+    const int64_t nch = eg_tokenise_chunks(nbytes), cap = (int64_t)num_sms() * 8;
+    ped_emit_kernel<<<(unsigned)(nch < cap ? nch : cap), TK_THREADS, 0, (cudaStream_t)stream>>>(
+        d_text, nbytes, nch, d_prefix, ncols, d_alleles, out_rows, reinterpret_cast<unsigned long long*>(d_err_pos));
+    return check_launch("ped_emit_kernel");
+}
+// PLINK ped, stage 2: rows x 2*nsnp allele characters -> rows x (nsnp + 1) no-space ASCII.  d_state: 2*nsnp bytes, written
+// when first_piece != 0 and carried to the next piece otherwise.  d_keys: 2 x uint64, set to UINT64_MAX by the caller:
+// [0] smallest (row_base + row) * nsnp + snp where a third allele appears, [1] the same for the first missing allele.
+extern "C" int eg_dev_ped_genotypes(const uint8_t* d_alleles, int64_t rows, int64_t nsnp, int first_piece, int64_t row_base,
+                                    uint8_t* d_state, uint8_t* d_out, uint64_t* d_keys, void* stream) {
+    if (!d_alleles || !d_state || !d_out || !d_keys || rows < 0 || nsnp <= 0 || ((uintptr_t)d_alleles & 1))
+        return set_error(EG_ERR_ARG, "eg_dev_ped_genotypes: bad argument");
+    if (rows == 0) return EG_OK;
+    const int64_t nb = (nsnp + 255) / 256, cap = (int64_t)num_sms() * 8;
+    ped_genotype_kernel<<<(unsigned)(nb < cap ? nb : cap), 256, 0, (cudaStream_t)stream>>>(
+        d_alleles, rows, nsnp, first_piece, row_base, d_state, d_out, reinterpret_cast<unsigned long long*>(d_keys));
+    return check_launch("ped_genotype_kernel");
 }

@@ -87,7 +87,12 @@ int eg_extract_geno_rcpp(const char* f_name_ascii, double max_memory_in_Gbytes, 
  * Whitespace-separated genotype text -> the no-space ASCII file, tokenised on the device (csrc/ingest.cu).  *ok is the
  * reference's bool: 0 after the reference's messages for an unreadable input, a token that is none of BB / AB / AA /
  * missing, or a row whose token count is not dims[1] (rows before the offending one have been written, as in the
- * reference).  type "PLINK" is refused with EG_ERR_ARG: ped files stay with the package's CPU routine. */
+ * reference).
+ * type "PLINK": src/CreateASCIInospace_PLINK.cpp:16-248, dims = (rows, 6 + 2 * nsnp) of the ped file; the per-SNP allele
+ * state machine runs on the device too.  *ok = 0 after the reference's messages for a line with a wrong token count or a
+ * third allele at a locus; missing alleles ('0', '-') become heterozygotes with the reference's warning.  One deviation:
+ * allele tokens longer than one character, which the reference misreads character by character (:88-93), are
+ * EG_ERR_FORMAT. */
 int eg_createM_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const char* type, const char* AA, const char* AB,
                           const char* BB, double max_memory_in_Gbytes, const int64_t* dims, int quiet,
                           eg_message_fn message, void* message_ctx, const char* missing, int* ok);
@@ -226,6 +231,16 @@ int eg_dev_tokenise_scan(const uint8_t* d_text, int64_t nbytes, uint32_t* d_coun
 int eg_dev_tokenise_emit(const uint8_t* d_text, int64_t nbytes, const int64_t* d_prefix, int64_t cols, const char* AA,
                          const char* AB, const char* BB, const char* missing, uint8_t* d_out, int64_t out_rows,
                          uint64_t* d_err_pos, void* stream);
+/* PLINK ped files (CreateASCIInospace_PLINK.cpp:78-196) in two stages.  _alleles: token 6 + k of every line (ncols = 6 +
+ * 2 * nsnp tokens per line) -> d_alleles[row * (ncols - 6) + k]; *d_err_pos as above (a line whose token count is not
+ * ncols, or an allele token longer than one character).  _genotypes: the per-SNP allele state machine over `rows` rows ->
+ * rows * (nsnp + 1) bytes of no-space ASCII; d_state = 2 * nsnp bytes carried between the pieces of a file (first_piece
+ * != 0 initialises it from row 0); d_keys = 2 x uint64 set to UINT64_MAX by the caller: [0] the smallest
+ * (row_base + row) * nsnp + snp at which a third allele appears, [1] the same for the first missing allele. */
+int eg_dev_ped_alleles(const uint8_t* d_text, int64_t nbytes, const int64_t* d_prefix, int64_t ncols, uint8_t* d_alleles,
+                       int64_t out_rows, uint64_t* d_err_pos, void* stream);
+int eg_dev_ped_genotypes(const uint8_t* d_alleles, int64_t rows, int64_t nsnp, int first_piece, int64_t row_base,
+                         uint8_t* d_state, uint8_t* d_out, uint64_t* d_keys, void* stream);
 /* Rows [row0, row0 + nrows) of a row-major int8 store as no-space ASCII ('0' + code, '\n' after each row):
  * nrows * (cols + 1) bytes at d_out (16-byte aligned).  The writer of createMt_ASCII_rcpp.cpp:104-118. */
 int eg_dev_encode_ascii(const int8_t* d_store, int64_t pitch, int64_t cols, int64_t row0, int64_t nrows, uint8_t* d_out,

@@ -518,15 +518,147 @@ static int eo_CreateASCIInospace(const char *fname, const char *asciifname, cons
     return rc;
 }
 
-/* createM_ASCII_rcpp (src/createM_ASCII_rcpp.cpp:19-106), text files only: type "PLINK" (CreateASCIInospace_PLINK.cpp) is
- * not restated here, the compiled reference (oracle/_ref) covers it. */
+/* CreateASCIInospace_PLINK (src/CreateASCIInospace_PLINK.cpp:16-248).  dims = (rows, 6 + 2 * nsnp). */
+static int eo_CreateASCIInospace_PLINK(const char *fname, const char *asciifname, const long *dims, int quiet,
+                                       char *msgbuf, long msgcap, int *ok)
+{
+    (void)quiet;
+    *ok = 0;
+    const long n_of_cols_in_geno = (long)((dims[1] - 6) / 2.0); /* :20 */
+    FILE *in = fopen(fname, "r");
+    if (!in) { /* :38-42 */
+        eo_msg(msgbuf, msgcap, "ERROR: PLINK ped file could not be opened with filename  %s", fname);
+        eo_msg(msgbuf, msgcap, "ERROR: ReadMarkerData has terminated with errors.  ");
+        return EO_OK;
+    }
+    FILE *out = fopen(asciifname, "w");
+    if (!out) { fclose(in); return EO_ERR_OPEN; }
+    long nrv = dims[1] - 6 > 0 ? dims[1] - 6 : 0;
+    char *alleles0 = (char *)malloc((size_t)n_of_cols_in_geno + 1), *alleles1 = (char *)malloc((size_t)n_of_cols_in_geno + 1);
+    char *rowvec = (char *)calloc((size_t)nrv + 1, 1), *rowinfile = (char *)malloc((size_t)n_of_cols_in_geno + 2);
+    char *line = NULL;
+    size_t cap = 0;
+    ssize_t len;
+    long counter = 0;
+    int printOnlyOnce = 0, failed = 0;
+    while (!failed && (len = getline(&line, &cap, in)) >= 0) { /* :55 */
+        if (len > 0 && line[len - 1] == '\n') len--;
+        memset(rowinfile, '0', (size_t)n_of_cols_in_geno);
+        long numcols = 0; /* :64-67 number of whitespace-separated tokens */
+        ssize_t p = 0;
+        for (;;) {
+            while (p < len && eo_isspace((unsigned char)line[p])) p++;
+            if (p >= len) break;
+            while (p < len && !eo_isspace((unsigned char)line[p])) p++;
+            numcols++;
+        }
+        if (numcols != dims[1]) { /* :69-76 */
+            eo_msg(msgbuf, msgcap, "\n");
+            eo_msg(msgbuf, msgcap, "Error:  PLINK file contains an unequal number of columns per row.  ");
+            eo_msg(msgbuf, msgcap, "        The error has occurred at row %ld which contains %ld but ", counter + 1, numcols);
+            eo_msg(msgbuf, msgcap, "        it should contain %ld columns of data. ", dims[1]);
+            eo_msg(msgbuf, msgcap, "\n");
+            eo_msg(msgbuf, msgcap, " ReadMarkerData has terminated with errors");
+            failed = 1;
+            break;
+        }
+        p = 0;
+        for (int i = 0; i <= 5; i++) { /* :87-89 six string extractions */
+            while (p < len && eo_isspace((unsigned char)line[p])) p++;
+            while (p < len && !eo_isspace((unsigned char)line[p])) p++;
+        }
+        for (long i = 6; i < dims[1]; i++) { /* :90-92  operator>>(char&): ONE non-blank character each */
+            while (p < len && eo_isspace((unsigned char)line[p])) p++;
+            if (p < len) rowvec[i - 6] = line[p++]; /* a failed extraction leaves the element as it was */
+        }
+        if (counter == 0) { /* :99-111 */
+            for (long i = 0; i < n_of_cols_in_geno; i++) {
+                char a = rowvec[2 * i], b = rowvec[2 * i + 1];
+                if (a == '0' || b == '0' || a == '-' || b == '-') { alleles0[i] = 'I'; alleles1[i] = 'I'; }
+                else { alleles0[i] = a; alleles1[i] = b; }
+            }
+        }
+        for (long i = 0; i < n_of_cols_in_geno && !failed; i++) { /* :115-196 */
+            if (rowvec[2 * i] == '0' || rowvec[2 * i + 1] == '0' || rowvec[2 * i] == '-' || rowvec[2 * i + 1] == '-') {
+                if (printOnlyOnce == 0) { /* :119-129 */
+                    eo_msg(msgbuf, msgcap, "\n");
+                    eo_msg(msgbuf, msgcap, " Warning:  PLINK file contains missing alleles (i.e. 0 or - ) ");
+                    eo_msg(msgbuf, msgcap, "           These missing genotypes should be imputed before running Eagle.");
+                    eo_msg(msgbuf, msgcap, "           As an approximation, AMpus has set these missing genotypes to heterozygotes. ");
+                    eo_msg(msgbuf, msgcap, "           Since Eagle assumes an additive model, heterozygote genotypes do not contribute to the estimation of ");
+                    eo_msg(msgbuf, msgcap, "           the additive effects.  ");
+                    eo_msg(msgbuf, msgcap, "\n");
+                    printOnlyOnce = 1;
+                }
+                rowvec[2 * i] = 'I';
+                rowvec[2 * i + 1] = 'I';
+            }
+            for (int j = 1; j >= 0; --j) { /* :137 second allele first */
+                char x = rowvec[2 * i + j];
+                if (x != alleles0[i] && x != alleles1[i]) {
+                    if (x == 'I') { /* nothing */ }
+                    else if (alleles0[i] == 'I') alleles0[i] = x;
+                    else if (alleles1[i] == 'I') alleles1[i] = x;
+                    else if (alleles0[i] == alleles1[i]) alleles1[i] = x;
+                    else { /* :160-167 */
+                        eo_msg(msgbuf, msgcap, "\n");
+                        eo_msg(msgbuf, msgcap, "Error:  PLINK file cannot contain more than two alleles at a locus.");
+                        eo_msg(msgbuf, msgcap, "        The error has occurred at snp locus %ld for individual %ld", i + 1, counter + 1);
+                        eo_msg(msgbuf, msgcap, "\n");
+                        eo_msg(msgbuf, msgcap, " ReadMarkerData has terminated with errors");
+                        failed = 1;
+                        break;
+                    }
+                }
+                /* :177-190, evaluated in both passes of j; the pass j == 0 decides */
+                if (rowvec[2 * i] == 'I' || rowvec[2 * i + 1] == 'I') rowinfile[i] = '1';
+                else if (rowvec[2 * i + 1] != rowvec[2 * i]) rowinfile[i] = '1';
+                else if (rowvec[2 * i] == alleles0[i]) rowinfile[i] = '0';
+                else rowinfile[i] = '2';
+            }
+        }
+        if (failed) break;
+        fwrite(rowinfile, 1, (size_t)n_of_cols_in_geno, out); /* :198-199 */
+        fputc('\n', out);
+        counter++;
+    }
+    if (!failed) { /* :203-236 */
+        int nrowsp = dims[0] < 5 ? (int)dims[0] : 5, ncolsp = dims[1] < 25 ? (int)dims[1] : 24;
+        eo_msg(msgbuf, msgcap, " First %d lines and %d columns of the PLINK ped file. ", nrowsp, ncolsp);
+        rewind(in);
+        char tmp[256] = "";
+        long c2 = 0;
+        while (c2 < nrowsp && (len = getline(&line, &cap, in)) >= 0) {
+            if (len > 0 && line[len - 1] == '\n') len--;
+            char rowline[8192] = "";
+            ssize_t p = 0;
+            for (int i = 0; i < ncolsp; i++) {
+                while (p < len && eo_isspace((unsigned char)line[p])) p++;
+                ssize_t t0 = p;
+                while (p < len && !eo_isspace((unsigned char)line[p])) p++;
+                if (p > t0) snprintf(tmp, sizeof(tmp), "%.*s", (int)(p - t0), line + t0);
+                strncat(rowline, tmp, sizeof(rowline) - strlen(rowline) - 2);
+                strcat(rowline, " ");
+            }
+            eo_msg(msgbuf, msgcap, "%s", rowline);
+            c2++;
+        }
+        *ok = 1;
+    }
+    free(line); free(alleles0); free(alleles1); free(rowvec); free(rowinfile);
+    fclose(in); fclose(out);
+    return EO_OK;
+}
+
+/* createM_ASCII_rcpp (src/createM_ASCII_rcpp.cpp:19-106) */
 int eo_createM_ASCII(const char *f_name, const char *f_name_ascii, const char *type, const char *AA, const char *AB,
                      const char *BB, double max_memory_in_Gbytes, const long *dims, int quiet, const char *missing,
                      char *msgbuf, long msgcap, int *ok)
 {
     (void)max_memory_in_Gbytes; /* :88-96: both branches call the same routine */
     if (msgbuf && msgcap > 0) msgbuf[0] = 0;
-    if (strcmp(type, "PLINK") == 0) return EO_ERR_SOFT;
+    if (strcmp(type, "PLINK") == 0) /* :71-78 */
+        return eo_CreateASCIInospace_PLINK(f_name, f_name_ascii, dims, quiet, msgbuf, msgcap, ok);
     if (!quiet) eo_msg(msgbuf, msgcap, " A text file is being assumed as the input data file type. "); /* :85-86 */
     return eo_CreateASCIInospace(f_name, f_name_ascii, dims, AA, AB, BB, quiet, missing, msgbuf, msgcap, ok);
 }

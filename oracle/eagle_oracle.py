@@ -183,8 +183,8 @@ def _messages(buf):
 
 
 def createM_ASCII_rcpp(f_name, f_name_ascii, type, AA, AB, BB, max_memory_in_Gbytes, dims, quiet, missing):
-    """createM_ASCII_rcpp.cpp:19-106 + CreateASCIInospace.cpp:17-164 (text files; PLINK only through the compiled
-    reference).  -> (ok, [message, ...]); the no-space ASCII file is written to f_name_ascii."""
+    """createM_ASCII_rcpp.cpp:19-106 + CreateASCIInospace.cpp:17-164 and, for type "PLINK",
+    CreateASCIInospace_PLINK.cpp:16-248.  -> (ok, [message, ...]); the no-space ASCII file is written to f_name_ascii."""
     buf = C.create_string_buffer(1 << 16)
     ok = C.c_int(0)
     e = lambda x: x.encode() if isinstance(x, str) else os.fsencode(x)

@@ -125,6 +125,21 @@ def test_mmt_selected_loci(synth_small):
     assert np.array_equal(api.calculateMMt_rcpp(s["M"], 8, 1, [NA, 5.0], dims), eo.calculateMMt_rcpp(s["M"], 8, 1, [NA], dims))
 
 
+def test_mmt_product_is_kept_with_the_resident_store(synth_small):
+    """SummaryAM calls calculateMMt_rcpp again with the selected loci (R/summary_am.R:142): the repeat reuses the int32
+    product kept with the store (no second contraction) and still equals the oracle for every selection."""
+    s = synth_small
+    dims = (s["n"], s["L"])
+    api.cache_clear()
+    first = api.calculateMMt_rcpp(s["M"], 8, 1, [7.0, 1500.0], dims)   # the first call already carries a selection
+    assert api.last_timing()["syrk_ms"] > 0
+    for sel in ([NA], [7.0, 1500.0], [2.0], [NA]):
+        got = api.calculateMMt_rcpp(s["M"], 8, 1, sel, dims)
+        assert api.last_timing()["syrk_ms"] == 0.0
+        assert np.array_equal(got, eo.calculateMMt_rcpp(s["M"], 8, 1, sel, dims)), sel
+    assert np.array_equal(first, eo.calculateMMt_rcpp(s["M"], 8, 1, [7.0, 1500.0], dims))
+
+
 @pytest.mark.parametrize("n,L", [(1, 1), (1, 200), (2, 127), (3, 128), (129, 129), (128, 4096), (257, 1000),
                                  (300, 5000), (513, 777), (640, 20000)])
 def test_mmt_ragged_sizes(tmp_path, n, L):

@@ -144,7 +144,159 @@ def test_oracle_ingest_matches_reference_code(ingest_cases, tmp_path, demo):
                 assert (len(m1) > 10) == (mem < 1 and not quiet)   # the block situation announces itself
 
 
+# ---------------------------------------------------------------------------------------------------- PLINK ped files
+def write_ped(path, A, sep=" ", final_newline=True, crlf=False):
+    """A: (rows, nsnp, 2) array of single-character alleles; six leading ped fields per line."""
+    lines = []
+    for r in range(A.shape[0]):
+        head = [f"FAM{r // 3}", f"ind{r}", "0", "0", str(1 + r % 2), f"{r * 0.5:.1f}"]
+        lines.append(sep.join(head + [chr(c) for c in A[r].reshape(-1)]) + ("\r" if crlf else ""))
+    with open(path, "wb") as f:
+        f.write(("\n".join(lines) + ("\n" if final_newline else "")).encode())
+
+
+def ped_alleles(rows, nsnp, seed, missing=0.0, mono=0.1):
+    rng = np.random.default_rng(seed)
+    pairs = [(a, b) for a in "ACGT12" for b in "ACGT12" if a != b]
+    A = np.empty((rows, nsnp, 2), np.uint8)
+    for i in range(nsnp):
+        a, b = pairs[int(rng.integers(len(pairs)))]
+        if rng.random() < mono:
+            b = a
+        f = 0.1 + 0.8 * rng.random()
+        A[:, i, :] = np.where(rng.random((rows, 2)) < f, ord(a), ord(b))
+    if missing:
+        m = rng.random((rows, nsnp)) < missing
+        kind = rng.integers(4, size=(rows, nsnp))
+        A[:, :, 0] = np.where(m & (kind != 1), np.where(kind == 3, ord("-"), ord("0")), A[:, :, 0])
+        A[:, :, 1] = np.where(m & (kind != 0), np.where(kind == 3, ord("-"), ord("0")), A[:, :, 1])
+    return A
+
+
+def ped_cases(tmp):
+    out = []
+
+    def add(name, A, ok=True, mutate=None, dims=None, **kw):
+        p = os.path.join(tmp, name + ".ped")
+        write_ped(p, A, **kw)
+        if mutate:
+            b = mutate(bytearray(open(p, "rb").read()))
+            open(p, "wb").write(bytes(b))
+        out.append((name, p, dims or (A.shape[0], 6 + 2 * A.shape[1]), ok))
+
+    def third(A, row, snp, later=()):
+        B = A.copy()
+        B[row, snp, 1] = ord("Z")
+        for (r, s_) in later:
+            B[r, s_, 0] = ord("Y")
+        return B
+
+    A = ped_alleles(31, 211, 1)
+    add("ped_plain", A)
+    add("ped_tabs_crlf", A, sep="\t", crlf=True)
+    add("ped_no_final_newline", A, final_newline=False)
+    add("ped_missing", ped_alleles(31, 211, 2, missing=0.05))
+    first_missing = ped_alleles(17, 64, 3, missing=0.02)
+    first_missing[0, :20, :] = ord("0")                        # the first row initialises the allele table with 'I'
+    first_missing[1, :10, 0] = ord("-")
+    add("ped_first_rows_missing", first_missing)
+    indel = ped_alleles(12, 40, 4)
+    indel[:, 5, :] = np.where(np.random.default_rng(0).random((12, 2)) < 0.5, ord("I"), ord("D"))   # 'I' is the missing mark
+    add("ped_indel_I_allele", indel)
+    add("ped_one_snp", ped_alleles(9, 1, 5))
+    wide = ped_alleles(40, 9000, 6, missing=0.01)              # 36 KB per line: lines span tokeniser chunks
+    add("ped_wide", wide)
+    mono_then_new = ped_alleles(10, 8, 7, mono=1.0)
+    mono_then_new[6:, 3, :] = ord("T") if mono_then_new[0, 3, 0] != ord("T") else ord("G")           # second allele appears late
+    add("ped_late_second_allele", mono_then_new)
+    # ---- failures
+    full = ped_alleles(31, 211, 8, mono=0.0)
+    add("ped_third_allele", third(full, 20, 100, later=[(20, 150), (25, 3)]), ok=False)
+    add("ped_third_allele_row0", third(full, 0, 0), ok=False)          # A B in row 0, then Z: needs a row where both are known
+    add("ped_third_allele_after_missing", third(ped_alleles(31, 211, 9, missing=0.05, mono=0.0), 29, 210), ok=False)
+    add("ped_short_row", full, ok=False, mutate=lambda b: b[:b.index(b"\n", 6000) - 2] + b[b.index(b"\n", 6000):])
+    add("ped_short_row_after_third_allele", third(full, 3, 7), ok=False,
+        mutate=lambda b: b[:b.index(b"\n", 6000) - 2] + b[b.index(b"\n", 6000):])
+    add("ped_third_allele_after_short_row", third(full, 30, 7), ok=False,
+        mutate=lambda b: b[:b.index(b"\n", 6000) - 2] + b[b.index(b"\n", 6000):])
+    add("ped_empty_line", full, ok=False, mutate=lambda b: b[:b.index(b"\n", 3000)] + b"\n" + b[b.index(b"\n", 3000):])
+    add("ped_wrong_dims", full, ok=False, dims=(31, 6 + 2 * 210))
+    return out
+
+
+@pytest.fixture(scope="module")
+def plink_cases(tmp_path_factory):
+    return ped_cases(str(tmp_path_factory.mktemp("ped")))
+
+
+def run_oracle_ped(case, out_path, quiet=False):
+    name, p, dims, ok = case
+    got_ok, msgs = eo.createM_ASCII_rcpp(p, out_path, "PLINK", "", "", "", 8.0, dims, quiet, "")
+    return got_ok, msgs, open(out_path, "rb").read()
+
+
+def test_oracle_plink_known_answers(plink_cases, tmp_path):
+    by = {c[0]: c for c in plink_cases}
+    for case in plink_cases:
+        ok, msgs, data = run_oracle_ped(case, str(tmp_path / "o.ascii"))
+        assert ok == case[3], case[0]
+    # a hand-checked file: SNP 1 A/G, SNP 2 monomorphic then a new allele, SNP 3 with a missing call
+    p = str(tmp_path / "tiny.ped")
+    open(p, "w").write("f i1 0 0 1 0  A A  C C  T T\nf i2 0 0 1 0  A G  C C  0 T\nf i3 0 0 1 0  G G  T T  G G\n")
+    ok, msgs, data = run_oracle_ped(("tiny", p, (3, 12), True), str(tmp_path / "o.ascii"))
+    assert ok and data == b"000\n101\n222\n" and any("missing alleles" in m for m in msgs)
+    ok, msgs, data = run_oracle_ped(by["ped_third_allele"], str(tmp_path / "o.ascii"))
+    assert "        The error has occurred at snp locus 101 for individual 21" in msgs and len(data) == 20 * 212
+    ok, msgs, data = run_oracle_ped(by["ped_short_row_after_third_allele"], str(tmp_path / "o.ascii"))
+    assert "        The error has occurred at snp locus 8 for individual 4" in msgs
+    ok, msgs, data = run_oracle_ped(by["ped_third_allele_after_short_row"], str(tmp_path / "o.ascii"))
+    assert any("unequal number of columns" in m for m in msgs) and not any("more than two alleles" in m for m in msgs)
+
+
+@pytest.mark.skipif(not eo.reference_available(), reason="oracle/_ref/libeagle_ref.so not built")
+def test_oracle_plink_matches_reference_code(plink_cases, tmp_path):
+    for case in plink_cases:
+        mine = run_oracle_ped(case, str(tmp_path / "mine.ascii"))
+        with eo.use_reference():
+            ref = run_oracle_ped(case, str(tmp_path / "ref.ascii"))
+        assert mine == ref, case[0]
+    # multi-character allele tokens: the reference reads them character by character; so does the restatement
+    p = str(tmp_path / "multi.ped")
+    open(p, "w").write("f i1 0 0 1 0 AC G T T\nf i2 0 0 1 0 A C GT T\n")
+    case = ("multi", p, (2, 10), True)
+    mine = run_oracle_ped(case, str(tmp_path / "mine.ascii"))
+    with eo.use_reference():
+        ref = run_oracle_ped(case, str(tmp_path / "ref.ascii"))
+    assert mine == ref
+    mine = eo.createM_ASCII_rcpp(str(tmp_path / "absent.ped"), str(tmp_path / "o"), "PLINK", "", "", "", 8, (2, 10), True, "")
+    with eo.use_reference():
+        ref = eo.createM_ASCII_rcpp(str(tmp_path / "absent.ped"), str(tmp_path / "o"), "PLINK", "", "", "", 8, (2, 10), True, "")
+    assert mine == ref and not mine[0] and len(mine[1]) == 2
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("piece", [None, 40000, 3000])
+def test_gpu_plink_matches_oracle(api, plink_cases, tmp_path, piece, monkeypatch):
+    if piece:
+        monkeypatch.setenv("EAGLE_INGEST_PIECE_BYTES", str(piece))   # the allele table is carried from piece to piece
+    for case in plink_cases:
+        name, p, dims, ok = case
+        ref = run_oracle_ped(case, str(tmp_path / "ref.ascii"))
+        msgs = []
+        got_ok = api.createM_ASCII_rcpp(p, str(tmp_path / "gpu.ascii"), "PLINK", "", "", "", 8.0, dims, True, msgs.append, "")
+        assert got_ok == ref[0] == ok, name
+        assert msgs == ref[1], name
+        assert open(tmp_path / "gpu.ascii", "rb").read() == ref[2], name
+    msgs = []
+    assert api.createM_ASCII_rcpp(str(tmp_path / "absent.ped"), str(tmp_path / "g"), "PLINK", "", "", "", 8, (2, 10), True, msgs.append) is False
+    assert len(msgs) == 2 and msgs[0].startswith("ERROR: PLINK ped file could not be opened")
+    p = str(tmp_path / "multi.ped")
+    open(p, "w").write("f i1 0 0 1 0 A G T T\nf i2 0 0 1 0 A C GT T\n")
+    with pytest.raises(Exception, match="allele \"GT\" in row 2 is not a single character"):
+        api.createM_ASCII_rcpp(p, str(tmp_path / "g"), "PLINK", "", "", "", 8, (2, 10), True, None)
+
+
 @pytest.fixture(scope="module")
 def api():
     from eagleeverything_b200 import api as a
