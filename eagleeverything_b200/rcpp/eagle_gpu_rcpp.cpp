@@ -1,6 +1,7 @@
 // Rcpp glue for libeaglegpu.so -- replaces the BODIES of five files in MyPackage/Eagle/src/
 // (ReadBlock.cpp, calculateMMt_rcpp.cpp, calculate_a_and_vara_rcpp.cpp,
-// calculate_reduced_a_rcpp.cpp, extract_geno_rcpp.cpp).  The exported prototypes are unchanged,
+// calculate_reduced_a_rcpp.cpp, extract_geno_rcpp.cpp) and, optionally, of the two ingest exports
+// (createM_ASCII_rcpp.cpp, createMt_ASCII_rcpp.cpp).  The exported prototypes are unchanged,
 // so RcppExports.cpp / RcppExports.R / NAMESPACE / every R file stay byte-identical and AM(),
 // SummaryAM() etc. run untouched (reference: src/RcppExports.cpp:9, 37, 54, 73, 129 and the
 // registration table :154-170).
@@ -91,6 +92,36 @@ Eigen::VectorXi extract_geno_rcpp(Rcpp::CharacterVector f_name_ascii, double max
     Eigen::VectorXi column_of_genos(dims[0]);
     check(eg_extract_geno_rcpp(fname.c_str(), max_memory_in_Gbytes, selected_locus, d.data(), column_of_genos.data()));
     return column_of_genos;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the two ingest exports ReadMarker() calls (R/ReadMarker.R), same prototypes
+// as src/createM_ASCII_rcpp.cpp:19-29 and src/createMt_ASCII_rcpp.cpp:15-19 (registered with 11 and 7 arguments,
+// RcppExports.cpp:154-170).  Replacing their bodies removes CreateASCIInospace.cpp and CreateASCIInospace_PLINK.cpp
+// from the build as well.
+// ---------------------------------------------------------------------------------------------------
+
+// [[Rcpp::export]]
+bool createM_ASCII_rcpp(Rcpp::CharacterVector f_name, Rcpp::CharacterVector f_name_ascii, Rcpp::CharacterVector type,
+                        std::string AA, std::string AB, std::string BB, double max_memory_in_Gbytes, std::vector<long> dims,
+                        bool quiet, Rcpp::Function message, std::string missing) {
+    std::string fname = Rcpp::as<std::string>(f_name), fascii = Rcpp::as<std::string>(f_name_ascii),
+                ftype = Rcpp::as<std::string>(type);
+    std::vector<int64_t> d = dims64(dims);
+    int ok = 0;
+    check(eg_createM_ASCII_rcpp(fname.c_str(), fascii.c_str(), ftype.c_str(), AA.c_str(), AB.c_str(), BB.c_str(),
+                                max_memory_in_Gbytes, d.data(), quiet, r_message, &message, missing.c_str(), &ok));
+    return ok != 0;  // false after the reference's own messages (bad token, ragged row, third allele, unreadable file)
+}
+
+// [[Rcpp::export]]
+void createMt_ASCII_rcpp(Rcpp::CharacterVector f_name, Rcpp::CharacterVector f_name_ascii, Rcpp::CharacterVector type,
+                         double max_memory_in_Gbytes, std::vector<long> dims, bool quiet, Rcpp::Function message) {
+    std::string fname = Rcpp::as<std::string>(f_name), fascii = Rcpp::as<std::string>(f_name_ascii),
+                ftype = Rcpp::as<std::string>(type);
+    std::vector<int64_t> d = dims64(dims);
+    check(eg_createMt_ASCII_rcpp(fname.c_str(), fascii.c_str(), ftype.c_str(), max_memory_in_Gbytes, d.data(), quiet, r_message,
+                                 &message));
 }
 
 // ---------------------------------------------------------------------------------------------------
