@@ -1,0 +1,298 @@
+"""AM(): the multi-locus forward search that calls the hot path (reference: R/AM.R:260, 395-504).
+
+R is not installed in this image, so the loop an R user runs -- AM() -> emma.REMLE -> calc_extBIC -> find_qtl ->
+calculate_a_and_vara -> which.max -- is mirrored here on top of this package's own mirrors of the Rcpp exports and of
+the R algebra functions (api.py), i.e. on top of libeaglegpu's C ABI: every n x n operation (the three
+eigendecompositions of EMMA, K^1/2 and K^-1/2, H, P, the reduced BLUP and its variance matrix), M.Mt, the genotype
+column extraction and the a / var(a) scan run on the device; what stays on the host is what stays in R when the library
+is dropped into the package -- the loop itself, EMMA's one-dimensional likelihood search over delta on n-vectors
+(R/emma_REMLE.R:44-76, R/emma_MLE.R:34-56, uniroot) and the extended BIC (R/calc_extBIC.R:6-9).
+
+Two things the R code recomputes in every iteration although their input never changes after iteration 1
+(K = MMt/max(MMt) + 0.95 I is fixed: R/AM.R:414-423) are computed once here: eigen(K) inside emma.MLE and
+K^1/2, K^-1/2 inside find_qtl.  Same inputs, same outputs; nothing else is reordered.
+
+Single trait, no Z matrix (Z never reaches find_qtl in the reference snapshot: R/AM.R:450-452, R/find_qtl.R:1-2).
+bench.py --search times this loop at BASELINE config 3; tests/test_am.py checks it against the golden demo results.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+from . import api
+
+NA = api.NA_REAL
+
+
+# ----------------------------------------------------------------------------- genotype back ends
+class FileGeno:
+    """The R route: M.ascii / Mt.ascii on disk, the three Rcpp exports called with the reference's arguments."""
+
+    def __init__(self, asciifileM, asciifileMt, dim_of_ascii_M, availmemGb=8.0, ncpu=1):
+        self.M, self.Mt = asciifileM, asciifileMt
+        self.n, self.L = int(dim_of_ascii_M[0]), int(dim_of_ascii_M[1])
+        self.mem, self.ncpu = availmemGb, ncpu
+
+    def mmt(self, selected0):
+        return api.calculateMMt_rcpp(self.M, self.mem, self.ncpu, selected0, (self.n, self.L), True, None)
+
+    def a_and_vara(self, selected0, S, V, a):
+        r = api.calculate_a_and_vara_rcpp(self.Mt, selected0, S, V, self.mem, (self.L, self.n), a, True, None)
+        return r["a"].reshape(-1), r["vara"].reshape(-1)
+
+    def extract(self, locus0):
+        return api.extract_geno_rcpp(self.M, self.mem, locus0, (self.n, self.L))
+
+
+class ResidentGeno:
+    """Stores already resident in HBM (api.GenotypeStore handles for M and Mt): no files involved."""
+
+    def __init__(self, M_store, Mt_store):
+        i = M_store.info()
+        self.Ms, self.Mts, self.n, self.L = M_store, Mt_store, i["rows"], i["cols"]
+
+    @staticmethod
+    def _idx(selected0):
+        s = np.atleast_1d(np.asarray(selected0, dtype=np.float64))
+        return [] if np.isnan(s[0]) else [int(v) for v in s]
+
+    def mmt(self, selected0):
+        return self.Ms.mmt(self._idx(selected0))
+
+    def a_and_vara(self, selected0, S, V, a):
+        return self.Mts.a_and_vara(S, V, a, self._idx(selected0))
+
+    def extract(self, locus0):
+        return self.Ms.extract_col(locus0)
+
+
+# ----------------------------------------------------------------------------- base-R pieces that stay on the host
+def _uniroot(f, lower, upper, tol=np.finfo(float).eps ** 0.25, maxiter=1000):
+    """uniroot() = R_zeroin2: Brent / Dekker 'zeroin' (Forsythe, Malcolm & Moler; netlib zeroin.c), R's default tol."""
+    a, b = float(lower), float(upper)
+    fa, fb = f(a), f(b)
+    c, fc = a, fa
+    eps = np.finfo(float).eps
+    if fa == 0.0:
+        return a
+    if fb == 0.0:
+        return b
+    for _ in range(maxiter + 1):
+        prev = b - a
+        if abs(fc) < abs(fb):
+            a, b, c = b, c, b
+            fa, fb, fc = fb, fc, fb
+        tol_act = 2 * eps * abs(b) + tol / 2
+        step = (c - b) / 2
+        if abs(step) <= tol_act or fb == 0.0:
+            return b
+        if abs(prev) >= tol_act and abs(fa) > abs(fb):
+            cb = c - b
+            if a == c:
+                t1 = fb / fa
+                p, q = cb * t1, 1.0 - t1
+            else:
+                q0, t1, t2 = fa / fc, fb / fc, fb / fa
+                p = t2 * (cb * q0 * (q0 - t1) - (b - a) * (t1 - 1.0))
+                q = (q0 - 1.0) * (t1 - 1.0) * (t2 - 1.0)
+            if p > 0:
+                q = -q
+            else:
+                p = -p
+            if p < 0.75 * cb * q - abs(tol_act * q) / 2 and p < abs(prev * q / 2):
+                step = p / q
+        if abs(step) < tol_act:
+            step = tol_act if step > 0 else -tol_act
+        a, fa = b, fb
+        b += step
+        fb = f(b)
+        if (fb > 0 and fc > 0) or (fb < 0 and fc < 0):
+            c, fc = a, fa
+    return b
+
+
+def _lchoose(n, k):
+    return math.lgamma(n + 1) - math.lgamma(k + 1) - math.lgamma(n - k + 1)
+
+
+def _delta_search(dLL, logdelta, llim, ulim, esp, LL, dLLf):
+    """R/emma_REMLE.R:54-76 and R/emma_MLE.R:34-56: boundary candidates, then a root of dLL in every grid cell where
+    it changes sign from + to -; the first maximum of the likelihood among the candidates."""
+    m = len(logdelta)
+    cand, ll = [], []
+    if dLL[0] < esp:
+        cand.append(llim)
+        ll.append(LL(llim))
+    if dLL[m - 2] > 0 - esp:
+        cand.append(ulim)
+        ll.append(LL(ulim))
+    for i in range(m - 1):
+        if dLL[i] * dLL[i + 1] < 0 - esp * esp and dLL[i] > 0 and dLL[i + 1] < 0:
+            r = _uniroot(dLLf, logdelta[i], logdelta[i + 1])
+            cand.append(r)
+            ll.append(LL(r))
+    k = int(np.argmax(ll))
+    return math.exp(cand[k]), ll[k]
+
+
+class _Emma:
+    """emma.REMLE / emma.MLE without Z (R/emma_REMLE.R:27-131, R/emma_MLE.R:2-117): the eigendecompositions on the
+    device (api.emma_eigen_R_wo_Z / emma_eigen_L_wo_Z), the search over delta here."""
+
+    def __init__(self, K, stats):
+        self.K, self.stats = K, stats
+        self._xi = None      # eigen(K): K is fixed after iteration 1
+        self._last = None    # (X id, lam, etasq): REMLE and MLE of one iteration share eigen(S(K+I)S)
+
+    def _eig_R(self, y, X):
+        key = X.shape[1]
+        if self._last is None or self._last[0] != key:
+            t0 = time.perf_counter()
+            r = api.emma_eigen_R_wo_Z(self.K, X)
+            etas = r["vectors"].T @ y
+            self._last = (key, r["values"], etas * etas)
+            self.stats["emma_eigen_s"] += time.perf_counter() - t0
+        return self._last[1], self._last[2]
+
+    def _xi_K(self):
+        if self._xi is None:
+            t0 = time.perf_counter()
+            self._xi = api.emma_eigen_L_wo_Z(self.K, vectors=False)["values"]
+            self.stats["emma_eigen_s"] += time.perf_counter() - t0
+        return self._xi
+
+    @staticmethod
+    def _grid(ngrids, llim, ulim):
+        logdelta = np.arange(ngrids + 1) / ngrids * (ulim - llim) + llim
+        return logdelta, np.exp(logdelta)
+
+    def REMLE(self, y, X, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
+        n, q = len(y), X.shape[1]
+        if np.linalg.det(X.T @ X) == 0:
+            return dict(REML=0.0, delta=0.0, ve=0.0, vg=0.0)
+        lam, etasq = self._eig_R(y, X)
+        logdelta, delta = self._grid(ngrids, llim, ulim)
+        Lam = lam[:, None] + delta[None, :]
+        E = etasq[:, None]
+        dLL = 0.5 * delta * ((n - q) * (E / (Lam * Lam)).sum(0) / (E / Lam).sum(0) - (1.0 / Lam).sum(0))
+        nq = len(etasq)
+
+        def LL(ld):
+            d = math.exp(ld)
+            return 0.5 * (nq * (math.log(nq / (2 * math.pi)) - 1 - math.log((etasq / (lam + d)).sum())) - np.log(lam + d).sum())
+
+        def dLLf(ld):
+            ldel = lam + math.exp(ld)
+            return 0.5 * (nq * (etasq / (ldel * ldel)).sum() / (etasq / ldel).sum() - (1.0 / ldel).sum())
+
+        maxdelta, maxLL = _delta_search(dLL, logdelta, llim, ulim, esp, LL, dLLf)
+        maxva = (etasq / (lam + maxdelta)).sum() / (n - q)
+        return dict(REML=maxLL, delta=maxdelta, ve=maxva * maxdelta, vg=maxva)
+
+    def MLE(self, y, X, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
+        n = len(y)
+        if np.linalg.det(X.T @ X) == 0:
+            return dict(ML=0.0, delta=0.0, ve=0.0, vg=0.0)
+        xi = self._xi_K()
+        lam, etasq = self._eig_R(y, X)
+        logdelta, delta = self._grid(ngrids, llim, ulim)
+        Lam = lam[:, None] + delta[None, :]
+        Xis = xi[:, None] + delta[None, :]
+        E = etasq[:, None]
+        dLL = 0.5 * delta * (n * (E / (Lam * Lam)).sum(0) / (E / Lam).sum(0) - (1.0 / Xis).sum(0))
+        nn = len(xi)
+
+        def LL(ld):
+            d = math.exp(ld)
+            return 0.5 * (nn * (math.log(nn / (2 * math.pi)) - 1 - math.log((etasq / (lam + d)).sum())) - np.log(xi + d).sum())
+
+        def dLLf(ld):
+            d = math.exp(ld)
+            ldel = lam + d
+            return 0.5 * (nn * (etasq / (ldel * ldel)).sum() / (etasq / ldel).sum() - (1.0 / (xi + d)).sum())
+
+        maxdelta, maxLL = _delta_search(dLL, logdelta, llim, ulim, esp, LL, dLLf)
+        maxva = (etasq / (lam + maxdelta)).sum() / n
+        return dict(ML=maxLL, delta=maxdelta, ve=maxva * maxdelta, vg=maxva)
+
+
+# ----------------------------------------------------------------------------- the loop
+def AM(geno, y, X0=None, maxit=20, message=None):
+    """R/AM.R:260, 395-504.  geno: FileGeno or ResidentGeno; y: trait (no NAs); X0: fixed-effects design matrix before
+    any marker (default: the intercept).  -> dict(selected = 1-based loci of the final model, all_picked, extBIC,
+    vc = last variance components, seconds = where the time went)."""
+    say = message or (lambda s: None)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n, L = geno.n, geno.L
+    X = np.ones((n, 1)) if X0 is None else np.asarray(X0, dtype=np.float64).reshape(n, -1)
+    stats = dict(mmt_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0, extract_s=0.0, total_s=0.0)
+    t_all = time.perf_counter()
+    selected = [NA]            # AM.R:260
+    new_locus = NA             # AM.R:261
+    extBIC = []
+    itnum, cont = 1, True
+    K = emma = roots = vc = None
+    while cont:
+        if not math.isnan(new_locus):    # constructX.R:11-20: the picked marker's genotypes join the fixed effects
+            t0 = time.perf_counter()
+            X = np.column_stack([X, np.asarray(geno.extract(int(new_locus) - 1), dtype=np.float64)])
+            stats["extract_s"] += time.perf_counter() - t0
+        if itnum == 1:                   # AM.R:414-423, calcMMt.R:5-13: K = MMt / max(MMt) + 0.95 I
+            t0 = time.perf_counter()
+            MMt = np.asarray(geno.mmt(np.asarray(selected)))
+            K = MMt / MMt.max() + np.diag(np.full(n, 0.95))
+            del MMt
+            stats["mmt_s"] += time.perf_counter() - t0
+            emma = _Emma(K, stats)
+        t0 = time.perf_counter()
+        e0 = stats["emma_eigen_s"]
+        vc = emma.REMLE(y, X)                                                   # AM.R:428
+        ml = emma.MLE(y, X, llim=-100.0, ulim=100.0)                             # calc_extBIC.R:6
+        stats["emma_search_s"] += time.perf_counter() - t0 - (stats["emma_eigen_s"] - e0)
+        bic = -2 * ml["ML"] + (X.shape[1] + 1) * math.log(n)                     # calc_extBIC.R:7-9
+        extBIC.append(bic + 2 * _lchoose(L, X.shape[1] - 1))
+        say(f" iteration {itnum}: extBIC = {extBIC[-1]:.4f}")
+        if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) == len(extBIC) - 1:   # AM.R:448
+            # find_qtl.R:5-83
+            t0 = time.perf_counter()
+            if roots is None:            # calculateMMt_sqrt_and_sqrtinv.R: K is the same in every iteration
+                roots = api.calculateMMt_sqrt_and_sqrtinv(K, message=message)
+                if roots is None:
+                    raise ValueError("M %*% t(M) is not positive definite")
+            H = api.calculateH(K, vc["ve"], vc["vg"], message=message)
+            P = api.calculateP(H, X)
+            del H
+            hat_a = api.calculate_reduced_a(vc["vg"], P, roots["sqrt_MMt"], y).reshape(-1)
+            del P
+            V = api.calculate_reduced_vara(X, vc["ve"], vc["vg"], K, roots["sqrt_MMt"])
+            stats["algebra_s"] += time.perf_counter() - t0
+            t0 = time.perf_counter()
+            sel = np.asarray(selected, dtype=np.float64)
+            if not np.any(np.isnan(sel)):                                        # calculate_a_and_vara.R:23
+                sel = sel - 1
+            a, vara = geno.a_and_vara(sel, roots["inverse_sqrt_MMt"], V, hat_a)
+            del V
+            with np.errstate(divide="ignore", invalid="ignore"):
+                tsq = a * a / vara                                               # find_qtl.R:71
+            new_locus = int(np.flatnonzero(tsq == np.nanmax(tsq))[0]) + 1         # :76-80 first maximum, NaN ignored
+            stats["scan_s"] += time.perf_counter() - t0
+            selected.append(new_locus)                                           # AM.R:455
+            say(f" iteration {itnum}: picked locus {new_locus}")
+        else:
+            cont = False
+        itnum += 1
+        if itnum > maxit:                                                        # AM.R:465
+            cont = False
+    if itnum > maxit:                                                            # AM.R:477-481
+        final = selected
+    elif len(selected) > 1:                                                      # AM.R:485-492
+        final = selected[:-1]
+    else:
+        final = selected
+    stats["total_s"] = time.perf_counter() - t_all
+    return dict(selected=[int(s) for s in final if not math.isnan(s)],
+                all_picked=[int(s) for s in selected if not math.isnan(s)], extBIC=extBIC, vc=vc,
+                iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()})

@@ -1,0 +1,51 @@
+"""The product-side mirror of AM()'s forward search (eagleeverything_b200/am.py; reference R/AM.R:395-504 with
+find_qtl, emma.REMLE / emma.MLE and calc_extBIC) against the golden results of the shipped demo data (SURVEY.md section 4,
+tests/golden/demo.npz) and against the oracle's restated driver on a synthetic set: identical selected-QTL sequence,
+extBIC trace to 1e-8 (EMMA's root search stops at uniroot's 1e-4 tolerance; the eigenvalues come from cuSOLVER here and
+from LAPACK there)."""
+import numpy as np
+import pytest
+
+from eagleeverything_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def am():
+    from eagleeverything_b200 import am as m
+    from eagleeverything_b200 import device
+    device.init(0)
+    return m
+
+
+def test_demo_forward_search_golden(am, demo):
+    z = demo["z"]
+    g = am.FileGeno(demo["M"], demo["Mt"], (demo["n"], demo["L"]))
+    r = am.AM(g, z["trait1"])
+    assert r["selected"] == list(z["am1_selected"]) == [2207, 4503, 873]
+    assert r["all_picked"] == list(z["am1_all_picked"])
+    np.testing.assert_allclose(r["extBIC"], z["am1_extBIC"], rtol=1e-8)
+    X0 = np.column_stack([np.ones(demo["n"]), z["pc1"], z["pc2"]])
+    r2 = am.AM(g, z["trait2"], X0=X0)
+    assert r2["selected"] == list(z["am2_selected"]) and r2["all_picked"] == list(z["am2_all_picked"])
+    np.testing.assert_allclose(r2["extBIC"], z["am2_extBIC"], rtol=1e-8)
+    assert r["seconds"]["total_s"] > 0 and r["iterations"] == len(r["extBIC"])
+
+
+def test_resident_stores_equal_files_and_oracle_driver(am, synth_small):
+    from eagleeverything_b200 import api
+    from oracle import am_driver as oam
+    from oracle import eagle_oracle as eo
+    s = synth_small
+    y, qtl = synth.phenotype(s["G"])
+    ro = oam.AM(eo, s["geno"], y, maxit=6)
+    rf = am.AM(am.FileGeno(s["M"], s["Mt"], (s["n"], s["L"])), y, maxit=6)
+    M = api.GenotypeStore.from_host_ascii(synth.ascii_image(s["G"]), s["n"], s["L"])
+    rr = am.AM(am.ResidentGeno(M, M.transpose()), y, maxit=6)
+    assert rf["all_picked"] == rr["all_picked"] == ro["all_picked"] and rf["selected"] == rr["selected"] == ro["selected"]
+    np.testing.assert_allclose(rf["extBIC"], ro["extBIC"], rtol=1e-8)
+    np.testing.assert_allclose(rr["extBIC"], rf["extBIC"], rtol=1e-12)
+    # maxit reached: every picked locus stays in the model (AM.R:477-481)
+    r2 = am.AM(am.FileGeno(s["M"], s["Mt"], (s["n"], s["L"])), y, maxit=2)
+    assert r2["selected"] == r2["all_picked"] == ro["all_picked"][:2]
