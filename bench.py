@@ -427,6 +427,12 @@ def run_gpu(args):
         else:
             rf.setdefault("traffic", None)
     cpu = None
+    search = None
+    if args.search and world == 1:   # after every per-kernel statistic of the timed step has been read
+        try:
+            search = run_forward_search(args, torch, n, L, img)
+        except Exception as ex:  # noqa: BLE001
+            search = {"note": f"failed: {type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu:
         try:
             cpu = cpu_reference_sample(n, L, budget_s=args.cpu_budget)
@@ -449,7 +455,7 @@ def run_gpu(args):
             "busbw_gbs": 2.0 * (world - 1) / world * 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
             "note": "NCCL int32 sum of the n x n partial M.Mt; measured reference on this pool: 725 GB/s bus bandwidth "
                     "for an 8-rank all-reduce at 1 GiB (B200_PROFILING.md)"}),
-        "gpu_launches": launches, "library_ceilings": ceil,
+        "gpu_launches": launches, "library_ceilings": ceil, "forward_search": search,
         "picked_marker": int(res[1]) if not hasattr(res[1], "item") else int(res[1].item()),
     }
     jprint(out)
@@ -583,6 +589,56 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
             "timing": "host clock around a synchronised region (max with CUDA events), max over ranks"}
 
 
+def run_forward_search(args, torch, n, L, img):
+    """BASELINE config 3 as it is worded: the full multi-locus AM() forward search (<= 10 QTL), through the mirror of the
+    R loop (eagleeverything_b200/am.py) over the host-level C ABI -- stores resident in HBM, every n x n matrix crossing
+    the ABI as a host buffer exactly as R would pass it.  Phenotype: SURVEY.md 8(d), 5 planted QTL."""
+    import numpy as np
+    from eagleeverything_b200 import am, api, synth
+    nbytes = n * (L + 1)
+    img_h = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
+    img_h[:nbytes].copy_(img[:nbytes]); img_h[nbytes:].zero_()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    M = api.GenotypeStore.from_host_ptr(img_h.data_ptr(), n, L)
+    Mt = M.transpose()
+    t_load = time.perf_counter() - t0
+    del img_h
+    qtl = np.linspace(L // 10, L - L // 10 - 1, 5).astype(np.int64)          # synth.phenotype's evenly spaced loci
+    rng = np.random.default_rng(synth.PHENO_SEED)
+    y = 10.0 + rng.standard_normal(n)
+    for b, j in zip([1.0, 0.8, 0.6, 0.5, 0.4], qtl):
+        y = y + b * M.extract_col(int(j)).astype(np.float64)
+    msgs = []
+    r = am.AM(am.ResidentGeno(M, Mt), y, maxit=args.search_maxit, message=msgs.append)
+    M.free(); Mt.free()
+    scans = len(r["all_picked"])
+    # the same search with every n x n matrix resident in HBM (device-level ABI; nothing but vectors crosses PCIe)
+    from eagleeverything_b200 import device
+    resident = None
+    try:
+        kb = device.decode_kb(img, L + 1, n, L)[0]
+        tT = device.transpose_kb(kb, n, L)
+        rr = am.AM_resident(kb, tT, n, L, y, maxit=args.search_maxit)
+        del kb, tT
+        resident = {"iterations": rr["iterations"], "selected_loci_1based": rr["selected"], "all_picked_1based": rr["all_picked"],
+                    "same_sequence_as_host_matrix_route": rr["all_picked"] == r["all_picked"], "seconds": rr["seconds"],
+                    "extBIC_max_rel_diff": float(max(abs(a - b) / abs(b) for a, b in zip(rr["extBIC"], r["extBIC"]))),
+                    "markers_per_s_whole_search": len(rr["all_picked"]) * L / rr["seconds"]["total_s"],
+                    "path": "am.AM_resident: device-level C ABI, K / roots / H / P / V / eigenvectors never leave HBM"}
+    except Exception as ex:  # noqa: BLE001
+        resident = {"note": f"failed: {type(ex).__name__}: {ex}"}
+    return {"workload": f"AM() forward search, n={n}, L={L}, maxit={args.search_maxit}", "iterations": r["iterations"],
+            "selected_loci_1based": r["selected"], "all_picked_1based": r["all_picked"],
+            "planted_qtl_1based": [int(j) + 1 for j in qtl],
+            "planted_recovered": int(sum(1 for j in qtl if int(j) + 1 in r["selected"])),
+            "extBIC": [round(x, 4) for x in r["extBIC"]], "seconds": r["seconds"],
+            "upload_decode_transpose_s": round(t_load, 4), "scans": scans,
+            "markers_per_s_whole_search": scans * L / r["seconds"]["total_s"] if r["seconds"]["total_s"] > 0 else None,
+            "path": "eagleeverything_b200/am.py (mirror of R/AM.R:395-504) over the host-level C ABI; EMMA's 1-D search on the host",
+            "resident": resident}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -593,6 +649,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--search", action="store_true", help="also run the full multi-locus AM() forward search (N=1)")
+    ap.add_argument("--search-maxit", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (shapes that leave no room for its copies)")
     args = ap.parse_args()
     if args.impl == "reference":

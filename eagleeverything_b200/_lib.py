@@ -102,6 +102,7 @@ SIGNATURES = {
     "eg_emma_eigen_R_wo_Z": (C.c_int, [_dp, _dp, _i64, C.c_int, _dp, _dp]),
     "eg_dev_eigen_sym": (C.c_int, [_vp, _i64, _vp, _vp]),
     "eg_dev_emma_SKS": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp]),
+    "eg_dev_emma_eigen_R_wo_Z": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eg_dev_sqrt_and_sqrtinv": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(C.c_int), _dp, _vp]),
     "eg_dev_calculateH": (C.c_int, [_vp, _i64, C.c_double, C.c_double, _vp, _vp]),
     "eg_dev_calculateP": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),

@@ -296,3 +296,121 @@ def AM(geno, y, X0=None, maxit=20, message=None):
     return dict(selected=[int(s) for s in final if not math.isnan(s)],
                 all_picked=[int(s) for s in selected if not math.isnan(s)], extBIC=extBIC, vc=vc,
                 iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()})
+
+
+# ----------------------------------------------------------------------------- everything resident in HBM
+def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None):
+    """The same search with every n x n matrix living in HBM from the first iteration to the last (the B200-first form:
+    nothing but n-vectors, the q-column design matrix and scalars crosses PCIe after the genotypes are resident).
+    store_kb: the K-blocked int8 M store (device.decode_kb), storeT: the row-major Mt store (device.transpose_kb);
+    torch owns the buffers, the device-level C ABI (eg_dev_*) does the work, EMMA's 1-D search stays on the host.
+    Same results as AM() up to the summation order of two matrix-vector products (tests/test_am.py)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib, device
+    lib = _lib.require_gpu()
+    say = message or (lambda s: None)
+    dev = store_kb.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())                                      # noqa: E731
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)             # noqa: E731
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    X = np.ones((n, 1)) if X0 is None else np.asarray(X0, dtype=np.float64).reshape(n, -1)
+    stats = dict(mmt_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0, extract_s=0.0, total_s=0.0)
+
+    def timed(key, t0):
+        torch.cuda.synchronize()
+        stats[key] += time.perf_counter() - t0
+
+    t_all = time.perf_counter()
+    y_d = torch.from_numpy(y).to(dev)
+    K = torch.empty((n, n), **f64)       # column-major n x n buffers; K, its roots and V are symmetric
+    U = torch.empty((n, n), **f64)
+    w1 = torch.empty((n, n), **f64)
+    w2 = torch.empty((n, n), **f64)
+    vals = torch.empty(n, **f64)
+    etas = torch.empty(n, **f64)
+    tmp_n = torch.empty(n, **f64)
+    hat_a = torch.empty(n, **f64)
+    sq = inv = None
+    xi = None
+    selected, new_locus, extBIC = [NA], NA, []
+    itnum, cont, vc = 1, True, None
+    emma = _Emma(None, stats)
+    while cont:
+        if not math.isnan(new_locus):
+            t0 = time.perf_counter()
+            col = device.extract_col(store_kb, n, int(new_locus) - 1, kblocked=True)
+            X = np.column_stack([X, col.cpu().numpy().astype(np.float64)])
+            timed("extract_s", t0)
+        q = X.shape[1]
+        X_d = torch.from_numpy(np.asfortranarray(X).T.copy()).to(dev)          # q x n row-major = n x q column-major
+        small = torch.empty(4 * n * q + 3 * q * q + 16, **f64)
+        if itnum == 1:
+            t0 = time.perf_counter()
+            C32 = device.syrk_kb(store_kb, n, L)
+            device.mmt_finalize(C32, n, out=K)
+            del C32
+            K.div_(K.max())                                                      # calcMMt.R:13  MMt/max(MMt) + 0.95 I
+            K.diagonal().add_(0.95)
+            timed("mmt_s", t0)
+        # ---- emma.REMLE and emma.MLE share eigen(S (K + I) S) of this iteration; eigen(K) is computed once
+        t0 = time.perf_counter()
+        _lib.check(lib.eg_dev_emma_eigen_R_wo_Z(p(K), p(X_d), p(y_d), n, q, p(vals), p(etas), p(U), p(w1), p(w2), p(small), st()))
+        lam = vals[: n - q].cpu().numpy()
+        et = etas[: n - q].cpu().numpy()
+        emma._last = (q, lam, et * et)
+        if xi is None:
+            U.copy_(K)
+            _lib.check(lib.eg_dev_eigen_sym(p(U), n, p(vals), st()))
+            xi = vals.cpu().numpy().copy()
+            emma._xi = xi
+        timed("emma_eigen_s", t0)
+        t0 = time.perf_counter()
+        vc = emma.REMLE(y, X)
+        ml = emma.MLE(y, X, llim=-100.0, ulim=100.0)
+        stats["emma_search_s"] += time.perf_counter() - t0
+        bic = -2 * ml["ML"] + (q + 1) * math.log(n)
+        extBIC.append(bic + 2 * _lchoose(L, q - 1))
+        say(f" iteration {itnum}: extBIC = {extBIC[-1]:.4f}")
+        if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) == len(extBIC) - 1:
+            t0 = time.perf_counter()
+            if sq is None:
+                sq, inv = torch.empty((n, n), **f64), torch.empty((n, n), **f64)
+                not_pd, tr = C.c_int(0), C.c_double(0.0)
+                _lib.check(lib.eg_dev_sqrt_and_sqrtinv(p(K), n, p(sq), p(inv), p(w1), C.byref(not_pd), C.byref(tr), st()))
+                if not_pd.value:
+                    raise ValueError("M %*% t(M) is not positive definite")
+            _lib.check(lib.eg_dev_calculateH(p(K), n, float(vc["ve"]), float(vc["vg"]), p(w1), st()))          # H in w1
+            _lib.check(lib.eg_dev_calculateP(p(w1), p(X_d), n, q, p(w2), p(small), st()))                       # P in w2
+            _lib.check(lib.eg_dev_calculate_reduced_a(float(vc["vg"]), p(w2), p(sq), p(y_d), n, p(tmp_n), p(hat_a), st()))
+            _lib.check(lib.eg_dev_calculate_reduced_vara(p(X_d), q, float(vc["ve"]), float(vc["vg"]), p(sq), n, p(U), p(w1),
+                                                         p(small), st()))                                         # V in U
+            timed("algebra_s", t0)
+            t0 = time.perf_counter()
+            Wp = device.scan_prepare(inv, U, hat_a, n, tmp=w2.view(-1))
+            a, vara = device.scan(storeT, L, n, Wp)
+            best, idx = device.argmax_tsq(a, vara)
+            new_locus = int(idx.item()) + 1
+            del Wp, a, vara
+            timed("scan_s", t0)
+            selected.append(new_locus)
+            say(f" iteration {itnum}: picked locus {new_locus}")
+        else:
+            cont = False
+        itnum += 1
+        if itnum > maxit:
+            cont = False
+    if itnum > maxit:
+        final = selected
+    elif len(selected) > 1:
+        final = selected[:-1]
+    else:
+        final = selected
+    torch.cuda.synchronize()
+    stats["total_s"] = time.perf_counter() - t_all
+    return dict(selected=[int(s) for s in final if not math.isnan(s)],
+                all_picked=[int(s) for s in selected if not math.isnan(s)], extBIC=extBIC, vc=vc,
+                iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()})

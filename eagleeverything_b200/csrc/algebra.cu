@@ -364,6 +364,28 @@ extern "C" int eg_dev_emma_SKS(const double* d_K, const double* d_X, int64_t n, 
     return EG_OK;
 }
 
+// Device-resident emma.eigen.R.wo.Z (R/emma_eigen_R_wo_Z.R:4-20) plus the projection EMMA takes of it: d_U (n x n)
+// receives the eigenvectors of S (K + I) S in its columns (all n; the first n - q are the ones R keeps), d_values[0, n-q)
+// the eigenvalues minus 1, and, when d_y / d_etas are given, d_etas[0, n-q) = U[, 1:(n-q)]^T y (R/emma_REMLE.R:40).
+// d_w1, d_w2: n*n doubles of scratch each; d_small: 2*n*q + 2*q*q doubles.
+extern "C" int eg_dev_emma_eigen_R_wo_Z(const double* d_K, const double* d_X, const double* d_y, int64_t n, int q, double* d_values,
+                                        double* d_etas, double* d_U, double* d_w1, double* d_w2, double* d_small, void* stream) {
+    if (!d_K || !d_X || !d_values || !d_U || !d_w1 || !d_w2 || !d_small || n <= 0 || q <= 0 || q >= n || (!d_y != !d_etas))
+        return set_error(EG_ERR_ARG, "eg_dev_emma_eigen_R_wo_Z: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    EG_TRY(eg_dev_emma_SKS(d_K, d_X, n, q, d_w1, d_w2, d_small, st));  // S in w1, K + I in w2
+    const double one = 1.0, zero = 0.0;
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_w1, (int)n, d_w2, (int)n, &zero, d_U, (int)n));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_U, (int)n, d_w1, (int)n, &zero, d_w2, (int)n));
+    EG_CUDA(cudaMemcpyAsync(d_U, d_w2, (size_t)n * n * 8, cudaMemcpyDeviceToDevice, st));
+    EG_TRY(eg_dev_eigen_sym(d_U, n, d_values, st));
+    add_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_values, n - q, -1.0);
+    EG_TRY(check_launch("add_scalar_kernel"));
+    if (d_y)
+        EG_BLAS(cublasDgemv(ctx_cublas(), CUBLAS_OP_T, (int)n, (int)(n - q), &one, d_U, (int)n, d_y, 1, &zero, d_etas, 1));
+    return EG_OK;
+}
+
 // ================================================================== host level (what an R-facing glue binds)
 namespace {
 struct HostDev {

@@ -279,6 +279,11 @@ int eg_emma_eigen_R_wo_Z(const double* K, const double* X, int64_t n, int q, dou
 int eg_dev_eigen_sym(double* d_A, int64_t n, double* d_values, void* stream);
 int eg_dev_emma_SKS(const double* d_K, const double* d_X, int64_t n, int q, double* d_out, double* d_tmp, double* d_small,
                     void* stream);
+/* emma.eigen.R.wo.Z with everything resident: d_U (n x n) <- eigenvectors of S (K + I) S (R keeps the first n - q),
+ * d_values[0, n-q) <- eigenvalues - 1, and d_etas[0, n-q) <- U[, 1:(n-q)]^T y when d_y / d_etas are given (both or
+ * neither).  d_w1, d_w2: n*n doubles of scratch each; d_small: 2*n*q + 2*q*q doubles. */
+int eg_dev_emma_eigen_R_wo_Z(const double* d_K, const double* d_X, const double* d_y, int64_t n, int q, double* d_values,
+                             double* d_etas, double* d_U, double* d_w1, double* d_w2, double* d_small, void* stream);
 int eg_dev_sqrt_and_sqrtinv(const double* d_K, int64_t n, double* d_sqrt, double* d_invsqrt, double* d_tmp, int* not_pd,
                             double* trace_check, void* stream);
 int eg_dev_calculateH(const double* d_K, int64_t n, double varE, double varG, double* d_H, void* stream);

@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 900 python -m pytest tests/test_am.py -q -m gpu -p no:cacheprovider -x 2>&1 | tail -15

@@ -49,3 +49,32 @@ def test_resident_stores_equal_files_and_oracle_driver(am, synth_small):
     # maxit reached: every picked locus stays in the model (AM.R:477-481)
     r2 = am.AM(am.FileGeno(s["M"], s["Mt"], (s["n"], s["L"])), y, maxit=2)
     assert r2["selected"] == r2["all_picked"] == ro["all_picked"][:2]
+
+
+def test_search_with_everything_resident_in_hbm(am, demo, synth_small):
+    import torch
+    from eagleeverything_b200 import device
+
+    def stores(G):
+        n, L = G.shape
+        img = torch.from_numpy(np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+        kb, err = device.decode_kb(img, L + 1, n, L)
+        assert err[0].item() == 0
+        return kb, device.transpose_kb(kb, n, L)
+
+    z = demo["z"]
+    kb, t = stores(demo["G"])
+    r = am.AM_resident(kb, t, demo["n"], demo["L"], z["trait1"])
+    assert r["selected"] == list(z["am1_selected"]) and r["all_picked"] == list(z["am1_all_picked"])
+    np.testing.assert_allclose(r["extBIC"], z["am1_extBIC"], rtol=1e-8)
+    X0 = np.column_stack([np.ones(demo["n"]), z["pc1"], z["pc2"]])
+    r2 = am.AM_resident(kb, t, demo["n"], demo["L"], z["trait2"], X0=X0)
+    assert r2["selected"] == list(z["am2_selected"]) and r2["all_picked"] == list(z["am2_all_picked"])
+    np.testing.assert_allclose(r2["extBIC"], z["am2_extBIC"], rtol=1e-8)
+    s = synth_small
+    y, _ = synth.phenotype(s["G"])
+    kb, t = stores(s["G"])
+    rr = am.AM_resident(kb, t, s["n"], s["L"], y, maxit=6)
+    rf = am.AM(am.FileGeno(s["M"], s["Mt"], (s["n"], s["L"])), y, maxit=6)
+    assert rr["all_picked"] == rf["all_picked"] and rr["selected"] == rf["selected"]
+    np.testing.assert_allclose(rr["extBIC"], rf["extBIC"], rtol=1e-8)
