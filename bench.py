@@ -9,6 +9,9 @@ A "step" is one pass of the hot path over one synthetic data set of the BASELINE
 `value` = markers/s of the whole job with the ASCII image, S, V and a_hat already resident in HBM;
 `e2e`   = the same through the C ABI with HOST (pinned) buffers, H2D/D2H inside the timed region.
 Markers are sharded over the N ranks (strong scaling: the data set is fixed, L/N markers per GPU).
+`forward_search` (N=1, after the timed region): BASELINE config 3 as it is worded -- the full multi-locus AM() forward
+search (<= 10 QTL, 5 planted) through eagleeverything_b200/am.py; --no-search skips it, --search-host adds the route with
+every n x n matrix crossing the host-level ABI.
 
 --impl reference times the CPU restatement of the reference path (numpy/OpenBLAS, all host threads)
 on a bounded sample of the same workload; it is the only leg that imports oracle/.
@@ -428,7 +431,7 @@ def run_gpu(args):
             rf.setdefault("traffic", None)
     cpu = None
     search = None
-    if args.search and world == 1:   # after every per-kernel statistic of the timed step has been read
+    if world == 1 and not args.no_search and args.workload in ("c2", "c3"):   # after every per-kernel statistic has been read
         try:
             search = run_forward_search(args, torch, n, L, img)
         except Exception as ex:  # noqa: BLE001
@@ -590,53 +593,56 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
 
 
 def run_forward_search(args, torch, n, L, img):
-    """BASELINE config 3 as it is worded: the full multi-locus AM() forward search (<= 10 QTL), through the mirror of the
-    R loop (eagleeverything_b200/am.py) over the host-level C ABI -- stores resident in HBM, every n x n matrix crossing
-    the ABI as a host buffer exactly as R would pass it.  Phenotype: SURVEY.md 8(d), 5 planted QTL."""
+    """BASELINE config 3 as it is worded: the full multi-locus AM() forward search (<= 10 QTL) on the synthetic data set
+    of SURVEY.md 8(d) (5 planted QTL), through the mirror of the R loop in eagleeverything_b200/am.py.  Default: every
+    n x n matrix resident in HBM (am.AM_resident, device-level C ABI).  --search-host adds the route an R session would
+    take today: every matrix crossing the host-level ABI as a host buffer (am.AM over api.*)."""
     import numpy as np
-    from eagleeverything_b200 import am, api, synth
-    nbytes = n * (L + 1)
-    img_h = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
-    img_h[:nbytes].copy_(img[:nbytes]); img_h[nbytes:].zero_()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    M = api.GenotypeStore.from_host_ptr(img_h.data_ptr(), n, L)
-    Mt = M.transpose()
-    t_load = time.perf_counter() - t0
-    del img_h
+    from eagleeverything_b200 import am, api, device, synth
     qtl = np.linspace(L // 10, L - L // 10 - 1, 5).astype(np.int64)          # synth.phenotype's evenly spaced loci
+    t0 = time.perf_counter()
+    kb = device.decode_kb(img, L + 1, n, L)[0]
+    tT = device.transpose_kb(kb, n, L)
+    torch.cuda.synchronize()
+    t_stores = time.perf_counter() - t0
     rng = np.random.default_rng(synth.PHENO_SEED)
     y = 10.0 + rng.standard_normal(n)
     for b, j in zip([1.0, 0.8, 0.6, 0.5, 0.4], qtl):
-        y = y + b * M.extract_col(int(j)).astype(np.float64)
-    msgs = []
-    r = am.AM(am.ResidentGeno(M, Mt), y, maxit=args.search_maxit, message=msgs.append)
-    M.free(); Mt.free()
-    scans = len(r["all_picked"])
-    # the same search with every n x n matrix resident in HBM (device-level ABI; nothing but vectors crosses PCIe)
-    from eagleeverything_b200 import device
-    resident = None
-    try:
-        kb = device.decode_kb(img, L + 1, n, L)[0]
-        tT = device.transpose_kb(kb, n, L)
-        rr = am.AM_resident(kb, tT, n, L, y, maxit=args.search_maxit)
-        del kb, tT
-        resident = {"iterations": rr["iterations"], "selected_loci_1based": rr["selected"], "all_picked_1based": rr["all_picked"],
-                    "same_sequence_as_host_matrix_route": rr["all_picked"] == r["all_picked"], "seconds": rr["seconds"],
-                    "extBIC_max_rel_diff": float(max(abs(a - b) / abs(b) for a, b in zip(rr["extBIC"], r["extBIC"]))),
-                    "markers_per_s_whole_search": len(rr["all_picked"]) * L / rr["seconds"]["total_s"],
-                    "path": "am.AM_resident: device-level C ABI, K / roots / H / P / V / eigenvectors never leave HBM"}
-    except Exception as ex:  # noqa: BLE001
-        resident = {"note": f"failed: {type(ex).__name__}: {ex}"}
-    return {"workload": f"AM() forward search, n={n}, L={L}, maxit={args.search_maxit}", "iterations": r["iterations"],
-            "selected_loci_1based": r["selected"], "all_picked_1based": r["all_picked"],
-            "planted_qtl_1based": [int(j) + 1 for j in qtl],
-            "planted_recovered": int(sum(1 for j in qtl if int(j) + 1 in r["selected"])),
-            "extBIC": [round(x, 4) for x in r["extBIC"]], "seconds": r["seconds"],
-            "upload_decode_transpose_s": round(t_load, 4), "scans": scans,
-            "markers_per_s_whole_search": scans * L / r["seconds"]["total_s"] if r["seconds"]["total_s"] > 0 else None,
-            "path": "eagleeverything_b200/am.py (mirror of R/AM.R:395-504) over the host-level C ABI; EMMA's 1-D search on the host",
-            "resident": resident}
+        y = y + b * device.extract_col(kb, n, int(j), kblocked=True).cpu().numpy().astype(np.float64)
+    rr = am.AM_resident(kb, tT, n, L, y, maxit=args.search_maxit)
+    del kb, tT
+    torch.cuda.empty_cache()
+    out = {"workload": f"AM() forward search, n={n}, L={L}, maxit={args.search_maxit}, 5 planted QTL",
+           "iterations": rr["iterations"], "selected_loci_1based": rr["selected"], "all_picked_1based": rr["all_picked"],
+           "planted_qtl_1based": [int(j) + 1 for j in qtl],
+           "planted_recovered": int(sum(1 for j in qtl if int(j) + 1 in rr["selected"])),
+           "extBIC": [round(x, 4) for x in rr["extBIC"]], "seconds": rr["seconds"],
+           "decode_transpose_s": round(t_stores, 4), "scans": len(rr["all_picked"]),
+           "markers_per_s_whole_search": len(rr["all_picked"]) * L / rr["seconds"]["total_s"],
+           "path": "am.AM_resident (mirror of R/AM.R:395-504): device-level C ABI, K / roots / H / P / V / eigenvectors never "
+                   "leave HBM; EMMA's 1-D likelihood search on the host"}
+    if args.search_host:
+        try:
+            nbytes = n * (L + 1)
+            img_h = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
+            img_h[:nbytes].copy_(img[:nbytes]); img_h[nbytes:].zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            M = api.GenotypeStore.from_host_ptr(img_h.data_ptr(), n, L)
+            Mt = M.transpose()
+            t_load = time.perf_counter() - t0
+            del img_h
+            r = am.AM(am.ResidentGeno(M, Mt), y, maxit=args.search_maxit)
+            M.free(); Mt.free()
+            out["host_matrix_route"] = {
+                "iterations": r["iterations"], "all_picked_1based": r["all_picked"], "seconds": r["seconds"],
+                "upload_decode_transpose_s": round(t_load, 4), "same_sequence": r["all_picked"] == rr["all_picked"],
+                "extBIC_max_rel_diff": float(max(abs(a - b) / abs(b) for a, b in zip(rr["extBIC"], r["extBIC"]))),
+                "markers_per_s_whole_search": len(r["all_picked"]) * L / r["seconds"]["total_s"],
+                "path": "am.AM over the host-level C ABI: every n x n matrix crosses as a (pageable) host buffer, as from R"}
+        except Exception as ex:  # noqa: BLE001
+            out["host_matrix_route"] = {"note": f"failed: {type(ex).__name__}: {ex}"}
+    return out
 
 
 def main():
@@ -649,7 +655,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--search", action="store_true", help="also run the full multi-locus AM() forward search (N=1)")
+    ap.add_argument("--search", action="store_true", help="(default at N=1 for c2 / c3; kept for compatibility)")
+    ap.add_argument("--no-search", action="store_true", help="skip the full multi-locus AM() forward search after the timed step")
+    ap.add_argument("--search-host", action="store_true", help="also run the search with every matrix crossing the host-level ABI")
     ap.add_argument("--search-maxit", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (shapes that leave no room for its copies)")
     args = ap.parse_args()

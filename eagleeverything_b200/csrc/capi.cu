@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -111,14 +113,63 @@ int scan_mode() {
 int launch_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp,
                 const int64_t* d_zero_rows, int n_zero, double* d_a, double* d_vara, cudaStream_t st);
 
-// Stream-ordered allocations from the device's default memory pool (release threshold raised in
-// eg_init): multi-GB buffers are recycled between calls instead of going to the driver every time
-// (cudaMalloc + cudaFree of the stores and workspaces cost ~100 ms per forward step at n=10k x L=1M).
+// Stream-ordered allocations from the device's default memory pool (release threshold raised in eg_init), with an
+// exact-size recycling list on top: every forward step asks for the same handful of multi-GB sizes (two 10 GB stores,
+// n x n workspaces, staging buffers), and handing a freed block straight back to the next request of the same size keeps
+// the driver pool from splitting a 10 GB block for an 800 MB request and then having to map 10 GB of fresh memory for
+// the next store -- measured as random 0.2 - 0.9 s stalls inside eg_store_from_host_ascii / eg_store_a_and_vara
+// (scripts/e2e_probe.py: steps of 540 ms turning into 1,200 - 1,400 ms).  Everything here is ordered on g_ctx.stream.
+struct FreeBlock {
+    void* p;
+    size_t bytes;
+};
+static std::mutex g_pool_mu;
+static std::vector<FreeBlock> g_free_blocks;
+static std::unordered_map<void*, size_t> g_live_blocks;
+static size_t g_free_bytes = 0, g_recycle_limit = 0;
+
+static void pool_flush_locked() {
+    for (auto& b : g_free_blocks) cudaFreeAsync(b.p, g_ctx.stream);
+    g_free_blocks.clear();
+    g_free_bytes = 0;
+}
 static cudaError_t pool_alloc(void** p, size_t bytes) {
-    return cudaMallocAsync(p, bytes ? bytes : 16, g_ctx.stream);
+    if (!bytes) bytes = 16;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_free_blocks.size(); i++)
+        if (g_free_blocks[i].bytes == bytes) {
+            *p = g_free_blocks[i].p;
+            g_free_bytes -= bytes;
+            g_free_blocks.erase(g_free_blocks.begin() + i);
+            g_live_blocks[*p] = bytes;
+            return cudaSuccess;
+        }
+    cudaError_t e = cudaMallocAsync(p, bytes, g_ctx.stream);
+    if (e != cudaSuccess && !g_free_blocks.empty()) {  // make room: give the recycled blocks back and try once more
+        cudaGetLastError();
+        pool_flush_locked();
+        cudaStreamSynchronize(g_ctx.stream);
+        e = cudaMallocAsync(p, bytes, g_ctx.stream);
+    }
+    if (e == cudaSuccess) g_live_blocks[*p] = bytes;
+    return e;
 }
 static void pool_free(void* p) {
-    if (p) cudaFreeAsync(p, g_ctx.stream);
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_live_blocks.find(p);
+    const size_t bytes = it == g_live_blocks.end() ? 0 : it->second;
+    if (it != g_live_blocks.end()) g_live_blocks.erase(it);
+    if (bytes >= ((size_t)1 << 20) && g_free_bytes + bytes <= g_recycle_limit) {
+        g_free_blocks.push_back({p, bytes});
+        g_free_bytes += bytes;
+    } else {
+        cudaFreeAsync(p, g_ctx.stream);
+    }
+}
+static void pool_flush() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    pool_flush_locked();
 }
 
 // RAII device buffer (valid on g_ctx.stream)
@@ -704,6 +755,12 @@ extern "C" int eg_init(int device) {
         uint64_t keep = UINT64_MAX;
         EG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
+    {   // recycle at most half of the device memory (EAGLE_GPU_RECYCLE_GB overrides; 0 switches the list off)
+        size_t free_b = 0, total_b = 0;
+        EG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const char* env = getenv("EAGLE_GPU_RECYCLE_GB");
+        g_recycle_limit = env ? (size_t)(atof(env) * 1e9) : total_b / 2;
+    }
     g_ctx.device = device;
     g_ctx.ready = true;
     return EG_OK;
@@ -716,6 +773,7 @@ extern "C" void eg_cache_clear(void) {
         delete e.store;
     }
     g_ctx.cache.clear();
+    if (g_ctx.ready) pool_flush();
     if (g_ctx.ready) {  // hand the recycled memory back to the driver
         cudaStreamSynchronize(g_ctx.stream);
         cudaMemPool_t pool;

@@ -391,3 +391,26 @@ def test_store_shards_sum_to_full_and_transpose(synth_small, scan_mode):
     xa, xv = rows.a_and_vara(S, V, a)
     assert np.array_equal(xa, ra[1000:2000]) and np.array_equal(xv, rv[1000:2000])
     assert np.array_equal(full.extract_col(77), s["G"][:, 77].astype(np.int32) - 1)
+
+
+def test_recycled_device_buffers_are_reused_and_released(synth_small):
+    """Freed stores go to an exact-size recycling list (capi.cu pool_alloc): the next store of the same shape gets the same
+    block back, and eg_cache_clear hands everything to the driver again."""
+    import torch
+    n, L = 1500, 40000
+    img = synth.ascii_image(synth.genotypes(n, L, seed=3))
+    api.cache_clear()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    a = api.GenotypeStore.from_host_ascii(img, n, L)
+    pa = a.info()["device_ptr"]
+    want = a.mmt()
+    a.free()
+    b = api.GenotypeStore.from_host_ascii(img, n, L)
+    assert b.info()["device_ptr"] == pa
+    assert np.array_equal(b.mmt(), want)                      # a recycled (dirty) block decodes to the same store
+    bt = b.transpose()
+    b.free(); bt.free()
+    api.cache_clear()
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)
