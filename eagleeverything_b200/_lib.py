@@ -47,6 +47,8 @@ SIGNATURES = {
     "eg_createM_ASCII_rcpp": (C.c_int, [C.c_char_p] * 6 + [C.c_double, _lp, C.c_int, MESSAGE_FN, _vp, C.c_char_p,
                                         C.POINTER(C.c_int)]),
     "eg_createMt_ASCII_rcpp": (C.c_int, [C.c_char_p] * 3 + [C.c_double, _lp, C.c_int, MESSAGE_FN, _vp]),
+    "eg_ReshapeM_rcpp": (C.c_int, [C.c_char_p, C.c_char_p, _lp, _i64, _lp, _lp]),
+    "eg_getRowColumn": (C.c_int, [C.c_char_p, _lp]),
     "eg_tokenise_chunks": (_i64, [_i64]),
     "eg_tokenise_chunk_bytes": (_i64, []),
     "eg_dev_tokenise_scan": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),

@@ -128,6 +128,25 @@ def createMt_ASCII_rcpp(f_name, f_name_ascii, type, max_memory_in_Gbytes, dims, 
                                           float(max_memory_in_Gbytes), _dims(dims), int(bool(quiet)), cb, None))
 
 
+def ReshapeM_rcpp(fnameM, fnameMt, indxNA, dims):
+    """ReshapeM_rcpp.cpp:16-117: writes fnameM + "tmp" / fnameMt + "tmp" without the individuals indxNA (0-based, decreasing
+    as R passes them); dims = (n, L).  -> [rows kept, L]."""
+    lib = _lib.require_gpu()
+    idx = np.asarray(list(indxNA), dtype=np.int64)
+    out = (C.c_int64 * 2)()
+    _lib.check(lib.eg_ReshapeM_rcpp(os.fsencode(fnameM), os.fsencode(fnameMt), idx.ctypes.data_as(C.POINTER(C.c_int64)), len(idx),
+                                    _dims(dims), out))
+    return [int(out[0]), int(out[1])]
+
+
+def getRowColumn(fname):
+    """getRowColumn.cpp:19-72 -> [rows, columns] of a marker text file."""
+    lib = _lib.require_gpu()
+    out = (C.c_int64 * 2)()
+    _lib.check(lib.eg_getRowColumn(os.fsencode(fname), out))
+    return [int(out[0]), int(out[1])]
+
+
 # ------------------------------------------------------------------ resident stores (host buffers in, handles out)
 class GenotypeStore:
     """A decoded int8 genotype matrix resident in HBM (eg_store_t)."""

@@ -1593,6 +1593,58 @@ static int create_ascii_nospace_plink(const char* fname, const char* asciifname,
     *ok = 1;
     return EG_OK;
 }
+// A row-major store as a no-space ASCII file: encode in row blocks of ~256 MB, two page-locked buffers, the D2H of block k
+// running while block k-1 is written.
+static int write_store_ascii(const eg_store* T, const char* path) {
+    if (!T->pitch) return set_error(EG_ERR_ARG, "write_store_ascii: needs a row-major store");
+    const int64_t rows = T->rows, cols = T->cols, line = cols + 1;
+    OutFile outf;
+    outf.f = fopen(path, "wb");
+    int rc = outf.f ? EG_OK : set_error(EG_ERR_OPEN, "ERROR: Could not open  %s for writing", path);
+    int64_t block_rows = (256LL << 20) / line;
+    if (block_rows < 1) block_rows = 1;
+    if (block_rows > rows) block_rows = rows;
+    DevBuf denc[2];
+    PinnedBuf henc[2];
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2 && rc == EG_OK; i++) {
+        rc = denc[i].alloc((size_t)block_rows * line + 16, "ASCII rows");
+        if (rc == EG_OK) rc = henc[i].ensure((size_t)block_rows * line + 16, "ASCII rows");
+        if (rc == EG_OK) rc = check_cuda(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    int64_t pending_rows[2] = {0, 0};
+    int k = 0;
+    for (int64_t r = 0; rc == EG_OK && r < rows; r += block_rows, k++) {
+        const int b = k & 1;
+        const int64_t nr = r + block_rows <= rows ? block_rows : rows - r;
+        rc = eg_dev_encode_ascii(T->d, T->pitch, cols, r, nr, denc[b].as<uint8_t>(), g_ctx.stream);
+        if (rc == EG_OK)
+            rc = check_cuda(cudaMemcpyAsync(henc[b].p, denc[b].p, (size_t)nr * line, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H of ASCII rows");
+        if (rc == EG_OK) rc = check_cuda(cudaEventRecord(done[b], g_ctx.stream), "cudaEventRecord");
+        pending_rows[b] = nr;
+        if (rc == EG_OK && k >= 1) {  // write the previous block while this one is in flight
+            const int pb = b ^ 1;
+            rc = check_cuda(cudaEventSynchronize(done[pb]), "ASCII rows");
+            const size_t wb = (size_t)pending_rows[pb] * line;
+            if (rc == EG_OK && fwrite(henc[pb].p, 1, wb, outf.f) != wb) rc = set_error(EG_ERR_OPEN, "short write to %s", path);
+            pending_rows[pb] = 0;
+        }
+    }
+    if (rc == EG_OK && k >= 1) {
+        const int pb = (k - 1) & 1;
+        rc = check_cuda(cudaEventSynchronize(done[pb]), "ASCII rows");
+        const size_t wb = (size_t)pending_rows[pb] * line;
+        if (rc == EG_OK && fwrite(henc[pb].p, 1, wb, outf.f) != wb) rc = set_error(EG_ERR_OPEN, "short write to %s", path);
+    }
+    cudaStreamSynchronize(g_ctx.stream);
+    for (int i = 0; i < 2; i++)
+        if (done[i]) cudaEventDestroy(done[i]);
+    if (outf.f) {
+        if (fclose(outf.f) != 0 && rc == EG_OK) rc = set_error(EG_ERR_OPEN, "short write to %s", path);
+        outf.f = nullptr;
+    }
+    return rc;
+}
 }  // namespace eg
 
 extern "C" int eg_createM_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const char* type, const char* AA, const char* AB,
@@ -1625,53 +1677,7 @@ extern "C" int eg_createMt_ASCII_rcpp(const char* f_name, const char* f_name_asc
     EG_TRY(cached_store(f_name, n, L, true, &M));
     eg_store* Mt = nullptr;
     EG_TRY(eg_store_transpose(M, &Mt));
-    OutFile outf;
-    outf.f = fopen(f_name_ascii, "wb");
-    int rc = outf.f ? EG_OK : set_error(EG_ERR_OPEN, "ERROR: Could not open  %s for writing", f_name_ascii);
-    // encode in row blocks of ~256 MB, two page-locked buffers: the D2H of block k runs while block k-1 is written
-    const int64_t line = n + 1;
-    int64_t block_rows = (256LL << 20) / line;
-    if (block_rows < 1) block_rows = 1;
-    if (block_rows > L) block_rows = L;
-    DevBuf denc[2];
-    PinnedBuf henc[2];
-    cudaEvent_t done[2] = {nullptr, nullptr};
-    for (int i = 0; i < 2 && rc == EG_OK; i++) {
-        rc = denc[i].alloc((size_t)block_rows * line + 16, "ASCII rows");
-        if (rc == EG_OK) rc = henc[i].ensure((size_t)block_rows * line + 16, "ASCII rows");
-        if (rc == EG_OK) rc = check_cuda(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming), "cudaEventCreate");
-    }
-    int64_t pending_rows[2] = {0, 0};
-    int k = 0;
-    for (int64_t r = 0; rc == EG_OK && r < L; r += block_rows, k++) {
-        const int b = k & 1;
-        const int64_t nr = r + block_rows <= L ? block_rows : L - r;
-        rc = eg_dev_encode_ascii(Mt->d, Mt->pitch, n, r, nr, denc[b].as<uint8_t>(), g_ctx.stream);
-        if (rc == EG_OK)
-            rc = check_cuda(cudaMemcpyAsync(henc[b].p, denc[b].p, (size_t)nr * line, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H of Mt.ascii rows");
-        if (rc == EG_OK) rc = check_cuda(cudaEventRecord(done[b], g_ctx.stream), "cudaEventRecord");
-        pending_rows[b] = nr;
-        if (rc == EG_OK && k >= 1) {  // write the previous block while this one is in flight
-            const int pb = b ^ 1;
-            rc = check_cuda(cudaEventSynchronize(done[pb]), "Mt.ascii rows");
-            const size_t wb = (size_t)pending_rows[pb] * line;
-            if (rc == EG_OK && fwrite(henc[pb].p, 1, wb, outf.f) != wb) rc = set_error(EG_ERR_OPEN, "short write to %s", f_name_ascii);
-            pending_rows[pb] = 0;
-        }
-    }
-    if (rc == EG_OK && k >= 1) {
-        const int pb = (k - 1) & 1;
-        rc = check_cuda(cudaEventSynchronize(done[pb]), "Mt.ascii rows");
-        const size_t wb = (size_t)pending_rows[pb] * line;
-        if (rc == EG_OK && fwrite(henc[pb].p, 1, wb, outf.f) != wb) rc = set_error(EG_ERR_OPEN, "short write to %s", f_name_ascii);
-    }
-    cudaStreamSynchronize(g_ctx.stream);
-    for (int i = 0; i < 2; i++)
-        if (done[i]) cudaEventDestroy(done[i]);
-    if (outf.f) {
-        if (fclose(outf.f) != 0 && rc == EG_OK) rc = set_error(EG_ERR_OPEN, "short write to %s", f_name_ascii);
-        outf.f = nullptr;
-    }
+    int rc = write_store_ascii(Mt, f_name_ascii);
     if (rc != EG_OK) {
         eg_store_free(Mt);
         return rc;
@@ -1693,5 +1699,132 @@ extern "C" int eg_createMt_ASCII_rcpp(const char* f_name, const char* f_name_asc
     say(message, message_ctx, " Available memory (gigabytes): %.15g", max_memory_in_Gbytes);
     say(message, message_ctx, "\n\n");
     say(message, message_ctx, " The marker file has been Uploaded");
+    return EG_OK;
+}
+
+// ReshapeM_rcpp(fnameM, fnameMt, indxNA, dims)                                      src/ReshapeM_rcpp.cpp:16-117
+// Writes <fnameM>tmp (M.ascii without the rows listed in indxNA, 0-based) and <fnameMt>tmp (Mt.ascii with those
+// characters erased from every line, one after the other in the order given -- R passes them in decreasing order,
+// R/check_for_NA_in_trait.R:5), returns newdims = (rows kept, line length of M.ascii).  On the device this is a row
+// gather of the resident M store and a column gather of Mt (= its transpose when the two index maps agree); both
+// results are encoded back to ASCII for the files AM() switches to (R/AM.R:353-370) and stay resident under those names.
+extern "C" int eg_ReshapeM_rcpp(const char* fnameM, const char* fnameMt, const int64_t* indxNA, int64_t n_indx, const int64_t* dims,
+                                int64_t* newdims) {
+    if (!fnameM || !fnameMt || !dims || !newdims || n_indx < 0 || (n_indx > 0 && !indxNA))
+        return set_error(EG_ERR_ARG, "ReshapeM_rcpp: null argument");
+    const int64_t n = dims[0], L = dims[1];
+    EG_TRY(ensure_init());
+    struct stat stt;
+    if (stat(fnameM, &stt) != 0) return set_error(EG_ERR_OPEN, "\n\nERROR: Could not open  %s\n\n\n", fnameM);    // :44-47
+    if (stat(fnameMt, &stt) != 0) return set_error(EG_ERR_OPEN, "\n\nERROR: Could not open  %s\n\n\n", fnameMt);  // :86-89
+    // rows of M: a line is dropped when its number equals any entry (:60-64)
+    std::vector<char> drop((size_t)n, 0);
+    for (int64_t i = 0; i < n_indx; i++)
+        if (indxNA[i] >= 0 && indxNA[i] < n) drop[(size_t)indxNA[i]] = 1;
+    std::vector<int64_t> rows_keep;
+    for (int64_t r = 0; r < n; r++)
+        if (!drop[(size_t)r]) rows_keep.push_back(r);
+    // columns of Mt: line.erase(indxNA[ii], 1) one after the other (:104-106); std::string::erase throws beyond the end
+    std::vector<int64_t> cols_keep((size_t)n);
+    for (int64_t c = 0; c < n; c++) cols_keep[(size_t)c] = c;
+    for (int64_t i = 0; i < n_indx; i++) {
+        if (indxNA[i] < 0 || indxNA[i] > (int64_t)cols_keep.size())
+            return set_error(EG_ERR_ARG, "ReshapeM_rcpp: basic_string::erase: position %lld is beyond a line of %zu characters",
+                             (long long)indxNA[i], cols_keep.size());
+        if (indxNA[i] < (int64_t)cols_keep.size()) cols_keep.erase(cols_keep.begin() + indxNA[i]);
+    }
+    if (rows_keep.empty() || cols_keep.empty()) return set_error(EG_ERR_ARG, "ReshapeM_rcpp: no individual left");
+    eg_store* M = nullptr;
+    EG_TRY(cached_store(fnameM, n, L, true, &M));
+    const int64_t n1 = (int64_t)rows_keep.size(), n2 = (int64_t)cols_keep.size();
+    DevBuf dmap;
+    EG_TRY(dmap.alloc((size_t)(n1 > n2 ? n1 : n2) * sizeof(int64_t), "ReshapeM index map"));
+    EG_CUDA(cudaMemcpyAsync(dmap.p, rows_keep.data(), (size_t)n1 * sizeof(int64_t), cudaMemcpyHostToDevice, g_ctx.stream));
+    eg_store *M1 = nullptr, *T1 = nullptr, *Mrm = nullptr, *Mt1 = nullptr;
+    auto cleanup = [&](int rc) {
+        cudaStreamSynchronize(g_ctx.stream);
+        eg_store_free(M1);
+        if (Mt1 != T1) eg_store_free(Mt1);
+        eg_store_free(T1);
+        eg_store_free(Mrm);
+        return rc;
+    };
+    EG_TRY(store_alloc(n1, L, true, &M1));
+    int rc = eg_dev_gather_rows(M->d, n, L, 0, dmap.as<int64_t>(), n1, M1->d, 0, g_ctx.stream);
+    if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "ReshapeM row gather");
+    if (rc == EG_OK) rc = eg_store_transpose(M1, &T1);                       // L x n1, row-major
+    if (rc == EG_OK) rc = eg_store_transpose(T1, &Mrm);                      // n1 x L, row-major: the lines of M.asciitmp
+    if (rc != EG_OK) return cleanup(rc);
+    std::string outM = std::string(fnameM) + "tmp", outMt = std::string(fnameMt) + "tmp";  // :51, :93
+    rc = write_store_ascii(Mrm, outM.c_str());
+    eg_store_free(Mrm);
+    Mrm = nullptr;
+    if (rc != EG_OK) return cleanup(rc);
+    if (rows_keep == cols_keep) {
+        Mt1 = T1;
+    } else {  // an index list that is not decreasing: the erased characters are not the dropped rows
+        eg_store* Mt = nullptr;
+        rc = cached_store(fnameMt, L, n, false, &Mt);
+        if (rc == EG_OK) rc = store_alloc(L, n2, false, &Mt1);
+        if (rc == EG_OK) rc = check_cuda(cudaMemcpyAsync(dmap.p, cols_keep.data(), (size_t)n2 * sizeof(int64_t), cudaMemcpyHostToDevice, g_ctx.stream), "H2D");
+        if (rc == EG_OK) rc = eg_dev_gather_cols(Mt->d, L, Mt->pitch, dmap.as<int64_t>(), n2, Mt1->d, Mt1->pitch, g_ctx.stream);
+        if (rc == EG_OK) rc = check_cuda(cudaStreamSynchronize(g_ctx.stream), "ReshapeM column gather");
+        if (rc != EG_OK) return cleanup(rc);
+    }
+    rc = write_store_ascii(Mt1, outMt.c_str());
+    if (rc != EG_OK) return cleanup(rc);
+    newdims[0] = n1;  // :67
+    newdims[1] = L;   // :71  length of the last line read
+    {   // the reshaped stores are what the following calls on the two new files need
+        std::string key;
+        eg_store* keepT = Mt1;
+        if (cache_key(outMt.c_str(), L, n2, false, key) == EG_OK) cache_insert(key, keepT);
+        else eg_store_free(keepT);
+        if (Mt1 != T1) eg_store_free(T1);
+        if (cache_key(outM.c_str(), n1, L, true, key) == EG_OK) cache_insert(key, M1);
+        else eg_store_free(M1);
+    }
+    return EG_OK;
+}
+
+// getRowColumn(fname)                                                                src/getRowColumn.cpp:19-72
+// dimen[0] = number of lines (an unterminated last line counts), dimen[1] = whitespace-separated tokens of the first
+// line.  The line count is the tokeniser's newline scan over the file in pieces.
+extern "C" int eg_getRowColumn(const char* fname, int64_t* dimen) {
+    if (!fname || !dimen) return set_error(EG_ERR_ARG, "getRowColumn: null argument");
+    EG_TRY(ensure_init());
+    TextFile in;
+    if (!in.open_ro(fname)) return set_error(EG_ERR_OPEN, "\n\n ERROR: Could not open  %s\n\n\n", fname);  // :36-39
+    dimen[0] = dimen[1] = 0;
+    if (in.size == 0) return EG_OK;
+    const char* envp = getenv("EAGLE_INGEST_PIECE_BYTES");
+    int64_t piece_max = envp ? atoll(envp) : (256LL << 20);
+    if (piece_max < 64) piece_max = 64;
+    cudaStream_t st = g_ctx.stream;
+    DevBuf dtext, dcounts, dprefix;
+    const int64_t cap = (int64_t)in.size < piece_max ? (int64_t)in.size : piece_max;
+    const int64_t nch_max = eg_tokenise_chunks(cap);
+    EG_TRY(dtext.alloc((size_t)cap + 64, "text piece"));
+    EG_TRY(dcounts.alloc((size_t)nch_max * 2 * sizeof(uint32_t), "tokeniser counts"));
+    EG_TRY(dprefix.alloc((size_t)(nch_max + 1) * 2 * sizeof(int64_t), "tokeniser prefix"));
+    for (size_t off = 0; off < in.size; off += (size_t)cap) {
+        const int64_t nb = (int64_t)(in.size - off < (size_t)cap ? in.size - off : (size_t)cap);
+        const int64_t nch = eg_tokenise_chunks(nb);
+        EG_CUDA(cudaMemcpyAsync(dtext.p, in.p + off, (size_t)nb, cudaMemcpyHostToDevice, st));
+        EG_TRY(eg_dev_tokenise_scan(dtext.as<uint8_t>(), nb, dcounts.as<uint32_t>(), dprefix.as<int64_t>(), st));
+        int64_t totals[2] = {0, 0};
+        EG_CUDA(cudaMemcpyAsync(totals, dprefix.as<int64_t>() + 2 * nch, sizeof(totals), cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        dimen[0] += totals[1];
+    }
+    if (in.p[in.size - 1] != '\n') dimen[0]++;
+    const void* nlp = memchr(in.p, '\n', in.size);
+    const size_t e = nlp ? (size_t)((const uint8_t*)nlp - in.p) : in.size;
+    for (size_t c = 0; c < e;) {  // :58-65  tokens of the first line
+        while (c < e && host_ws(in.p[c])) c++;
+        if (c >= e) break;
+        while (c < e && !host_ws(in.p[c])) c++;
+        dimen[1]++;
+    }
     return EG_OK;
 }

@@ -124,6 +124,23 @@ void createMt_ASCII_rcpp(Rcpp::CharacterVector f_name, Rcpp::CharacterVector f_n
                                  &message));
 }
 
+// [[Rcpp::export]]
+std::vector<long> ReshapeM_rcpp(Rcpp::CharacterVector fnameM, Rcpp::CharacterVector fnameMt, std::vector<long> indxNA,
+                                std::vector<long> dims) {
+    std::string fM = Rcpp::as<std::string>(fnameM), fMt = Rcpp::as<std::string>(fnameMt);
+    std::vector<int64_t> d = dims64(dims), idx(indxNA.begin(), indxNA.end());
+    int64_t nd[2] = {0, 0};
+    check(eg_ReshapeM_rcpp(fM.c_str(), fMt.c_str(), idx.data(), (int64_t)idx.size(), d.data(), nd));
+    return std::vector<long>{(long)nd[0], (long)nd[1]};
+}
+
+// [[Rcpp::export]]
+std::vector<long> getRowColumn(std::string fname) {
+    int64_t nd[2] = {0, 0};
+    check(eg_getRowColumn(fname.c_str(), nd));
+    return std::vector<long>{(long)nd[0], (long)nd[1]};
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the n x n algebra between two scans.  These are NEW exports (the
 // reference does this work in R: R/calculateMMt_sqrt_and_sqrtinv.R:26-31, R/calculateH.R:36, R/calculateP.R:27-28,

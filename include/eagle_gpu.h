@@ -105,6 +105,18 @@ int eg_createM_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const ch
 int eg_createMt_ASCII_rcpp(const char* f_name, const char* f_name_ascii, const char* type, double max_memory_in_Gbytes,
                            const int64_t* dims, int quiet, eg_message_fn message, void* message_ctx);
 
+/* ReshapeM_rcpp(fnameM, fnameMt, indxNA, dims)                                    src/ReshapeM_rcpp.cpp:16-117
+ * dims = (n, L) of M.ascii; indxNA: 0-based individuals whose trait is NA, in decreasing order as R passes them.  Writes
+ * <fnameM>tmp without those lines and <fnameMt>tmp with those characters erased from every line (erased one after the
+ * other, as the reference does); newdims[0] = lines kept, newdims[1] = L.  A row / column gather of the resident stores
+ * and the ASCII encoder; the reshaped stores stay resident under the two new file names.  A missing file is EG_ERR_OPEN
+ * with the reference's Rcpp::stop text. */
+int eg_ReshapeM_rcpp(const char* fnameM, const char* fnameMt, const int64_t* indxNA, int64_t n_indx, const int64_t* dims,
+                     int64_t* newdims);
+/* getRowColumn(fname)                                                              src/getRowColumn.cpp:19-72
+ * dimen[0] = lines of the file (an unterminated last line counts), dimen[1] = whitespace-separated tokens of line 1. */
+int eg_getRowColumn(const char* fname, int64_t* dimen);
+
 /* ================================================================ resident genotype stores
  * A store is a decoded genotype matrix held in HBM as int8, `rows` x `cols`, holding the NEGATED reference value
  * 1 - code (AA = +1, AB = 0, BB = -1; csrc/decode.cu explains why: power); every entry point that returns genotypes or

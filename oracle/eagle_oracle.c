@@ -733,6 +733,88 @@ int eo_createMt_ASCII(const char *f_name, const char *f_name_ascii, const char *
     return EO_OK;
 }
 
+/* ReshapeM_rcpp (src/ReshapeM_rcpp.cpp:16-117).  indxNA 0-based.  Writes <fnameM>tmp and <fnameMt>tmp. */
+int eo_ReshapeM(const char *fnameM, const char *fnameMt, const long *indxNA, long n_indx, const long *dims, long *newdims)
+{
+    (void)dims;
+    newdims[0] = newdims[1] = 0;
+    FILE *in = fopen(fnameM, "r");
+    if (!in) return EO_ERR_OPEN; /* :44-47 */
+    size_t ln = strlen(fnameM);
+    char *outname = (char *)malloc(ln + 4);
+    memcpy(outname, fnameM, ln); memcpy(outname + ln, "tmp", 4); /* :51 */
+    FILE *out = fopen(outname, "w");
+    free(outname);
+    if (!out) { fclose(in); return EO_ERR_OPEN; }
+    char *line = NULL;
+    size_t cap = 0;
+    ssize_t len;
+    long rownum = 0;
+    while ((len = getline(&line, &cap, in)) >= 0) { /* :58-75 */
+        if (len > 0 && line[len - 1] == '\n') len--;
+        int writeline = 1;
+        for (long ii = 0; ii < n_indx; ii++)
+            if (indxNA[ii] == rownum) writeline = 0;
+        if (writeline) {
+            fwrite(line, 1, (size_t)len, out);
+            fputc('\n', out);
+            newdims[0]++;
+        }
+        rownum++;
+        newdims[1] = (long)len;
+    }
+    fclose(in); fclose(out);
+    in = fopen(fnameMt, "r");
+    if (!in) { free(line); return EO_ERR_OPEN; } /* :86-89 */
+    ln = strlen(fnameMt);
+    outname = (char *)malloc(ln + 4);
+    memcpy(outname, fnameMt, ln); memcpy(outname + ln, "tmp", 4); /* :93 */
+    out = fopen(outname, "w");
+    free(outname);
+    if (!out) { fclose(in); free(line); return EO_ERR_OPEN; }
+    int rc = EO_OK;
+    while (!rc && (len = getline(&line, &cap, in)) >= 0) { /* :99-110 */
+        if (len > 0 && line[len - 1] == '\n') len--;
+        for (long ii = 0; ii < n_indx; ii++) { /* line.erase(indxNA[ii], 1), one after the other */
+            if (indxNA[ii] < 0 || indxNA[ii] > len) { rc = EO_ERR_SHORT; break; } /* std::out_of_range in the reference */
+            if (indxNA[ii] < len) {
+                memmove(line + indxNA[ii], line + indxNA[ii] + 1, (size_t)(len - indxNA[ii] - 1));
+                len--;
+            }
+        }
+        if (rc) break;
+        fwrite(line, 1, (size_t)len, out);
+        fputc('\n', out);
+    }
+    free(line);
+    fclose(in); fclose(out);
+    return rc;
+}
+
+/* getRowColumn (src/getRowColumn.cpp:19-72) */
+int eo_getRowColumn(const char *fname, long *dimen)
+{
+    dimen[0] = dimen[1] = 0;
+    FILE *in = fopen(fname, "r");
+    if (!in) return EO_ERR_OPEN; /* :36-39 */
+    char *line = NULL;
+    size_t cap = 0;
+    ssize_t len;
+    while ((len = getline(&line, &cap, in)) >= 0) dimen[0]++; /* :43-47 */
+    rewind(in); /* :51-52 */
+    len = getline(&line, &cap, in);
+    if (len > 0 && line[len - 1] == '\n') len--;
+    for (ssize_t p = 0; p < len;) { /* :58-65 */
+        while (p < len && eo_isspace((unsigned char)line[p])) p++;
+        if (p >= len) break;
+        while (p < len && !eo_isspace((unsigned char)line[p])) p++;
+        dimen[1]++;
+    }
+    free(line);
+    fclose(in);
+    return EO_OK;
+}
+
 int eo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -49,6 +49,8 @@ def _bind(path):
     L.eo_extract_geno.argtypes = [C.c_char_p, C.c_double, C.c_long, lp, ip, ip]
     L.eo_createM_ASCII.argtypes = [C.c_char_p] * 6 + [C.c_double, lp, C.c_int, C.c_char_p, C.c_char_p, C.c_long, ip]
     L.eo_createMt_ASCII.argtypes = [C.c_char_p] * 3 + [C.c_double, lp, C.c_int, C.c_char_p, C.c_long]
+    L.eo_ReshapeM.argtypes = [C.c_char_p, C.c_char_p, lp, C.c_long, lp, lp]
+    L.eo_getRowColumn.argtypes = [C.c_char_p, lp]
     L.eo_num_threads.restype = C.c_int
     if hasattr(L, "ref_last_error"):
         L.ref_last_error.restype = C.c_char_p
@@ -200,6 +202,21 @@ def createMt_ASCII_rcpp(f_name, f_name_ascii, type, max_memory_in_Gbytes, dims, 
     _check(lib().eo_createMt_ASCII(os.fsencode(f_name), os.fsencode(f_name_ascii), type.encode(), float(max_memory_in_Gbytes),
                                    _dims(dims), int(bool(quiet)), buf, len(buf)), "createMt_ASCII_rcpp")
     return _messages(buf)
+
+
+def ReshapeM_rcpp(fnameM, fnameMt, indxNA, dims):
+    """ReshapeM_rcpp.cpp:16-117 -> [rows kept, line length]; writes fnameM + "tmp" and fnameMt + "tmp"."""
+    idx = (C.c_long * max(1, len(indxNA)))(*[int(i) for i in indxNA])
+    out = (C.c_long * 2)()
+    _check(lib().eo_ReshapeM(os.fsencode(fnameM), os.fsencode(fnameMt), idx, len(indxNA), _dims(dims), out), "ReshapeM_rcpp")
+    return [int(out[0]), int(out[1])]
+
+
+def getRowColumn(fname):
+    """getRowColumn.cpp:19-72 -> [rows, columns]."""
+    out = (C.c_long * 2)()
+    _check(lib().eo_getRowColumn(os.fsencode(fname), out), "getRowColumn")
+    return [int(out[0]), int(out[1])]
 
 
 def num_threads() -> int:

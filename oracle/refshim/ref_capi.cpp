@@ -25,6 +25,10 @@ bool createM_ASCII_rcpp(Rcpp::CharacterVector f_name, Rcpp::CharacterVector f_na
 void createMt_ASCII_rcpp(Rcpp::CharacterVector f_name, Rcpp::CharacterVector f_name_ascii, Rcpp::CharacterVector type,
                          double max_memory_in_Gbytes, std::vector<long> dims, bool quiet, Rcpp::Function message);
 
+std::vector<long> ReshapeM_rcpp(Rcpp::CharacterVector fnameM, Rcpp::CharacterVector fnameMt, std::vector<long> indxNA,
+                                std::vector<long> dims);
+std::vector<long> getRowColumn(std::string fname);
+
 static thread_local std::string g_what;
 // messages joined with the ASCII record separator into a caller-provided buffer
 static void join_msgs(const std::vector<std::string>& msgs, char* buf, long cap) {
@@ -124,6 +128,22 @@ int eo_createMt_ASCII(const char* f, const char* fascii, const char* type, doubl
         std::vector<std::string> msgs;
         createMt_ASCII_rcpp(f, fascii, type, mem, std::vector<long>{dims[0], dims[1]}, quiet != 0, Rcpp::Function(&msgs));
         join_msgs(msgs, msgbuf, msgcap);
+    })
+}
+
+int eo_ReshapeM(const char* fM, const char* fMt, const long* indxNA, long n_indx, const long* dims, long* newdims) {
+    GUARD({
+        std::vector<long> r = ReshapeM_rcpp(fM, fMt, std::vector<long>(indxNA, indxNA + n_indx), std::vector<long>{dims[0], dims[1]});
+        newdims[0] = r[0];
+        newdims[1] = r[1];
+    })
+}
+
+int eo_getRowColumn(const char* f, long* dimen) {
+    GUARD({
+        std::vector<long> r = getRowColumn(f);
+        dimen[0] = r[0];
+        dimen[1] = r[1];
     })
 }
 

@@ -274,6 +274,86 @@ def test_oracle_plink_matches_reference_code(plink_cases, tmp_path):
     assert mine == ref and not mine[0] and len(mine[1]) == 2
 
 
+# ---------------------------------------------------------------------------------------------------- ReshapeM, getRowColumn
+RESHAPE_CASES = [[], [5], [202], [0], [150, 77, 3], [202, 201, 0], [7, 7], [3, 77, 150], [10, 10, 9]]   # the last three: not decreasing
+
+
+def _reshape_files(tmp_path, synth_small, tag):
+    import shutil
+    m, mt = str(tmp_path / f"M{tag}.ascii"), str(tmp_path / f"Mt{tag}.ascii")
+    shutil.copy(synth_small["M"], m)
+    shutil.copy(synth_small["Mt"], mt)
+    return m, mt
+
+
+def test_oracle_reshape_and_rowcolumn_known_answers(synth_small, tmp_path, ingest_cases):
+    s = synth_small
+    m, mt = _reshape_files(tmp_path, s, "o")
+    assert eo.ReshapeM_rcpp(m, mt, [150, 77, 3], (s["n"], s["L"])) == [s["n"] - 3, s["L"]]
+    keep = [i for i in range(s["n"]) if i not in (3, 77, 150)]
+    assert open(m + "tmp", "rb").read() == synth.ascii_image(s["G"][keep]).tobytes()
+    assert open(mt + "tmp", "rb").read() == synth.ascii_image(s["G"][keep].T.copy()).tobytes()
+    by = {c[0]: c for c in ingest_cases}
+    assert eo.getRowColumn(by["plain"][1]) == [23, 157] and eo.getRowColumn(by["no_final_newline"][1]) == [23, 157]
+    assert eo.getRowColumn(by["ragged_blanks"][1]) == [23, 157] and eo.getRowColumn(by["blank_tail"][1]) == [24, 157]
+    assert eo.getRowColumn(s["M"]) == [s["n"], 1]
+
+
+@pytest.mark.skipif(not eo.reference_available(), reason="oracle/_ref/libeagle_ref.so not built")
+def test_oracle_reshape_and_rowcolumn_match_reference_code(synth_small, tmp_path, ingest_cases, plink_cases):
+    s = synth_small
+    for k, idx in enumerate(RESHAPE_CASES):
+        m1, mt1 = _reshape_files(tmp_path, s, f"a{k}")
+        m2, mt2 = _reshape_files(tmp_path, s, f"b{k}")
+        mine = eo.ReshapeM_rcpp(m1, mt1, idx, (s["n"], s["L"]))
+        with eo.use_reference():
+            ref = eo.ReshapeM_rcpp(m2, mt2, idx, (s["n"], s["L"]))
+        assert mine == ref, idx
+        assert open(m1 + "tmp", "rb").read() == open(m2 + "tmp", "rb").read(), idx
+        assert open(mt1 + "tmp", "rb").read() == open(mt2 + "tmp", "rb").read(), idx
+    for case in list(ingest_cases) + list(plink_cases):
+        mine = eo.getRowColumn(case[1])
+        with eo.use_reference():
+            assert eo.getRowColumn(case[1]) == mine, case[0]
+    with eo.use_reference():
+        with pytest.raises(eo.OracleError, match="ERROR: Could not open"):
+            eo.getRowColumn(str(tmp_path / "absent"))
+
+
+@pytest.mark.gpu
+def test_gpu_reshape_and_rowcolumn_match_oracle(api, synth_small, tmp_path, ingest_cases, plink_cases, monkeypatch):
+    s = synth_small
+    dims = (s["n"], s["L"])
+    for k, idx in enumerate(RESHAPE_CASES):
+        m1, mt1 = _reshape_files(tmp_path, s, f"g{k}")
+        m2, mt2 = _reshape_files(tmp_path, s, f"r{k}")
+        assert api.ReshapeM_rcpp(m1, mt1, idx, dims) == eo.ReshapeM_rcpp(m2, mt2, idx, dims), idx
+        assert open(m1 + "tmp", "rb").read() == open(m2 + "tmp", "rb").read(), idx
+        assert open(mt1 + "tmp", "rb").read() == open(mt2 + "tmp", "rb").read(), idx
+    # the reshaped stores serve the calls AM() makes on the two new files (R/AM.R:353-370)
+    n1 = s["n"] - 3
+    m, mt = _reshape_files(tmp_path, s, "chain")
+    assert api.ReshapeM_rcpp(m, mt, [150, 77, 3], dims) == [n1, s["L"]]
+    assert np.array_equal(api.calculateMMt_rcpp(m + "tmp", 8.0, 1, [api.NA_REAL], (n1, s["L"])),
+                          eo.calculateMMt_rcpp(m + "tmp", 8.0, 1, [eo.NA_REAL], (n1, s["L"])))
+    S, V, a = synth.scan_inputs(n1, 3)
+    got = api.calculate_a_and_vara_rcpp(mt + "tmp", [api.NA_REAL], S, V, 8.0, (s["L"], n1), a)
+    want = eo.calculate_a_and_vara_rcpp(mt + "tmp", [eo.NA_REAL], S, V, 8.0, (s["L"], n1), a)
+    np.testing.assert_allclose(got["vara"], want["vara"], rtol=1e-9, atol=1e-12 * np.abs(want["vara"]).max())
+    np.testing.assert_allclose(got["a"], want["a"], rtol=1e-9, atol=1e-12 * np.abs(want["a"]).max())
+    with pytest.raises(Exception, match="Could not open"):
+        api.ReshapeM_rcpp(str(tmp_path / "absent"), mt, [1], dims)
+    with pytest.raises(Exception, match="beyond a line"):
+        api.ReshapeM_rcpp(m, mt, [s["n"] + 5], dims)
+    for piece in (None, 1000):
+        if piece:
+            monkeypatch.setenv("EAGLE_INGEST_PIECE_BYTES", str(piece))
+        for case in list(ingest_cases) + list(plink_cases):
+            assert api.getRowColumn(case[1]) == eo.getRowColumn(case[1]), case[0]
+    with pytest.raises(Exception, match="ERROR: Could not open"):
+        api.getRowColumn(str(tmp_path / "absent"))
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("piece", [None, 40000, 3000])
