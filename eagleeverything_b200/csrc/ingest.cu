@@ -166,7 +166,7 @@ __device__ __noinline__ int classify_token(const uint8_t* __restrict__ text, int
 // The output is a stream compaction of the events: a token start writes its code, a '\n' writes '\n', and the byte goes
 // to offset (tokens before) + (newlines before) -- as long as every earlier row holds exactly L tokens that IS
 // row * (L + 1) + column.  Each 4 KB step stages its bytes in shared memory and writes them out as aligned 16-byte vectors.
-// One-character tokens (the usual 0/1/2 or A/H/B files) are classified from registers against the one-character codes;
+// One-character tokens (the usual 0/1/2 or A/H/B files) are classified by a 256-entry table in shared memory;
 // longer tokens (e.g. the missing-value string "NA") go through classify_token.
 __global__ void __launch_bounds__(TK_THREADS) tok_emit_kernel(const uint8_t* __restrict__ text, int64_t nbytes, int64_t nchunks,
                                                               const int64_t* __restrict__ prefix, int64_t L, const TokCodes codes_param,
@@ -176,20 +176,31 @@ __global__ void __launch_bounds__(TK_THREADS) tok_emit_kernel(const uint8_t* __r
     __shared__ TokCodes codes;  // dynamic indexing of a kernel parameter would put it on every thread's stack
     if (threadIdx.x < sizeof(TokCodes) / 4) reinterpret_cast<uint32_t*>(&codes)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&codes_param)[threadIdx.x];
     __syncthreads();
-    const uint32_t c1[4] = {codes.s[0][0], codes.s[1][0], codes.s[2][0], codes.s[3][0]};
-    const uint32_t o1[4] = {codes.out[0], codes.out[1], codes.out[2], codes.out[3]};
-    const bool has[4] = {codes.len[0] == 1, codes.len[1] == 1, codes.len[2] == 1, codes.len[3] == 1};
     __shared__ __align__(16) uint8_t stage[TK_STEP + 32];  // at most one event per text byte
+    __shared__ uint8_t lut1[256];  // one-character token -> output byte, 0 = none of the codes
+    lut1[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int q = 3; q >= 0; q--)  // the first match in BB, AB, AA, missing order wins: written last
+            if (codes.len[q] == 1) lut1[codes.s[q][0]] = codes.out[q];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         int64_t base_tok = prefix[2 * ch], base_nl = prefix[2 * ch + 1];
+        const uint4 blank = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+        uint4 vnext = blank;  // the vector of the NEXT step is in flight while this one is processed
+        {
+            const int64_t q0 = ch * TK_CHUNK + threadIdx.x * 16;
+            if (q0 < nbytes) vnext = *reinterpret_cast<const uint4*>(text + q0);
+        }
         for (int s = 0; s < TK_STEPS; s++) {
             const int64_t p0 = ch * TK_CHUNK + (int64_t)s * TK_STEP + threadIdx.x * 16;
             if (ch * TK_CHUNK + (int64_t)s * TK_STEP >= nbytes) break;  // CTA-uniform
-            uint4 v = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+            const uint4 v = vnext;
+            vnext = blank;
+            if (s + 1 < TK_STEPS && p0 + TK_STEP < nbytes) vnext = *reinterpret_cast<const uint4*>(text + p0 + TK_STEP);
             uint32_t ws = 0xFFFFu, nl = 0, ts = 0;
             if (p0 < nbytes) {
-                v = *reinterpret_cast<const uint4*>(text + p0);
                 byte_masks(v, p0, nbytes, ws, nl);
                 ts = token_starts(ws, text, p0);
             }
@@ -215,30 +226,27 @@ __global__ void __launch_bounds__(TK_THREADS) tok_emit_kernel(const uint8_t* __r
             uint32_t e = tl + rl;                               // = its first slot in the stage
             // does the byte after this vector end a token that starts at byte 15?
             const bool single15 = (ts & 0x8000u) && (p0 + 16 >= nbytes || is_ws(text[p0 + 16]));
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            if (ts | nl) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if ((nl >> i) & 1u) {
-                        if (base_tok + tl != (base_nl + rl + 1) * L) atomicMin(err_pos, (unsigned long long)(p0 + i));
-                        stage[e++] = '\n';
-                        rl++;
-                    } else if ((ts >> i) & 1u) {
-                        uint32_t ob = 0;  // 0: none of the codes
-                        const bool single = (i < 15) ? ((ws >> (i + 1)) & 1u) : single15;
-                        if (single) {
-                            const uint32_t b = (w4[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-#pragma unroll
-                            for (int q = 3; q >= 0; q--)
-                                if (has[q] && b == c1[q]) ob = o1[q];  // first match in BB, AB, AA, missing order wins
-                        } else {
-                            const int k = classify_token(text, p0 + i, nbytes, codes);
-                            if (k >= 0) ob = codes.out[k];
-                        }
-                        if (!ob) atomicMin(err_pos, (unsigned long long)(p0 + i));
-                        stage[e++] = ob ? (uint8_t)ob : (uint8_t)'?';
-                        tl++;
+            const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            uint32_t ev = ts | nl;
+            while (ev) {  // events in byte order; every lane of a dense file has the same number of them
+                const int i = __ffs(ev) - 1;
+                ev &= ev - 1;
+                if ((nl >> i) & 1u) {
+                    if (base_tok + tl != (base_nl + rl + 1) * L) atomicMin(err_pos, (unsigned long long)(p0 + i));
+                    stage[e++] = '\n';
+                    rl++;
+                } else {
+                    const bool single = (i < 15) ? ((ws >> (i + 1)) & 1u) : single15;
+                    uint32_t ob;
+                    if (single) {
+                        ob = lut1[(uint32_t)((i < 8 ? lo : hi) >> (8 * (i & 7))) & 0xFFu];
+                    } else {
+                        const int k = classify_token(text, p0 + i, nbytes, codes);
+                        ob = k >= 0 ? codes.out[k] : 0u;
                     }
+                    if (!ob) atomicMin(err_pos, (unsigned long long)(p0 + i));
+                    stage[e++] = ob ? (uint8_t)ob : (uint8_t)'?';
+                    tl++;
                 }
             }
             // a last line without '\n' is a row too (getline returns it): the thread that holds the last byte closes it
