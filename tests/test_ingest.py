@@ -354,6 +354,122 @@ def test_gpu_reshape_and_rowcolumn_match_oracle(api, synth_small, tmp_path, inge
         api.getRowColumn(str(tmp_path / "absent"))
 
 
+# ---------------------------------------------------------------------------------------------------- seeded fuzz
+SEPS = [" ", "  ", "\t", " \t", "\r", "\v", "\f", "   \t  "]
+
+
+def fuzz_text_case(rng, path):
+    """A random marker text file: random codes (1-3 characters, possibly equal or prefixes of each other), random blank runs,
+    and -- in half of the cases -- one defect (foreign token, short / long / blank row, missing final newline)."""
+    alpha = list("012ABHN-x")
+    code = lambda: "".join(rng.choice(alpha, size=int(rng.integers(1, 4))))
+    AA, AB, BB, missing = code(), code(), code(), code()
+    if rng.random() < 0.15:
+        AB = "NA"
+    rows, cols = int(rng.integers(1, 30)), int(rng.integers(1, 40))
+    lines = []
+    for r in range(rows):
+        toks = [str(rng.choice([AA, AB if AB != "NA" else AA, BB, missing], p=[0.4, 0.25, 0.25, 0.1])) for _ in range(cols)]
+        lead = str(rng.choice(["", " ", "\t "]))
+        lines.append(lead + "".join(t + str(rng.choice(SEPS)) for t in toks).rstrip(" ") if rng.random() < 0.5 else
+                     lead + str(rng.choice(SEPS[:3])).join(toks))
+    defect = rng.random()
+    r = int(rng.integers(rows))
+    if defect < 0.12:
+        lines[r] = lines[r] + " " + str(rng.choice(["zz", "3", AA + BB + "q"]))           # one token too many (maybe foreign)
+    elif defect < 0.24:
+        parts = lines[r].split()
+        lines[r] = " ".join(parts[:-1])                                                   # one token short (maybe empty line)
+    elif defect < 0.36:
+        parts = lines[r].split()
+        parts[int(rng.integers(len(parts)))] = str(rng.choice(["?", "22x", AA + "_"]))
+        lines[r] = " ".join(parts)                                                        # a foreign token
+    elif defect < 0.42:
+        lines.insert(r, "")                                                               # an empty line
+    text = "\n".join(lines) + ("" if rng.random() < 0.25 else "\n") + ("  " if rng.random() < 0.05 else "")
+    with open(path, "wb") as f:
+        f.write(text.encode("latin-1"))
+    return (rows, cols), AA, AB, BB, missing
+
+
+def fuzz_ped_case(rng, path):
+    rows, nsnp = int(rng.integers(1, 14)), int(rng.integers(1, 24))
+    pool = list("ACGT12")
+    lines = []
+    al = [(str(rng.choice(pool)), str(rng.choice(pool))) for _ in range(nsnp)]
+    for r in range(rows):
+        toks = [f"F{r}", f"I{r}", "0", "0", "1", "-9"]
+        for i in range(nsnp):
+            for _ in range(2):
+                u = rng.random()
+                toks.append("0" if u < 0.04 else "-" if u < 0.06 else "I" if u < 0.08 else
+                            str(rng.choice(pool)) if u < 0.085 else al[i][int(rng.integers(2))])
+        sep = str(rng.choice([" ", "\t", "  "]))
+        lines.append(sep.join(toks))
+    if rng.random() < 0.15:
+        r = int(rng.integers(rows))
+        lines[r] = lines[r] + " A" if rng.random() < 0.5 else " ".join(lines[r].split()[:-1])
+    with open(path, "wb") as f:
+        f.write(("\n".join(lines) + ("" if rng.random() < 0.2 else "\n")).encode())
+    return (rows, 6 + 2 * nsnp)
+
+
+@pytest.mark.skipif(not eo.reference_available(), reason="oracle/_ref/libeagle_ref.so not built")
+def test_oracle_ingest_fuzz_against_reference_code(tmp_path):
+    rng = np.random.default_rng(2026)
+    p = str(tmp_path / "f.txt")
+    n_bad = 0
+    for k in range(300):
+        dims, AA, AB, BB, missing = fuzz_text_case(rng, p)
+        mine = eo.createM_ASCII_rcpp(p, str(tmp_path / "a"), "text", AA, AB, BB, 8.0, dims, True, missing)
+        with eo.use_reference():
+            ref = eo.createM_ASCII_rcpp(p, str(tmp_path / "b"), "text", AA, AB, BB, 8.0, dims, True, missing)
+        assert mine == ref, (k, open(p, "rb").read())
+        too_long = not mine[0] and any("which contains" in m and int(m.split("contains")[1].split()[0]) > dims[1] for m in mine[1])
+        if not too_long:   # beyond dims[1] tokens the reference writes outside its row buffer
+            assert open(tmp_path / "a", "rb").read() == open(tmp_path / "b", "rb").read(), k
+        n_bad += not mine[0]
+        assert eo.getRowColumn(p) == _ref(eo.getRowColumn, p)
+    assert 60 < n_bad < 240
+    for k in range(200):
+        dims = fuzz_ped_case(rng, p)
+        mine = eo.createM_ASCII_rcpp(p, str(tmp_path / "a"), "PLINK", "", "", "", 8.0, dims, True, "")
+        with eo.use_reference():
+            ref = eo.createM_ASCII_rcpp(p, str(tmp_path / "b"), "PLINK", "", "", "", 8.0, dims, True, "")
+        assert mine == ref, (k, open(p, "rb").read())
+        assert open(tmp_path / "a", "rb").read() == open(tmp_path / "b", "rb").read(), k
+
+
+def _ref(fn, *a):
+    with eo.use_reference():
+        return fn(*a)
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_fuzz_against_oracle(api, tmp_path, monkeypatch):
+    rng = np.random.default_rng(2026)
+    p = str(tmp_path / "f.txt")
+    for k in range(300):
+        dims, AA, AB, BB, missing = fuzz_text_case(rng, p)
+        monkeypatch.setenv("EAGLE_INGEST_PIECE_BYTES", str(int(rng.choice([64, 200, 1000, 1 << 28]))))
+        ref = eo.createM_ASCII_rcpp(p, str(tmp_path / "b"), "text", AA, AB, BB, 8.0, dims, True, missing)
+        msgs = []
+        ok = api.createM_ASCII_rcpp(p, str(tmp_path / "a"), "text", AA, AB, BB, 8.0, dims, True, msgs.append, missing)
+        assert (ok, msgs) == ref, (k, open(p, "rb").read())
+        too_long = not ok and any("which contains" in m and int(m.split("contains")[1].split()[0]) > dims[1] for m in msgs)
+        if not too_long:
+            assert open(tmp_path / "a", "rb").read() == open(tmp_path / "b", "rb").read(), k
+        assert api.getRowColumn(p) == eo.getRowColumn(p)
+    for k in range(200):
+        dims = fuzz_ped_case(rng, p)
+        monkeypatch.setenv("EAGLE_INGEST_PIECE_BYTES", str(int(rng.choice([64, 300, 1 << 28]))))
+        ref = eo.createM_ASCII_rcpp(p, str(tmp_path / "b"), "PLINK", "", "", "", 8.0, dims, True, "")
+        msgs = []
+        ok = api.createM_ASCII_rcpp(p, str(tmp_path / "a"), "PLINK", "", "", "", 8.0, dims, True, msgs.append, "")
+        assert (ok, msgs) == ref, (k, open(p, "rb").read())
+        assert open(tmp_path / "a", "rb").read() == open(tmp_path / "b", "rb").read(), k
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("piece", [None, 40000, 3000])
