@@ -445,6 +445,69 @@ def _ref(fn, *a):
         return fn(*a)
 
 
+def fuzz_reshape_case(rng, tmp_path, tag):
+    """Random small M.ascii / Mt.ascii pair and a random index list: decreasing (what R passes), or shuffled / with
+    repeats (the reference then erases shifted characters from the Mt lines)."""
+    n, L = int(rng.integers(2, 40)), int(rng.integers(1, 60))
+    G = synth.genotypes(n, L, seed=int(rng.integers(1 << 30)))
+    m, mt = str(tmp_path / f"M{tag}.ascii"), str(tmp_path / f"Mt{tag}.ascii")
+    npo.write_ascii(m, G)
+    npo.write_ascii(mt, G.T)
+    k = int(rng.integers(0, min(n - 1, 6) + 1))
+    idx = sorted((int(i) for i in rng.choice(n, size=k, replace=False)), reverse=True)
+    u = rng.random()
+    if u < 0.2 and k > 1:
+        rng.shuffle(idx)
+    elif u < 0.3 and k > 0 and len(idx) < n - 1:
+        idx.append(idx[int(rng.integers(len(idx)))])
+    # keep every erase position inside the (shrinking) line: the reference throws otherwise
+    size = n
+    ok = True
+    for i in idx:
+        ok &= i <= size
+        size -= i < size
+    return (m, mt, [int(i) for i in idx], (n, L)) if ok and size > 0 and len(set(idx)) < n else None
+
+
+@pytest.mark.skipif(not eo.reference_available(), reason="oracle/_ref/libeagle_ref.so not built")
+def test_oracle_reshape_fuzz_against_reference_code(tmp_path):
+    rng = np.random.default_rng(77)
+    done = 0
+    for k in range(150):
+        a = fuzz_reshape_case(rng, tmp_path, "a")
+        if a is None:
+            continue
+        m, mt, idx, dims = a
+        import shutil
+        m2, mt2 = str(tmp_path / "Mb.ascii"), str(tmp_path / "Mtb.ascii")
+        shutil.copy(m, m2); shutil.copy(mt, mt2)
+        assert eo.ReshapeM_rcpp(m, mt, idx, dims) == _ref(eo.ReshapeM_rcpp, m2, mt2, idx, dims), idx
+        assert open(m + "tmp", "rb").read() == open(m2 + "tmp", "rb").read(), idx
+        assert open(mt + "tmp", "rb").read() == open(mt2 + "tmp", "rb").read(), idx
+        done += 1
+    assert done > 100
+
+
+@pytest.mark.gpu
+def test_gpu_reshape_fuzz_against_oracle(api, tmp_path):
+    import shutil
+    rng = np.random.default_rng(77)
+    done = 0
+    for k in range(150):
+        a = fuzz_reshape_case(rng, tmp_path, "a")
+        if a is None:
+            continue
+        m, mt, idx, dims = a
+        m2, mt2 = str(tmp_path / "Mb.ascii"), str(tmp_path / "Mtb.ascii")
+        shutil.copy(m, m2); shutil.copy(mt, mt2)
+        api.cache_clear()   # the same two paths are rewritten every round, possibly within one mtime tick of the file system
+        assert api.ReshapeM_rcpp(m, mt, idx, dims) == eo.ReshapeM_rcpp(m2, mt2, idx, dims), idx
+        assert open(m + "tmp", "rb").read() == open(m2 + "tmp", "rb").read(), (idx, dims)
+        assert open(mt + "tmp", "rb").read() == open(mt2 + "tmp", "rb").read(), (idx, dims)
+        done += 1
+    assert done > 100
+
+
 @pytest.mark.gpu
 def test_gpu_ingest_fuzz_against_oracle(api, tmp_path, monkeypatch):
     rng = np.random.default_rng(2026)
