@@ -465,14 +465,28 @@ static int check_image_size(const MappedFile& f, const char* path, int64_t rows,
     return EG_OK;
 }
 
-// cache key: (realpath, size, mtime, dims, layout)
+// cache key: (realpath, size, mtime, hash of the first and last 4 KB, dims, layout)
 static int cache_key(const char* path, int64_t rows, int64_t cols, bool kblocked, std::string& key) {
     struct stat st;
     if (stat(path, &st) != 0) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s", path);
+    // FNV-1a over the first and the last 4 KB: a file rewritten with the same size inside one timestamp tick of the file
+    // system (coarse mtime) must not be served from the stale store
+    uint64_t h = 1469598103934665603ull;
+    {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return set_error(EG_ERR_OPEN, "ERROR: Could not open  %s", path);
+        unsigned char blk[4096];
+        const off_t offs[2] = {0, st.st_size > 4096 ? st.st_size - 4096 : 0};
+        for (int k = 0; k < (st.st_size > 4096 ? 2 : 1); k++) {
+            const ssize_t got = pread(fd, blk, sizeof(blk), offs[k]);
+            for (ssize_t i = 0; i < got; i++) h = (h ^ blk[i]) * 1099511628211ull;
+        }
+        close(fd);
+    }
     char* rp = realpath(path, nullptr);
     char buf[4400];
-    snprintf(buf, sizeof(buf), "%s|%lld|%lld.%09ld|%lldx%lld|%c", rp ? rp : path, (long long)st.st_size,
-             (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (long long)rows, (long long)cols,
+    snprintf(buf, sizeof(buf), "%s|%lld|%lld.%09ld|%016llx|%lldx%lld|%c", rp ? rp : path, (long long)st.st_size,
+             (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (unsigned long long)h, (long long)rows, (long long)cols,
              kblocked ? 'K' : 'R');
     free(rp);
     key = buf;

@@ -414,3 +414,20 @@ def test_recycled_device_buffers_are_reused_and_released(synth_small):
     api.cache_clear()
     torch.cuda.synchronize()
     assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)
+
+
+def test_path_cache_sees_a_rewrite_with_the_same_size_and_mtime(tmp_path):
+    """Resident stores are keyed by (path, size, mtime, a hash of the first and last 4 KB, dims): a file rewritten in place
+    with identical size and timestamp is decoded again, not served from the stale store."""
+    import os
+    n, L = 40, 300
+    G1, G2 = synth.genotypes(n, L, seed=1), synth.genotypes(n, L, seed=2)
+    m = str(tmp_path / "M.ascii")
+    npo.write_ascii(m, G1)
+    st = os.stat(m)
+    K1 = api.calculateMMt_rcpp(m, 8, 1, [NA], (n, L))
+    npo.write_ascii(m, G2)
+    os.utime(m, ns=(st.st_atime_ns, st.st_mtime_ns))
+    assert os.stat(m).st_mtime_ns == st.st_mtime_ns and os.stat(m).st_size == st.st_size
+    K2 = api.calculateMMt_rcpp(m, 8, 1, [NA], (n, L))
+    assert np.array_equal(K2, eo.calculateMMt_rcpp(m, 8, 1, [NA], (n, L))) and not np.array_equal(K1, K2)
