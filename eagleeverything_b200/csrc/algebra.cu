@@ -373,11 +373,26 @@ extern "C" int eg_dev_emma_eigen_R_wo_Z(const double* d_K, const double* d_X, co
     if (!d_K || !d_X || !d_values || !d_U || !d_w1 || !d_w2 || !d_small || n <= 0 || q <= 0 || q >= n || (!d_y != !d_etas))
         return set_error(EG_ERR_ARG, "eg_dev_emma_eigen_R_wo_Z: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    EG_TRY(eg_dev_emma_SKS(d_K, d_X, n, q, d_w1, d_w2, d_small, st));  // S in w1, K + I in w2
-    const double one = 1.0, zero = 0.0;
-    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_w1, (int)n, d_w2, (int)n, &zero, d_U, (int)n));
-    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, d_U, (int)n, d_w1, (int)n, &zero, d_w2, (int)n));
-    EG_CUDA(cudaMemcpyAsync(d_U, d_w2, (size_t)n * n * 8, cudaMemcpyDeviceToDevice, st));
+    EG_TRY(ensure_init_pub());
+    EG_TRY(alg_init(st));
+    (void)d_w2;
+    // S A S with S = I - B X^T, B = X (X^T X)^-1 and A = K + I, expanded:  A - B (A X)^T - (A X) B^T + B (X^T A X) B^T.
+    // Four products with inner dimension q instead of the two n^3 products of R's S %*% (K + I) %*% S (4 n^3 FP64 flops per
+    // iteration on a GPU whose FP64 rate is the scarce resource); the host-level eg_emma_eigen_R_wo_Z keeps R's form.
+    const double one = 1.0, zero = 0.0, minus = -1.0;
+    double *B = d_small, *XtX = B + (size_t)n * q, *Xi = XtX + (size_t)q * q;
+    double *AX = d_w1, *C = AX + (size_t)n * q, *BC = C + (size_t)q * q;
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_T, CUBLAS_OP_N, q, q, (int)n, &one, d_X, (int)n, d_X, (int)n, &zero, XtX, q));
+    EG_TRY(small_inverse(XtX, q, Xi, st, "solve(crossprod(X, X))"));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, q, q, &one, d_X, (int)n, Xi, q, &zero, B, (int)n));
+    axpby_eye_kernel<<<grid_cols(n), 256, 0, st>>>(d_K, n, 1.0, 1.0, d_U);  // A = K + I
+    EG_TRY(check_launch("axpby_eye_kernel"));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, q, (int)n, &one, d_U, (int)n, d_X, (int)n, &zero, AX, (int)n));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_T, CUBLAS_OP_N, q, q, (int)n, &one, d_X, (int)n, AX, (int)n, &zero, C, q));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, q, q, &one, B, (int)n, C, q, &zero, BC, (int)n));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)n, q, &minus, B, (int)n, AX, (int)n, &one, d_U, (int)n));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)n, q, &minus, AX, (int)n, B, (int)n, &one, d_U, (int)n));
+    EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)n, q, &one, BC, (int)n, B, (int)n, &one, d_U, (int)n));
     EG_TRY(eg_dev_eigen_sym(d_U, n, d_values, st));
     add_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_values, n - q, -1.0);
     EG_TRY(check_launch("add_scalar_kernel"));
