@@ -171,3 +171,71 @@ def unpack_2bit(words, cols):
     shifts = (2 * np.arange(32, dtype=np.uint64))[None, None, :]
     codes = ((words[:, :, None] >> shifts) & np.uint64(3)).reshape(rows, wpr * 32)
     return codes[:, :cols].astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------- ingest
+# Independent restatements in plain Python of what the two ingest routines WRITE and WHY they stop, used to cross-check
+# oracle/eagle_oracle.c (which is itself checked against the compiled reference).  Small inputs only.
+_WS = b" \t\n\v\f\r"
+
+
+def tokenise_text(data: bytes, cols: int, AA: str, AB: str, BB: str, missing: str):
+    """CreateASCIInospace.cpp:67-125 -> (ok, rows written as bytes, reason).  reason: None | ("token", row1, token) |
+    ("columns", row1, count)."""
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()  # getline does not return an empty piece after the final newline
+    out = bytearray()
+    codes = [(BB.encode(), b"2"), (AB.encode(), b"1"), (AA.encode(), b"0"), (missing.encode(), b"1")]
+    for r, line in enumerate(lines):
+        row = bytearray()
+        for tok in line.translate(bytes.maketrans(_WS, b" " * len(_WS))).split():
+            for c, o in codes:
+                if tok == c:
+                    row += o
+                    break
+            else:
+                return False, bytes(out), ("token", r + 1, tok.decode("latin-1"))
+        if len(row) != cols:
+            return False, bytes(out), ("columns", r + 1, len(row))
+        out += row + b"\n"
+    return True, bytes(out), None
+
+
+def plink_genotypes(data: bytes, ncols: int):
+    """CreateASCIInospace_PLINK.cpp:55-200 for single-character allele tokens -> (ok, rows written, reason, warned).
+    reason: None | ("columns", row1, count) | ("alleles", snp1, row1)."""
+    nsnp = (ncols - 6) // 2
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    a0, a1 = [None] * nsnp, [None] * nsnp
+    out = bytearray()
+    warned = False
+    for r, line in enumerate(lines):
+        toks = line.translate(bytes.maketrans(_WS, b" " * len(_WS))).split()
+        if len(toks) != ncols:
+            return False, bytes(out), ("columns", r + 1, len(toks)), warned
+        al = [t[:1] for t in toks[6:]]
+        row = bytearray()
+        for i in range(nsnp):
+            a, b = al[2 * i], al[2 * i + 1]
+            miss = a in (b"0", b"-") or b in (b"0", b"-")
+            if r == 0:
+                a0[i], a1[i] = (b"I", b"I") if miss else (a, b)
+            if miss:
+                warned = True
+                a = b = b"I"
+            for x in (b, a):  # the second allele is looked at first (:137)
+                if x != a0[i] and x != a1[i] and x != b"I":
+                    if a0[i] == b"I":
+                        a0[i] = x
+                    elif a1[i] == b"I":
+                        a1[i] = x
+                    elif a0[i] == a1[i]:
+                        a1[i] = x
+                    else:
+                        return False, bytes(out), ("alleles", i + 1, r + 1), warned
+            row += b"1" if (a == b"I" or b == b"I" or a != b) else (b"0" if a == a0[i] else b"2")
+        out += row + b"\n"
+    return True, bytes(out), None, warned

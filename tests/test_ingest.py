@@ -445,6 +445,35 @@ def _ref(fn, *a):
         return fn(*a)
 
 
+def test_second_restatement_agrees_with_the_c_oracle_on_the_fuzz_corpus(tmp_path):
+    """oracle/np_oracle.py holds an independent plain-Python restatement of what the two ingest routines write and why
+    they stop; it must agree with oracle/eagle_oracle.c (files, verdict, row / token / count in the messages)."""
+    rng = np.random.default_rng(2026)
+    p = str(tmp_path / "f.txt")
+    for k in range(300):
+        dims, AA, AB, BB, missing = fuzz_text_case(rng, p)
+        ok, msgs = eo.createM_ASCII_rcpp(p, str(tmp_path / "a"), "text", AA, AB, BB, 8.0, dims, True, missing)
+        ok2, rows2, why = npo.tokenise_text(open(p, "rb").read(), dims[1], AA, AB, BB, missing)
+        assert ok == ok2, k
+        too_long = why is not None and why[0] == "columns" and why[2] > dims[1]
+        if not too_long:
+            assert open(tmp_path / "a", "rb").read() == rows2, k
+        if why and why[0] == "token":
+            assert msgs[1] == f" For example , {why[2]} in row {why[1]}", k
+        elif why:
+            assert msgs[2] == f"        The error has occurred at row {why[1]} which contains {why[2]} but ", k
+    for k in range(200):
+        dims = fuzz_ped_case(rng, p)
+        ok, msgs = eo.createM_ASCII_rcpp(p, str(tmp_path / "a"), "PLINK", "", "", "", 8.0, dims, True, "")
+        ok2, rows2, why, warned = npo.plink_genotypes(open(p, "rb").read(), dims[1])
+        assert ok == ok2 and open(tmp_path / "a", "rb").read() == rows2, k
+        assert warned == any("missing alleles" in m for m in msgs), k
+        if why and why[0] == "alleles":
+            assert f"        The error has occurred at snp locus {why[1]} for individual {why[2]}" in msgs, k
+        elif why:
+            assert f"        The error has occurred at row {why[1]} which contains {why[2]} but " in msgs, k
+
+
 def fuzz_reshape_case(rng, tmp_path, tag):
     """Random small M.ascii / Mt.ascii pair and a random index list: decreasing (what R passes), or shuffled / with
     repeats (the reference then erases shifted characters from the Mt lines)."""
