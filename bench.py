@@ -56,56 +56,96 @@ def load_peaks():
 
 
 # ====================================================================== CPU arm (reference restatement)
-def cpu_reference_sample(n, L, budget_s=20.0):
-    """Times the reference's CPU path (numpy restatement: byte decode -> FP64, OpenBLAS dgemm for
-    M.Mt and Mt*W, row-dot) on a bounded marker sample at full n, and extrapolates linearly in L
-    (every stage is linear in the marker count; the n^3 pre-products W = S(VS) are counted once,
-    estimated from the dgemm rate measured on the sample).  Returns markers/s and details."""
-    import numpy as np
+REF_SAMPLE_MARKERS = 4096     # fixed: independent of --steps, so every run of either arm times the same sample
 
-    from oracle import np_oracle as npo  # the CPU checker doubles as the CPU baseline
+
+def host_cores():
     try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    from eagleeverything_b200 import synth
-    # pick the sample so that ~4*Ls*n^2 flops at ~10 GFLOP/s/thread fit the budget
-    est_rate = 1.0e10 * threads
-    Ls = int(min(L, max(256, budget_s * est_rate / (4.0 * n * n + 1))))
-    Ls = max(128, Ls // 128 * 128)
-    G = synth.genotypes(n, Ls, seed=GENO_SEED, n_total=n)
-    img = synth.ascii_image(G)
-    S, V, a = synth.scan_inputs(min(n, 2048))
-    if n > 2048:  # big synthetic S, V without an O(n^2) python loop
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def bench_config(w, n, L, world):
+    """The `config` object, identical in both arms (the driver compares them key by key)."""
+    return {"workload": w["name"], "n": n, "L": L, "n_gpus": world}
+
+
+class CpuReference:
+    """The reference's CPU path for one forward step, timed on a bounded marker sample at full n.
+
+    What runs is the C restatement's control flow (oracle/eagle_oracle.c: the in-memory branches of
+    calculateMMt_rcpp.cpp:84-95 and calculate_a_and_vara_rcpp.cpp:76-112 -- ReadBlock's getline decode of M.ascii and
+    Mt.ascii from real files, the products, the OpenMP row-dot loop) with its dense products routed to the OpenBLAS
+    that numpy bundles (the reference runs them in Eigen's GEBP kernel; the restatement's plain loops are 10x slower
+    than either).  Threads are set explicitly to every host core (torchrun exports OMP_NUM_THREADS=1).
+    Stages linear in the marker count (decode of both files, M.Mt, Mt*v, Mt*W, row dots) are scaled by L / sample;
+    the two n^3 pre-products and S*a are counted once per step, as measured (calculate_a_and_vara_rcpp.cpp:90,97-98)."""
+
+    def __init__(self, n, L, Ls=REF_SAMPLE_MARKERS):
+        import tempfile
+
+        import numpy as np
+
+        from eagleeverything_b200 import synth
+        from oracle import eagle_oracle as eo  # the CPU checker doubles as the CPU baseline
+        from oracle import np_oracle as npo
+        self.eo, self.n, self.L, self.Ls = eo, n, L, int(min(L, Ls))
+        self.cores = host_cores()
+        self.blas = eo.use_openblas_dgemm(self.cores)
+        self.dir = tempfile.TemporaryDirectory(prefix="eagle_ref_")
+        G = synth.genotypes(n, self.Ls, seed=GENO_SEED, n_total=n)
+        self.m, self.mt = os.path.join(self.dir.name, "M.ascii"), os.path.join(self.dir.name, "Mt.ascii")
+        npo.write_ascii(self.m, G)
+        npo.write_ascii(self.mt, np.ascontiguousarray(G.T))
+        del G
         rng = np.random.default_rng(1)
         S = rng.standard_normal((n, n)); S = (S + S.T) * (0.5 / np.sqrt(n)) + 2 * np.eye(n)
         V = rng.standard_normal((n, n)); V = (V + V.T) * (0.5 / np.sqrt(n)) + 1.5 * np.eye(n)
-        a = rng.standard_normal(n)
-    t = {}
-    t0 = time.perf_counter()
-    M = img[:, :Ls].astype(np.float64) - 49.0                    # ReadBlock.cpp:52-55
-    t["decode"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    K = M @ M.T                                                  # calculateMMt_rcpp.cpp:95
-    t["mmt"] = time.perf_counter() - t0
-    Mt = np.ascontiguousarray(M.T)                                # the reference decodes Mt.ascii separately
-    W = S  # stand-in with the right shape for the big product (same flops as the real W)
-    t0 = time.perf_counter()
-    T = Mt @ W                                                   # calculate_a_and_vara_rcpp.cpp:103
-    vara = np.einsum("ij,ij->i", T, Mt)                          # :107-112
-    av = Mt @ (S @ a)                                            # :90-91
-    t["scan"] = time.perf_counter() - t0
-    gemm_rate = 2.0 * Ls * n * n / max(t["scan"], 1e-9)
-    t_w_est = 4.0 * n ** 3 / gemm_rate                           # :97-98, once per call
-    per_marker = (2 * t["decode"] + t["mmt"] + t["scan"]) / Ls   # both M.ascii and Mt.ascii are decoded
-    total = per_marker * L + t_w_est
-    _ = (K[0, 0], vara[0], av[0])
-    return dict(value=L / total, unit=METRIC, cores=threads, kind="port",
-                sample=f"numpy/OpenBLAS restatement on {Ls} of {L} markers at n={n} "
-                       f"(decode {t['decode']:.2f}s, M.Mt {t['mmt']:.2f}s, scan {t['scan']:.2f}s; dgemm "
-                       f"{gemm_rate / 1e9:.0f} GFLOP/s; W=S(VS) estimated {t_w_est:.1f}s; linear extrapolation in L)",
-                seconds=sum(t.values()))
+        self.S, self.V, self.a = np.asfortranarray(S), np.asfortranarray(V), rng.standard_normal(n)
+
+    def step(self):
+        """One timed pass over the sample -> (markers/s extrapolated to the whole workload, stage seconds)."""
+        eo, n, L, Ls = self.eo, self.n, self.L, self.Ls
+        t0 = time.perf_counter()
+        K = eo.calculateMMt_rcpp(self.m, 1e9, self.cores, [eo.NA_REAL], (n, Ls))
+        st = eo.last_stages()
+        t = {"decode_M": st["readblock"], "mmt": st["mmt_gemm"]}
+        r = eo.calculate_a_and_vara_rcpp(self.mt, [eo.NA_REAL], self.S, self.V, 1e9, (Ls, n), self.a)
+        st = eo.last_stages()
+        t.update(decode_Mt=st["readblock"], S_a=st["S_a"], pre_products=st["pre_products"], Mt_W=st["Mt_W"],
+                 rowdots=st["rowdots"], Mt_v=st["Mt_v"])
+        wall = time.perf_counter() - t0
+        _ = (K[0, 0], r["a"][0], r["vara"][0])
+        linear = t["decode_M"] + t["mmt"] + t["decode_Mt"] + t["Mt_v"] + t["Mt_W"] + t["rowdots"]
+        const = t["S_a"] + t["pre_products"]
+        total = linear * (L / Ls) + const
+        t["gemm_gflops"] = 2.0 * Ls * n * n / max(t["Mt_W"], 1e-9) / 1e9
+        return L / total, t, wall
+
+    def baseline(self, value, t, wall):
+        return dict(value=value, unit=METRIC, cores=self.cores, kind="port",
+                    sample=f"oracle/eagle_oracle.c control flow (ReadBlock getline decode from files, in-memory branches) "
+                           f"with {self.blas} for the products, {self.cores} threads, on {self.Ls} of {self.L} markers at "
+                           f"n={self.n}: decode M {t['decode_M']:.2f}s + Mt {t['decode_Mt']:.2f}s, M.Mt {t['mmt']:.2f}s, "
+                           f"Mt*W {t['Mt_W']:.2f}s ({t['gemm_gflops']:.0f} GFLOP/s), row dots {t['rowdots']:.2f}s, Mt*v "
+                           f"{t['Mt_v']:.2f}s scaled by L/sample; W=S(VS) {t['pre_products']:.2f}s and S*a {t['S_a']:.3f}s "
+                           f"counted once",
+                    seconds=wall, stage_seconds={k: round(v, 4) for k, v in t.items()})
+
+
+def cpu_reference_sample(n, L, steps=1, warmup=0):
+    ref = CpuReference(n, L)
+    for _ in range(warmup):
+        ref.step()
+    vals, last = [], None
+    for _ in range(max(1, steps)):
+        last = ref.step()
+        vals.append(last[0])
+    v = sum(vals) / len(vals)
+    out = ref.baseline(v, last[1], last[2])
+    out["per_step_values"] = [round(x, 1) for x in vals]
+    return out
 
 
 def run_reference(args):
@@ -114,22 +154,20 @@ def run_reference(args):
         return
     w = WORKLOADS[args.workload]
     n, L = w["n"], w["L"]
-    budget = 15.0
-    if args.warmup > 0:
-        cpu_reference_sample(n, L, budget_s=1.0)
-    vals, last = [], None
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        last = cpu_reference_sample(n, L, budget_s=budget / max(1, args.steps))
-        vals.append(last["value"])
+    # every step costs the same whatever --steps is; cap the repetitions so that the arm ends within a few minutes
+    steps = max(1, min(args.steps, 8))
+    last = cpu_reference_sample(n, L, steps=steps, warmup=min(args.warmup, 1))
     wall = time.perf_counter() - t0
-    v = sum(vals) / len(vals)
-    last["value"] = v
+    v = last["value"]
     jprint({"impl": "reference", "metric": METRIC, "value": v, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * L / v, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "n": n, "L": L, "note": "CPU restatement of the reference path; "
-                       "the reference itself (R + RcppEigen) cannot be built in this image"},
+            "config": bench_config(w, n, L, world),
+            "note": "CPU restatement of the reference path; the reference itself (R + RcppEigen) cannot be built in this "
+                    f"image.  {steps} timed passes over the same fixed {REF_SAMPLE_MARKERS}-marker sample (of the --steps "
+                    f"{args.steps} asked for: a pass takes seconds and every pass times the same work)",
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall})
@@ -438,17 +476,18 @@ def run_gpu(args):
             search = {"note": f"failed: {type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_reference_sample(n, L, budget_s=args.cpu_budget)
+            cpu = cpu_reference_sample(n, L, steps=1, warmup=0)
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     out = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": w["name"], "n": n, "L": L, "markers_per_gpu": Lg, "parallelism": f"markers/{world}",
-                   "l2": f"inputs larger than L2 ({(dec_bytes + 16.0 * n * n) / 1e9:.1f} GB streamed per step)",
-                   "note": "dtype f64 = the scan's results (a, var(a)); decode is u8, M.Mt is s8 x s8 -> s32 (bit-exact); "
-                           "var(a) is contracted on int8 slices of the FP64 matrix (exact) or on FP64 DMMA"},
+        "config": bench_config(w, n, L, world),
+        "config_detail": {"markers_per_gpu": Lg, "parallelism": f"markers/{world}",
+                          "l2": f"inputs larger than L2 ({(dec_bytes + 16.0 * n * n) / 1e9:.1f} GB streamed per step)",
+                          "note": "dtype f64 = the scan's results (a, var(a)); decode is u8, M.Mt is s8 x s8 -> s32 "
+                                  "(bit-exact); var(a) is contracted on int8 slices of the FP64 matrix (exact) or on FP64 DMMA"},
         "stage_ms": stages, "mmt_int8_tops": syrk_tops, "decode_gbs": dec_gbs,
         "scan_mode": "int8 slices (tcgen05)" if mode == 1 else "fp64 (DMMA)", "scan_reference_equiv_fp64_tflops": scan_tf,
         "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,

@@ -61,11 +61,37 @@ static int eo_is_na(double x) { return isnan(x); }
 /* dense helpers (column-major)                                        */
 /* ------------------------------------------------------------------ */
 
+/* Timing baseline only (bench.py --impl reference / cpu_baseline): the reference's products run in Eigen's GEBP
+ * kernel, which this file's plain loops do not match in speed.  eo_set_dgemm() installs an optimised column-major
+ * dgemm with the ILP64 CBLAS signature (bench.py passes scipy_cblas_dgemm64_ of the OpenBLAS bundled with numpy) so
+ * that THIS control flow can be timed at a BLAS rate.  Never set by the tests: parity runs on the loops below.
+ * eo_last_stages(): wall seconds of the stages of the last export called (0 ReadBlock, 1 M.Mt product, 2 S*a and Mt*v,
+ * 3 the two n^3 pre-products, 4 Mt*W, 5 row dots, 6 Mt*v). */
+typedef void (*eo_dgemm_fn)(int order, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha,
+                            const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *C,
+                            int64_t ldc);
+static eo_dgemm_fn eo_dgemm_hook = NULL;
+void eo_set_dgemm(void *fn) { eo_dgemm_hook = (eo_dgemm_fn)fn; }
+static double eo_stage_s[8];
+static double eo_now(void)
+{
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return 0.0;
+#endif
+}
+void eo_last_stages(double *out) { memcpy(out, eo_stage_s, sizeof(eo_stage_s)); }
+
 /* C(m x n) = A(m x k) * op(B);  transb==0: B is k x n;  transb==1: B is n x k (C = A*B^T) */
 static void eo_gemm(long m, long n, long k, const double *A, long lda, const double *B, long ldb,
                     int transb, double *C, long ldc)
 {
     const long MB = 256, KB = 256;
+    if (eo_dgemm_hook) { /* 102 = CblasColMajor, 111 = CblasNoTrans, 112 = CblasTrans */
+        eo_dgemm_hook(102, 111, transb ? 112 : 111, m, n, k, 1.0, A, lda, B, ldb, 0.0, C, ldc);
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 8)
     for (long j = 0; j < n; j++) {
         double *c = C + j * ldc;
@@ -163,12 +189,16 @@ int eo_calculateMMt(const char *f_name_ascii, double max_memory_in_Gbytes, int n
         if (branch) *branch = 0;
         double *genoMat = (double *)malloc(sizeof(double) * (size_t)n * (size_t)L);
         if (!genoMat) return EO_ERR_ALLOC;
+        double t0 = eo_now();
         int rc = eo_ReadBlock(f_name_ascii, 0, L, n, genoMat); /* :86 */
+        eo_stage_s[0] = eo_now() - t0;
         if (rc) { free(genoMat); return rc; }
         if (have_sel) /* :88-92 */
             for (long ii = 0; ii < n_selected; ii++)
                 memset(genoMat + (long)selected_loci[ii] * n, 0, sizeof(double) * (size_t)n);
+        t0 = eo_now();
         eo_gemm(n, n, L, genoMat, n, genoMat, n, 1, MMt, n); /* :95 */
+        eo_stage_s[1] = eo_now() - t0;
         free(genoMat);
         return EO_OK;
     }
@@ -262,19 +292,27 @@ int eo_calculate_a_and_vara(const char *f_name_ascii, const double *selected_loc
         double *Mt = (double *)malloc(sizeof(double) * (size_t)L * (size_t)n);
         double *T = (double *)malloc(sizeof(double) * (size_t)L * (size_t)n);
         if (!Mt || !T) { free(Mt); free(T); rc = EO_ERR_ALLOC; goto done; }
+        double t0 = eo_now();
         rc = eo_ReadBlock(f_name_ascii, 0, n, L, Mt); /* :76 */
+        eo_stage_s[0] = eo_now() - t0;
         if (!rc) {
             if (have_sel) /* :79-84  Mt.row(sel).setZero() */
                 for (long ii = 0; ii < n_selected; ii++) {
                     long r = (long)selected_loci[ii];
                     for (long k = 0; k < n; k++) Mt[r + k * L] = 0.0;
                 }
+            t0 = eo_now();
             eo_gemv(n, n, inv_MMt_sqrt, n, a, ans_part1);           /* :90 */
+            eo_stage_s[2] = eo_now() - t0; t0 = eo_now();
             eo_gemv(L, n, Mt, L, ans_part1, out_a);                 /* :91 */
+            eo_stage_s[6] = eo_now() - t0; t0 = eo_now();
             eo_gemm(n, n, n, dim_reduced_vara, n, inv_MMt_sqrt, n, 0, W1, n); /* :97 */
             eo_gemm(n, n, n, inv_MMt_sqrt, n, W1, n, 0, W, n);      /* :98 */
+            eo_stage_s[3] = eo_now() - t0; t0 = eo_now();
             eo_gemm(L, n, n, Mt, L, W, n, 0, T, L);                 /* :103 */
+            eo_stage_s[4] = eo_now() - t0; t0 = eo_now();
             eo_rowdots(L, n, T, Mt, out_vara);                      /* :107-112 */
+            eo_stage_s[5] = eo_now() - t0;
         }
         free(Mt); free(T);
         goto done;

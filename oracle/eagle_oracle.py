@@ -52,6 +52,9 @@ def _bind(path):
     L.eo_ReshapeM.argtypes = [C.c_char_p, C.c_char_p, lp, C.c_long, lp, lp]
     L.eo_getRowColumn.argtypes = [C.c_char_p, lp]
     L.eo_num_threads.restype = C.c_int
+    if hasattr(L, "eo_set_dgemm"):
+        L.eo_set_dgemm.argtypes = [C.c_void_p]
+        L.eo_last_stages.argtypes = [dp]
     if hasattr(L, "ref_last_error"):
         L.ref_last_error.restype = C.c_char_p
     return L
@@ -221,3 +224,35 @@ def getRowColumn(fname):
 
 def num_threads() -> int:
     return int(lib().eo_num_threads())
+
+
+# ----------------------------------------------------------------------------- timing baseline only (bench.py)
+_blas = None
+
+
+def use_openblas_dgemm(threads: int) -> str:
+    """bench.py's CPU legs only: route the oracle's dense products through the OpenBLAS that numpy bundles (the
+    reference runs them in Eigen's GEBP kernel, which the plain loops of eagle_oracle.c do not match in speed) and set
+    the thread counts explicitly -- torchrun exports OMP_NUM_THREADS=1.  Returns a description of the BLAS."""
+    global _blas
+    import glob
+    cands = sorted(glob.glob(os.path.join(os.path.dirname(np.__file__), "..", "numpy.libs", "libscipy_openblas64_*.so")))
+    if not cands:
+        raise OracleError("numpy's bundled OpenBLAS (ILP64) not found")
+    if _blas is None:
+        _blas = C.CDLL(cands[0])
+    _blas.scipy_openblas_set_num_threads64_.argtypes = [C.c_int]
+    _blas.scipy_openblas_set_num_threads64_(int(threads))
+    lib().eo_set_dgemm(C.cast(_blas.scipy_cblas_dgemm64_, C.c_void_p))
+    return "OpenBLAS bundled with numpy " + np.__version__ + " (scipy_cblas_dgemm64_)"
+
+
+def use_plain_loops():
+    lib().eo_set_dgemm(None)
+
+
+def last_stages():
+    """seconds: ReadBlock, M.Mt product, S*a, the two n^3 pre-products, Mt*W, row dots, Mt*v of the last export called"""
+    out = (C.c_double * 8)()
+    lib().eo_last_stages(out)
+    return dict(zip(["readblock", "mmt_gemm", "S_a", "pre_products", "Mt_W", "rowdots", "Mt_v"], list(out)[:7]))
