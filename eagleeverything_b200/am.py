@@ -298,9 +298,172 @@ def AM(geno, y, X0=None, maxit=20, message=None):
                 iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()})
 
 
+# ----------------------------------------------------------------------------- everything resident, in the basis of eigen(K)
+def eigbasis_inputs(xi, Xt, yt, ve, vg):
+    """The inputs of the scan from eigenbasis quantities (host, O(n q^2)): with K = U diag(xi) U^T, Xt = U^T X, yt = U^T y,
+         Dh = 1 / (ve + vg xi)                                  H^-1 = U diag(Dh) U^T                  (R/calculateH.R:36)
+         C  = Xt^T Dh Xt = L L^T                                t(X) Hinv X                            (R/calculateP.R:28)
+         W  = K^-1/2 V K^-1/2 = vg^2 P = U diag(vg^2 Dh) U^T - E E^T,   E = U Et,  Et = vg Dh Xt L^-T
+                                              (R/calculate_reduced_vara.R:21-35, src/calculate_a_and_vara_rcpp.cpp:97-98)
+         v  = K^-1/2 a_hat = vg P y = U vt,   vt = vg (Dh yt - Dh Xt C^-1 Xt^T Dh yt)
+                                              (R/calculate_reduced_a.R:31, src/calculate_a_and_vara_rcpp.cpp:90)
+    -> (w, Et, vt).  tests/test_gpu_algebra.py checks W and v against the oracle's restatement of R's dense formulas."""
+    Dh = 1.0 / (ve + vg * xi)
+    B = Dh[:, None] * Xt
+    Cq = Xt.T @ B
+    Lc = np.linalg.cholesky(Cq)
+    Et = vg * np.linalg.solve(Lc, B.T).T
+    vt = vg * (Dh * yt - B @ np.linalg.solve(Cq, B.T @ yt))
+    return vg * vg * Dh, np.asfortranarray(Et), vt
+
+
+def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None):
+    """AM()'s forward search (R/AM.R:260, 395-504) with the genotypes resident in HBM and the n x n algebra of every
+    iteration carried out in the basis of eigen(K) (csrc/eigbasis.cu): K = MMt/max(MMt) + 0.95 I never changes after the
+    first iteration (R/AM.R:414-423), so it is decomposed ONCE; after that an iteration costs
+      * EMMA's eigen(S (K + I) S) (R/emma_eigen_R_wo_Z.R:7-20): a secular solve, O(q n^2), no n x n matrix;
+      * H, P, K^+-1/2, a_hat, V (R/find_qtl.R:5-43): n-vectors and n x q panels on the host (eigbasis_inputs);
+      * the scan's right-hand side W: ONE n^3 product on the int8 tensor cores (eg_dev_scan_prepare_eig);
+      * the a / var(a) scan and the pick (src/calculate_a_and_vara_rcpp.cpp, R/find_qtl.R:71-83).
+    Same picks and extBIC trace as the dense route (AM_resident_dense / AM over the host ABI; tests/test_am.py).
+
+    store_kb: K-blocked int8 M store of THIS rank's markers (device.decode_kb), storeT: the row-major Mt store of the same
+    markers (device.transpose_kb); L: the number of markers of the whole data set.  shard (dist.Shard or None): marker
+    shards over torch.distributed ranks -- partial M.Mt all-reduced (int32), scans sharded, the pick by the sharded
+    first-maximum rule, the picked column broadcast by its owner; the n x n algebra is replicated."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib, device
+    lib = _lib.require_gpu()
+    say = message or (lambda s: None)
+    dev = store_kb.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())                                      # noqa: E731
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)             # noqa: E731
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))                       # noqa: E731
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    X = np.ones((n, 1)) if X0 is None else np.asarray(X0, dtype=np.float64).reshape(n, -1)
+    Lloc = storeT.shape[0]
+    stats = dict(mmt_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0, extract_s=0.0, total_s=0.0)
+
+    def timed(key, t0):
+        torch.cuda.synchronize()
+        stats[key] += time.perf_counter() - t0
+
+    t_all = time.perf_counter()
+    # ---- M M^T (AM.R:414-417), K (calcMMt.R:13), eigen(K) once
+    t0 = time.perf_counter()
+    U = torch.empty((n, n), **f64)           # K, then its eigenvectors (columns; column-major)
+    C32 = device.syrk_kb(store_kb, n, Lloc)
+    if shard is not None:
+        shard.allreduce_mmt(C32)
+    device.mmt_finalize(C32, n, out=U)
+    del C32
+    U.div_(U.max())
+    U.diagonal().add_(0.95)
+    timed("mmt_s", t0)
+    t0 = time.perf_counter()
+    vals = torch.empty(n, **f64)
+    _lib.check(lib.eg_dev_eigen_sym(p(U), n, p(vals), st()))                     # values decreasing, as R's eigen()
+    xi = vals.cpu().numpy().copy()
+    if not np.all(np.where(np.abs(xi) < 1e-8, 0.0, xi) > 0):                     # matrixcalc::is.positive.definite's screen
+        raise ValueError("M %*% t(M) is not positive definite")                  # calculateMMt_sqrt_and_sqrtinv.R:15-23
+    Ut = torch.empty((n, n), **f64)
+    _lib.check(lib.eg_dev_transpose_f64(p(U), n, p(Ut), st()))
+    Wp = torch.empty(lib.eg_scan_wp_elems(n), **f64)
+    work2 = torch.empty((n, n), **f64) if n < 1024 else None
+
+    def to_eig(v):                                                               # U^T v for an n-vector on the host
+        d_in = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
+        d_out = torch.empty(n, **f64)
+        _lib.check(lib.eg_dev_eigbasis_apply(p(U), n, p(d_in), 1, 1, p(d_out), st()))
+        return d_out.cpu().numpy()
+
+    yt = to_eig(y)
+    Xt = np.column_stack([to_eig(X[:, c]) for c in range(X.shape[1])])
+    timed("emma_eigen_s", t0)
+    emma = _Emma(None, stats)
+    emma._xi = xi
+    selected, new_locus, extBIC = [NA], NA, []
+    itnum, cont, vc = 1, True, None
+    sec_stats = []
+    while cont:
+        if not math.isnan(new_locus):                                            # constructX.R:11-20
+            t0 = time.perf_counter()
+            g = int(new_locus) - 1
+            if shard is None:
+                col = device.extract_col(store_kb, n, g, kblocked=True)
+            else:
+                col = shard.fetch_col(lambda j: device.extract_col(store_kb, n, j, kblocked=True), n, g, dev)
+            xnew = col.cpu().numpy().astype(np.float64)
+            X = np.column_stack([X, xnew])
+            Xt = np.column_stack([Xt, to_eig(xnew)])
+            timed("extract_s", t0)
+        q = X.shape[1]
+        # ---- emma.REMLE and emma.MLE share eigen(S (K + I) S) of this iteration
+        t0 = time.perf_counter()
+        lam, et = np.empty(n - q), np.empty(n - q)
+        s4 = (C.c_int64 * 4)()
+        Xtf = np.asfortranarray(Xt)
+        _lib.check(lib.eg_emma_eigen_R_wo_Z_eigbasis(dp(xi), dp(Xtf), dp(yt), n, q, dp(lam), dp(et), s4))
+        sec_stats.append(list(s4))
+        emma._last = (q, lam, et * et)
+        timed("emma_eigen_s", t0)
+        t0 = time.perf_counter()
+        vc = emma.REMLE(y, X)                                                     # AM.R:428
+        ml = emma.MLE(y, X, llim=-100.0, ulim=100.0)                             # calc_extBIC.R:6
+        stats["emma_search_s"] += time.perf_counter() - t0
+        bic = -2 * ml["ML"] + (q + 1) * math.log(n)
+        extBIC.append(bic + 2 * _lchoose(L, q - 1))
+        say(f" iteration {itnum}: extBIC = {extBIC[-1]:.4f}")
+        if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) == len(extBIC) - 1:   # AM.R:448
+            t0 = time.perf_counter()
+            w, Et, vt = eigbasis_inputs(xi, Xt, yt, float(vc["ve"]), float(vc["vg"]))
+            d_w = torch.from_numpy(w).to(dev)
+            d_Et = torch.from_numpy(Et.T.copy()).to(dev)                         # q x n row-major = n x q column-major
+            d_vt = torch.from_numpy(vt).to(dev)
+            work = torch.empty(n * q, **f64)
+            _lib.check(lib.eg_dev_scan_prepare_eig(p(U), p(Ut), n, p(d_w), p(d_Et), q, p(d_vt), p(work),
+                                                   p(work2) if work2 is not None else None, p(Wp), st()))
+            timed("algebra_s", t0)
+            t0 = time.perf_counter()
+            a, vara = device.scan(storeT, Lloc, n, Wp)
+            best, idx = device.argmax_tsq(a, vara)
+            if shard is None:
+                new_locus = int(idx.item()) + 1
+            else:
+                new_locus = int(shard.global_argmax(best, idx)[1]) + 1
+            del a, vara
+            timed("scan_s", t0)
+            selected.append(new_locus)
+            say(f" iteration {itnum}: picked locus {new_locus}")
+        else:
+            cont = False
+        itnum += 1
+        if itnum > maxit:
+            cont = False
+    if itnum > maxit:
+        final = selected
+    elif len(selected) > 1:
+        final = selected[:-1]
+    else:
+        final = selected
+    torch.cuda.synchronize()
+    stats["total_s"] = time.perf_counter() - t_all
+    return dict(selected=[int(s) for s in final if not math.isnan(s)],
+                all_picked=[int(s) for s in selected if not math.isnan(s)], extBIC=extBIC, vc=vc,
+                iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()},
+                secular={"max_root_iterations": max(s[2] for s in sec_stats), "deflated_poles": sum(s[1] for s in sec_stats),
+                         "roots": sum(s[3] for s in sec_stats)})
+
+
 # ----------------------------------------------------------------------------- everything resident in HBM
-def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None):
-    """The same search with every n x n matrix living in HBM from the first iteration to the last (the B200-first form:
+def AM_resident_dense(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None):
+    """(Round-1 form, kept as a cross-check of AM_resident: R's dense formulas executed one for one on the device --
+    cuSOLVER dsyevd / potrf / potri and cuBLAS products every iteration.)
+    The same search with every n x n matrix living in HBM from the first iteration to the last (the B200-first form:
     nothing but n-vectors, the q-column design matrix and scalars crosses PCIe after the genotypes are resident).
     store_kb: the K-blocked int8 M store (device.decode_kb), storeT: the row-major Mt store (device.transpose_kb);
     torch owns the buffers, the device-level C ABI (eg_dev_*) does the work, EMMA's 1-D search stays on the host.

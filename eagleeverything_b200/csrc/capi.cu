@@ -99,6 +99,7 @@ cublasHandle_t ctx_cublas() { return g_ctx.cublas; }
 void syrk_release_cache();
 void scan_i8_release();
 void algebra_release();
+void eigbasis_release();
 void prep_i8_release();
 int launch_prepare_i8(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1, double* d_tmp,
                       double* d_Wp, int64_t Kpad, cudaStream_t st, bool* done);
@@ -804,6 +805,7 @@ extern "C" int eg_shutdown(void) {
     scan_i8_release();
     prep_i8_release();
     algebra_release();
+    eigbasis_release();
     if (g_ctx.cublas) cublasDestroy(g_ctx.cublas);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);

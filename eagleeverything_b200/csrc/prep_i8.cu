@@ -252,12 +252,15 @@ prep_i8_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constant_
 // ------------------------------------------------------------------ slicing of the columns of a column-major matrix
 // |x| bit patterns order like unsigned integers, and NaN > Inf > finite: a plain integer max finds the column's
 // largest magnitude and lets a NaN / Inf poison the column.
+// rowscale (optional): the matrix sliced is diag(rowscale) * A  (one rounding per entry)
 __global__ void __launch_bounds__(256) pi_colscale_kernel(const double* __restrict__ A, int64_t rows, int64_t ld,
-                                                          int32_t* __restrict__ expo, double* __restrict__ scale) {
+                                                          int32_t* __restrict__ expo, double* __restrict__ scale,
+                                                          const double* __restrict__ rowscale) {
     const int64_t c = blockIdx.x;
     unsigned long long m = 0;
     for (int64_t i = threadIdx.x; i < rows; i += 256) {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(A[i + c * ld]) & 0x7FFFFFFFFFFFFFFFull;
+        const double x = rowscale ? A[i + c * ld] * rowscale[i] : A[i + c * ld];
+        const unsigned long long b = (unsigned long long)__double_as_longlong(x) & 0x7FFFFFFFFFFFFFFFull;
         m = b > m ? b : m;
     }
     __shared__ unsigned long long sh[8];
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(256) pi_colscale_kernel(const double* __restri
 // Q[s][c][k], k contiguous (Kp bytes per row, zero beyond `rows`); thread -> 4 consecutive k of one column
 __global__ void __launch_bounds__(256) pi_slice_kernel(const double* __restrict__ A, int64_t rows, int64_t ld,
                                                        const int32_t* __restrict__ expo, int8_t* __restrict__ Q, int64_t Kp,
-                                                       int64_t slice_stride) {
+                                                       int64_t slice_stride, const double* __restrict__ rowscale) {
     const int64_t c = blockIdx.y;
     const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (i0 >= Kp) return;
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(256) pi_slice_kernel(const double* __restrict_
     for (int d = 0; d < 4; d++) {
         const int64_t i = i0 + d;
         if (i < rows) {
-            const double xs = ldexp(A[i + c * ld], 55 - e);
+            const double xs = ldexp(rowscale ? A[i + c * ld] * rowscale[i] : A[i + c * ld], 55 - e);
             long long X = fabs(xs) < 3.6e16 ? __double2ll_rn(xs) : 0;  // |xs| <= 127 * 2^48 unless the column is poisoned
 #pragma unroll
             for (int s = PI_SLICES - 1; s > 0; s--) {
@@ -389,11 +392,11 @@ static bool pi_grow(T** ptr, size_t* cap, size_t need) {
 }
 
 static int pi_slice(const double* d_A, int64_t rows, int64_t ld, int64_t ncols, int8_t* Q, int64_t Kp, int32_t* expo,
-                    double* scale, cudaStream_t st) {
-    pi_colscale_kernel<<<(unsigned)ncols, 256, 0, st>>>(d_A, rows, ld, expo, scale);
+                    double* scale, cudaStream_t st, const double* d_rowscale = nullptr) {
+    pi_colscale_kernel<<<(unsigned)ncols, 256, 0, st>>>(d_A, rows, ld, expo, scale, d_rowscale);
     EG_TRY(check_launch("pi_colscale_kernel"));
     pi_slice_kernel<<<dim3((unsigned)((Kp / 4 + 255) / 256), (unsigned)ncols), 256, 0, st>>>(d_A, rows, ld, expo, Q, Kp,
-                                                                                          Kp * ncols);
+                                                                                          Kp * ncols, d_rowscale);
     return check_launch("pi_slice_kernel");
 }
 
@@ -528,6 +531,36 @@ int launch_prepare_i8(const double* d_S, const double* d_V, int64_t n, int64_t c
     EG_TRY(pi_slice(d_tmp, n, n, nc, g_pi.qX, Kp, eX, sX, st));
     // :98   W[0:col1, col0:col1] = S[0:col1, :] * X   (rows of S read as its columns: S symmetric)
     EG_TRY(pi_product(g_pi.qS, n, sS, 0, col1, g_pi.qX, nc, sX, 0, nc, n, Kp, d_Wp + col0 * Kpad, Kpad, true, col0, st));
+    *done = true;
+    return EG_OK;
+}
+
+// W0 = A A^T (upper triangle, into Wp with ld = Kpad) for A = U diag(rs), given Ut = U^T column-major (so that column i
+// of diag(rs) Ut is row i of A) -- the ONE n^3 product the scan's right-hand side needs per forward iteration once the
+// algebra runs in the basis of eigen(K) (csrc/eigbasis.cu): both operands are the same set of digit slices.
+// *done = false when the slices do not fit: the caller takes the cuBLAS path.
+int launch_prepare_eig_i8(const double* d_Ut, const double* d_rs, int64_t n, double* d_Wp, int64_t Kpad, cudaStream_t st,
+                          bool* done) {
+    *done = false;
+    g_pi_marks = 0;
+    g_pi_ops = 0.0;
+    int dev = 0;
+    EG_CUDA(cudaGetDevice(&dev));
+    if (g_pi.device != dev) {
+        if (g_pi.device >= 0) prep_i8_release();
+        g_pi.device = dev;
+    }
+    if (n * 16384 >= ((int64_t)1 << 31)) return EG_OK;
+    const int64_t Kp = round_up(n, 128);
+    size_t free_b = 0, total_b = 0;
+    EG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = (size_t)PI_SLICES * Kp * (size_t)n;
+    if (need > g_pi.qS_cap && need - g_pi.qS_cap + ((size_t)2 << 30) > free_b) return EG_OK;
+    if (!pi_grow(&g_pi.qS, &g_pi.qS_cap, need) || !pi_grow(&g_pi.sc, &g_pi.sc_cap, (size_t)n) ||
+        !pi_grow(&g_pi.ex, &g_pi.ex_cap, (size_t)n))
+        return EG_OK;
+    EG_TRY(pi_slice(d_Ut, n, n, n, g_pi.qS, Kp, g_pi.ex, g_pi.sc, st, d_rs));
+    EG_TRY(pi_product(g_pi.qS, n, g_pi.sc, 0, n, g_pi.qS, n, g_pi.sc, 0, n, n, Kp, d_Wp, Kpad, true, 0, st));
     *done = true;
     return EG_OK;
 }

@@ -76,3 +76,34 @@ def gather_sharded(vec: torch.Tensor, L: int, world: int, group=None):
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat([o[:s] for o, s in zip(outs, sizes)])
+
+
+class Shard:
+    """This rank's marker shard of a data set of L markers, and the three exchanges a sharded forward search needs
+    (am.AM_resident): the int32 all-reduce of the partial M.Mt, the sharded first-maximum pick, and the broadcast of a
+    picked marker's genotype column by the rank that owns it."""
+
+    def __init__(self, L: int, world: int, rank: int, group=None):
+        self.L, self.world, self.rank, self.group = L, world, rank, group
+        self.ranges = [shard_range(L, world, r) for r in range(world)]
+        self.c0, self.c1 = self.ranges[rank]
+
+    def allreduce_mmt(self, C32):
+        return allreduce_partial_mmt(C32, self.group)
+
+    def global_argmax(self, best, idx_local):
+        return global_argmax(best, idx_local, self.c0, self.group)
+
+    def owner(self, g: int) -> int:
+        for r, (a, b) in enumerate(self.ranges):
+            if a <= g < b:
+                return r
+        raise ValueError(f"marker {g} outside [0, {self.L})")
+
+    def fetch_col(self, extract_local, n: int, g: int, device):
+        """extract_local(j) -> int32[n] device tensor of LOCAL marker j; every rank receives marker g's column."""
+        r = self.owner(g)
+        col = extract_local(g - self.c0) if r == self.rank else torch.empty(n, dtype=torch.int32, device=device)
+        if self.world > 1:
+            dist.broadcast(col, src=r, group=self.group)
+        return col

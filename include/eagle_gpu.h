@@ -305,6 +305,29 @@ int eg_dev_calculate_reduced_a(double varG, const double* d_P, const double* d_s
 int eg_dev_calculate_reduced_vara(const double* d_X, int q, double varE, double varG, const double* d_sqrt, int64_t n,
                                   double* d_V, double* d_D, double* d_small, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The same algebra in the basis of eigen(K), csrc/eigbasis.cu + csrc/secular.cuh.  K = MMt/max(MMt) + 0.95 I is fixed after
+ * the first forward iteration (R/AM.R:414-423): with K = U diag(xi) U^T computed once (eg_dev_eigen_sym), H^-1, K^+-1/2 and
+ * D^-1 are diagonal in U and P, V are diagonal + rank q, so an iteration costs O(q n^2) + ONE n^3 product instead of the
+ * reference's dense eigendecomposition, three dense inversions and ~10 n^3 products.
+ * ------------------------------------------------------------------------------------------------ */
+/* emma.eigen.R.wo.Z (R/emma_eigen_R_wo_Z.R:7-20) followed by etas = t(vectors) %*% y (R/emma_REMLE.R:40), given
+ * xi[n] = eigen(K)$values (any order), Xt = U^T X (n x q column-major) and yt = U^T y in the same order: the n - q
+ * non-trivial eigenvalues of S (K + I) S minus 1 (decreasing) and the matching etas (up to sign), by q rank-one
+ * compressions of the diagonal solved through their secular equations on the device -- O(q n^2), no n x n matrix.
+ * Host pointers.  stats4 (may be NULL): compressions done, poles deflated, worst root-finder iteration count, roots. */
+int eg_emma_eigen_R_wo_Z_eigbasis(const double* xi, const double* Xt, const double* yt, int64_t n, int q, double* out_values,
+                                  double* out_etas, int64_t* stats4);
+int eg_dev_transpose_f64(const double* d_in, int64_t n, double* d_out, void* stream);
+/* d_out (n x r) = U^T d_in (to_eigenbasis != 0) or U d_in */
+int eg_dev_eigbasis_apply(const double* d_U, int64_t n, const double* d_in, int r, int to_eigenbasis, double* d_out, void* stream);
+/* The scan's right-hand side (what eg_dev_scan_prepare builds from S, V, a) from eigenbasis quantities:
+ * W = U diag(w) U^T - E E^T with E = U Et (n x q, q may be 0), folded into d_Wp; v = U vt into its column n.
+ * d_Ut = U^T (eg_dev_transpose_f64).  d_work: n * max(q,1) doubles; d_work2: n*n doubles, only read when the product runs
+ * in FP64 (n < 1024, or the digit slices do not fit) and may be NULL otherwise. */
+int eg_dev_scan_prepare_eig(const double* d_U, const double* d_Ut, int64_t n, const double* d_w, const double* d_Et, int q,
+                            const double* d_vt, double* d_work, double* d_work2, double* d_Wp, void* stream);
+
 /* How var(a) is contracted (same result within the stated tolerance, both deterministic):
  *   1  exact int8 slices of U on the tcgen05 int8 tensor cores, scan_i8.cu -- the default;
  *   0  FP64 tensor cores (DMMA), scan_f64.cu (also: environment EAGLE_SCAN_MODE=f64). */

@@ -129,3 +129,90 @@ def test_emma_eigendecompositions(problem):
     eg, eo_ = (rr["vectors"].T @ y) ** 2, (U.T @ y) ** 2
     assert np.abs(eg - eo_).max() <= 1e-7 * eo_.max()
     assert np.abs(rr["vectors"].T @ X).max() < 1e-8 * n                                # orthogonal to the fixed effects
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same algebra in the basis of eigen(K) (csrc/eigbasis.cu, csrc/secular.cuh): what am.AM_resident runs.
+def test_secular_emma_eigen_on_device(problem):
+    """eg_emma_eigen_R_wo_Z_eigbasis (q rank-one compressions solved by their secular equations, O(q n^2)) against the
+    oracle's dense restatement of R/emma_eigen_R_wo_Z.R:7-20 + R/emma_REMLE.R:40: eigenvalues, and eta^2 through the
+    order-free sums EMMA's likelihoods consume."""
+    import ctypes as C
+    from eagleeverything_b200 import _lib
+    from oracle import am_driver as am
+    lib = _lib.require_gpu()
+    K, X, y, n, q = (problem[k] for k in ("K", "X", "y", "n", "q"))
+    xi, U = am.r_eigen_sym(K)
+    Xt, yt = np.asfortranarray(U.T @ X), np.ascontiguousarray(U.T @ y)
+    vals, etas, st = np.empty(n - q), np.empty(n - q), (C.c_int64 * 4)()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    _lib.check(lib.eg_emma_eigen_R_wo_Z_eigbasis(dp(xi), dp(Xt), dp(yt), n, q, dp(vals), dp(etas), st))
+    lam, Ur = am.emma_eigen_R_wo_Z(K, X)
+    assert st[0] == q and st[2] < 60 and np.all(np.diff(vals) <= 0)
+    np.testing.assert_allclose(vals, lam, rtol=0, atol=1e-12 * np.abs(xi).max())
+    e_ref = (Ur.T @ y) ** 2
+    for d in (1e-5, 1e-2, 1.0, 1e2):
+        np.testing.assert_allclose((etas ** 2 / (vals + d)).sum(), (e_ref / (lam + d)).sum(), rtol=1e-11)
+        np.testing.assert_allclose((etas ** 2 / (vals + d) ** 2).sum(), (e_ref / (lam + d) ** 2).sum(), rtol=1e-11)
+    # a design matrix without full column rank is refused
+    Xd = np.asfortranarray(np.column_stack([Xt[:, 0], 3.0 * Xt[:, 0]]))
+    v2, e2 = np.empty(n - 2), np.empty(n - 2)
+    assert lib.eg_emma_eigen_R_wo_Z_eigbasis(dp(xi), dp(Xd), dp(yt), n, 2, dp(v2), dp(e2), None) == _lib.EG_ERR_ARG
+    assert b"rank deficient" in lib.eg_last_error()
+
+
+@pytest.mark.parametrize("mode", ["auto", "i8", "f64"])
+def test_scan_rhs_from_the_eigenbasis_equals_the_dense_route(problem, mode, monkeypatch):
+    """eg_dev_scan_prepare_eig (W = U diag(w) U^T - E E^T: one digit-slice SYRK on the int8 tensor cores, or DSYRK) against
+    eg_dev_scan_prepare fed with the oracle's dense S, V, a_hat (R/find_qtl.R:5-45): the packed right-hand side of the scan
+    to 1e-9 of its largest entry, and a / var(a) of a marker panel."""
+    import ctypes as C
+    import torch
+    from eagleeverything_b200 import _lib, am as pam, device
+    from oracle import am_driver as am
+    if mode != "auto":
+        monkeypatch.setenv("EAGLE_PREP_MODE", mode)
+    lib = device.init(0)
+    K, X, y, ve, vg, n, q = (problem[k] for k in ("K", "X", "y", "ve", "vg", "n", "q"))
+    S, V, hat_a = am.scan_inputs(K, K, X, y, ve, vg)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    Wp_ref = device.scan_prepare(cu(S), cu(V), cu(np.asarray(hat_a).reshape(-1)), n)
+    xi, U = am.r_eigen_sym(K)
+    w, Et, vt = pam.eigbasis_inputs(xi, U.T @ X, U.T @ y, ve, vg)
+    dU, dUt = cu(U.T.copy()), cu(U.copy())       # row-major torch tensors: U^T row-major == U column-major
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    Wp = torch.empty(lib.eg_scan_wp_elems(n), dtype=torch.float64, device="cuda")
+    work = torch.empty(n * q, dtype=torch.float64, device="cuda")
+    work2 = torch.empty(n * n, dtype=torch.float64, device="cuda")
+    _lib.check(lib.eg_dev_scan_prepare_eig(p(dU), p(dUt), n, p(cu(w)), p(cu(Et.T.copy())), q, p(cu(vt)), p(work), p(work2), p(Wp),
+                                           None))
+    torch.cuda.synchronize()
+    a, b = Wp.cpu().numpy(), Wp_ref.cpu().numpy()
+    assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+    L = 1500
+    G = synth.genotypes(n, L, seed=n + 3)
+    img = torch.from_numpy(np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    kb, _ = device.decode_kb(img, L + 1, n, L)
+    tT = device.transpose_kb(kb, n, L)
+    a1, v1 = device.scan(tT, L, n, Wp)
+    a0, v0 = device.scan(tT, L, n, Wp_ref)
+    a1, v1, a0, v0 = (t.cpu().numpy() for t in (a1, v1, a0, v0))
+    assert np.abs(a1 - a0).max() <= 1e-9 * np.abs(a0).max()
+    assert np.abs(v1 - v0).max() <= 1e-9 * np.abs(v0).max()
+
+
+def test_dense_and_eigenbasis_searches_agree(synth_small):
+    """am.AM_resident (eigenbasis) against am.AM_resident_dense (R's formulas one for one on the device)."""
+    import torch
+    from eagleeverything_b200 import am as pam, device
+    device.init(0)
+    s = synth_small
+    y, _ = synth.phenotype(s["G"])
+    img = torch.from_numpy(np.concatenate([synth.ascii_image(s["G"]).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    kb, _ = device.decode_kb(img, s["L"] + 1, s["n"], s["L"])
+    tT = device.transpose_kb(kb, s["n"], s["L"])
+    r1 = pam.AM_resident(kb, tT, s["n"], s["L"], y, maxit=6)
+    r0 = pam.AM_resident_dense(kb, tT, s["n"], s["L"], y, maxit=6)
+    assert r1["all_picked"] == r0["all_picked"] and r1["selected"] == r0["selected"]
+    np.testing.assert_allclose(r1["extBIC"], r0["extBIC"], rtol=1e-9)
+    assert r1["secular"]["max_root_iterations"] < 60
