@@ -376,6 +376,16 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
     value = L / (ms_step * 1e-3)
 
+    # ---------------- results of the last step, hashed (the same hashes must come out at every N) and, at N > 1, compared
+    # bit for bit with a single-GPU run of the same data set computed here (rank 0) -- a mismatch fails the run
+    checks = result_checks(args, torch, dist, device, egd, lib, n, L, Lg, c0, world, rank, K, oa, ov, S, V, ah, res)
+    if checks.get("failed"):
+        if rank == 0:
+            jprint({"metric": METRIC, "value": None, "n_gpus": world, "error": "multi-rank parity failed", "checks": checks})
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(3)
+
     # ---------------- end to end with host buffers (H2D of the image / S / V / a, D2H of K, a, vara)
     if args.no_e2e:
         e2e = {"value": None, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "skipped (--no-e2e)"}
@@ -384,15 +394,35 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         e2e = run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img, S, V, ah)
 
+    mode = int(lib.eg_get_scan_mode())
+    k_ms, k_ops, p_ms, p_ops = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    _lib.check(lib.eg_last_scan_kernel(C.byref(k_ms), C.byref(k_ops)))   # CUDA events around the scan kernel itself
+    _lib.check(lib.eg_last_prep_kernels(C.byref(p_ms), C.byref(p_ops)))
+    # BASELINE config 3 as it is worded: the full forward search, marker-sharded at N > 1 (collective calls: every rank)
+    search = None
+    if not args.no_search and args.workload in ("c2", "c3"):
+        try:
+            search = run_forward_search(args, torch, dist, egd, n, L, Lg, c0, world, rank, img)
+        except Exception as ex:  # noqa: BLE001
+            search = {"note": f"failed: {type(ex).__name__}: {ex}"}
+    extras = None
+    if world >= 8 and args.workload == "c3" and not args.no_extras:
+        del img, S, V, ah
+        torch.cuda.empty_cache()
+        extras = {}
+        for wl in ("c5", "c4"):
+            try:
+                extras[wl] = run_extra_workload(args, wl, torch, dist, device, egd, lib, world, rank)
+            except Exception as ex:  # noqa: BLE001
+                extras[wl] = {"note": f"failed: {type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     stages = dict(zip(STAGES, stage_ms))
-    mode = int(lib.eg_get_scan_mode())
-    k_ms, k_ops = C.c_double(), C.c_double()
-    _lib.check(lib.eg_last_scan_kernel(C.byref(k_ms), C.byref(k_ops)))   # CUDA events around the scan kernel itself
     k_ms, k_ops = k_ms.value, k_ops.value
     # reference-equivalent FP64 work of the scan (full T = Mt*W, row-dot): 2n(n+1)+2n flops per marker
     scan_ref_flops = (2.0 * n * (n + 1) + 2.0 * n) * Lg
@@ -442,8 +472,6 @@ def run_gpu(args):
                            "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas},
         roofline["kernel"]: roofline,
     }
-    p_ms, p_ops = C.c_double(), C.c_double()
-    _lib.check(lib.eg_last_prep_kernels(C.byref(p_ms), C.byref(p_ops)))
     if p_ms.value > 0:
         p_rate = p_ops.value / (p_ms.value * 1e-3) / 1e12
         rooflines["prep_i8_kernel"] = {"bound": "tensor", "achieved": p_rate, "unit": "TOP/s (int8)", "peak": int8_peak,
@@ -468,12 +496,6 @@ def run_gpu(args):
         else:
             rf.setdefault("traffic", None)
     cpu = None
-    search = None
-    if world == 1 and not args.no_search and args.workload in ("c2", "c3"):   # after every per-kernel statistic has been read
-        try:
-            search = run_forward_search(args, torch, n, L, img)
-        except Exception as ex:  # noqa: BLE001
-            search = {"note": f"failed: {type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu:
         try:
             cpu = cpu_reference_sample(n, L, steps=1, warmup=0)
@@ -497,7 +519,8 @@ def run_gpu(args):
             "busbw_gbs": 2.0 * (world - 1) / world * 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
             "note": "NCCL int32 sum of the n x n partial M.Mt; measured reference on this pool: 725 GB/s bus bandwidth "
                     "for an 8-rank all-reduce at 1 GiB (B200_PROFILING.md)"}),
-        "gpu_launches": launches, "library_ceilings": ceil, "forward_search": search,
+        "gpu_launches": launches, "library_ceilings": ceil, "forward_search": search, "checks": checks,
+        "extra_workloads": extras,
         "picked_marker": int(res[1]) if not hasattr(res[1], "item") else int(res[1].item()),
     }
     jprint(out)
@@ -631,36 +654,233 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
             "timing": "host clock around a synchronised region (max with CUDA events), max over ranks"}
 
 
-def run_forward_search(args, torch, n, L, img):
+def _sha(t):
+    import hashlib
+    return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()
+
+
+def result_checks(args, torch, dist, device, egd, lib, n, L, Lg, c0, world, rank, K, oa, ov, S, V, ah, res):
+    """sha256 of the results of the last timed step -- K (after the all-reduce), a, var(a) over ALL markers, the pick -- so
+    that the lines of a scaling run can be compared with each other; and at N > 1 (when the whole data set fits one GPU)
+    the same step recomputed on rank 0 alone and compared bit for bit: the all-reduced K, every shard of a / var(a), the
+    pick.  `failed` is set on any mismatch (the run then exits non-zero)."""
+    out = {}
+    a_all = egd.gather_sharded(oa, L, world) if world > 1 else oa
+    v_all = egd.gather_sharded(ov, L, world) if world > 1 else ov
+    picked = int(res[1]) if not hasattr(res[1], "item") else int(res[1].item())
+    if world > 1:   # every rank holds the same K after the all-reduce: compare 128-bit fingerprints across ranks
+        kv = K.view(torch.int64).reshape(-1)
+        fp = torch.stack([kv.sum(), (kv * (torch.arange(kv.numel(), device=kv.device, dtype=torch.int64) | 1)).sum()])
+        fps = torch.empty(2 * world, dtype=torch.int64, device=kv.device)
+        dist.all_gather_into_tensor(fps, fp)
+        out["K_identical_on_all_ranks"] = bool((fps.view(world, 2) == fp).all().item())
+    if rank == 0:
+        out.update(K_sha256=_sha(K), a_sha256=_sha(a_all), vara_sha256=_sha(v_all), picked_marker=picked)
+    fits = 3.0 * n * (L + 1) + 60.0 * n * n < 120e9
+    if world > 1 and not args.no_parity:
+        if fits:
+            if rank == 0:
+                img_f = device.synth_ascii(n, L, GENO_SEED, col_offset=0, n_total=n)
+                kb, err = device.decode_kb(img_f, L + 1, n, L)
+                del img_f
+                tT = device.transpose_kb(kb, n, L)
+                C32 = device.syrk_kb(kb, n, L)
+                del kb
+                K1 = device.mmt_finalize(C32, n)
+                del C32
+                Wp1 = device.scan_prepare(S, V, ah, n)
+                a1, v1 = device.scan(tT, L, n, Wp1)
+                b1, i1 = device.argmax_tsq(a1, v1)
+                out["vs_single_gpu"] = {
+                    "K_bit_identical": bool(torch.equal(K1, K)), "a_bit_identical": bool(torch.equal(a1, a_all)),
+                    "vara_bit_identical": bool(torch.equal(v1, v_all)), "pick_identical": int(i1.item()) == picked,
+                    "how": "the same data set decoded, contracted and scanned on rank 0 alone in this run; compared with the "
+                           "all-reduced K and the gathered shards of a / var(a)"}
+                del K1, Wp1, a1, v1, tT
+                torch.cuda.empty_cache()
+                ok = all(v for k, v in out["vs_single_gpu"].items() if k != "how")
+            flag = torch.tensor([1 if (rank != 0 or ok) else 0], device="cuda")
+            dist.broadcast(flag, src=0)
+            if not out.get("K_identical_on_all_ranks", True) or int(flag.item()) == 0:
+                out["failed"] = True
+        else:
+            out["vs_single_gpu"] = {"note": "data set does not fit one GPU: spot checks instead (extra_workloads)"}
+            if not out.get("K_identical_on_all_ranks", True):
+                out["failed"] = True
+    return out
+
+
+def spot_check(torch, dist, device, egd, n, Lg, world, kb, tT, K, S, V, ah, oa, ov, rows=64, markers=1024):
+    """Parity at sizes where nothing can be recomputed whole: `rows` rows of K and a / var(a) of `markers` of this rank's
+    markers recomputed with plain FP64 torch products from the decoded genotypes (an independent evaluation of
+    calculateMMt_rcpp.cpp:95 and calculate_a_and_vara_rcpp.cpp:90-112) -- K rows exactly, a / var(a) to 1e-9."""
+    g = torch.Generator(device="cpu"); g.manual_seed(99)
+    ridx = torch.randperm(n, generator=g)[:rows].cuda()
+    # M of this shard as doubles (reference sign: stores hold the negated value, products do not see it)
+    part = torch.zeros((rows, n), dtype=torch.float64, device="cuda")
+    step = max(1024, int(2e9 / (8 * n)))
+    for b0 in range(0, Lg, step):
+        b1 = min(Lg, b0 + step)
+        Mt_blk = tT[b0:b1, :n].to(torch.float64)              # (markers, n)
+        part += Mt_blk[:, ridx].T @ Mt_blk
+    if world > 1:
+        dist.all_reduce(part)
+    k_ok = bool(torch.equal(part, K[ridx, :]))
+    midx = torch.randperm(Lg, generator=g)[:markers].cuda()
+    Mj = tT[midx, :n].to(torch.float64).T.contiguous()          # n x markers, stored value = -(reference value)
+    T1 = S @ Mj
+    vara_ref = (T1 * (V @ T1)).sum(0)
+    a_ref = -(Mj.T @ (S @ ah))
+    av, vv = oa[midx], ov[midx]
+    tol_v = 1e-9 * vara_ref.abs() + 4 * (n + 10) * 2.2e-16 * (T1.abs() * (V @ T1).abs()).sum(0)
+    tol_a = 1e-9 * a_ref.abs() + 4 * (n + 10) * 2.2e-16 * (Mj.abs().T @ (S @ ah).abs())
+    a_ok = bool(((av - a_ref).abs() <= tol_a).all().item())
+    v_ok = bool(((vv - vara_ref).abs() <= tol_v).all().item())
+    flags = torch.tensor([int(k_ok), int(a_ok), int(v_ok)], device="cuda")
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    return {"K_rows_checked": rows, "K_rows_exact": bool(flags[0].item()), "markers_checked_per_rank": markers,
+            "a_within_1e-9": bool(flags[1].item()), "vara_within_1e-9": bool(flags[2].item()),
+            "max_rel_err_vara": float(((vv - vara_ref).abs() / vara_ref.abs().clamp_min(1e-300)).max().item()),
+            "how": "FP64 torch products from the decoded genotypes on every rank (K rows all-reduced)"}
+
+
+def run_extra_workload(args, wl, torch, dist, device, egd, lib, world, rank):
+    """One forward step of a shape that needs the 8 GPUs (BASELINE configs 4 and 5), recorded beside the headline run.
+    c5 (n = 20,000 x L = 2,000,000, fixed-effect covariates): a REAL first iteration of AM() with X = [1, x1, x2] -- M.Mt,
+    eigen(K), EMMA's REML / ML through the secular solve, the eigenbasis right-hand side, the sharded scan and pick
+    (am.AM_resident, maxit = 1) -- plus a kernel-level step with spot-check parity.
+    c4 (n = 50,000 x L = 600,000): decode, M.Mt with the 10 GB int32 all-reduce, pre-products and scan on synthetic S, V
+    (an eigendecomposition of order 50,000 is not part of this path), with spot-check parity."""
+    import numpy as np
+    from eagleeverything_b200 import am
+    w = WORKLOADS[wl]
+    n, L = w["n"], w["L"]
+    c0, c1 = egd.shard_range(L, world, rank)
+    Lg = c1 - c0
+    out = {"workload": w["name"], "n": n, "L": L, "n_gpus": world}
+    img = device.synth_ascii(n, Lg, GENO_SEED, col_offset=c0, n_total=n)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+
+    def sync():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    sync()
+    ev[0].record()
+    kb, err = device.decode_kb(img, Lg + 1, n, Lg)
+    del img
+    tT = device.transpose_kb(kb, n, Lg)
+    ev[1].record()
+    C32 = device.syrk_kb(kb, n, Lg)
+    ev[2].record()
+    egd.allreduce_partial_mmt(C32)
+    ev[3].record()
+    K = device.mmt_finalize(C32, n)
+    del C32
+    ev[4].record()
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    S = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g)
+    S = (S + S.T) * (0.5 / n ** 0.5); S.diagonal().add_(2.0)
+    V = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g)
+    V = (V + V.T) * (0.5 / n ** 0.5); V.diagonal().add_(1.5)
+    ah = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    sync()
+    ev[5].record()
+    Wp = device.scan_prepare_sharded(S, V, ah, n, rank, world)
+    ev[6].record()
+    oa, ov = device.scan(tT, Lg, n, Wp)
+    best, idx = device.argmax_tsq(oa, ov)
+    pick = egd.global_argmax(best, idx, c0)
+    ev[7].record()
+    sync()
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(7)]
+    tt = torch.tensor(ms, dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = tt.tolist()
+    step_ms = ms[0] + ms[1] + ms[2] + ms[3] + ms[5] + ms[6]
+    out["kernel_step"] = {"stage_ms": dict(zip(["decode_transpose", "syrk", "allreduce", "finalize", "(inputs)", "prepare", "scan_argmax"],
+                                               [round(x, 3) for x in ms])),
+                          "ms_per_step": step_ms, "markers_per_s": L / (step_ms * 1e-3),
+                          "mmt_int8_tops_per_gpu": float(Lg) * n * (n + 1) / (ms[1] * 1e-3) / 1e12,
+                          "allreduce_busbw_gbs": 2.0 * (world - 1) / world * 4.0 * n * n / (ms[2] * 1e-3) / 1e9,
+                          "picked_marker": int(pick[1]), "inputs": "synthetic symmetric S, V, a_hat", "steps": 1}
+    del Wp
+    out["spot_check"] = spot_check(torch, dist, device, egd, n, Lg, world, kb, tT, K, S, V, ah, oa, ov)
+    del S, V, K, oa, ov
+    torch.cuda.empty_cache()
+    if wl == "c5":
+        rng = np.random.default_rng(11)
+        X0 = np.column_stack([np.ones(n), rng.standard_normal(n), rng.integers(0, 2, n).astype(np.float64)])
+        shard = egd.Shard(L, world, rank)
+        qtl = np.linspace(L // 10, L - L // 10 - 1, 5).astype(np.int64)
+        y = 10.0 + rng.standard_normal(n) + 0.5 * X0[:, 1] - 0.3 * X0[:, 2]
+        for b, j in zip([1.0, 0.8, 0.6, 0.5, 0.4], qtl):
+            col = shard.fetch_col(lambda jj: device.extract_col(kb, n, jj, kblocked=True), n, int(j), "cuda")
+            y = y + b * col.cpu().numpy().astype(np.float64)
+        sync()
+        r = am.AM_resident(kb, tT, n, L, y, X0=X0, maxit=1, shard=shard)
+        sec = torch.tensor([r["seconds"][k] for k in sorted(r["seconds"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        out["forward_iteration_with_covariates"] = {
+            "design": "intercept + 2 fixed-effect covariates (q = 3); no Z (in the reference snapshot Z only enters EMMA, "
+                      "R/AM.R:428,436, and a non-square Z cannot pass find_qtl, R/calculateP.R:22-25)",
+            "picked_1based": r["all_picked"], "planted_qtl_1based": [int(j) + 1 for j in qtl], "extBIC": r["extBIC"],
+            "vc": {k: float(v) for k, v in r["vc"].items()}, "seconds_max_over_ranks": dict(zip(sorted(r["seconds"]), [round(x, 4) for x in sec.tolist()])),
+            "secular": r["secular"]}
+    del kb, tT
+    return out
+
+
+def run_forward_search(args, torch, dist, egd, n, L, Lg, c0, world, rank, img):
     """BASELINE config 3 as it is worded: the full multi-locus AM() forward search (<= 10 QTL) on the synthetic data set
-    of SURVEY.md 8(d) (5 planted QTL), through the mirror of the R loop in eagleeverything_b200/am.py.  Default: every
-    n x n matrix resident in HBM (am.AM_resident, device-level C ABI).  --search-host adds the route an R session would
-    take today: every matrix crossing the host-level ABI as a host buffer (am.AM over api.*)."""
+    of SURVEY.md 8(d) (5 planted QTL), through the mirror of the R loop in eagleeverything_b200/am.py -- everything
+    resident in HBM, the n x n algebra in the basis of eigen(K) (am.AM_resident).  At N > 1 the markers are sharded as in
+    the timed step: partial M.Mt all-reduced, scans sharded, sharded pick, the picked column broadcast by its owner; the
+    n x n algebra is replicated.  --search-host (N = 1) adds the route an R session would take today: every matrix
+    crossing the host-level ABI as a host buffer (am.AM over api.*)."""
     import numpy as np
     from eagleeverything_b200 import am, api, device, synth
     qtl = np.linspace(L // 10, L - L // 10 - 1, 5).astype(np.int64)          # synth.phenotype's evenly spaced loci
+    shard = egd.Shard(L, world, rank) if world > 1 else None
     t0 = time.perf_counter()
-    kb = device.decode_kb(img, L + 1, n, L)[0]
-    tT = device.transpose_kb(kb, n, L)
+    kb = device.decode_kb(img, Lg + 1, n, Lg)[0]
+    tT = device.transpose_kb(kb, n, Lg)
     torch.cuda.synchronize()
     t_stores = time.perf_counter() - t0
     rng = np.random.default_rng(synth.PHENO_SEED)
     y = 10.0 + rng.standard_normal(n)
     for b, j in zip([1.0, 0.8, 0.6, 0.5, 0.4], qtl):
-        y = y + b * device.extract_col(kb, n, int(j), kblocked=True).cpu().numpy().astype(np.float64)
-    rr = am.AM_resident(kb, tT, n, L, y, maxit=args.search_maxit)
+        if shard is None:
+            col = device.extract_col(kb, n, int(j), kblocked=True)
+        else:
+            col = shard.fetch_col(lambda jj: device.extract_col(kb, n, jj, kblocked=True), n, int(j), "cuda")
+        y = y + b * col.cpu().numpy().astype(np.float64)
+    if world > 1:
+        torch.cuda.synchronize(); dist.barrier()
+    rr = am.AM_resident(kb, tT, n, L, y, maxit=args.search_maxit, shard=shard)
     del kb, tT
     torch.cuda.empty_cache()
-    out = {"workload": f"AM() forward search, n={n}, L={L}, maxit={args.search_maxit}, 5 planted QTL",
+    secs = rr["seconds"]
+    if world > 1:   # the slowest rank defines the time; the picks must agree everywhere
+        keys = sorted(secs)
+        tt = torch.tensor([secs[k] for k in keys], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        secs = dict(zip(keys, [round(x, 4) for x in tt.tolist()]))
+        mine = torch.tensor(rr["all_picked"] + [-1] * (args.search_maxit + 1 - len(rr["all_picked"])), dtype=torch.int64, device="cuda")
+        allp = torch.empty(world * mine.numel(), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allp, mine)
+        if not bool((allp.view(world, -1) == mine).all().item()):
+            raise RuntimeError("ranks disagree on the selected loci")
+    out = {"workload": f"AM() forward search, n={n}, L={L}, maxit={args.search_maxit}, 5 planted QTL", "n_gpus": world,
            "iterations": rr["iterations"], "selected_loci_1based": rr["selected"], "all_picked_1based": rr["all_picked"],
            "planted_qtl_1based": [int(j) + 1 for j in qtl],
            "planted_recovered": int(sum(1 for j in qtl if int(j) + 1 in rr["selected"])),
-           "extBIC": [round(x, 4) for x in rr["extBIC"]], "seconds": rr["seconds"],
+           "extBIC": [round(x, 6) for x in rr["extBIC"]], "seconds": secs, "secular": rr["secular"],
            "decode_transpose_s": round(t_stores, 4), "scans": len(rr["all_picked"]),
-           "markers_per_s_whole_search": len(rr["all_picked"]) * L / rr["seconds"]["total_s"],
-           "path": "am.AM_resident (mirror of R/AM.R:395-504): device-level C ABI, K / roots / H / P / V / eigenvectors never "
-                   "leave HBM; EMMA's 1-D likelihood search on the host"}
-    if args.search_host:
+           "markers_per_s_whole_search": len(rr["all_picked"]) * L / secs["total_s"],
+           "path": "am.AM_resident (mirror of R/AM.R:395-504): device-level C ABI; eigen(K) once, then per iteration a secular "
+                   "solve for EMMA's eigenproblem, ONE n^3 product (int8 digit slices) for the scan's right-hand side, the "
+                   "sharded scan and pick; EMMA's 1-D likelihood search on the host"}
+    if args.search_host and world == 1:
         try:
             nbytes = n * (L + 1)
             img_h = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
@@ -699,6 +919,8 @@ def main():
     ap.add_argument("--search-host", action="store_true", help="also run the search with every matrix crossing the host-level ABI")
     ap.add_argument("--search-maxit", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (shapes that leave no room for its copies)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the in-run comparison with a single-GPU evaluation")
+    ap.add_argument("--no-extras", action="store_true", help="N = 8: skip the one-step config 5 / config 4 legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

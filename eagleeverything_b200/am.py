@@ -307,7 +307,7 @@ def eigbasis_inputs(xi, Xt, yt, ve, vg):
                                               (R/calculate_reduced_vara.R:21-35, src/calculate_a_and_vara_rcpp.cpp:97-98)
          v  = K^-1/2 a_hat = vg P y = U vt,   vt = vg (Dh yt - Dh Xt C^-1 Xt^T Dh yt)
                                               (R/calculate_reduced_a.R:31, src/calculate_a_and_vara_rcpp.cpp:90)
-    -> (w, Et, vt).  tests/test_gpu_algebra.py checks W and v against the oracle's restatement of R's dense formulas."""
+    -> (w, Et, vt).  tests/test_gpu_algebra.py and tests/test_secular_cpu.py check W and v against R's dense formulas."""
     Dh = 1.0 / (ve + vg * xi)
     B = Dh[:, None] * Xt
     Cq = Xt.T @ B
