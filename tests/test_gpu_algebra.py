@@ -184,8 +184,8 @@ def test_scan_rhs_from_the_eigenbasis_equals_the_dense_route(problem, mode, monk
     Wp = torch.empty(lib.eg_scan_wp_elems(n), dtype=torch.float64, device="cuda")
     work = torch.empty(n * q, dtype=torch.float64, device="cuda")
     work2 = torch.empty(n * n, dtype=torch.float64, device="cuda")
-    _lib.check(lib.eg_dev_scan_prepare_eig(p(dU), p(dUt), n, p(cu(w)), p(cu(Et.T.copy())), q, p(cu(vt)), p(work), p(work2), p(Wp),
-                                           None))
+    d_w, d_Et, d_vt = cu(w), cu(Et.T.copy()), cu(vt)         # n x q column-major = (q, n) row-major
+    _lib.check(lib.eg_dev_scan_prepare_eig(p(dU), p(dUt), n, p(d_w), p(d_Et), q, p(d_vt), p(work), p(work2), p(Wp), None))
     torch.cuda.synchronize()
     a, b = Wp.cpu().numpy(), Wp_ref.cpu().numpy()
     assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
