@@ -32,6 +32,8 @@ _vp = C.c_void_p
 # name -> (restype, argtypes); every symbol include/eagle_gpu.h declares
 SIGNATURES = {
     "eg_init": (C.c_int, [C.c_int]),
+    "eg_init_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "eg_gpu_count": (C.c_int, []),
     "eg_shutdown": (C.c_int, []),
     "eg_last_error": (C.c_char_p, []),
     "eg_abi_version": (C.c_int, []),

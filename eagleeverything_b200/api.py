@@ -354,3 +354,21 @@ def last_timing():
 
 def cache_clear():
     _lib.load().eg_cache_clear()
+
+
+def init_multi(ngpu, devs=None):
+    """eg_init_multi: the reference's `ngpu` argument (R/AM.R:185-196) made live -- one process, one host thread per GPU,
+    stores sharded by markers, NCCL over NVLink for the one exchange of each export.  Every function of this module then
+    works unchanged on the sharded stores."""
+    lib = _lib.require_gpu()
+    arr = None if devs is None else (C.c_int * int(ngpu))(*[int(d) for d in devs])
+    _lib.check(lib.eg_init_multi(int(ngpu), arr))
+    return int(lib.eg_gpu_count())
+
+
+def gpu_count():
+    return int(_lib.load().eg_gpu_count())
+
+
+def shutdown():
+    _lib.check(_lib.load().eg_shutdown())

@@ -29,7 +29,7 @@ struct AlgCtx {
     size_t work_cap = 0;  // doubles
     int* d_info = nullptr;
 };
-static AlgCtx g_alg;
+static thread_local AlgCtx g_alg;
 
 void algebra_release() {
     if (g_alg.solver) cusolverDnDestroy(g_alg.solver);
@@ -375,13 +375,14 @@ extern "C" int eg_dev_emma_eigen_R_wo_Z(const double* d_K, const double* d_X, co
     cudaStream_t st = (cudaStream_t)stream;
     EG_TRY(ensure_init_pub());
     EG_TRY(alg_init(st));
-    (void)d_w2;
     // S A S with S = I - B X^T, B = X (X^T X)^-1 and A = K + I, expanded:  A - B (A X)^T - (A X) B^T + B (X^T A X) B^T.
     // Four products with inner dimension q instead of the two n^3 products of R's S %*% (K + I) %*% S (4 n^3 FP64 flops per
     // iteration on a GPU whose FP64 rate is the scarce resource); the host-level eg_emma_eigen_R_wo_Z keeps R's form.
     const double one = 1.0, zero = 0.0, minus = -1.0;
+    // scratch: d_small = B (n q) | XtX (q q) | Xi (q q) | AX (n q);  C (q q) in d_w1, BC (n q) in d_w2 -- each inside its
+    // documented size for every q < n (a layout with all three in d_w1 overran it from q ~ 0.41 n)
     double *B = d_small, *XtX = B + (size_t)n * q, *Xi = XtX + (size_t)q * q;
-    double *AX = d_w1, *C = AX + (size_t)n * q, *BC = C + (size_t)q * q;
+    double *AX = Xi + (size_t)q * q, *C = d_w1, *BC = d_w2;
     EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_T, CUBLAS_OP_N, q, q, (int)n, &one, d_X, (int)n, d_X, (int)n, &zero, XtX, q));
     EG_TRY(small_inverse(XtX, q, Xi, st, "solve(crossprod(X, X))"));
     EG_BLAS(cublasDgemm(ctx_cublas(), CUBLAS_OP_N, CUBLAS_OP_N, (int)n, q, q, &one, d_X, (int)n, Xi, q, &zero, B, (int)n));

@@ -2,6 +2,7 @@
 // reference-facing entry points declared in include/eagle_gpu.h.  No CPU compute path exists
 // here: every entry point either runs the CUDA kernels or fails with an error code.
 #include <cublas_v2.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -12,7 +13,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <string>
 #include <vector>
@@ -28,6 +32,13 @@ struct eg_store {
     // M stores uploaded from a host image: rows x rows int32, M * M^T over all columns of the store, accumulated chunk
     // by chunk UNDER the host-to-device copy (store_from_image); eg_store_mmt then only finalizes.  nullptr otherwise.
     int32_t* C32 = nullptr;
+    int pins = 0;   // > 0 while an entry point works on the store: cache eviction under memory pressure skips it
+    // Marker-sharded stores (eg_init_multi with more than one GPU): nparts > 1, part[r] lives on GPU slot r and holds the
+    // markers [off[r], off[r+1]) -- columns of an M store, rows of an Mt store; d == nullptr, rows / cols are the totals.
+    int nparts = 0;
+    eg_store* part[16] = {};
+    int64_t off[17] = {};
+    bool mt_orientation = false;   // composite stores: which axis is sharded (row-major parts: rows)
 };
 
 namespace eg {
@@ -62,6 +73,12 @@ struct CacheEntry {
     eg_store* store;
     uint64_t stamp;
 };
+struct FreeBlock {
+    void* p;
+    size_t bytes;
+};
+// One context per GPU.  Slot 0 is the device of eg_init(); eg_init_multi(ngpu, devs) fills slots 0 .. ngpu-1 and starts one
+// host thread per slot.  Every thread works on the slot its thread-local pointer names (the calling thread: slot 0).
 struct Context {
     bool ready = false;
     int device = -1;
@@ -73,8 +90,22 @@ struct Context {
     uint64_t clock = 0;
     int32_t* d_err = nullptr;
     double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // exact-size recycling list on top of the stream-ordered pool (see pool_alloc)
+    std::mutex pool_mu;
+    std::vector<FreeBlock> free_blocks;
+    std::unordered_map<void*, size_t> live_blocks;
+    size_t free_bytes = 0, recycle_limit = 0;
+    cudaEvent_t scan_ev[2] = {nullptr, nullptr};   // around the dominant scan kernel of the last eg_dev_scan on this GPU
+    double scan_ops = 0.0;
+    void reset() {
+        ready = false; device = -1; sms = 0; stream = copy_stream = nullptr; cublas = nullptr; cache.clear(); clock = 0;
+        d_err = nullptr; for (double& t : timing) t = 0; free_blocks.clear(); live_blocks.clear(); free_bytes = 0; recycle_limit = 0; scan_ev[0] = scan_ev[1] = nullptr; scan_ops = 0.0;
+    }
 };
-static Context g_ctx;
+constexpr int EG_MAX_GPUS = 16;
+static Context g_ctxs[EG_MAX_GPUS];
+static thread_local Context* t_ctx = &g_ctxs[0];
+#define g_ctx (*t_ctx)
 
 int num_sms() {
     if (g_ctx.sms > 0) return g_ctx.sms;
@@ -120,14 +151,11 @@ int launch_scan(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const d
 // the driver pool from splitting a 10 GB block for an 800 MB request and then having to map 10 GB of fresh memory for
 // the next store -- measured as random 0.2 - 0.9 s stalls inside eg_store_from_host_ascii / eg_store_a_and_vara
 // (scripts/e2e_probe.py: steps of 540 ms turning into 1,200 - 1,400 ms).  Everything here is ordered on g_ctx.stream.
-struct FreeBlock {
-    void* p;
-    size_t bytes;
-};
-static std::mutex g_pool_mu;
-static std::vector<FreeBlock> g_free_blocks;
-static std::unordered_map<void*, size_t> g_live_blocks;
-static size_t g_free_bytes = 0, g_recycle_limit = 0;
+#define g_pool_mu g_ctx.pool_mu
+#define g_free_blocks g_ctx.free_blocks
+#define g_live_blocks g_ctx.live_blocks
+#define g_free_bytes g_ctx.free_bytes
+#define g_recycle_limit g_ctx.recycle_limit
 
 static void pool_flush_locked() {
     for (auto& b : g_free_blocks) cudaFreeAsync(b.p, g_ctx.stream);
@@ -229,25 +257,41 @@ static int parse_selected(const double* sel, int64_t nsel, int64_t limit, std::v
 }
 
 // ------------------------------------------------------------------ stores
+static thread_local bool t_is_worker = false;   // a GPU slot's worker thread (eg_init_multi): never evicts, never fans out
+struct Pin {   // RAII: a store an entry point is working on is not evictable (nor are the parts of a sharded store)
+    eg_store* s;
+    explicit Pin(const eg_store* st) : s(const_cast<eg_store*>(st)) { if (s) s->pins++; }
+    ~Pin() { if (s) s->pins--; }
+    Pin(const Pin&) = delete;
+    Pin& operator=(const Pin&) = delete;
+};
+static void free_store_tree(eg_store* s);
+// Drops the least recently used cached store of this slot that no entry point holds; false when none is left.
+static bool cache_evict_one() {
+    size_t lru = g_ctx.cache.size();
+    for (size_t i = 0; i < g_ctx.cache.size(); i++)
+        if (g_ctx.cache[i].store->pins == 0 && (lru == g_ctx.cache.size() || g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp)) lru = i;
+    if (lru == g_ctx.cache.size()) return false;
+    eg_store* victim = g_ctx.cache[lru].store;
+    g_ctx.cache.erase(g_ctx.cache.begin() + lru);
+    free_store_tree(victim);
+    cudaStreamSynchronize(g_ctx.stream);
+    return true;
+}
 static int store_alloc(int64_t rows, int64_t cols, bool kblocked, eg_store** out) {
     eg_store* s = new eg_store();
     s->rows = rows;
     s->cols = cols;
     s->pitch = kblocked ? 0 : store_pitch(cols);
-    cudaError_t e = pool_alloc((void**)&s->d, s->bytes() + 256);
+    const char* inject = getenv("EAGLE_TEST_FAIL_ALLOC");   // tests: every allocation attempt of a store fails
+    const bool fail = inject && inject[0] == '1';
+    cudaError_t e = fail ? cudaErrorMemoryAllocation : pool_alloc((void**)&s->d, s->bytes() + 256);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        // evict cached stores (least recently used first) and retry once per eviction
-        while (e != cudaSuccess && !g_ctx.cache.empty()) {
-            size_t lru = 0;
-            for (size_t i = 1; i < g_ctx.cache.size(); i++)
-                if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
-            pool_free(g_ctx.cache[lru].store->C32);
-            pool_free(g_ctx.cache[lru].store->d);
-            delete g_ctx.cache[lru].store;
-            g_ctx.cache.erase(g_ctx.cache.begin() + lru);
-            cudaStreamSynchronize(g_ctx.stream);
-            e = pool_alloc((void**)&s->d, s->bytes() + 256);
+        // evict cached stores (least recently used first, never one that a caller still holds) and retry once per
+        // eviction; worker threads of a multi-GPU set leave eviction to the orchestrating thread (store_from_image_any)
+        while (e != cudaSuccess && !t_is_worker && cache_evict_one()) {
+            e = fail ? cudaErrorMemoryAllocation : pool_alloc((void**)&s->d, s->bytes() + 256);
             if (e != cudaSuccess) cudaGetLastError();
         }
         if (e != cudaSuccess) {
@@ -466,6 +510,8 @@ static int check_image_size(const MappedFile& f, const char* path, int64_t rows,
     return EG_OK;
 }
 
+static int store_from_image_any(const uint8_t* image, int64_t cols_total, int64_t row0, int64_t row1, int64_t col0,
+                                int64_t col1, bool kblocked, eg_store** out, bool allow_multi);
 // cache key: (realpath, size, mtime, hash of the first and last 4 KB, dims, layout)
 static int cache_key(const char* path, int64_t rows, int64_t cols, bool kblocked, std::string& key) {
     struct stat st;
@@ -496,25 +542,25 @@ static int cache_key(const char* path, int64_t rows, int64_t cols, bool kblocked
 static void cache_insert(const std::string& key, eg_store* s) {
     const char* envmax = getenv("EAGLE_GPU_CACHE_ENTRIES");
     const size_t maxe = envmax ? (size_t)atoi(envmax) : 4;
-    while (g_ctx.cache.size() >= (maxe ? maxe : 1)) {
-        size_t lru = 0;
-        for (size_t i = 1; i < g_ctx.cache.size(); i++)
-            if (g_ctx.cache[i].stamp < g_ctx.cache[lru].stamp) lru = i;
-        pool_free(g_ctx.cache[lru].store->C32);
-        pool_free(g_ctx.cache[lru].store->d);
-        delete g_ctx.cache[lru].store;
-        g_ctx.cache.erase(g_ctx.cache.begin() + lru);
-    }
+    for (size_t i = 0; i < g_ctx.cache.size();)   // a rewritten file: the entry under the same key is stale by construction
+        if (g_ctx.cache[i].key == key && g_ctx.cache[i].store->pins == 0) {
+            free_store_tree(g_ctx.cache[i].store);
+            g_ctx.cache.erase(g_ctx.cache.begin() + i);
+        } else i++;
+    while (g_ctx.cache.size() >= (maxe ? maxe : 1))
+        if (!cache_evict_one()) break;   // everything left is held by a caller
     g_ctx.cache.push_back({key, s, ++g_ctx.clock});
 }
-static int cached_store(const char* path, int64_t rows, int64_t cols, bool kblocked, eg_store** out) {
+// allow_multi: with a multi-GPU set the store may be marker-sharded over the GPUs (the hot-path exports); callers that
+// need one plain store (ingest, ReshapeM, the packed container) pass false and get it on the first GPU.
+static int cached_store(const char* path, int64_t rows, int64_t cols, bool kblocked, eg_store** out, bool allow_multi = true) {
     EG_TRY(ensure_init());
     if (!path) return set_error(EG_ERR_ARG, "null file name");
     if (rows <= 0 || cols <= 0) return set_error(EG_ERR_ARG, "dims must be positive");
     std::string key;
     EG_TRY(cache_key(path, rows, cols, kblocked, key));
     for (auto& e : g_ctx.cache)
-        if (e.key == key) {
+        if (e.key == key && (allow_multi || e.store->nparts <= 1)) {
             e.stamp = ++g_ctx.clock;
             *out = e.store;
             return EG_OK;
@@ -523,7 +569,7 @@ static int cached_store(const char* path, int64_t rows, int64_t cols, bool kbloc
     EG_TRY(f.open_ro(path));
     EG_TRY(check_image_size(f, path, rows, cols));
     eg_store* s = nullptr;
-    EG_TRY(store_from_image(f.p, cols, 0, rows, 0, cols, kblocked, &s));
+    EG_TRY(store_from_image_any(f.p, cols, 0, rows, 0, cols, kblocked, &s, allow_multi));
     cache_insert(key, s);
     *out = s;
     return EG_OK;
@@ -630,33 +676,18 @@ __global__ void __launch_bounds__(256) symmetry_kernel(const double* __restrict_
 // keep_product: cache the int32 product with the store (stores of the path cache: calculateMMt_rcpp is called again by
 // SummaryAM with other selected loci, R/summary_am.R:142 -- the repeat then costs a copy, the rank-k correction and the
 // finalize pass instead of a second contraction)
+static int partial_product(const eg_store* M, const std::vector<int64_t>& zero_cols, DevBuf& C, bool keep_product);
+static int mmt_of_composite(const eg_store* M, const std::vector<int64_t>& zero_cols, double* out_host, bool keep_product);
+static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zero_rows, const double* S, const double* V,
+                             const double* a, double* out_a, double* out_vara);
 static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols, double* out_host, bool keep_product = false) {
+    Pin pin(M);
+    if (M->nparts > 1) return mmt_of_composite(M, zero_cols, out_host, keep_product);
     const int64_t n = M->rows;
     DevBuf C, D;
-    EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
+    EG_TRY(partial_product(M, zero_cols, C, keep_product));
     EG_TRY(D.alloc((size_t)n * n * sizeof(double), "MMt output"));
     cudaStream_t st = g_ctx.stream;
-    if (M->C32) {  // accumulated under the upload (store_from_image_kb): keep it intact for later calls
-        EG_CUDA(cudaMemcpyAsync(C.p, M->C32, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-        g_ctx.timing[1] = 0.0;
-    } else {
-        EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
-        Timer t(st);
-        EG_TRY(M->pitch ? eg_dev_syrk_i8(M->d, n, M->cols, M->pitch, C.as<int32_t>(), n, st)
-                        : eg_dev_syrk_i8_kb(M->d, n, M->cols, C.as<int32_t>(), n, st));
-        g_ctx.timing[1] = t.stop();
-        if (keep_product) {
-            int32_t* keep = nullptr;
-            if (pool_alloc((void**)&keep, (size_t)n * n * sizeof(int32_t)) == cudaSuccess) {
-                EG_CUDA(cudaMemcpyAsync(keep, C.p, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-                const_cast<eg_store*>(M)->C32 = keep;
-            } else {
-                cudaGetLastError();  // no room: contract again next time
-            }
-        }
-    }
-    if (!zero_cols.empty())
-        EG_TRY(eg_dev_syrk_zero_cols(M->d, n, M->pitch, zero_cols.data(), (int64_t)zero_cols.size(), C.as<int32_t>(), n, st));
     {
         Timer t(st);
         EG_TRY(eg_dev_mmt_finalize(C.as<int32_t>(), n, n, D.as<double>(), st));
@@ -676,6 +707,8 @@ static int scan_of_store(const eg_store* Mt, const std::vector<int64_t>& zero_ro
     const int64_t L = Mt->rows, n = Mt->cols;
     if (!Mt->pitch)
         return set_error(EG_ERR_ARG, "the scan needs an Mt store (markers as rows); transpose the M store first");
+    Pin pin(Mt);
+    if (Mt->nparts > 1) return scan_of_composite(Mt, zero_rows, S, V, a, out_a, out_vara);
     cudaStream_t st = g_ctx.stream;
     DevBuf dS, dV, da, dT, dW, oa, ov;
     EG_TRY(dS.alloc((size_t)n * n * 8, "inv_MMt_sqrt"));
@@ -742,28 +775,111 @@ extern "C" int eg_device_count(void) {
     return n;
 }
 
-extern "C" int eg_init(int device) {
-    if (g_ctx.ready && g_ctx.device == device) return check_cuda(cudaSetDevice(device), "cudaSetDevice");
-    if (g_ctx.ready) eg_shutdown();
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return set_error(EG_ERR_CUDA, "no usable CUDA device (%s); libeaglegpu has no CPU fallback",
-                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+// ------------------------------------------------------------------ multi-GPU plumbing
+// One process, one host thread per GPU (the reference's user calls AM(..., ngpu = ) from a single R session:
+// R/AM.R:185-196).  NCCL is bound at run time (dlopen of libnccl.so.2, re-using a copy that is already loaded in the
+// process, e.g. the one torch bundles) so that single-GPU users carry no dependency on it.
+namespace eg {
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+    void* h = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+constexpr int NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // ncclInt32, ncclFloat64, ncclSum (nccl.h, stable ABI values)
+
+struct WorkerPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::function<int(int)> job;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    std::vector<int> rc;
+    std::vector<std::string> err;
+};
+struct Multi {
+    int n = 0;  // 0 / 1: single GPU
+    int devs[EG_MAX_GPUS] = {};
+    ncclComm_t comm[EG_MAX_GPUS] = {};
+    WorkerPool* pool = nullptr;
+};
+static Multi g_multi;
+
+static void worker_main(int r) {
+    t_ctx = &g_ctxs[r];
+    t_is_worker = true;
+    cudaSetDevice(g_ctxs[r].device);
+    WorkerPool& P = *g_multi.pool;
+    uint64_t seen = 0;
+    for (;;) {
+        std::function<int(int)> job;
+        {
+            std::unique_lock<std::mutex> lk(P.mu);
+            P.cv.wait(lk, [&] { return P.stop || P.gen != seen; });
+            if (P.stop) return;
+            seen = P.gen;
+            job = P.job;
+        }
+        g_err[0] = 0;
+        const int rc = job(r);
+        {
+            std::lock_guard<std::mutex> lk(P.mu);
+            P.rc[r] = rc;
+            P.err[r] = g_err;
+            if (--P.pending == 0) P.cv_done.notify_all();
+        }
     }
-    if (device < 0 || device >= ndev) return set_error(EG_ERR_ARG, "eg_init: device %d of %d", device, ndev);
+}
+// run fn(r) on the thread of every GPU slot; the first failure (lowest slot) becomes the caller's error
+static int run_all(const std::function<int(int)>& fn) {
+    WorkerPool& P = *g_multi.pool;
+    {
+        std::unique_lock<std::mutex> lk(P.mu);
+        P.job = fn;
+        P.pending = g_multi.n;
+        for (int r = 0; r < g_multi.n; r++) P.rc[r] = EG_OK;
+        P.gen++;
+        P.cv.notify_all();
+        P.cv_done.wait(lk, [&] { return P.pending == 0; });
+    }
+    for (int r = 0; r < g_multi.n; r++)
+        if (P.rc[r] != EG_OK) return set_error(P.rc[r], "GPU %d: %s", g_multi.devs[r], P.err[r].c_str());
+    return EG_OK;
+}
+static int check_nccl(int rc, const char* what) {
+    if (rc == 0) return EG_OK;
+    return set_error(EG_ERR_CUDA, "NCCL error in %s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+}
+#define EG_NCCL(expr) EG_TRY(::eg::check_nccl((expr), #expr))
+
+// contiguous, `align`-aligned split of [0, total) over nparts (the same rule as eagleeverything_b200/dist.py::shard_range)
+static void shard_range(int64_t total, int nparts, int r, int64_t align, int64_t* a, int64_t* b) {
+    const int64_t blocks = (total + align - 1) / align, base = blocks / nparts, extra = blocks % nparts;
+    const int64_t b0 = r * base + (r < extra ? r : extra), b1 = b0 + base + (r < extra ? 1 : 0);
+    *a = b0 * align < total ? b0 * align : total;
+    *b = b1 * align < total ? b1 * align : total;
+}
+
+static int init_slot(Context& c, int device) {
     EG_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     EG_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
         return set_error(EG_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device,
                          prop.major, prop.minor);
-    g_ctx.sms = prop.multiProcessorCount;
-    EG_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    EG_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
-    if (cublasCreate(&g_ctx.cublas) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasCreate failed");
-    EG_CUDA(cudaMalloc(&g_ctx.d_err, 4 * sizeof(int32_t)));
+    c.sms = prop.multiProcessorCount;
+    EG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    EG_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    if (cublasCreate(&c.cublas) != CUBLAS_STATUS_SUCCESS) return set_error(EG_ERR_CUDA, "cublasCreate failed");
+    EG_CUDA(cudaMalloc(&c.d_err, 4 * sizeof(int32_t)));
     {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
         cudaMemPool_t pool;
         EG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -774,30 +890,15 @@ extern "C" int eg_init(int device) {
         size_t free_b = 0, total_b = 0;
         EG_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const char* env = getenv("EAGLE_GPU_RECYCLE_GB");
-        g_recycle_limit = env ? (size_t)(atof(env) * 1e9) : total_b / 2;
+        c.recycle_limit = env ? (size_t)(atof(env) * 1e9) : total_b / 2;
     }
-    g_ctx.device = device;
-    g_ctx.ready = true;
+    c.device = device;
+    c.ready = true;
     return EG_OK;
 }
-
-extern "C" void eg_cache_clear(void) {
-    for (auto& e : g_ctx.cache) {
-        pool_free(e.store->C32);
-        pool_free(e.store->d);
-        delete e.store;
-    }
-    g_ctx.cache.clear();
-    if (g_ctx.ready) pool_flush();
-    if (g_ctx.ready) {  // hand the recycled memory back to the driver
-        cudaStreamSynchronize(g_ctx.stream);
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    }
-}
-
-extern "C" int eg_shutdown(void) {
-    if (!g_ctx.ready) return EG_OK;
+// runs on the thread that owns the slot (its thread-local workspaces are released with it)
+static void shutdown_slot() {
+    if (!g_ctx.ready) return;
     cudaSetDevice(g_ctx.device);
     cudaDeviceSynchronize();
     eg_cache_clear();
@@ -806,11 +907,370 @@ extern "C" int eg_shutdown(void) {
     prep_i8_release();
     algebra_release();
     eigbasis_release();
+    if (g_ctx.scan_ev[0]) { cudaEventDestroy(g_ctx.scan_ev[0]); cudaEventDestroy(g_ctx.scan_ev[1]); }
     if (g_ctx.cublas) cublasDestroy(g_ctx.cublas);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
     if (g_ctx.d_err) cudaFree(g_ctx.d_err);
-    g_ctx = Context();
+    g_ctx.reset();
+}
+static int check_devices(int* ndev_out) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(EG_ERR_CUDA, "no usable CUDA device (%s); libeaglegpu has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    *ndev_out = ndev;
+    return EG_OK;
+}
+
+// ------------------------------------------------------------------ marker-sharded (composite) stores
+static void free_store_tree(eg_store* s) {
+    if (!s) return;
+    if (s->nparts > 1) {
+        auto drop = [s](int r) {
+            eg_store* p = r < s->nparts ? s->part[r] : nullptr;
+            if (p) {
+                pool_free(p->C32);
+                pool_free(p->d);
+                delete p;
+            }
+            return EG_OK;
+        };
+        if (g_multi.n > 1 && g_multi.pool && !t_is_worker) run_all(drop);
+        delete s;
+        return;
+    }
+    pool_free(s->C32);
+    pool_free(s->d);
+    delete s;
+}
+static eg_store* new_composite(int64_t rows, int64_t cols, bool kblocked) {
+    eg_store* S = new eg_store();
+    S->rows = rows;
+    S->cols = cols;
+    S->pitch = kblocked ? 0 : store_pitch(cols);
+    S->nparts = g_multi.n;
+    S->mt_orientation = !kblocked;
+    const int64_t markers = kblocked ? cols : rows;
+    for (int r = 0; r < g_multi.n; r++) {
+        int64_t a, b;
+        shard_range(markers, g_multi.n, r, 128, &a, &b);
+        S->off[r] = a;
+        S->off[r + 1] = b;
+    }
+    return S;
+}
+// run_all with eviction on the orchestrating thread: when a GPU runs out of memory, drop one unheld cached store and retry
+static int run_all_evicting(const std::function<int(int)>& fn, const std::function<void()>& undo) {
+    for (;;) {
+        const int rc = run_all(fn);
+        if (rc != EG_ERR_ALLOC) return rc;
+        const std::string msg = g_err;
+        if (undo) undo();
+        if (!cache_evict_one()) return set_error(EG_ERR_ALLOC, "%s", msg.c_str());
+    }
+}
+// Rows [row0,row1) x columns [col0,col1) of a host image -> a store; with a multi-GPU set (and allow_multi) a composite
+// whose parts are the marker shards, every GPU pulling and decoding its own byte ranges concurrently.
+static int store_from_image_any(const uint8_t* image, int64_t cols_total, int64_t row0, int64_t row1, int64_t col0,
+                                int64_t col1, bool kblocked, eg_store** out, bool allow_multi) {
+    if (g_multi.n <= 1 || !allow_multi || t_is_worker) return store_from_image(image, cols_total, row0, row1, col0, col1, kblocked, out);
+    EG_TRY(ensure_init());
+    if (!image || row1 <= row0 || col1 <= col0 || col0 < 0 || col1 > cols_total || row0 < 0)
+        return set_error(EG_ERR_ARG, "genotype store: bad image range");
+    eg_store* S = new_composite(row1 - row0, col1 - col0, kblocked);
+    auto undo = [S]() {
+        run_all([S](int r) {
+            if (S->part[r]) { pool_free(S->part[r]->C32); pool_free(S->part[r]->d); delete S->part[r]; S->part[r] = nullptr; }
+            return EG_OK;
+        });
+    };
+    const int rc = run_all_evicting([&](int r) -> int {
+        const int64_t a = S->off[r], b = S->off[r + 1];
+        if (a == b) return EG_OK;
+        return kblocked ? store_from_image(image, cols_total, row0, row1, col0 + a, col0 + b, true, &S->part[r])
+                        : store_from_image(image, cols_total, row0 + a, row0 + b, col0, col1, false, &S->part[r]);
+    }, undo);
+    if (rc != EG_OK) {
+        const std::string msg = g_err;
+        undo();
+        delete S;
+        return set_error(rc, "%s", msg.c_str());
+    }
+    g_ctx.timing[0] = 0;
+    for (int r = 0; r < g_multi.n; r++) g_ctx.timing[0] = std::max(g_ctx.timing[0], g_ctxs[r].timing[0]);
+    *out = S;
+    return EG_OK;
+}
+
+// Partial product of one plain store into C (n x n int32, zeroed / overwritten here), zeroed columns corrected.
+static int partial_product(const eg_store* M, const std::vector<int64_t>& zero_cols, DevBuf& C, bool keep_product) {
+    const int64_t n = M->rows;
+    cudaStream_t st = g_ctx.stream;
+    EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
+    const char* envk = getenv("EAGLE_KEEP_PRODUCT");   // "0": contract again on every call (bench.py's steady-state leg)
+    const bool reuse = !(envk && envk[0] == '0');
+    if (M->C32 && reuse) {  // accumulated under the upload (store_from_image_kb): keep it intact for later calls
+        EG_CUDA(cudaMemcpyAsync(C.p, M->C32, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        g_ctx.timing[1] = 0.0;
+    } else {
+        EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
+        Timer t(st);
+        EG_TRY(M->pitch ? eg_dev_syrk_i8(M->d, n, M->cols, M->pitch, C.as<int32_t>(), n, st)
+                        : eg_dev_syrk_i8_kb(M->d, n, M->cols, C.as<int32_t>(), n, st));
+        g_ctx.timing[1] = t.stop();
+        if (keep_product && reuse && !M->C32) {
+            int32_t* keep = nullptr;
+            if (pool_alloc((void**)&keep, (size_t)n * n * sizeof(int32_t)) == cudaSuccess) {
+                EG_CUDA(cudaMemcpyAsync(keep, C.p, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                const_cast<eg_store*>(M)->C32 = keep;
+            } else {
+                cudaGetLastError();  // no room: contract again next time
+            }
+        }
+    }
+    if (!zero_cols.empty())
+        EG_TRY(eg_dev_syrk_zero_cols(M->d, n, M->pitch, zero_cols.data(), (int64_t)zero_cols.size(), C.as<int32_t>(), n, st));
+    return EG_OK;
+}
+
+// M.Mt of a composite store: every GPU contracts its marker shard, ONE int32 all-reduce (exact, order-free) over NVLink,
+// every GPU finalizes and returns its own block of rows of K to the host (the n x n result crosses PCIe once, in parallel).
+static int mmt_of_composite(const eg_store* M, const std::vector<int64_t>& zero_cols, double* out_host, bool keep_product) {
+    const int64_t n = M->rows;
+    const int N = M->nparts;
+    EG_TRY(run_all([&](int r) -> int {
+        cudaStream_t st = g_ctx.stream;
+        DevBuf C, D;
+        const eg_store* part = M->part[r];
+        if (part) {
+            std::vector<int64_t> z;
+            for (int64_t c : zero_cols)
+                if (c >= M->off[r] && c < M->off[r + 1]) z.push_back(c - M->off[r]);
+            EG_TRY(partial_product(part, z, C, keep_product));
+        } else {
+            EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
+            EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
+        }
+        EG_TRY(D.alloc((size_t)n * n * sizeof(double), "MMt output"));
+        {
+            Timer t(st);
+            EG_NCCL(g_nccl.AllReduce(C.p, C.p, (size_t)n * n, NCCL_INT32, NCCL_SUM, g_multi.comm[r], st));
+            g_ctx.timing[2] = t.stop();
+        }
+        EG_TRY(eg_dev_mmt_finalize(C.as<int32_t>(), n, n, D.as<double>(), st));
+        int64_t i0, i1;
+        shard_range(n, N, r, 1, &i0, &i1);
+        Timer t(st);
+        if (i1 > i0)
+            EG_CUDA(cudaMemcpyAsync(out_host + i0 * n, D.as<double>() + i0 * n, (size_t)(i1 - i0) * n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+        EG_CUDA(cudaStreamSynchronize(st));
+        g_ctx.timing[3] = t.stop();
+        return EG_OK;
+    }));
+    return EG_OK;
+}
+
+// The scan on a composite Mt store.  S and V cross PCIe once: GPU r uploads columns [k0_r, k1_r) of each and the blocks are
+// exchanged over NVLink (one grouped broadcast); the columns of W = S (V S) are split over the GPUs at equal cost and
+// exchanged the same way; every GPU scans its own markers and writes its slice of a / var(a) straight into the caller's
+// vectors.
+static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zero_rows, const double* S, const double* V,
+                             const double* a, double* out_a, double* out_vara) {
+    const int64_t n = Mt->cols;
+    const int N = Mt->nparts;
+    const int64_t Kpad = round_up(n, 32);
+    return run_all([&](int r) -> int {
+        cudaStream_t st = g_ctx.stream;
+        const eg_store* part = Mt->part[r];
+        const int64_t L = part ? part->rows : 0;
+        DevBuf dS, dV, da, dT, dW, oa, ov;
+        EG_TRY(dS.alloc((size_t)n * n * 8, "inv_MMt_sqrt"));
+        EG_TRY(dV.alloc((size_t)n * n * 8, "dim_reduced_vara"));
+        EG_TRY(da.alloc((size_t)n * 8, "a"));
+        EG_TRY(dW.alloc((size_t)eg_scan_wp_elems(n) * 8, "packed W"));
+        EG_TRY(oa.alloc((size_t)(L ? L : 1) * 8, "a out"));
+        EG_TRY(ov.alloc((size_t)(L ? L : 1) * 8, "vara out"));
+        {
+            Timer t(st);
+            int64_t k0, k1;
+            shard_range(n, N, r, 1, &k0, &k1);
+            if (k1 > k0) {
+                EG_CUDA(cudaMemcpyAsync(dS.as<double>() + k0 * n, S + k0 * n, (size_t)(k1 - k0) * n * 8, cudaMemcpyHostToDevice, st));
+                EG_CUDA(cudaMemcpyAsync(dV.as<double>() + k0 * n, V + k0 * n, (size_t)(k1 - k0) * n * 8, cudaMemcpyHostToDevice, st));
+            }
+            EG_CUDA(cudaMemcpyAsync(da.p, a, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            EG_NCCL(g_nccl.GroupStart());
+            for (int q = 0; q < N; q++) {
+                int64_t q0, q1;
+                shard_range(n, N, q, 1, &q0, &q1);
+                if (q1 == q0) continue;
+                EG_NCCL(g_nccl.Broadcast(dS.as<double>() + q0 * n, dS.as<double>() + q0 * n, (size_t)(q1 - q0) * n, NCCL_FLOAT64, q, g_multi.comm[r], st));
+                EG_NCCL(g_nccl.Broadcast(dV.as<double>() + q0 * n, dV.as<double>() + q0 * n, (size_t)(q1 - q0) * n, NCCL_FLOAT64, q, g_multi.comm[r], st));
+            }
+            EG_NCCL(g_nccl.GroupEnd());
+            g_ctx.timing[4] = t.stop();
+        }
+        {
+            Timer t(st);
+            int sym = 0;
+            EG_TRY(eg_dev_inputs_symmetric(dS.as<double>(), dV.as<double>(), n, &sym, st));
+            std::vector<int64_t> cuts(N + 1, n);
+            for (int q = 0; q < N; q++) {
+                if (sym) {   // cost of columns [0,c): n c (V S) + c^2 / 2 (upper part of S X)  ->  equal-cost cuts
+                    int64_t c = (int64_t)llround((double)n * (sqrt(1.0 + 3.0 * q / N) - 1.0) / 32.0) * 32;
+                    cuts[q] = c < n ? c : n;
+                } else {
+                    cuts[q] = std::min<int64_t>(n, (int64_t)q * ((n + N - 1) / N));
+                }
+            }
+            int64_t widest = 1;
+            for (int q = 0; q < N; q++) widest = std::max(widest, cuts[q + 1] - cuts[q]);
+            EG_TRY(dT.alloc((size_t)n * widest * 8, "scan scratch"));
+            EG_CUDA(cudaMemsetAsync(dW.p, 0, (size_t)eg_scan_wp_elems(n) * 8, st));
+            EG_TRY(eg_dev_scan_prepare_cols(dS.as<double>(), dV.as<double>(), n, cuts[r], cuts[r + 1], sym, dT.as<double>(), dW.as<double>(), st));
+            EG_NCCL(g_nccl.GroupStart());
+            for (int q = 0; q < N; q++)
+                if (cuts[q + 1] > cuts[q])
+                    EG_NCCL(g_nccl.Broadcast(dW.as<double>() + cuts[q] * Kpad, dW.as<double>() + cuts[q] * Kpad,
+                                             (size_t)(cuts[q + 1] - cuts[q]) * Kpad, NCCL_FLOAT64, q, g_multi.comm[r], st));
+            EG_NCCL(g_nccl.GroupEnd());
+            EG_TRY(eg_dev_scan_fold(dS.as<double>(), da.as<double>(), n, sym, dW.as<double>(), st));
+            g_ctx.timing[5] = t.stop();
+        }
+        if (L > 0) {
+            std::vector<int64_t> z;
+            for (int64_t c : zero_rows)
+                if (c >= Mt->off[r] && c < Mt->off[r + 1]) z.push_back(c - Mt->off[r]);
+            {
+                Timer t(st);
+                EG_TRY(eg_dev_scan(part->d, L, n, part->pitch, dW.as<double>(), z.empty() ? nullptr : z.data(), (int64_t)z.size(),
+                                   oa.as<double>(), ov.as<double>(), st));
+                g_ctx.timing[6] = t.stop();
+            }
+            Timer t(st);
+            EG_CUDA(cudaMemcpyAsync(out_a + Mt->off[r], oa.p, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+            EG_CUDA(cudaMemcpyAsync(out_vara + Mt->off[r], ov.p, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+            EG_CUDA(cudaStreamSynchronize(st));
+            g_ctx.timing[7] = t.stop();
+        } else {
+            EG_CUDA(cudaStreamSynchronize(st));
+        }
+        return EG_OK;
+    });
+}
+}  // namespace eg
+
+extern "C" int eg_init(int device) {
+    if (g_multi.n <= 1 && g_ctxs[0].ready && g_ctxs[0].device == device) return check_cuda(cudaSetDevice(device), "cudaSetDevice");
+    if (g_ctxs[0].ready || g_multi.n > 1) eg_shutdown();
+    int ndev = 0;
+    EG_TRY(check_devices(&ndev));
+    if (device < 0 || device >= ndev) return set_error(EG_ERR_ARG, "eg_init: device %d of %d", device, ndev);
+    t_ctx = &g_ctxs[0];
+    return init_slot(g_ctxs[0], device);
+}
+
+// eg_init_multi(ngpu, devs): the marker-sharded form.  devs == NULL: devices 0 .. ngpu-1.
+extern "C" int eg_init_multi(int ngpu, const int* devs) {
+    if (ngpu < 1 || ngpu > EG_MAX_GPUS) return set_error(EG_ERR_ARG, "eg_init_multi: ngpu = %d (1 .. %d)", ngpu, EG_MAX_GPUS);
+    if (ngpu == 1) return eg_init(devs ? devs[0] : 0);
+    bool same = g_multi.n == ngpu;
+    for (int r = 0; same && r < ngpu; r++) same = g_multi.devs[r] == (devs ? devs[r] : r);
+    if (same) return check_cuda(cudaSetDevice(g_multi.devs[0]), "cudaSetDevice");
+    if (g_ctxs[0].ready || g_multi.n > 1) eg_shutdown();
+    int ndev = 0;
+    EG_TRY(check_devices(&ndev));
+    for (int r = 0; r < ngpu; r++) {
+        const int d = devs ? devs[r] : r;
+        if (d < 0 || d >= ndev) return set_error(EG_ERR_ARG, "eg_init_multi: device %d of %d", d, ndev);
+        for (int q = 0; q < r; q++)
+            if ((devs ? devs[q] : q) == d) return set_error(EG_ERR_ARG, "eg_init_multi: device %d listed twice", d);
+    }
+    if (!g_nccl.h) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // a copy already in the process (torch's) wins
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return set_error(EG_ERR_CUDA, "eg_init_multi: libnccl.so.2 not found (%s)", dlerror());
+        g_nccl.h = h;
+        *(void**)&g_nccl.CommInitAll = dlsym(h, "ncclCommInitAll");
+        *(void**)&g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+        *(void**)&g_nccl.AllReduce = dlsym(h, "ncclAllReduce");
+        *(void**)&g_nccl.Broadcast = dlsym(h, "ncclBroadcast");
+        *(void**)&g_nccl.GroupStart = dlsym(h, "ncclGroupStart");
+        *(void**)&g_nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
+        *(void**)&g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+        if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+            return set_error(EG_ERR_CUDA, "eg_init_multi: libnccl.so.2 lacks a required symbol");
+    }
+    for (int r = 0; r < ngpu; r++) {
+        g_multi.devs[r] = devs ? devs[r] : r;
+        int rc = init_slot(g_ctxs[r], g_multi.devs[r]);
+        if (rc != EG_OK) {
+            g_multi.n = 0;
+            return rc;
+        }
+    }
+    EG_NCCL(g_nccl.CommInitAll(g_multi.comm, ngpu, g_multi.devs));
+    g_multi.n = ngpu;
+    g_multi.pool = new WorkerPool();
+    g_multi.pool->rc.assign(ngpu, EG_OK);
+    g_multi.pool->err.assign(ngpu, std::string());
+    for (int r = 0; r < ngpu; r++) g_multi.pool->th.emplace_back(worker_main, r);
+    t_ctx = &g_ctxs[0];
+    return check_cuda(cudaSetDevice(g_multi.devs[0]), "cudaSetDevice");
+}
+extern "C" int eg_gpu_count(void) { return g_multi.n > 1 ? g_multi.n : (g_ctxs[0].ready ? 1 : 0); }
+
+extern "C" void eg_cache_clear(void) {
+    for (auto& e : g_ctx.cache) free_store_tree(e.store);
+    g_ctx.cache.clear();
+    if (g_multi.n > 1 && t_ctx == &g_ctxs[0] && g_multi.pool)   // called by the user: the parts' pools live on the workers
+        run_all([](int) {
+            pool_flush();
+            cudaStreamSynchronize(g_ctx.stream);
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+            return EG_OK;
+        });
+    else if (g_ctx.ready) {
+        pool_flush();
+        cudaStreamSynchronize(g_ctx.stream);  // hand the recycled memory back to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
+}
+
+extern "C" int eg_shutdown(void) {
+    if (g_multi.n > 1) {
+        t_ctx = &g_ctxs[0];
+        eg_cache_clear();   // composite stores: parts are freed on their own threads
+        // the calling thread's own workspaces on device 0 (single-GPU entry points it ran itself)
+        cudaSetDevice(g_ctxs[0].device);
+        syrk_release_cache(); scan_i8_release(); prep_i8_release(); algebra_release(); eigbasis_release();
+        run_all([](int r) {
+            if (g_multi.comm[r]) g_nccl.CommDestroy(g_multi.comm[r]);
+            g_multi.comm[r] = nullptr;
+            shutdown_slot();
+            return EG_OK;
+        });
+        {
+            std::lock_guard<std::mutex> lk(g_multi.pool->mu);
+            g_multi.pool->stop = true;
+            g_multi.pool->cv.notify_all();
+        }
+        for (auto& t : g_multi.pool->th) t.join();
+        delete g_multi.pool;
+        g_multi.pool = nullptr;
+        g_multi.n = 0;
+        return EG_OK;
+    }
+    t_ctx = &g_ctxs[0];
+    shutdown_slot();
     return EG_OK;
 }
 
@@ -823,8 +1283,8 @@ extern "C" int eg_get_scan_mode(void) { return scan_mode(); }
 
 namespace eg {
 // CUDA events around the dominant scan kernel of the last eg_dev_scan call (for roofline reporting)
-static cudaEvent_t g_scan_ev[2] = {nullptr, nullptr};
-static double g_scan_ops = 0.0;
+#define g_scan_ev g_ctx.scan_ev
+#define g_scan_ops g_ctx.scan_ops
 void scan_kernel_mark(int which, cudaStream_t st, double ops) {
     if (!g_scan_ev[0]) {
         cudaEventCreate(&g_scan_ev[0]);
@@ -865,12 +1325,12 @@ extern "C" int eg_last_timing(double* out_ms, int n_out) {
 extern "C" int eg_store_from_host_ascii(const uint8_t* image, int64_t rows, int64_t cols, int64_t col0, int64_t col1,
                                         eg_store_t** out) {
     if (!out) return set_error(EG_ERR_ARG, "null out");
-    return store_from_image(image, cols, 0, rows, col0, col1, true, out);  // M orientation: K-blocked
+    return store_from_image_any(image, cols, 0, rows, col0, col1, true, out, true);  // M orientation: K-blocked
 }
 extern "C" int eg_store_from_host_ascii_rows(const uint8_t* image, int64_t rows, int64_t cols, int64_t row0,
                                              int64_t row1, eg_store_t** out) {
     if (!out || row1 > rows) return set_error(EG_ERR_ARG, "bad row range");
-    return store_from_image(image, cols, row0, row1, 0, cols, false, out);  // Mt orientation: row-major
+    return store_from_image_any(image, cols, row0, row1, 0, cols, false, out, true);  // Mt orientation: row-major
 }
 // ------------------------------------------------------------------ packed 2-bit container (pack2.cu)
 // Host words in, K-blocked (M orientation) or row-major (Mt orientation) store out: H2D of rows*wpr*8 bytes in two
@@ -928,6 +1388,7 @@ extern "C" int eg_store_from_host_packed(const uint64_t* words, int64_t rows, in
 // store -> host words (rows * eg_packed_words_per_row(cols) uint64): what an ingest step writes to disk once
 extern "C" int eg_store_to_host_packed(const eg_store_t* s, uint64_t* out_words) {
     if (!s || !out_words) return set_error(EG_ERR_ARG, "eg_store_to_host_packed: bad argument");
+    if (s->nparts > 1) return set_error(EG_ERR_ARG, "eg_store_to_host_packed: the store is sharded over several GPUs");
     EG_TRY(ensure_init());
     const int64_t wpr = eg_packed_words_per_row(s->cols);
     DevBuf w;
@@ -943,6 +1404,8 @@ extern "C" int eg_store_to_host_packed(const eg_store_t* s, uint64_t* out_words)
 extern "C" int eg_store_drop_individuals(const eg_store_t* in, const int64_t* idx, int64_t k, int individuals_are_rows,
                                          eg_store_t** out) {
     if (!in || !out || k < 0 || (k > 0 && !idx)) return set_error(EG_ERR_ARG, "eg_store_drop_individuals: bad argument");
+    if (in->nparts > 1) return set_error(EG_ERR_ARG, "eg_store_drop_individuals: the store is sharded over several GPUs");
+    Pin pin_in(in);
     EG_TRY(ensure_init());
     const int64_t n_in = individuals_are_rows ? in->rows : in->cols;
     std::vector<char> drop((size_t)n_in, 0);
@@ -985,11 +1448,38 @@ extern "C" int eg_store_from_file(const char* path, int64_t rows, int64_t cols, 
     MappedFile f;
     EG_TRY(f.open_ro(path));
     EG_TRY(check_image_size(f, path, rows, cols));
-    return store_from_image(f.p, cols, 0, rows, col0, col1, true, out);
+    return store_from_image_any(f.p, cols, 0, rows, col0, col1, true, out, true);
 }
 extern "C" int eg_store_transpose(const eg_store_t* in, eg_store_t** out) {
     if (!in || !out) return set_error(EG_ERR_ARG, "null argument");
     EG_TRY(ensure_init());
+    Pin pin(in);
+    if (in->nparts > 1) {   // marker shards transpose in place: part r (n x L_r) -> (L_r x n), no exchange
+        if (in->mt_orientation) return set_error(EG_ERR_ARG, "eg_store_transpose: sharded Mt stores are not transposed back");
+        eg_store* S = new_composite(in->cols, in->rows, false);
+        for (int r = 0; r <= in->nparts; r++) S->off[r] = in->off[r];
+        auto undo = [S]() {
+            run_all([S](int r) {
+                if (S->part[r]) { pool_free(S->part[r]->d); delete S->part[r]; S->part[r] = nullptr; }
+                return EG_OK;
+            });
+        };
+        const int rc = run_all_evicting([&](int r) -> int {
+            const eg_store* p = in->part[r];
+            if (!p) return EG_OK;
+            EG_TRY(store_alloc(p->cols, p->rows, false, &S->part[r]));
+            EG_TRY(eg_dev_transpose_kb_i8(p->d, p->rows, p->cols, S->part[r]->d, S->part[r]->pitch, g_ctx.stream));
+            return check_cuda(cudaStreamSynchronize(g_ctx.stream), "transpose");
+        }, undo);
+        if (rc != EG_OK) {
+            const std::string msg = g_err;
+            undo();
+            delete S;
+            return set_error(rc, "%s", msg.c_str());
+        }
+        *out = S;
+        return EG_OK;
+    }
     eg_store* s = nullptr;
     EG_TRY(store_alloc(in->cols, in->rows, false, &s));  // the transpose is always a row-major (Mt-type) store
     int rc = in->pitch ? eg_dev_transpose_i8(in->d, in->rows, in->cols, in->pitch, s->d, s->pitch, g_ctx.stream)
@@ -1004,9 +1494,7 @@ extern "C" int eg_store_transpose(const eg_store_t* in, eg_store_t** out) {
 }
 extern "C" int eg_store_free(eg_store_t* s) {
     if (!s) return EG_OK;
-    pool_free(s->C32);
-    pool_free(s->d);
-    delete s;
+    free_store_tree(s);
     return EG_OK;
 }
 extern "C" int eg_store_info(const eg_store_t* s, int64_t* rows, int64_t* cols, int64_t* pitch, void** device_ptr) {
@@ -1014,7 +1502,7 @@ extern "C" int eg_store_info(const eg_store_t* s, int64_t* rows, int64_t* cols, 
     if (rows) *rows = s->rows;
     if (cols) *cols = s->cols;
     if (pitch) *pitch = s->pitch;
-    if (device_ptr) *device_ptr = s->d;
+    if (device_ptr) *device_ptr = s->d;   // NULL for a store sharded over several GPUs
     return EG_OK;
 }
 extern "C" int eg_store_mmt(const eg_store_t* M, const int64_t* zero_cols, int64_t n_zero, double* out_MMt_host) {
@@ -1043,6 +1531,14 @@ extern "C" int eg_store_a_and_vara(const eg_store_t* Mt, const int64_t* zero_row
 extern "C" int eg_store_extract_col(const eg_store_t* M, int64_t col, int32_t* out) {
     if (!M || !out || col < 0 || col >= M->cols) return set_error(EG_ERR_ARG, "eg_store_extract_col: bad argument");
     EG_TRY(ensure_init());
+    Pin pin(M);
+    if (M->nparts > 1) {   // the GPU that owns the marker answers
+        if (M->mt_orientation) return set_error(EG_ERR_ARG, "eg_store_extract_col: needs an M store");
+        return run_all([&](int r) -> int {
+            if (!(col >= M->off[r] && col < M->off[r + 1])) return EG_OK;
+            return eg_store_extract_col(M->part[r], col - M->off[r], out);
+        });
+    }
     DevBuf d;
     EG_TRY(d.alloc((size_t)M->rows * 4, "column"));
     EG_TRY(eg_dev_extract_col(M->d, M->rows, M->pitch, col, d.as<int32_t>(), g_ctx.stream));
@@ -1228,7 +1724,8 @@ extern "C" int eg_calculate_reduced_a_rcpp(const char* f_name_ascii, double varG
     if (!dims || !P || !y || !out_ar) return set_error(EG_ERR_ARG, "calculate_reduced_a_rcpp: null argument");
     const int64_t n = dims[0], L = dims[1];  // dims of M; the file is Mt.ascii (L lines of n characters)
     eg_store* Mt = nullptr;
-    EG_TRY(cached_store(f_name_ascii, L, n, false, &Mt));
+    EG_TRY(cached_store(f_name_ascii, L, n, false, &Mt, false));   // a plain store on the first GPU
+    Pin pin_mt(Mt);
     std::vector<int64_t> z;
     EG_TRY(parse_selected(selected_loci, n_selected_loci, L, z, "calculate_reduced_a_rcpp"));
     if (!quiet) say(message, message_ctx, "Inside internal function calculate_reduced_a_rcpp. GPU %d ", g_ctx.device);
@@ -1690,7 +2187,8 @@ extern "C" int eg_createMt_ASCII_rcpp(const char* f_name, const char* f_name_asc
         if (stat(f_name, &stt) != 0) return set_error(EG_ERR_OPEN, "\n\nERROR: Could not open  %s\n\n\n", f_name);
     }
     eg_store* M = nullptr;
-    EG_TRY(cached_store(f_name, n, L, true, &M));
+    EG_TRY(cached_store(f_name, n, L, true, &M, false));
+    Pin pin_m(M);   // held while the transpose is allocated (eviction under memory pressure must skip it)
     eg_store* Mt = nullptr;
     EG_TRY(eg_store_transpose(M, &Mt));
     int rc = write_store_ascii(Mt, f_name_ascii);
@@ -1751,7 +2249,8 @@ extern "C" int eg_ReshapeM_rcpp(const char* fnameM, const char* fnameMt, const i
     }
     if (rows_keep.empty() || cols_keep.empty()) return set_error(EG_ERR_ARG, "ReshapeM_rcpp: no individual left");
     eg_store* M = nullptr;
-    EG_TRY(cached_store(fnameM, n, L, true, &M));
+    EG_TRY(cached_store(fnameM, n, L, true, &M, false));
+    Pin pin_m(M);
     const int64_t n1 = (int64_t)rows_keep.size(), n2 = (int64_t)cols_keep.size();
     DevBuf dmap;
     EG_TRY(dmap.alloc((size_t)(n1 > n2 ? n1 : n2) * sizeof(int64_t), "ReshapeM index map"));
@@ -1780,7 +2279,8 @@ extern "C" int eg_ReshapeM_rcpp(const char* fnameM, const char* fnameMt, const i
         Mt1 = T1;
     } else {  // an index list that is not decreasing: the erased characters are not the dropped rows
         eg_store* Mt = nullptr;
-        rc = cached_store(fnameMt, L, n, false, &Mt);
+        rc = cached_store(fnameMt, L, n, false, &Mt, false);
+        Pin pin_mt(rc == EG_OK ? Mt : nullptr);
         if (rc == EG_OK) rc = store_alloc(L, n2, false, &Mt1);
         if (rc == EG_OK) rc = check_cuda(cudaMemcpyAsync(dmap.p, cols_keep.data(), (size_t)n2 * sizeof(int64_t), cudaMemcpyHostToDevice, g_ctx.stream), "H2D");
         if (rc == EG_OK) rc = eg_dev_gather_cols(Mt->d, L, Mt->pitch, dmap.as<int64_t>(), n2, Mt1->d, Mt1->pitch, g_ctx.stream);

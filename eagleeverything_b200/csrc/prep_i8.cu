@@ -360,9 +360,9 @@ struct PrepWorkspace {
 static thread_local PrepWorkspace g_pi;
 
 // CUDA events around the two prep_i8_kernel launches of the last launch_prepare_i8 (roofline reporting)
-static cudaEvent_t g_pi_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-static double g_pi_ops = 0.0;
-static int g_pi_marks = 0;
+static thread_local cudaEvent_t g_pi_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static thread_local double g_pi_ops = 0.0;
+static thread_local int g_pi_marks = 0;
 void prep_kernel_times(double* ms, double* ops) {
     *ms = 0.0;
     *ops = g_pi_ops;

@@ -40,6 +40,17 @@ typedef void (*eg_message_fn)(void* ctx, const char* text);
 
 /* ---------------------------------------------------------------- lifecycle */
 int eg_init(int device);            /* bind this process/thread to one GPU; idempotent */
+/* The reference's `ngpu` argument made live (R/AM.R:185-196; forced to 0 at R/AM.R:214): ONE process, one host thread per
+ * GPU, NCCL (ncclCommInitAll; libnccl.so.2 is bound at run time, so single-GPU users do not depend on it).  devs == NULL:
+ * devices 0 .. ngpu-1.  After this call the genotype stores built by the entry points below are sharded by markers over the
+ * GPUs -- columns of M.ascii, rows of Mt.ascii, 128-aligned contiguous ranges -- and calculateMMt_rcpp,
+ * calculate_a_and_vara_rcpp, extract_geno_rcpp and the eg_store_* calls work on the shards internally: every GPU decodes and
+ * contracts its own markers, the partial M.Mt is summed by ONE int32 all-reduce over NVLink, S and V are uploaded once (a
+ * 1/ngpu slice per GPU, exchanged over NVLink), the scan's outputs go from every GPU straight into the caller's vectors.
+ * Results are bit-identical to the single-GPU ones.  Ingest, ReshapeM, the packed container and the n x n algebra run on
+ * the first GPU of the set.  ngpu == 1 is eg_init(devs ? devs[0] : 0). */
+int eg_init_multi(int ngpu, const int* devs);
+int eg_gpu_count(void);             /* GPUs of the current set (0 before eg_init / eg_init_multi) */
 int eg_shutdown(void);              /* frees every cached genotype store and workspace */
 const char* eg_last_error(void);
 int eg_abi_version(void);

@@ -342,3 +342,30 @@ def test_config3_full_size_properties(dev):
     best, idx = device.argmax_tsq(oa, ov)
     tsq = oa * oa / ov
     assert best.item() == tsq.max().item() and idx.item() == int((tsq == tsq.max()).nonzero()[0].item())
+
+
+def test_cache_eviction_never_frees_a_store_in_use(tmp_path, monkeypatch):
+    """createMt_ASCII_rcpp holds the M store of its input while the transpose is allocated; when that allocation fails and
+    the path cache is searched for memory to give back, the held store must survive (it used to be freed and then read):
+    the call fails with EG_ERR_ALLOC and the cached store still answers.  EAGLE_TEST_FAIL_ALLOC injects the failure."""
+    from eagleeverything_b200 import _lib, api
+    from oracle import np_oracle as npo
+    n, L = 64, 1000
+    G = synth.genotypes(n, L, seed=3)
+    m, mt, m2 = str(tmp_path / "M.ascii"), str(tmp_path / "Mt.ascii"), str(tmp_path / "M2.ascii")
+    npo.write_ascii(m, G)
+    npo.write_ascii(m2, G[:, ::-1])
+    api.cache_clear()
+    K0 = api.calculateMMt_rcpp(m, 8, 1, [api.NA_REAL], (n, L))
+    api.calculateMMt_rcpp(m2, 8, 1, [api.NA_REAL], (n, L))              # a second cached store, not held by anyone
+    monkeypatch.setenv("EAGLE_TEST_FAIL_ALLOC", "1")
+    with pytest.raises(_lib.EagleGpuError) as ei:
+        api.createMt_ASCII_rcpp(m, mt, "text", 8, (n, L))               # evicts M2's store, never M's
+    assert ei.value.code == _lib.EG_ERR_ALLOC
+    monkeypatch.delenv("EAGLE_TEST_FAIL_ALLOC")
+    assert np.array_equal(api.calculateMMt_rcpp(m, 8, 1, [api.NA_REAL], (n, L)), K0)
+    api.createMt_ASCII_rcpp(m, mt, "text", 8, (n, L))
+    want = (G.T + ord("0")).astype(np.uint8)
+    want = np.concatenate([want, np.full((L, 1), ord("\n"), np.uint8)], axis=1).tobytes()
+    assert open(mt, "rb").read() == want
+    api.cache_clear()
