@@ -392,7 +392,12 @@ def run_gpu(args):
     else:
         del store, storeT, C32, K, Wp, tmp, oa, ov
         torch.cuda.empty_cache()
+        if world > 1 and rank != 0:   # the ranks' GPUs are driven by rank 0 alone in this leg; inputs are rebuilt after it
+            img = S = V = ah = None
+            torch.cuda.empty_cache()
         e2e = run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img, S, V, ah)
+        if world > 1 and rank != 0:
+            img = device.synth_ascii(n, Lg, GENO_SEED, col_offset=c0, n_total=n)
 
     mode = int(lib.eg_get_scan_mode())
     k_ms, k_ops, p_ms, p_ops = C.c_double(), C.c_double(), C.c_double(), C.c_double()
@@ -528,130 +533,229 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def _wait_rank0(dist, rank, world, key):
+    """CPU-side rendezvous (the TCP store): the other ranks' GPUs must stay idle while rank 0 drives them itself."""
+    if world == 1:
+        return
+    from datetime import timedelta
+    store = dist.distributed_c10d._get_default_store()
+    if rank == 0:
+        store.set(key, "1")
+    else:
+        store.wait([key], timedelta(seconds=3600))
+
+
 def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img, S, V, ah):
-    """Same step through host buffers.  N=1: the host-level C ABI (eg_store_from_host_ascii,
-    eg_store_mmt, eg_store_transpose, eg_store_a_and_vara) on pinned memory.  N>1: per-rank pinned
-    shards, explicit H2D/D2H around the device-level calls (the all-reduce needs device buffers)."""
+    """The same step end to end through the C ABI a single R session would call, with HOST buffers in and out, on the
+    N GPUs of the run: ONE process (rank 0 of the launch; the other ranks release their GPUs and wait), eg_init_multi(N)
+    -- one host thread per GPU, NCCL inside the library -- then per step
+        eg_store_from_host_ascii (the whole M.ascii image: every GPU pulls and decodes its own marker columns, M.Mt of each
+        chunk accumulated under the copy)  ->  eg_store_mmt (all-reduce, K back to the host in parallel row blocks)
+        ->  eg_store_transpose  ->  eg_store_a_and_vara (S, V uploaded once in 1/N slices and exchanged over NVLink; a,
+        var(a) written by every GPU into the host vectors)  ->  the pick on the host vectors (find_qtl.R:71-80).
+    Extra legs: the drop-in route of the Rcpp exports on FILES with pageable S / V (first call and steady state), and at
+    N = 1 the packed 2-bit container."""
     from eagleeverything_b200 import _lib
-    img_bytes = n * (Lg + 1)
+    import numpy as np
+    vp = C.c_void_p
+    dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))  # noqa: E731
+    if rank != 0:
+        del img, S, V, ah
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        store = dist.distributed_c10d._get_default_store()
+        store.set("e2e_free_%d" % rank, "1")
+        _wait_rank0(dist, rank, world, "e2e_done")
+        return None
+    img_bytes = n * (L + 1)
     try:
+        if world > 1:
+            full = device.synth_ascii(n, L, GENO_SEED, col_offset=0, n_total=n)
+        else:
+            full = img
         img_h = torch.empty(img_bytes + 64, dtype=torch.uint8, pin_memory=True)
-        img_h[:img_bytes].copy_(img[:img_bytes]); img_h[img_bytes:].zero_()
+        img_h[:img_bytes].copy_(full[:img_bytes]); img_h[img_bytes:].zero_()
+        del full
         S_h = torch.empty((n, n), dtype=torch.float64, pin_memory=True); S_h.copy_(S)
         V_h = torch.empty((n, n), dtype=torch.float64, pin_memory=True); V_h.copy_(V)
         a_h = torch.empty(n, dtype=torch.float64, pin_memory=True); a_h.copy_(ah)
         K_h = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
-        oa_h = torch.empty(Lg, dtype=torch.float64, pin_memory=True)
-        ov_h = torch.empty(Lg, dtype=torch.float64, pin_memory=True)
+        oa_h = torch.empty(L, dtype=torch.float64, pin_memory=True)
+        ov_h = torch.empty(L, dtype=torch.float64, pin_memory=True)
     except RuntimeError as ex:
+        _wait_rank0(dist, rank, world, "e2e_done")
         return {"value": None, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": f"could not pin host buffers: {ex}"}
     torch.cuda.synchronize()
-    vp = C.c_void_p
-    dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))  # noqa: E731
+    torch.cuda.empty_cache()
+    if world > 1:   # the other ranks have released their memory
+        from datetime import timedelta
+        store = dist.distributed_c10d._get_default_store()
+        store.wait(["e2e_free_%d" % r for r in range(1, world)], timedelta(seconds=600))
+        _lib.check(lib.eg_init_multi(world, None))
+    ngpu = int(lib.eg_gpu_count())
+
+    def pick_host():
+        tsq = oa_h * oa_h / ov_h                     # the R side's pick (find_qtl.R:71-80) on the host result
+        return int(torch.argmax(torch.nan_to_num(tsq, nan=-1.0)))
 
     def step_host_abi():
         h, ht = vp(), vp()
-        _lib.check(lib.eg_store_from_host_ascii(vp(img_h.data_ptr()), n, Lg, 0, Lg, C.byref(h)))
+        _lib.check(lib.eg_store_from_host_ascii(vp(img_h.data_ptr()), n, L, 0, L, C.byref(h)))
         _lib.check(lib.eg_store_mmt(h, None, 0, dp(K_h)))
         _lib.check(lib.eg_store_transpose(h, C.byref(ht)))
         _lib.check(lib.eg_store_a_and_vara(ht, None, 0, dp(S_h), dp(V_h), dp(a_h), dp(oa_h), dp(ov_h)))
         lib.eg_store_free(h); lib.eg_store_free(ht)
-        tsq = oa_h * oa_h / ov_h                     # the R side's pick (find_qtl.R:71-80) on the host result
-        return int(torch.argmax(torch.nan_to_num(tsq, nan=-1.0)))
+        return pick_host()
 
-    if world > 1:
-        img_d = torch.empty_like(img)
-        Sd, Vd, ad = torch.empty_like(S), torch.empty_like(V), torch.empty_like(ah)
-        store = torch.empty(((Lg + 127) // 128, n, 128), dtype=torch.int8, device="cuda")
-        storeT = torch.empty((Lg, device.store_pitch(n)), dtype=torch.int8, device="cuda")
-        C32 = torch.empty((n, n), dtype=torch.int32, device="cuda")
-        Kd = torch.empty((n, n), dtype=torch.float64, device="cuda")
-        oa = torch.empty(Lg, dtype=torch.float64, device="cuda"); ov = torch.empty_like(oa)
-
-    def step_sharded():
-        img_d.copy_(img_h, non_blocking=True)
-        Sd.copy_(S_h, non_blocking=True); Vd.copy_(V_h, non_blocking=True); ad.copy_(a_h, non_blocking=True)
-        device.decode_kb(img_d, Lg + 1, n, Lg, out=store)
-        device.transpose_kb(store, n, Lg, out=storeT)
-        device.syrk_kb(store, n, Lg, C32=C32, zero=True)
-        egd.allreduce_partial_mmt(C32)
-        device.mmt_finalize(C32, n, out=Kd)
-        if rank == 0:
-            K_h.copy_(Kd, non_blocking=True)
-        Wp = device.scan_prepare_sharded(Sd, Vd, ad, n, rank, world)
-        device.scan(storeT, Lg, n, Wp, out_a=oa, out_vara=ov)
-        oa_h.copy_(oa, non_blocking=True); ov_h.copy_(ov, non_blocking=True)
-        best, idx = device.argmax_tsq(oa, ov)
-        return egd.global_argmax(best, idx, c0)[1]
-
-    fn = step_host_abi if world == 1 else step_sharded
     ksteps = max(1, min(args.steps, args.e2e_steps))
 
-    def time_host(f):
-        f()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(ksteps):
+    def time_host(f, reps=ksteps, warm=1):
+        for _ in range(warm):
             f()
-        e1.record()
         torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        # the host-level ABI synchronises internally on its own streams, so the host clock around the
-        # synchronised region is the honest end-to-end figure; report the device-event figure beside it
-        return max(wall_ms, e0.elapsed_time(e1)) / ksteps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = f()
+        wall_ms = (time.perf_counter() - t0) * 1e3   # every call of the host-level ABI synchronises before it returns
+        return wall_ms / reps, r
 
-    ms = time_host(fn)
-    abi_timing = None
-    if world == 1:
+    out = {}
+    try:
+        ms, picked = time_host(step_host_abi)
         t8 = (C.c_double * 8)()
         lib.eg_last_timing(t8, 8)
-        abi_timing = dict(zip(["h2d_decode_ms", "syrk_ms", "finalize_ms", "mmt_d2h_ms", "scan_h2d_ms", "prepare_ms",
+        abi_timing = dict(zip(["h2d_decode_ms", "syrk_ms", "allreduce_or_finalize_ms", "mmt_d2h_ms", "scan_h2d_ms", "prepare_ms",
                                "scan_ms", "scan_d2h_ms"], [round(x, 3) for x in t8]))
-    packed = None
-    if world == 1:
+        out = {"value": L / (ms * 1e-3), "unit": METRIC, "ms_per_step": ms, "steps": ksteps, "n_gpus": ngpu,
+               "h2d_bytes_per_step": int(img_bytes + 2 * n * n * 8 + n * 8), "d2h_bytes_per_step": int(n * n * 8 + 2 * L * 8),
+               "picked_marker": picked, "abi_stage_ms_gpu0_last_step": abi_timing,
+               "path": "host-level C ABI (eg_store_from_host_ascii / eg_store_mmt / eg_store_transpose / eg_store_a_and_vara) on pinned "
+                       "host buffers, ONE process" + (f", eg_init_multi({ngpu}): one host thread per GPU, NCCL inside the library" if ngpu > 1 else ""),
+               "timing": "host clock around the calls (each returns after its results are in host memory)"}
+    except Exception as ex:  # noqa: BLE001
+        out = {"value": None, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": f"failed: {type(ex).__name__}: {ex}"}
+    # ---- the drop-in route: the Rcpp exports on files, S / V / outputs in pageable memory as R owns them
+    if not args.no_dropin:
+        try:
+            out["dropin_files"] = run_dropin(args, torch, lib, device, n, L, img_h, S_h, V_h, a_h, time_host)
+        except Exception as ex:  # noqa: BLE001
+            out["dropin_files"] = {"note": f"failed: {type(ex).__name__}: {ex}"}
+    if ngpu == 1:
         # the same step from the packed 2-bit container (SURVEY.md 8(f) rank 2): 4x fewer bytes over PCIe
         try:
-            wpr = int(lib.eg_packed_words_per_row(Lg))
-            kb = torch.empty(((Lg + 127) // 128, n, 128), dtype=torch.int8, device="cuda")
-            device.decode_kb(img, Lg + 1, n, Lg, out=kb)
+            wpr = int(lib.eg_packed_words_per_row(L))
+            kb = torch.empty(((L + 127) // 128, n, 128), dtype=torch.int8, device="cuda")
+            device.decode_kb(img, L + 1, n, L, out=kb)
             wd = torch.empty((n, wpr), dtype=torch.int64, device="cuda")
-            _lib.check(lib.eg_dev_pack_2bit(vp(kb.data_ptr()), n, Lg, 0, vp(wd.data_ptr()), None))
+            _lib.check(lib.eg_dev_pack_2bit(vp(kb.data_ptr()), n, L, 0, vp(wd.data_ptr()), None))
             words_h = torch.empty((n, wpr), dtype=torch.int64, pin_memory=True); words_h.copy_(wd)
             del kb, wd
             torch.cuda.synchronize()
+            torch.cuda.empty_cache()
 
             def step_host_packed():
                 h, ht = vp(), vp()
-                _lib.check(lib.eg_store_from_host_packed(vp(words_h.data_ptr()), n, Lg, 1, C.byref(h)))
+                _lib.check(lib.eg_store_from_host_packed(vp(words_h.data_ptr()), n, L, 1, C.byref(h)))
                 _lib.check(lib.eg_store_mmt(h, None, 0, dp(K_h)))
                 _lib.check(lib.eg_store_transpose(h, C.byref(ht)))
                 _lib.check(lib.eg_store_a_and_vara(ht, None, 0, dp(S_h), dp(V_h), dp(a_h), dp(oa_h), dp(ov_h)))
                 lib.eg_store_free(h); lib.eg_store_free(ht)
-                tsq = oa_h * oa_h / ov_h
-                return int(torch.argmax(torch.nan_to_num(tsq, nan=-1.0)))
-            pms = time_host(step_host_packed)
-            packed = {"value": L / (pms * 1e-3), "unit": METRIC, "ms_per_step": pms,
-                      "h2d_bytes_per_step": int(n * wpr * 8 + 2 * n * n * 8 + n * 8), "picked_marker": step_host_packed(),
-                      "container": "2-bit packed genotypes (RcppFunctions.cpp.gpu:224-345 layout) instead of the ASCII image"}
+                return pick_host()
+            pms, ppick = time_host(step_host_packed)
+            out["from_packed_container"] = {
+                "value": L / (pms * 1e-3), "unit": METRIC, "ms_per_step": pms,
+                "h2d_bytes_per_step": int(n * wpr * 8 + 2 * n * n * 8 + n * 8), "picked_marker": ppick,
+                "container": "2-bit packed genotypes (RcppFunctions.cpp.gpu:224-345 layout) instead of the ASCII image"}
         except Exception as ex:  # noqa: BLE001
-            packed = {"value": None, "note": f"{type(ex).__name__}: {ex}"}
+            out["from_packed_container"] = {"value": None, "note": f"{type(ex).__name__}: {ex}"}
     if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = tt.item()
-    h2d = img_bytes + 2 * n * n * 8 + n * 8
-    d2h = (n * n * 8 if rank == 0 else 0) + 2 * Lg * 8
-    return {"value": L / (ms * 1e-3), "unit": METRIC, "ms_per_step": ms, "steps": ksteps,
-            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "abi_stage_ms": abi_timing,
-            "from_packed_container": packed,
-            "path": "host-level C ABI (eg_store_*) on pinned host buffers" if world == 1 else
-                    "pinned host shards -> H2D -> device-level C ABI -> all-reduce -> D2H",
-            "timing": "host clock around a synchronised region (max with CUDA events), max over ranks"}
+        _lib.check(lib.eg_shutdown())
+        _lib.check(lib.eg_init(int(os.environ.get("LOCAL_RANK", "0"))))
+    _wait_rank0(dist, rank, world, "e2e_done")
+    return out
+
+
+def run_dropin(args, torch, lib, device, n, L, img_h, S_h, V_h, a_h, time_host):
+    """What the untouched R package does per forward step, through the entry points its Rcpp glue binds
+    (src/RcppExports.cpp:37-71): calculateMMt_rcpp(M.ascii) and calculate_a_and_vara_rcpp(Mt.ascii, S, V, a) on FILES (in
+    the page cache), every matrix and vector in PAGEABLE host memory as R owns them.  `first_call`: nothing resident (a
+    fresh R session); `steady_state`: the genotype stores are resident under their path (every later iteration of AM(), or
+    an AM() that follows ReadMarker() in the same session) -- the contraction still runs (EAGLE_KEEP_PRODUCT=0)."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+
+    from eagleeverything_b200 import _lib
+    need = 2 * n * (L + 1) + (1 << 26)
+    base = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if shutil.disk_usage(cand).free > need * 1.2:
+                base = cand
+                break
+        except OSError:
+            pass
+    if base is None:
+        return {"note": "no room for the two ASCII files"}
+    d = tempfile.mkdtemp(prefix="eagle_bench_", dir=base)
+    vp = C.c_void_p
+    try:
+        m, mt = os.path.join(d, "M.ascii"), os.path.join(d, "Mt.ascii")
+        t0 = time.perf_counter()
+        img_np = img_h[: n * (L + 1)].numpy()
+        with open(m, "wb") as f:
+            f.write(memoryview(img_np))
+        # Mt.ascii through the library's own writer (createMt_ASCII_rcpp: decode, transpose, encode on the device)
+        dims = (C.c_int64 * 2)(n, L)
+        _lib.check(lib.eg_createMt_ASCII_rcpp(os.fsencode(m), os.fsencode(mt), b"text", 8.0, dims, 1, _lib.MESSAGE_FN(0), None))
+        lib.eg_cache_clear()
+        t_files = time.perf_counter() - t0
+        S_p, V_p, a_p = S_h.numpy().copy(), V_h.numpy().copy(), a_h.numpy().copy()      # pageable copies
+        K_p, oa_p, ov_p = np.empty((n, n)), np.empty(L), np.empty(L)
+        NA = np.array([float("nan")])
+        dpp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        dimsM, dimsMt = (C.c_int64 * 2)(n, L), (C.c_int64 * 2)(L, n)
+        os.environ["EAGLE_KEEP_PRODUCT"] = "0"
+        stage = {}
+
+        def step():
+            t1 = time.perf_counter()
+            _lib.check(lib.eg_calculateMMt_rcpp(os.fsencode(m), 8.0, 1, dpp(NA), 1, dimsM, 1, _lib.MESSAGE_FN(0), None, dpp(K_p)))
+            t2 = time.perf_counter()
+            _lib.check(lib.eg_calculate_a_and_vara_rcpp(os.fsencode(mt), dpp(NA), 1, dpp(S_p), dpp(V_p), 8.0, dimsMt, dpp(a_p), 1,
+                                                        _lib.MESSAGE_FN(0), None, dpp(oa_p), dpp(ov_p)))
+            t3 = time.perf_counter()
+            stage["calculateMMt_rcpp_ms"], stage["calculate_a_and_vara_rcpp_ms"] = (t2 - t1) * 1e3, (t3 - t2) * 1e3
+            with np.errstate(divide="ignore", invalid="ignore"):
+                tsq = oa_p * oa_p / ov_p
+            return int(np.nanargmax(tsq))
+
+        def cold():
+            lib.eg_cache_clear()
+            return step()
+        first_ms, pick1 = time_host(cold, reps=1, warm=0)
+        first_stage = {k: round(v, 2) for k, v in stage.items()}
+        steady_ms, pick2 = time_host(step, reps=3, warm=1)
+        steady_stage = {k: round(v, 2) for k, v in stage.items()}
+        t8 = (C.c_double * 8)()
+        lib.eg_last_timing(t8, 8)
+        return {"first_call": {"ms_per_step": first_ms, "value": L / (first_ms * 1e-3), "unit": METRIC, "stages": first_stage,
+                               "h2d_bytes": int(2 * n * (L + 1) + 2 * n * n * 8 + n * 8),
+                               "what": "cache cleared: both files read from the page cache, uploaded and decoded inside the calls"},
+                "steady_state": {"ms_per_step": steady_ms, "value": L / (steady_ms * 1e-3), "unit": METRIC, "stages": steady_stage,
+                                 "h2d_bytes": int(2 * n * n * 8 + n * 8), "d2h_bytes": int(n * n * 8 + 2 * L * 8),
+                                 "gpu0_stage_ms": dict(zip(["-", "syrk_ms", "allreduce_or_finalize_ms", "mmt_d2h_ms", "scan_h2d_ms",
+                                                            "prepare_ms", "scan_ms", "scan_d2h_ms"], [round(x, 3) for x in t8])),
+                                 "what": "genotype stores resident under their path; M.Mt contracted again on every call; S, V, a "
+                                         "uploaded from and K, a, var(a) returned to pageable memory"},
+                "picked_marker": [pick1, pick2], "files_in": base, "file_setup_s": round(t_files, 2),
+                "path": "eg_calculateMMt_rcpp(path) + eg_calculate_a_and_vara_rcpp(path, S, V, a): the entry points the Rcpp glue binds"}
+    finally:
+        os.environ.pop("EAGLE_KEEP_PRODUCT", None)
+        lib.eg_cache_clear()
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def _sha(t):
@@ -919,6 +1023,7 @@ def main():
     ap.add_argument("--search-host", action="store_true", help="also run the search with every matrix crossing the host-level ABI")
     ap.add_argument("--search-maxit", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (shapes that leave no room for its copies)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the file-based drop-in legs of the end-to-end measurement")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the in-run comparison with a single-GPU evaluation")
     ap.add_argument("--no-extras", action="store_true", help="N = 8: skip the one-step config 5 / config 4 legs")
     args = ap.parse_args()

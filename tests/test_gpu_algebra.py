@@ -216,3 +216,33 @@ def test_dense_and_eigenbasis_searches_agree(synth_small):
     assert r1["all_picked"] == r0["all_picked"] and r1["selected"] == r0["selected"]
     np.testing.assert_allclose(r1["extBIC"], r0["extBIC"], rtol=1e-9)
     assert r1["secular"]["max_root_iterations"] < 60
+
+
+def test_emma_eigen_R_resident_with_many_fixed_effects():
+    """q close to n / 2: the scratch layout of eg_dev_emma_eigen_R_wo_Z stays inside the documented buffer sizes."""
+    import ctypes as C
+    import torch
+    from eagleeverything_b200 import _lib, device
+    from oracle import am_driver as am
+    lib = device.init(0)
+    n, q = 12, 6
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((n, 3 * n))
+    K = A @ A.T / (3 * n) + 0.95 * np.eye(n)
+    X = np.column_stack([np.ones(n), rng.standard_normal((n, q - 1))])
+    y = rng.standard_normal(n)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    f64 = dict(dtype=torch.float64, device="cuda")
+    guard = 7.0
+    dK, dX, dy = cu(K), cu(X.T.copy()), cu(y)
+    vals, etas, U = torch.empty(n, **f64), torch.empty(n, **f64), torch.empty(n * n, **f64)
+    w1, w2 = torch.full((n * n + 64,), guard, **f64), torch.full((n * n + 64,), guard, **f64)
+    small = torch.full((2 * n * q + 2 * q * q + 64,), guard, **f64)
+    _lib.check(lib.eg_dev_emma_eigen_R_wo_Z(p(dK), p(dX), p(dy), n, q, p(vals), p(etas), p(U), p(w1), p(w2), p(small), None))
+    torch.cuda.synchronize()
+    for buf, size in ((w1, n * n), (w2, n * n), (small, 2 * n * q + 2 * q * q)):
+        assert bool((buf[size:] == guard).all().item()), "scratch overrun"
+    lam, Ur = am.emma_eigen_R_wo_Z(K, X)
+    np.testing.assert_allclose(vals[: n - q].cpu().numpy(), lam, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(etas[: n - q].cpu().numpy() ** 2, (Ur.T @ y) ** 2, rtol=1e-7, atol=1e-10)
