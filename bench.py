@@ -376,6 +376,10 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
     value = L / (ms_step * 1e-3)
 
+    mode = int(lib.eg_get_scan_mode())
+    k_ms, k_ops, p_ms, p_ops = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    _lib.check(lib.eg_last_scan_kernel(C.byref(k_ms), C.byref(k_ops)))   # CUDA events around the scan kernel of the last timed step
+    _lib.check(lib.eg_last_prep_kernels(C.byref(p_ms), C.byref(p_ops)))
     # ---------------- results of the last step, hashed (the same hashes must come out at every N) and, at N > 1, compared
     # bit for bit with a single-GPU run of the same data set computed here (rank 0) -- a mismatch fails the run
     checks = result_checks(args, torch, dist, device, egd, lib, n, L, Lg, c0, world, rank, K, oa, ov, S, V, ah, res)
@@ -399,10 +403,6 @@ def run_gpu(args):
         if world > 1 and rank != 0:
             img = device.synth_ascii(n, Lg, GENO_SEED, col_offset=c0, n_total=n)
 
-    mode = int(lib.eg_get_scan_mode())
-    k_ms, k_ops, p_ms, p_ops = C.c_double(), C.c_double(), C.c_double(), C.c_double()
-    _lib.check(lib.eg_last_scan_kernel(C.byref(k_ms), C.byref(k_ops)))   # CUDA events around the scan kernel itself
-    _lib.check(lib.eg_last_prep_kernels(C.byref(p_ms), C.byref(p_ops)))
     # BASELINE config 3 as it is worded: the full forward search, marker-sharded at N > 1 (collective calls: every rank)
     search = None
     if not args.no_search and args.workload in ("c2", "c3"):

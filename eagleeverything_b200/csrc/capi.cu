@@ -804,6 +804,9 @@ struct WorkerPool {
     bool stop = false;
     std::vector<int> rc;
     std::vector<std::string> err;
+    // agree(): host-side barrier of the GPU threads that ORs their status -- called before every collective so that a
+    // failure on one GPU makes all of them skip the exchange instead of leaving the others waiting inside NCCL forever
+    int bar_count = 0, bar_gen = 0, bar_rc = EG_OK, bar_result = EG_OK;
 };
 struct Multi {
     int n = 0;  // 0 / 1: single GPU
@@ -853,6 +856,33 @@ static int run_all(const std::function<int(int)>& fn) {
     for (int r = 0; r < g_multi.n; r++)
         if (P.rc[r] != EG_OK) return set_error(P.rc[r], "GPU %d: %s", g_multi.devs[r], P.err[r].c_str());
     return EG_OK;
+}
+static bool multi_trace() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("EAGLE_MULTI_TRACE"); on = e && e[0] == '1'; }
+    return on == 1;
+}
+#define MTRACE(...) do { if (multi_trace()) { fprintf(stderr, "[eagle gpu %d] ", g_ctx.device); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+// Every GPU thread calls agree(my status so far); all return the same value: EG_OK, or the first failure's code.  The
+// thread that failed keeps its own message; the others get a short note.
+static int agree(int rc) {
+    WorkerPool& P = *g_multi.pool;
+    std::unique_lock<std::mutex> lk(P.mu);
+    if (rc != EG_OK && P.bar_rc == EG_OK) P.bar_rc = rc;
+    const int gen = P.bar_gen;
+    if (++P.bar_count == g_multi.n) {
+        P.bar_result = P.bar_rc;
+        P.bar_rc = EG_OK;
+        P.bar_count = 0;
+        P.bar_gen++;
+        P.cv_done.notify_all();
+    } else {
+        P.cv_done.wait(lk, [&] { return P.bar_gen != gen; });
+    }
+    const int res = P.bar_result;
+    lk.unlock();
+    if (res != EG_OK && rc == EG_OK) return set_error(res, "another GPU of the set failed");
+    return rc != EG_OK ? rc : EG_OK;
 }
 static int check_nccl(int rc, const char* what) {
     if (rc == 0) return EG_OK;
@@ -1046,18 +1076,23 @@ static int mmt_of_composite(const eg_store* M, const std::vector<int64_t>& zero_
         cudaStream_t st = g_ctx.stream;
         DevBuf C, D;
         const eg_store* part = M->part[r];
-        if (part) {
-            std::vector<int64_t> z;
-            for (int64_t c : zero_cols)
-                if (c >= M->off[r] && c < M->off[r + 1]) z.push_back(c - M->off[r]);
-            EG_TRY(partial_product(part, z, C, keep_product));
-        } else {
-            EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
-            EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
-        }
-        EG_TRY(D.alloc((size_t)n * n * sizeof(double), "MMt output"));
+        auto local = [&]() -> int {
+            if (part) {
+                std::vector<int64_t> z;
+                for (int64_t c : zero_cols)
+                    if (c >= M->off[r] && c < M->off[r + 1]) z.push_back(c - M->off[r]);
+                EG_TRY(partial_product(part, z, C, keep_product));
+            } else {
+                EG_TRY(C.alloc((size_t)n * n * sizeof(int32_t), "MMt int32 accumulator"));
+                EG_CUDA(cudaMemsetAsync(C.p, 0, (size_t)n * n * sizeof(int32_t), st));
+            }
+            return D.alloc((size_t)n * n * sizeof(double), "MMt output");
+        };
+        MTRACE("mmt: partial product of markers [%lld, %lld)", (long long)M->off[r], (long long)M->off[r + 1]);
+        EG_TRY(agree(local()));
         {
             Timer t(st);
+            MTRACE("mmt: all-reduce of %lld x %lld int32", (long long)n, (long long)n);
             EG_NCCL(g_nccl.AllReduce(C.p, C.p, (size_t)n * n, NCCL_INT32, NCCL_SUM, g_multi.comm[r], st));
             g_ctx.timing[2] = t.stop();
         }
@@ -1070,6 +1105,7 @@ static int mmt_of_composite(const eg_store* M, const std::vector<int64_t>& zero_
                                     cudaMemcpyDeviceToHost, st));
         EG_CUDA(cudaStreamSynchronize(st));
         g_ctx.timing[3] = t.stop();
+        MTRACE("mmt: done");
         return EG_OK;
     }));
     return EG_OK;
@@ -1089,14 +1125,14 @@ static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zer
         const eg_store* part = Mt->part[r];
         const int64_t L = part ? part->rows : 0;
         DevBuf dS, dV, da, dT, dW, oa, ov;
-        EG_TRY(dS.alloc((size_t)n * n * 8, "inv_MMt_sqrt"));
-        EG_TRY(dV.alloc((size_t)n * n * 8, "dim_reduced_vara"));
-        EG_TRY(da.alloc((size_t)n * 8, "a"));
-        EG_TRY(dW.alloc((size_t)eg_scan_wp_elems(n) * 8, "packed W"));
-        EG_TRY(oa.alloc((size_t)(L ? L : 1) * 8, "a out"));
-        EG_TRY(ov.alloc((size_t)(L ? L : 1) * 8, "vara out"));
-        {
-            Timer t(st);
+        Timer t_up(st);
+        auto upload = [&]() -> int {
+            EG_TRY(dS.alloc((size_t)n * n * 8, "inv_MMt_sqrt"));
+            EG_TRY(dV.alloc((size_t)n * n * 8, "dim_reduced_vara"));
+            EG_TRY(da.alloc((size_t)n * 8, "a"));
+            EG_TRY(dW.alloc((size_t)eg_scan_wp_elems(n) * 8, "packed W"));
+            EG_TRY(oa.alloc((size_t)(L ? L : 1) * 8, "a out"));
+            EG_TRY(ov.alloc((size_t)(L ? L : 1) * 8, "vara out"));
             int64_t k0, k1;
             shard_range(n, N, r, 1, &k0, &k1);
             if (k1 > k0) {
@@ -1104,22 +1140,25 @@ static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zer
                 EG_CUDA(cudaMemcpyAsync(dV.as<double>() + k0 * n, V + k0 * n, (size_t)(k1 - k0) * n * 8, cudaMemcpyHostToDevice, st));
             }
             EG_CUDA(cudaMemcpyAsync(da.p, a, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-            EG_NCCL(g_nccl.GroupStart());
-            for (int q = 0; q < N; q++) {
-                int64_t q0, q1;
-                shard_range(n, N, q, 1, &q0, &q1);
-                if (q1 == q0) continue;
-                EG_NCCL(g_nccl.Broadcast(dS.as<double>() + q0 * n, dS.as<double>() + q0 * n, (size_t)(q1 - q0) * n, NCCL_FLOAT64, q, g_multi.comm[r], st));
-                EG_NCCL(g_nccl.Broadcast(dV.as<double>() + q0 * n, dV.as<double>() + q0 * n, (size_t)(q1 - q0) * n, NCCL_FLOAT64, q, g_multi.comm[r], st));
-            }
-            EG_NCCL(g_nccl.GroupEnd());
-            g_ctx.timing[4] = t.stop();
+            return EG_OK;
+        };
+        MTRACE("scan: upload of 1/%d of S and V", N);
+        EG_TRY(agree(upload()));
+        EG_NCCL(g_nccl.GroupStart());
+        for (int q = 0; q < N; q++) {
+            int64_t q0, q1;
+            shard_range(n, N, q, 1, &q0, &q1);
+            if (q1 == q0) continue;
+            EG_NCCL(g_nccl.Broadcast(dS.as<double>() + q0 * n, dS.as<double>() + q0 * n, (size_t)(q1 - q0) * n, NCCL_FLOAT64, q, g_multi.comm[r], st));
+            EG_NCCL(g_nccl.Broadcast(dV.as<double>() + q0 * n, dV.as<double>() + q0 * n, (size_t)(q1 - q0) * n, NCCL_FLOAT64, q, g_multi.comm[r], st));
         }
-        {
-            Timer t(st);
-            int sym = 0;
+        EG_NCCL(g_nccl.GroupEnd());
+        g_ctx.timing[4] = t_up.stop();
+        Timer t_prep(st);
+        int sym = 0;
+        std::vector<int64_t> cuts(N + 1, n);
+        auto products = [&]() -> int {
             EG_TRY(eg_dev_inputs_symmetric(dS.as<double>(), dV.as<double>(), n, &sym, st));
-            std::vector<int64_t> cuts(N + 1, n);
             for (int q = 0; q < N; q++) {
                 if (sym) {   // cost of columns [0,c): n c (V S) + c^2 / 2 (upper part of S X)  ->  equal-cost cuts
                     int64_t c = (int64_t)llround((double)n * (sqrt(1.0 + 3.0 * q / N) - 1.0) / 32.0) * 32;
@@ -1132,16 +1171,19 @@ static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zer
             for (int q = 0; q < N; q++) widest = std::max(widest, cuts[q + 1] - cuts[q]);
             EG_TRY(dT.alloc((size_t)n * widest * 8, "scan scratch"));
             EG_CUDA(cudaMemsetAsync(dW.p, 0, (size_t)eg_scan_wp_elems(n) * 8, st));
-            EG_TRY(eg_dev_scan_prepare_cols(dS.as<double>(), dV.as<double>(), n, cuts[r], cuts[r + 1], sym, dT.as<double>(), dW.as<double>(), st));
-            EG_NCCL(g_nccl.GroupStart());
-            for (int q = 0; q < N; q++)
-                if (cuts[q + 1] > cuts[q])
-                    EG_NCCL(g_nccl.Broadcast(dW.as<double>() + cuts[q] * Kpad, dW.as<double>() + cuts[q] * Kpad,
-                                             (size_t)(cuts[q + 1] - cuts[q]) * Kpad, NCCL_FLOAT64, q, g_multi.comm[r], st));
-            EG_NCCL(g_nccl.GroupEnd());
-            EG_TRY(eg_dev_scan_fold(dS.as<double>(), da.as<double>(), n, sym, dW.as<double>(), st));
-            g_ctx.timing[5] = t.stop();
-        }
+            return eg_dev_scan_prepare_cols(dS.as<double>(), dV.as<double>(), n, cuts[r], cuts[r + 1], sym, dT.as<double>(), dW.as<double>(), st);
+        };
+        MTRACE("scan: pre-products of my columns of W");
+        EG_TRY(agree(products()));
+        EG_NCCL(g_nccl.GroupStart());
+        for (int q = 0; q < N; q++)
+            if (cuts[q + 1] > cuts[q])
+                EG_NCCL(g_nccl.Broadcast(dW.as<double>() + cuts[q] * Kpad, dW.as<double>() + cuts[q] * Kpad,
+                                         (size_t)(cuts[q + 1] - cuts[q]) * Kpad, NCCL_FLOAT64, q, g_multi.comm[r], st));
+        EG_NCCL(g_nccl.GroupEnd());
+        EG_TRY(eg_dev_scan_fold(dS.as<double>(), da.as<double>(), n, sym, dW.as<double>(), st));
+        g_ctx.timing[5] = t_prep.stop();
+        MTRACE("scan: %lld markers", (long long)L);
         if (L > 0) {
             std::vector<int64_t> z;
             for (int64_t c : zero_rows)
@@ -1160,6 +1202,7 @@ static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zer
         } else {
             EG_CUDA(cudaStreamSynchronize(st));
         }
+        MTRACE("scan: done");
         return EG_OK;
     });
 }
@@ -1229,7 +1272,7 @@ extern "C" int eg_gpu_count(void) { return g_multi.n > 1 ? g_multi.n : (g_ctxs[0
 extern "C" void eg_cache_clear(void) {
     for (auto& e : g_ctx.cache) free_store_tree(e.store);
     g_ctx.cache.clear();
-    if (g_multi.n > 1 && t_ctx == &g_ctxs[0] && g_multi.pool)   // called by the user: the parts' pools live on the workers
+    if (g_multi.n > 1 && !t_is_worker && g_multi.pool)   // called by the user: the parts' pools live on the workers
         run_all([](int) {
             pool_flush();
             cudaStreamSynchronize(g_ctx.stream);
