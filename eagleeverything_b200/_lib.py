@@ -86,6 +86,7 @@ SIGNATURES = {
     "eg_dev_mmt_finalize": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "eg_scan_wp_elems": (_i64, [_i64]),
     "eg_dev_scan_prepare": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "eg_prep_uses_i8": (C.c_int, [_i64]),
     "eg_dev_symmetry": (C.c_int, [_vp, _i64, _dp, _dp, _vp]),
     "eg_dev_inputs_symmetric": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_int), _vp]),
     "eg_dev_scan_prepare_cols": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, _vp, _vp, _vp]),

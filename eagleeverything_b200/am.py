@@ -373,7 +373,7 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
     Ut = torch.empty((n, n), **f64)
     _lib.check(lib.eg_dev_transpose_f64(p(U), n, p(Ut), st()))
     Wp = torch.empty(lib.eg_scan_wp_elems(n), **f64)
-    work2 = torch.empty((n, n), **f64) if n < 1024 else None
+    work2 = torch.empty((n, n), **f64) if not lib.eg_prep_uses_i8(n) else None
 
     def to_eig(v):                                                               # U^T v for an n-vector on the host
         d_in = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)

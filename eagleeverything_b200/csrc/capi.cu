@@ -1156,27 +1156,30 @@ static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zer
         g_ctx.timing[4] = t_up.stop();
         Timer t_prep(st);
         int sym = 0;
+        bool split = false;
         std::vector<int64_t> cuts(N + 1, n);
         auto products = [&]() -> int {
             EG_TRY(eg_dev_inputs_symmetric(dS.as<double>(), dV.as<double>(), n, &sym, st));
+            split = sym && eg_prep_uses_i8(n);   // otherwise every GPU computes all of W itself (bit-identical to one GPU)
             for (int q = 0; q < N; q++) {
-                if (sym) {   // cost of columns [0,c): n c (V S) + c^2 / 2 (upper part of S X)  ->  equal-cost cuts
+                if (split) {   // cost of columns [0,c): n c (V S) + c^2 / 2 (upper part of S X)  ->  equal-cost cuts
                     int64_t c = (int64_t)llround((double)n * (sqrt(1.0 + 3.0 * q / N) - 1.0) / 32.0) * 32;
                     cuts[q] = c < n ? c : n;
                 } else {
-                    cuts[q] = std::min<int64_t>(n, (int64_t)q * ((n + N - 1) / N));
+                    cuts[q] = q == 0 ? 0 : n;
                 }
             }
             int64_t widest = 1;
             for (int q = 0; q < N; q++) widest = std::max(widest, cuts[q + 1] - cuts[q]);
-            EG_TRY(dT.alloc((size_t)n * widest * 8, "scan scratch"));
+            EG_TRY(dT.alloc((size_t)n * (split ? widest : n) * 8, "scan scratch"));
             EG_CUDA(cudaMemsetAsync(dW.p, 0, (size_t)eg_scan_wp_elems(n) * 8, st));
+            if (!split) return eg_dev_scan_prepare_cols(dS.as<double>(), dV.as<double>(), n, 0, n, sym, dT.as<double>(), dW.as<double>(), st);
             return eg_dev_scan_prepare_cols(dS.as<double>(), dV.as<double>(), n, cuts[r], cuts[r + 1], sym, dT.as<double>(), dW.as<double>(), st);
         };
         MTRACE("scan: pre-products of my columns of W");
         EG_TRY(agree(products()));
         EG_NCCL(g_nccl.GroupStart());
-        for (int q = 0; q < N; q++)
+        for (int q = 0; q < N && split; q++)
             if (cuts[q + 1] > cuts[q])
                 EG_NCCL(g_nccl.Broadcast(dW.as<double>() + cuts[q] * Kpad, dW.as<double>() + cuts[q] * Kpad,
                                          (size_t)(cuts[q + 1] - cuts[q]) * Kpad, NCCL_FLOAT64, q, g_multi.comm[r], st));
@@ -1609,6 +1612,17 @@ extern "C" int eg_dev_symmetry(const double* d_A, int64_t n, double* max_abs, do
     return EG_OK;
 }
 
+// Which path the n^3 pre-products of symmetric inputs take: the exact int8 digit-slice products (prep_i8.cu) from n = 512
+// (below that the fixed cost of slicing and of the 7 level passes outweighs two tiny DGEMMs); EAGLE_PREP_MODE=i8 / f64
+// forces one.  The digit-slice path is deterministic whatever the column split, so marker-sharded runs split the columns
+// of W over the GPUs only when it is taken (a library DGEMM rounds differently for different splits).
+extern "C" int eg_prep_uses_i8(int64_t n) {
+    const char* env_pm = getenv("EAGLE_PREP_MODE");
+    if (env_pm && env_pm[0] == 'i') return 1;
+    if (env_pm && env_pm[0] == 'f') return 0;
+    return n >= 512;
+}
+
 // Columns [col0, col1) of W = S * (V * S) into the packed Wp (ld = Kpad); d_tmp needs n * (col1-col0) doubles.
 // upper_only != 0: only rows 0 .. col1-1 of those columns are computed (enough when W is symmetric).
 extern "C" int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1,
@@ -1619,12 +1633,9 @@ extern "C" int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, in
     EG_TRY(ensure_init());
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t Kpad = round_up(n, 32), nc = col1 - col0;
-    // symmetric inputs: both products on the int8 tensor cores (prep_i8.cu) unless EAGLE_PREP_MODE=f64 or the
-    // digit slices do not fit in memory
-    // (below n ~ 3000 the fixed costs of slicing and of the 7 level passes outweigh the faster products: auto = by n;
-    // EAGLE_PREP_MODE=i8 / f64 forces a path)
-    const char* env_pm = getenv("EAGLE_PREP_MODE");
-    const bool want_i8 = env_pm && env_pm[0] == 'i' ? true : (env_pm && env_pm[0] == 'f' ? false : n >= 3072);
+    // symmetric inputs: both products on the int8 tensor cores (prep_i8.cu) unless EAGLE_PREP_MODE=f64, the digit slices
+    // do not fit in memory, or n is tiny (eg_prep_uses_i8)
+    const bool want_i8 = eg_prep_uses_i8(n) != 0;
     if (upper_only && want_i8) {
         bool done = false;
         EG_TRY(launch_prepare_i8(d_S, d_V, n, col0, col1, d_tmp, d_Wp, Kpad, st, &done));

@@ -325,8 +325,7 @@ extern "C" int eg_dev_scan_prepare_eig(const double* d_U, const double* d_Ut, in
     double* d_rs = d_Wp + n * Kpad;  // column n of Wp as scratch until v is written there
     eig_sqrt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_w, n, d_rs);
     EG_TRY(check_launch("eig_sqrt_kernel"));
-    const char* env_pm = getenv("EAGLE_PREP_MODE");
-    const bool want_i8 = env_pm && env_pm[0] == 'i' ? true : (env_pm && env_pm[0] == 'f' ? false : n >= 1024);
+    const bool want_i8 = eg_prep_uses_i8(n) != 0;
     bool done = false;
     if (want_i8) EG_TRY(launch_prepare_eig_i8(d_Ut, d_rs, n, d_Wp, Kpad, st, &done));
     const double one = 1.0, zero = 0.0;

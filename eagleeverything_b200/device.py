@@ -149,6 +149,15 @@ def scan_prepare_sharded(S, V, a, n, rank, world, Wp=None, tmp=None):
     sym = C.c_int(0)
     _lib.check(lib.eg_dev_inputs_symmetric(_ptr(S), _ptr(V), n, C.byref(sym), _stream()))
     sym = int(sym.value)
+    if not (sym and lib.eg_prep_uses_i8(n)):
+        # library DGEMMs round differently for different column splits: every rank computes all of W itself, which is
+        # bit-identical to the single-GPU evaluation (and negligible at the sizes where this path is taken)
+        if tmp is None or tmp.numel() < n * n:
+            tmp = torch.empty(n * n, dtype=torch.float64, device=S.device)
+        Wp.zero_()
+        _lib.check(lib.eg_dev_scan_prepare_cols(_ptr(S), _ptr(V), n, 0, n, sym, _ptr(tmp), _ptr(Wp), _stream()))
+        _lib.check(lib.eg_dev_scan_fold(_ptr(S), _ptr(a), n, sym, _ptr(Wp), _stream()))
+        return Wp
     if sym:
         # cost of columns [0,c): n*c (V*S) + c^2/2 (upper part of S*tmp)  ->  equal-cost cuts
         cuts = [min(n, int(round(n * ((1.0 + 3.0 * r / world) ** 0.5 - 1.0) / 32.0)) * 32) for r in range(world)] + [n]

@@ -223,6 +223,10 @@ int eg_dev_scan_prepare(const double* d_S, const double* d_V, const double* d_a,
  * then every rank folds the complete W.  When S and V are symmetric (eg_dev_inputs_symmetric: to 1e-13 of
  * their largest entry -- always the case under AM()) W is symmetric and `upper_only` / `w_is_upper` restrict
  * the second product to rows 0..col1-1 (3 n^3 instead of 4 n^3 flops). */
+/* 1 when the n^3 pre-products of symmetric inputs run as exact int8 digit-slice products (deterministic for any column
+ * split), 0 when they are two library DGEMMs (n < 512, or EAGLE_PREP_MODE=f64): sharded callers split the columns of W only
+ * in the first case. */
+int eg_prep_uses_i8(int64_t n);
 int eg_dev_symmetry(const double* d_A, int64_t n, double* max_abs, double* max_asym, void* stream);
 int eg_dev_inputs_symmetric(const double* d_S, const double* d_V, int64_t n, int* yes, void* stream);
 int eg_dev_scan_prepare_cols(const double* d_S, const double* d_V, int64_t n, int64_t col0, int64_t col1,
@@ -335,7 +339,7 @@ int eg_dev_eigbasis_apply(const double* d_U, int64_t n, const double* d_in, int 
 /* The scan's right-hand side (what eg_dev_scan_prepare builds from S, V, a) from eigenbasis quantities:
  * W = U diag(w) U^T - E E^T with E = U Et (n x q, q may be 0), folded into d_Wp; v = U vt into its column n.
  * d_Ut = U^T (eg_dev_transpose_f64).  d_work: n * max(q,1) doubles; d_work2: n*n doubles, only read when the product runs
- * in FP64 (n < 1024, or the digit slices do not fit) and may be NULL otherwise. */
+ * in FP64 (n < 512, or the digit slices do not fit) and may be NULL otherwise. */
 int eg_dev_scan_prepare_eig(const double* d_U, const double* d_Ut, int64_t n, const double* d_w, const double* d_Et, int q,
                             const double* d_vt, double* d_work, double* d_work2, double* d_Wp, void* stream);
 
