@@ -142,7 +142,7 @@ def cpu_reference_sample(n, L, steps=1, warmup=0):
     for _ in range(max(1, steps)):
         last = ref.step()
         vals.append(last[0])
-    v = sum(vals) / len(vals)
+    v = sorted(vals)[len(vals) // 2]          # median pass
     out = ref.baseline(v, last[1], last[2])
     out["per_step_values"] = [round(x, 1) for x in vals]
     return out
@@ -411,7 +411,7 @@ def run_gpu(args):
         except Exception as ex:  # noqa: BLE001
             search = {"note": f"failed: {type(ex).__name__}: {ex}"}
     extras = None
-    if world >= 8 and args.workload == "c3" and not args.no_extras:
+    if (world >= 8 or os.environ.get("EAGLE_BENCH_EXTRAS_SHRINK")) and world > 1 and args.workload == "c3" and not args.no_extras:
         del img, S, V, ah
         torch.cuda.empty_cache()
         extras = {}
@@ -503,7 +503,7 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_reference_sample(n, L, steps=1, warmup=0)
+            cpu = cpu_reference_sample(n, L, steps=3, warmup=0)
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     out = {
@@ -860,9 +860,12 @@ def run_extra_workload(args, wl, torch, dist, device, egd, lib, world, rank):
     from eagleeverything_b200 import am
     w = WORKLOADS[wl]
     n, L = w["n"], w["L"]
+    shrink = float(os.environ.get("EAGLE_BENCH_EXTRAS_SHRINK", "1"))   # smoke tests of this leg on fewer GPUs
+    if shrink > 1:
+        n, L = int(n / shrink) // 32 * 32, int(L / shrink) // 128 * 128
     c0, c1 = egd.shard_range(L, world, rank)
     Lg = c1 - c0
-    out = {"workload": w["name"], "n": n, "L": L, "n_gpus": world}
+    out = {"workload": w["name"] + (f" (shrunk by {shrink:g} for a smoke test)" if shrink > 1 else ""), "n": n, "L": L, "n_gpus": world}
     img = device.synth_ascii(n, Lg, GENO_SEED, col_offset=c0, n_total=n)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
 

@@ -346,7 +346,7 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
     y = np.asarray(y, dtype=np.float64).reshape(-1)
     X = np.ones((n, 1)) if X0 is None else np.asarray(X0, dtype=np.float64).reshape(n, -1)
     Lloc = storeT.shape[0]
-    stats = dict(mmt_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0, extract_s=0.0, total_s=0.0)
+    stats = dict(mmt_s=0.0, eigen_K_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0, extract_s=0.0, total_s=0.0)
 
     def timed(key, t0):
         torch.cuda.synchronize()
@@ -383,7 +383,7 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
 
     yt = to_eig(y)
     Xt = np.column_stack([to_eig(X[:, c]) for c in range(X.shape[1])])
-    timed("emma_eigen_s", t0)
+    timed("eigen_K_s", t0)
     emma = _Emma(None, stats)
     emma._xi = xi
     selected, new_locus, extBIC = [NA], NA, []

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostio.cuh"
 
 namespace eg {
 
@@ -416,13 +417,9 @@ struct HostDev {
         return EG_OK;
     }
 };
-int up(double* d, const double* h, size_t doubles, cudaStream_t st) {
-    return check_cuda(cudaMemcpyAsync(d, h, doubles * 8, cudaMemcpyHostToDevice, st), "H2D");
-}
-int down(double* h, const double* d, size_t doubles, cudaStream_t st) {
-    EG_CUDA(cudaMemcpyAsync(h, d, doubles * 8, cudaMemcpyDeviceToHost, st));
-    return check_cuda(cudaStreamSynchronize(st), "D2H");
-}
+// R-owned matrices are pageable: staged through the page-locked ring with parallel copier threads (hostio.cu)
+int up(double* d, const double* h, size_t doubles, cudaStream_t st) { return h2d_staged(d, h, doubles * 8, st); }
+int down(double* h, const double* d, size_t doubles, cudaStream_t st) { return d2h_staged(h, d, doubles * 8, st); }
 void say(eg_message_fn message, void* ctx, const char* text) {
     if (message) message(ctx, text);
 }

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostio.cuh"
 
 struct eg_store {
     int8_t* d = nullptr;
@@ -385,7 +386,7 @@ static int store_from_image_kb(const uint8_t* image, int64_t src_pitch_host, int
 // characters per line.  Row blocks are staged through two device buffers so that the H2D copy of
 // block k+1 overlaps the decode of block k.
 static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t row0, int64_t row1, int64_t col0,
-                            int64_t col1, bool kblocked, eg_store** out) {
+                            int64_t col1, bool kblocked, eg_store** out, int fd = -1) {
     EG_TRY(ensure_init());
     const int64_t rows = row1 - row0, w = col1 - col0, src_pitch_host = cols_total + 1;
     if (!image || rows <= 0 || w <= 0 || col0 < 0 || col1 > cols_total || row0 < 0)
@@ -429,18 +430,20 @@ static int store_from_image(const uint8_t* image, int64_t cols_total, int64_t ro
         const int b = k & 1;
         const int64_t nr = (r + block_rows <= rows) ? block_rows : rows - r;
         if (k >= 2) cudaStreamWaitEvent(g_ctx.copy_stream, decoded[b], 0);  // staging buffer free again
-        const uint8_t* src = image + (row0 + r) * src_pitch_host + col0;
-        cudaError_t e;
+        // pageable memory and files go through the page-locked ring with parallel copier threads (hostio.cu); the
+        // decode of this block then overlaps the staging of the next one
+        HostSrc hs;
+        hs.p = image;
+        hs.fd = fd;
+        const size_t soff = (size_t)(row0 + r) * (size_t)src_pitch_host + (size_t)col0;
         if (full_width) {
             // the very last line of a file may lack its '\n': never read past row1*pitch - 1
             size_t bytes = (size_t)nr * src_pitch_host;
             if (r + nr == rows) bytes -= 1;
-            e = cudaMemcpyAsync(stg[b].p, src, bytes, cudaMemcpyHostToDevice, g_ctx.copy_stream);
+            rc = h2d_staged_2d(stg[b].p, bytes, hs, soff, bytes, bytes, 1, g_ctx.copy_stream);
         } else {
-            e = cudaMemcpy2DAsync(stg[b].p, dev_pitch, src, src_pitch_host, w, nr, cudaMemcpyHostToDevice,
-                                  g_ctx.copy_stream);
+            rc = h2d_staged_2d(stg[b].p, (size_t)dev_pitch, hs, soff, (size_t)src_pitch_host, (size_t)w, (size_t)nr, g_ctx.copy_stream);
         }
-        rc = check_cuda(e, "H2D copy of the ASCII genotype image");
         if (rc != EG_OK) break;
         cudaEventRecord(copied[b], g_ctx.copy_stream);
         cudaStreamWaitEvent(g_ctx.stream, copied[b], 0);
@@ -511,7 +514,7 @@ static int check_image_size(const MappedFile& f, const char* path, int64_t rows,
 }
 
 static int store_from_image_any(const uint8_t* image, int64_t cols_total, int64_t row0, int64_t row1, int64_t col0,
-                                int64_t col1, bool kblocked, eg_store** out, bool allow_multi);
+                                int64_t col1, bool kblocked, eg_store** out, bool allow_multi, int fd = -1);
 // cache key: (realpath, size, mtime, hash of the first and last 4 KB, dims, layout)
 static int cache_key(const char* path, int64_t rows, int64_t cols, bool kblocked, std::string& key) {
     struct stat st;
@@ -569,7 +572,7 @@ static int cached_store(const char* path, int64_t rows, int64_t cols, bool kbloc
     EG_TRY(f.open_ro(path));
     EG_TRY(check_image_size(f, path, rows, cols));
     eg_store* s = nullptr;
-    EG_TRY(store_from_image_any(f.p, cols, 0, rows, 0, cols, kblocked, &s, allow_multi));
+    EG_TRY(store_from_image_any(f.p, cols, 0, rows, 0, cols, kblocked, &s, allow_multi, f.fd));
     cache_insert(key, s);
     *out = s;
     return EG_OK;
@@ -695,8 +698,7 @@ static int mmt_of_store(const eg_store* M, const std::vector<int64_t>& zero_cols
     }
     {
         Timer t(st);
-        EG_CUDA(cudaMemcpyAsync(out_host, D.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-        EG_CUDA(cudaStreamSynchronize(st));
+        EG_TRY(d2h_staged(out_host, D.p, (size_t)n * n * sizeof(double), st));
         g_ctx.timing[3] = t.stop();
     }
     return EG_OK;
@@ -720,8 +722,8 @@ static int scan_of_store(const eg_store* Mt, const std::vector<int64_t>& zero_ro
     EG_TRY(ov.alloc((size_t)L * 8, "vara out"));
     {
         Timer t(st);
-        EG_CUDA(cudaMemcpyAsync(dS.p, S, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
-        EG_CUDA(cudaMemcpyAsync(dV.p, V, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
+        EG_TRY(h2d_staged(dS.p, S, (size_t)n * n * 8, st));   // R-owned (pageable) matrices: page-locked ring, parallel copiers
+        EG_TRY(h2d_staged(dV.p, V, (size_t)n * n * 8, st));
         EG_CUDA(cudaMemcpyAsync(da.p, a, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         g_ctx.timing[4] = t.stop();
     }
@@ -937,6 +939,7 @@ static void shutdown_slot() {
     prep_i8_release();
     algebra_release();
     eigbasis_release();
+    hostio_release();
     if (g_ctx.scan_ev[0]) { cudaEventDestroy(g_ctx.scan_ev[0]); cudaEventDestroy(g_ctx.scan_ev[1]); }
     if (g_ctx.cublas) cublasDestroy(g_ctx.cublas);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
@@ -1006,8 +1009,8 @@ static int run_all_evicting(const std::function<int(int)>& fn, const std::functi
 // Rows [row0,row1) x columns [col0,col1) of a host image -> a store; with a multi-GPU set (and allow_multi) a composite
 // whose parts are the marker shards, every GPU pulling and decoding its own byte ranges concurrently.
 static int store_from_image_any(const uint8_t* image, int64_t cols_total, int64_t row0, int64_t row1, int64_t col0,
-                                int64_t col1, bool kblocked, eg_store** out, bool allow_multi) {
-    if (g_multi.n <= 1 || !allow_multi || t_is_worker) return store_from_image(image, cols_total, row0, row1, col0, col1, kblocked, out);
+                                int64_t col1, bool kblocked, eg_store** out, bool allow_multi, int fd) {
+    if (g_multi.n <= 1 || !allow_multi || t_is_worker) return store_from_image(image, cols_total, row0, row1, col0, col1, kblocked, out, fd);
     EG_TRY(ensure_init());
     if (!image || row1 <= row0 || col1 <= col0 || col0 < 0 || col1 > cols_total || row0 < 0)
         return set_error(EG_ERR_ARG, "genotype store: bad image range");
@@ -1021,8 +1024,8 @@ static int store_from_image_any(const uint8_t* image, int64_t cols_total, int64_
     const int rc = run_all_evicting([&](int r) -> int {
         const int64_t a = S->off[r], b = S->off[r + 1];
         if (a == b) return EG_OK;
-        return kblocked ? store_from_image(image, cols_total, row0, row1, col0 + a, col0 + b, true, &S->part[r])
-                        : store_from_image(image, cols_total, row0 + a, row0 + b, col0, col1, false, &S->part[r]);
+        return kblocked ? store_from_image(image, cols_total, row0, row1, col0 + a, col0 + b, true, &S->part[r], fd)
+                        : store_from_image(image, cols_total, row0 + a, row0 + b, col0, col1, false, &S->part[r], fd);
     }, undo);
     if (rc != EG_OK) {
         const std::string msg = g_err;
@@ -1100,9 +1103,7 @@ static int mmt_of_composite(const eg_store* M, const std::vector<int64_t>& zero_
         int64_t i0, i1;
         shard_range(n, N, r, 1, &i0, &i1);
         Timer t(st);
-        if (i1 > i0)
-            EG_CUDA(cudaMemcpyAsync(out_host + i0 * n, D.as<double>() + i0 * n, (size_t)(i1 - i0) * n * sizeof(double),
-                                    cudaMemcpyDeviceToHost, st));
+        if (i1 > i0) EG_TRY(d2h_staged(out_host + i0 * n, D.as<double>() + i0 * n, (size_t)(i1 - i0) * n * sizeof(double), st));
         EG_CUDA(cudaStreamSynchronize(st));
         g_ctx.timing[3] = t.stop();
         MTRACE("mmt: done");
@@ -1136,8 +1137,8 @@ static int scan_of_composite(const eg_store* Mt, const std::vector<int64_t>& zer
             int64_t k0, k1;
             shard_range(n, N, r, 1, &k0, &k1);
             if (k1 > k0) {
-                EG_CUDA(cudaMemcpyAsync(dS.as<double>() + k0 * n, S + k0 * n, (size_t)(k1 - k0) * n * 8, cudaMemcpyHostToDevice, st));
-                EG_CUDA(cudaMemcpyAsync(dV.as<double>() + k0 * n, V + k0 * n, (size_t)(k1 - k0) * n * 8, cudaMemcpyHostToDevice, st));
+                EG_TRY(h2d_staged(dS.as<double>() + k0 * n, S + k0 * n, (size_t)(k1 - k0) * n * 8, st));
+                EG_TRY(h2d_staged(dV.as<double>() + k0 * n, V + k0 * n, (size_t)(k1 - k0) * n * 8, st));
             }
             EG_CUDA(cudaMemcpyAsync(da.p, a, (size_t)n * 8, cudaMemcpyHostToDevice, st));
             return EG_OK;
@@ -1494,7 +1495,7 @@ extern "C" int eg_store_from_file(const char* path, int64_t rows, int64_t cols, 
     MappedFile f;
     EG_TRY(f.open_ro(path));
     EG_TRY(check_image_size(f, path, rows, cols));
-    return store_from_image_any(f.p, cols, 0, rows, col0, col1, true, out, true);
+    return store_from_image_any(f.p, cols, 0, rows, col0, col1, true, out, true, f.fd);
 }
 extern "C" int eg_store_transpose(const eg_store_t* in, eg_store_t** out) {
     if (!in || !out) return set_error(EG_ERR_ARG, "null argument");
@@ -1719,7 +1720,7 @@ extern "C" int eg_ReadBlock(const char* asciifname, int64_t start_row, int64_t n
         return set_error(EG_ERR_FORMAT, "ReadBlock: %s has %lld lines, rows [%lld,%lld) requested", asciifname,
                          (long long)nrows_file, (long long)start_row, (long long)(start_row + numrows_in_block));
     eg_store* s = nullptr;
-    EG_TRY(store_from_image(f.p, line, start_row, start_row + numrows_in_block, 0, numcols, false, &s));
+    EG_TRY(store_from_image(f.p, line, start_row, start_row + numrows_in_block, 0, numcols, false, &s, f.fd));
     DevBuf d;
     int rc = d.alloc((size_t)numrows_in_block * numcols * 8, "ReadBlock output");
     if (rc == EG_OK) {
