@@ -170,16 +170,23 @@ def scan_prepare_sharded(S, V, a, n, rank, world, Wp=None, tmp=None):
         tmp = torch.empty(need, dtype=torch.float64, device=S.device)
     Wp.zero_()
     _lib.check(lib.eg_dev_scan_prepare_cols(_ptr(S), _ptr(V), n, c0, c1, sym, _ptr(tmp), _ptr(Wp), _stream()))
-    # ONE collective: the column blocks (contiguous ranges of the column-major Wp, unequal widths) are all-gathered at the
-    # width of the widest one and copied into place
+    # ONE collective when its staging buffers are small: the column blocks (contiguous ranges of the column-major Wp,
+    # unequal widths) are all-gathered at the width of the widest one and copied into place.  At n = 50,000 those buffers
+    # would be 36 GB and push the digit slices of the pre-products out of memory: one broadcast per block there.
     wmax = max(cuts[r + 1] - cuts[r] for r in range(world))
-    mine = torch.zeros(wmax * Kpad, dtype=torch.float64, device=S.device)
-    mine[: (c1 - c0) * Kpad].copy_(Wp[c0 * Kpad:c1 * Kpad])
-    allb = torch.empty(world * wmax * Kpad, dtype=torch.float64, device=S.device)
-    dist.all_gather_into_tensor(allb, mine)
-    for r in range(world):
-        if r != rank and cuts[r + 1] > cuts[r]:
-            Wp[cuts[r] * Kpad:cuts[r + 1] * Kpad].copy_(allb[r * wmax * Kpad:r * wmax * Kpad + (cuts[r + 1] - cuts[r]) * Kpad])
+    if (world + 1) * wmax * Kpad * 8 <= (4 << 30):
+        mine = torch.zeros(wmax * Kpad, dtype=torch.float64, device=S.device)
+        mine[: (c1 - c0) * Kpad].copy_(Wp[c0 * Kpad:c1 * Kpad])
+        allb = torch.empty(world * wmax * Kpad, dtype=torch.float64, device=S.device)
+        dist.all_gather_into_tensor(allb, mine)
+        for r in range(world):
+            if r != rank and cuts[r + 1] > cuts[r]:
+                Wp[cuts[r] * Kpad:cuts[r + 1] * Kpad].copy_(allb[r * wmax * Kpad:r * wmax * Kpad + (cuts[r + 1] - cuts[r]) * Kpad])
+        del mine, allb
+    else:
+        for r in range(world):
+            if cuts[r + 1] > cuts[r]:
+                dist.broadcast(Wp[cuts[r] * Kpad:cuts[r + 1] * Kpad], src=r)
     _lib.check(lib.eg_dev_scan_fold(_ptr(S), _ptr(a), n, sym, _ptr(Wp), _stream()))
     return Wp
 

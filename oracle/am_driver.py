@@ -192,6 +192,141 @@ def emma_MLE(y, X, K, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
     return dict(ML=maxLL, delta=maxdelta, ve=maxva * maxdelta, vg=maxva)
 
 
+# ----------------------------------------------------------------------------- EMMA with an incidence matrix Z
+def _r_eigen_nonsym(A):
+    """eigen(A, symmetric=FALSE): eigenvalues by decreasing modulus; for the matrices of emma.eigen.*.w.Z (similar to
+    symmetric positive semi-definite ones) they are real; the reference keeps Re() (emma_eigen_R_w_Z.R:14-17)."""
+    w, v = np.linalg.eig(A)
+    w, v = np.real(w), np.real(v)
+    o = np.argsort(-np.abs(w), kind="stable")
+    return w[o], v[:, o]
+
+
+def emma_eigen_L_w_Z(Z, K, complete=True):
+    """emma_eigen_L_w_Z.R:2-14 (values only are consumed by emma.MLE)."""
+    if not complete:
+        vids = Z.sum(0) > 0
+        Z, K = Z[:, vids], K[np.ix_(vids, vids)]
+    w, _ = _r_eigen_nonsym(K @ (Z.T @ Z))
+    return w
+
+
+def emma_eigen_R_w_Z(Z, K, X, complete=True):
+    """emma_eigen_R_w_Z.R:2-23 -> (values[1:(t-q)], vectors n x (n-q): the first t-q pair with the values)."""
+    if not complete:
+        vids = Z.sum(0) > 0
+        Z, K = Z[:, vids], K[np.ix_(vids, vids)]
+    n, t = Z.shape
+    q = X.shape[1]
+    SZ = Z - X @ np.linalg.solve(X.T @ X, X.T @ Z)
+    w, v = _r_eigen_nonsym(K @ (Z.T @ SZ))
+    qrX, _ = np.linalg.qr(X)
+    Q, _ = np.linalg.qr(np.column_stack([SZ @ v[:, : t - q], qrX]), mode="complete")
+    return w[: t - q], Q[:, list(range(t - q)) + list(range(t, n))]
+
+
+def _emma_w_Z(y, X, K, Z, ngrids, llim, ulim, esp, ml):
+    """The Z branches of emma_REMLE.R:78-117 and emma_MLE.R:57-105 (ml: the ML form, with eigen(K Z'Z) and n in
+    place of n - q).  Note: emma.MLE passes `ngpu` in the position of `complete` (emma_MLE.R:60,63), i.e. complete = 0:
+    individuals without a record are dropped there; with every individual measured the two forms coincide."""
+    n, q = len(y), X.shape[1]
+    t = K.shape[0]
+    if np.linalg.det(X.T @ X) == 0:
+        return dict(ML=0.0, delta=0.0, ve=0.0, vg=0.0) if ml else dict(REML=0.0, delta=0.0, ve=0.0, vg=0.0)
+    lam, U = emma_eigen_R_w_Z(Z, K, X, complete=not ml)
+    xi = emma_eigen_L_w_Z(Z, K, complete=False) if ml else None
+    etas = U.T @ y
+    e1, e2sq = etas[: t - q], float((etas[t - q:] ** 2).sum())
+    e1sq = e1 * e1
+    logdelta = np.arange(ngrids + 1) / ngrids * (ulim - llim) + llim
+    delta = np.exp(logdelta)
+    Lambdas = lam[:, None] + delta[None, :]
+    E = e1sq[:, None]
+    if ml:
+        Xis = xi[:, None] + delta[None, :]
+        dLL = 0.5 * delta * (n * ((E / (Lambdas * Lambdas)).sum(0) + e2sq / (delta * delta)) / ((E / Lambdas).sum(0) + e2sq / delta)
+                             - ((1.0 / Xis).sum(0) + (n - t) / delta))
+
+        def LLfun(ld):   # emma.delta.ML.LL.w.Z (emma_misc.R)
+            d = math.exp(ld)
+            return 0.5 * (n * (math.log(n / (2 * math.pi)) - 1 - math.log((e1sq / (lam + d)).sum() + e2sq / d))
+                          - (np.log(xi + d).sum() + (n - len(xi)) * ld))
+
+        def dLLfun(ld):  # emma_delta_ML_dLL_w_Z.R:1-10
+            d = math.exp(ld)
+            ldel = lam + d
+            return 0.5 * (n * ((e1sq / (ldel * ldel)).sum() + e2sq / (d * d)) / ((e1sq / ldel).sum() + e2sq / d)
+                          - ((1.0 / (xi + d)).sum() + (n - len(xi)) / d))
+        denom = n
+    else:
+        dLL = 0.5 * delta * ((n - q) * ((E / (Lambdas * Lambdas)).sum(0) + e2sq / (delta * delta)) / ((E / Lambdas).sum(0) + e2sq / delta)
+                             - ((1.0 / Lambdas).sum(0) + (n - t) / delta))
+
+        def LLfun(ld):   # emma.delta.REML.LL.w.Z
+            tq = len(e1)
+            nq = n - t + tq
+            d = math.exp(ld)
+            return 0.5 * (nq * (math.log(nq / (2 * math.pi)) - 1 - math.log((e1sq / (lam + d)).sum() + e2sq / d))
+                          - (np.log(lam + d).sum() + (n - t) * ld))
+
+        def dLLfun(ld):  # emma.delta.REML.dLL.w.Z
+            tq = len(e1)
+            nq = n - t + tq
+            d = math.exp(ld)
+            ldel = lam + d
+            return 0.5 * (nq * ((e1sq / (ldel * ldel)).sum() + e2sq / (d * d)) / ((e1sq / ldel).sum() + e2sq / d)
+                          - ((1.0 / ldel).sum() + (n - t) / d))
+        denom = n - q
+    maxdelta, maxLL = _grid_opt(dLL, logdelta, llim, ulim, esp, LLfun, dLLfun)
+    maxva = ((e1sq / (lam + maxdelta)).sum() + e2sq / maxdelta) / denom
+    return {("ML" if ml else "REML"): maxLL, "delta": maxdelta, "ve": maxva * maxdelta, "vg": maxva}
+
+
+def emma_REMLE_Z(y, X, K, Z, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
+    return _emma_w_Z(y, X, K, Z, ngrids, llim, ulim, esp, ml=False)
+
+
+def emma_MLE_Z(y, X, K, Z, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
+    return _emma_w_Z(y, X, K, Z, ngrids, llim, ulim, esp, ml=True)
+
+
+def scan_inputs_Z(K, Z, X, y, ve, vg):
+    """What a Z-aware find_qtl feeds the scan with (NOT in the reference snapshot, where Z never
+    reaches find_qtl: AM.R:450-452, find_qtl.R:1-2, calculateP.R:22-25).  Model: y = X b + Z u + e, u ~ N(0, vg K).
+    H = ve I + vg Z K Z' (calculateH.R:36 with Z K Z' for K), P as calculateP.R:27-28; the marker scores are
+    a = vg M' Z' P y and var(a) = vg^2 diag(M' Z' P Z M), i.e. the scan of calculate_a_and_vara_rcpp with
+    v = vg Z' P y and W = vg^2 Z' P Z (t x t) in place of S a_hat and S V S.  Dense evaluation."""
+    n = Z.shape[0]
+    H = ve * np.eye(n) + vg * (Z @ K @ Z.T)
+    P = calculateP(H, X)
+    return vg * vg * (Z.T @ P @ Z), vg * (Z.T @ (P @ y))
+
+
+def AM_Z(backend_M, y, X0, Z, L, maxit=20):
+    """The forward search with repeated measures: EMMA with Z as the reference has it (AM.R:428,436), the Z-aware scan
+    inputs above, dense numpy throughout.  backend_M: the t x L matrix of -1/0/1 genotypes."""
+    y = np.asarray(y, dtype=np.float64)
+    M = np.asarray(backend_M, dtype=np.float64)
+    n = len(y)
+    X = np.ones((n, 1)) if X0 is None else np.asarray(X0, dtype=np.float64)
+    MMt = M @ M.T
+    K = MMt / MMt.max() + np.diag(np.full(M.shape[0], 0.95))
+    picked, extBIC, vc = [], [], None
+    for _ in range(maxit):
+        vc = emma_REMLE_Z(y, X, K, Z)
+        ml = emma_MLE_Z(y, X, K, Z, llim=-100.0, ulim=100.0)
+        extBIC.append(-2 * ml["ML"] + (X.shape[1] + 1) * math.log(n) + 2 * lchoose(L, X.shape[1] - 1))
+        if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) != len(extBIC) - 1:
+            break
+        W, v = scan_inputs_Z(K, Z, X, y, vc["ve"], vc["vg"])
+        a = M.T @ v
+        vara = np.einsum("ij,ij->j", M, W @ M)
+        picked.append(pick_locus(a, vara)[0])
+        X = np.column_stack([X, Z @ M[:, picked[-1] - 1]])
+    sel = picked if len(extBIC) == maxit and len(picked) == maxit else picked[:-1] if len(picked) > 0 and len(extBIC) > len(picked) else picked
+    return dict(all_picked=picked, selected=sel, extBIC=extBIC, vc=vc)
+
+
 # ----------------------------------------------------------------------------- n x n algebra
 def calculateH(MMt, varE, varG):
     """calculateH.R:36"""
