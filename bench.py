@@ -34,8 +34,7 @@ WORKLOADS = {
     "c2": dict(n=2000, L=500000, name="config 2: synthetic n=2,000 x L=500,000, single trait, one forward step"),
     "c3": dict(n=10000, L=1000000, name="config 3 shape: synthetic n=10,000 x L=1,000,000, one forward step"),
     # multi-GPU shapes (marker-sharded; they do not fit one GPU next to their n x n workspaces)
-    "c5": dict(n=20000, L=2000000, name="config 5 shape: synthetic n=20,000 x L=2,000,000, one forward step (Z and the "
-                                        "covariates only enter the R-side EMMA / design matrix, not this path)"),
+    "c5": dict(n=20000, L=2000000, name="config 5 shape: synthetic n=20,000 x L=2,000,000, one forward step"),
     "c4": dict(n=50000, L=600000, name="config 4 shape: synthetic n=50,000 x L=600,000, one forward step"),
 }
 METRIC = "markers/s"
@@ -851,9 +850,10 @@ def spot_check(torch, dist, device, egd, n, Lg, world, kb, tT, K, S, V, ah, oa, 
 
 def run_extra_workload(args, wl, torch, dist, device, egd, lib, world, rank):
     """One forward step of a shape that needs the 8 GPUs (BASELINE configs 4 and 5), recorded beside the headline run.
-    c5 (n = 20,000 x L = 2,000,000, fixed-effect covariates): a REAL first iteration of AM() with X = [1, x1, x2] -- M.Mt,
-    eigen(K), EMMA's REML / ML through the secular solve, the eigenbasis right-hand side, the sharded scan and pick
-    (am.AM_resident, maxit = 1) -- plus a kernel-level step with spot-check parity.
+    c5 (n = 20,000 x L = 2,000,000, Z incidence matrix for repeated measures and fixed-effect covariates): a REAL first
+    iteration of AM() with 30,000 records, X = [1, x1, x2] -- M.Mt, eigen(C^1/2 K C^1/2), EMMA's REML / ML with Z through the
+    secular solve, the Z-aware right-hand side, the sharded scan and pick (am.AM_resident, maxit = 1, Z = ...) -- plus a
+    kernel-level step with spot-check parity.
     c4 (n = 50,000 x L = 600,000): decode, M.Mt with the 10 GB int32 all-reduce, pre-products and scan on synthetic S, V
     (an eigendecomposition of order 50,000 is not part of this path), with spot-check parity."""
     import numpy as np
@@ -915,21 +915,26 @@ def run_extra_workload(args, wl, torch, dist, device, egd, lib, world, rank):
     del S, V, K, oa, ov
     torch.cuda.empty_cache()
     if wl == "c5":
-        rng = np.random.default_rng(11)
-        X0 = np.column_stack([np.ones(n), rng.standard_normal(n), rng.integers(0, 2, n).astype(np.float64)])
+        rng = np.random.default_rng(11)          # the same on every rank
+        nrec = n + n // 2                        # repeated measures: 1.5 records per individual
+        zidx = np.concatenate([np.arange(n), rng.integers(0, n, nrec - n)])
+        rng.shuffle(zidx)
+        X0 = np.column_stack([np.ones(nrec), rng.standard_normal(nrec), rng.integers(0, 2, nrec).astype(np.float64)])
         shard = egd.Shard(L, world, rank)
         qtl = np.linspace(L // 10, L - L // 10 - 1, 5).astype(np.int64)
-        y = 10.0 + rng.standard_normal(n) + 0.5 * X0[:, 1] - 0.3 * X0[:, 2]
+        y = 10.0 + rng.standard_normal(nrec) + 0.5 * X0[:, 1] - 0.3 * X0[:, 2] + 0.7 * rng.standard_normal(n)[zidx]
         for b, j in zip([1.0, 0.8, 0.6, 0.5, 0.4], qtl):
             col = shard.fetch_col(lambda jj: device.extract_col(kb, n, jj, kblocked=True), n, int(j), "cuda")
-            y = y + b * col.cpu().numpy().astype(np.float64)
+            y = y + b * col.cpu().numpy().astype(np.float64)[zidx]
         sync()
-        r = am.AM_resident(kb, tT, n, L, y, X0=X0, maxit=1, shard=shard)
+        r = am.AM_resident(kb, tT, n, L, y, X0=X0, maxit=1, shard=shard, Z=zidx)
         sec = torch.tensor([r["seconds"][k] for k in sorted(r["seconds"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-        out["forward_iteration_with_covariates"] = {
-            "design": "intercept + 2 fixed-effect covariates (q = 3); no Z (in the reference snapshot Z only enters EMMA, "
-                      "R/AM.R:428,436, and a non-square Z cannot pass find_qtl, R/calculateP.R:22-25)",
+        out["forward_iteration_with_Z_and_covariates"] = {
+            "design": f"{nrec} records of {n} individuals (incidence matrix Z, one 1 per row), intercept + 2 fixed-effect "
+                      "covariates (q = 3): EMMA's Z branches (R/emma_eigen_R_w_Z.R, R/emma_REMLE.R:78-131, R/emma_MLE.R:57-117) "
+                      "through the secular solve, and the scan fed with H = ve I + vg Z K Z' (the Z-aware find_qtl of SURVEY.md "
+                      "8(f) rank 4; the reference snapshot stops Z at EMMA)",
             "picked_1based": r["all_picked"], "planted_qtl_1based": [int(j) + 1 for j in qtl], "extBIC": r["extBIC"],
             "vc": {k: float(v) for k, v in r["vc"].items()}, "seconds_max_over_ranks": dict(zip(sorted(r["seconds"]), [round(x, 4) for x in sec.tolist()])),
             "secular": r["secular"]}

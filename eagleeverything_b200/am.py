@@ -219,6 +219,69 @@ class _Emma:
         return dict(ML=maxLL, delta=maxdelta, ve=maxva * maxdelta, vg=maxva)
 
 
+def emma_w_Z(n, t, q, lam, e1sq, e2sq, xi=None, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10):
+    """The Z branches of emma.REMLE (R/emma_REMLE.R:78-131; xi is None) and emma.MLE (R/emma_MLE.R:57-117; xi =
+    eigen(K Z'Z)$values) on what the eigen step delivers: lam = the t - q eigenvalues emma.eigen.R.w.Z keeps
+    (R/emma_eigen_R_w_Z.R:13-21), e1sq = the squares of the matching etas, e2sq = the sum of squares of the n - t other
+    etas.  n records, t individuals, q fixed effects."""
+    logdelta, delta = _Emma._grid(ngrids, llim, ulim)
+    Lam = lam[:, None] + delta[None, :]
+    E = e1sq[:, None]
+    ml = xi is not None
+    if ml:
+        Xis = xi[:, None] + delta[None, :]
+        nt = n - len(xi)
+        dLL = 0.5 * delta * (n * ((E / (Lam * Lam)).sum(0) + e2sq / (delta * delta)) / ((E / Lam).sum(0) + e2sq / delta)
+                             - ((1.0 / Xis).sum(0) + nt / delta))
+
+        def LL(ld):
+            d = math.exp(ld)
+            return 0.5 * (n * (math.log(n / (2 * math.pi)) - 1 - math.log((e1sq / (lam + d)).sum() + e2sq / d))
+                          - (np.log(xi + d).sum() + nt * ld))
+
+        def dLLf(ld):
+            d = math.exp(ld)
+            ldel = lam + d
+            return 0.5 * (n * ((e1sq / (ldel * ldel)).sum() + e2sq / (d * d)) / ((e1sq / ldel).sum() + e2sq / d)
+                          - ((1.0 / (xi + d)).sum() + nt / d))
+        denom = n
+    else:
+        nq = n - t + len(lam)
+        dLL = 0.5 * delta * ((n - q) * ((E / (Lam * Lam)).sum(0) + e2sq / (delta * delta)) / ((E / Lam).sum(0) + e2sq / delta)
+                             - ((1.0 / Lam).sum(0) + (n - t) / delta))
+
+        def LL(ld):
+            d = math.exp(ld)
+            return 0.5 * (nq * (math.log(nq / (2 * math.pi)) - 1 - math.log((e1sq / (lam + d)).sum() + e2sq / d))
+                          - (np.log(lam + d).sum() + (n - t) * ld))
+
+        def dLLf(ld):
+            d = math.exp(ld)
+            ldel = lam + d
+            return 0.5 * (nq * ((e1sq / (ldel * ldel)).sum() + e2sq / (d * d)) / ((e1sq / ldel).sum() + e2sq / d)
+                          - ((1.0 / ldel).sum() + (n - t) / d))
+        denom = n - q
+    maxdelta, maxLL = _delta_search(dLL, logdelta, llim, ulim, esp, LL, dLLf)
+    maxva = ((e1sq / (lam + maxdelta)).sum() + e2sq / maxdelta) / denom
+    return {("ML" if ml else "REML"): maxLL, "delta": maxdelta, "ve": maxva * maxdelta, "vg": maxva}
+
+
+def z_index(Z, t):
+    """Z (n records x t individuals, 0/1 with exactly one 1 per row: R/ReadZmat.R:47-85) as the index of each record's
+    individual; an index vector passes through.  Every individual needs at least one record here (emma.MLE drops the
+    others, emma.REMLE does not: R/emma_MLE.R:60-63 pass `ngpu` in the position of `complete`)."""
+    Z = np.asarray(Z)
+    if Z.ndim == 2:
+        if Z.shape[1] != t or not np.all((Z == 0) | (Z == 1)) or not np.all(Z.sum(1) == 1):
+            raise ValueError("Z must be a 0/1 matrix with one 1 per row and one column per individual")
+        idx = Z.argmax(1).astype(np.int64)
+    else:
+        idx = Z.astype(np.int64)
+    if idx.min() < 0 or idx.max() >= t or len(np.unique(idx)) != t:
+        raise ValueError("every individual needs at least one record in Z")
+    return idx
+
+
 # ----------------------------------------------------------------------------- the loop
 def AM(geno, y, X0=None, maxit=20, message=None):
     """R/AM.R:260, 395-504.  geno: FileGeno or ResidentGeno; y: trait (no NAs); X0: fixed-effects design matrix before
@@ -299,7 +362,7 @@ def AM(geno, y, X0=None, maxit=20, message=None):
 
 
 # ----------------------------------------------------------------------------- everything resident, in the basis of eigen(K)
-def eigbasis_inputs(xi, Xt, yt, ve, vg):
+def eigbasis_inputs(xi, Xt, yt, ve, vg, XtX=None, Xty=None):
     """The inputs of the scan from eigenbasis quantities (host, O(n q^2)): with K = U diag(xi) U^T, Xt = U^T X, yt = U^T y,
          Dh = 1 / (ve + vg xi)                                  H^-1 = U diag(Dh) U^T                  (R/calculateH.R:36)
          C  = Xt^T Dh Xt = L L^T                                t(X) Hinv X                            (R/calculateP.R:28)
@@ -311,13 +374,21 @@ def eigbasis_inputs(xi, Xt, yt, ve, vg):
     Dh = 1.0 / (ve + vg * xi)
     B = Dh[:, None] * Xt
     Cq = Xt.T @ B
+    rhs = B.T @ yt
+    if XtX is not None:
+        # repeated measures (Z): H = ve I + vg Z K Z' has the eigenvalues ve + vg xi on the t directions Z C^-1/2 h_j
+        # (xi, h_j: eigenpairs of C^1/2 K C^1/2, C = Z'Z) and ve on the other n - t; Xt, yt are the coordinates of X, y
+        # on the first, XtX - Xt'Xt and Xty - Xt'yt what they carry on the others.  The scan then runs on
+        # W = vg^2 Z' P Z = A diag(w) A' - E E' and v = vg Z' P y = A vt with A = C^1/2 [h_1 .. h_t] in place of U.
+        Cq = Cq + (XtX - Xt.T @ Xt) / ve
+        rhs = rhs + (Xty - Xt.T @ yt) / ve
     Lc = np.linalg.cholesky(Cq)
     Et = vg * np.linalg.solve(Lc, B.T).T
-    vt = vg * (Dh * yt - B @ np.linalg.solve(Cq, B.T @ yt))
+    vt = vg * (Dh * yt - B @ np.linalg.solve(Cq, rhs))
     return vg * vg * Dh, np.asfortranarray(Et), vt
 
 
-def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None):
+def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None, Z=None):
     """AM()'s forward search (R/AM.R:260, 395-504) with the genotypes resident in HBM and the n x n algebra of every
     iteration carried out in the basis of eigen(K) (csrc/eigbasis.cu): K = MMt/max(MMt) + 0.95 I never changes after the
     first iteration (R/AM.R:414-423), so it is decomposed ONCE; after that an iteration costs
@@ -330,7 +401,14 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
     store_kb: K-blocked int8 M store of THIS rank's markers (device.decode_kb), storeT: the row-major Mt store of the same
     markers (device.transpose_kb); L: the number of markers of the whole data set.  shard (dist.Shard or None): marker
     shards over torch.distributed ranks -- partial M.Mt all-reduced (int32), scans sharded, the pick by the sharded
-    first-maximum rule, the picked column broadcast by its owner; the n x n algebra is replicated."""
+    first-maximum rule, the picked column broadcast by its owner; the n x n algebra is replicated.
+
+    Z (repeated measures; BASELINE config 5): the records' incidence matrix (or each record's individual as an index
+    vector).  y and X0 then have one row per RECORD, n stays the number of individuals.  EMMA's Z branches
+    (R/emma_eigen_L_w_Z.R:2-14, R/emma_eigen_R_w_Z.R:2-23, R/emma_REMLE.R:78-131, R/emma_MLE.R:57-117) run on the
+    eigenpairs of C^1/2 K C^1/2 (C = Z'Z, computed once) through the same secular solve, and the scan is fed the Z-aware
+    H = ve I + vg Z K Z' (in the reference snapshot Z stops at EMMA and a non-square Z cannot
+    pass find_qtl: R/AM.R:450-452, R/calculateP.R:22-25)."""
     import ctypes as C
 
     import torch
@@ -344,7 +422,12 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)             # noqa: E731
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))                       # noqa: E731
     y = np.asarray(y, dtype=np.float64).reshape(-1)
-    X = np.ones((n, 1)) if X0 is None else np.asarray(X0, dtype=np.float64).reshape(n, -1)
+    zidx = None if Z is None else z_index(Z, n)
+    nrec = n if zidx is None else len(zidx)
+    if len(y) != nrec:
+        raise ValueError("y needs one value per record")
+    X = np.ones((nrec, 1)) if X0 is None else np.asarray(X0, dtype=np.float64).reshape(nrec, -1)
+    cnt = None if zidx is None else np.bincount(zidx, minlength=n).astype(np.float64)
     Lloc = storeT.shape[0]
     stats = dict(mmt_s=0.0, eigen_K_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0, extract_s=0.0, total_s=0.0)
 
@@ -366,23 +449,43 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
     timed("mmt_s", t0)
     t0 = time.perf_counter()
     vals = torch.empty(n, **f64)
+    if zidx is not None:                                                         # C^1/2 K C^1/2 (same spectrum as K Z'Z)
+        sc_d = torch.from_numpy(np.sqrt(cnt)).to(dev)
+        U.mul_(sc_d[:, None]).mul_(sc_d[None, :])
     _lib.check(lib.eg_dev_eigen_sym(p(U), n, p(vals), st()))                     # values decreasing, as R's eigen()
     xi = vals.cpu().numpy().copy()
     if not np.all(np.where(np.abs(xi) < 1e-8, 0.0, xi) > 0):                     # matrixcalc::is.positive.definite's screen
         raise ValueError("M %*% t(M) is not positive definite")                  # calculateMMt_sqrt_and_sqrtinv.R:15-23
+    if zidx is not None:
+        U.mul_(sc_d[None, :])                                                    # A = C^1/2 [h_1 .. h_t] (rows of the torch view = columns)
     Ut = torch.empty((n, n), **f64)
     _lib.check(lib.eg_dev_transpose_f64(p(U), n, p(Ut), st()))
     Wp = torch.empty(lib.eg_scan_wp_elems(n), **f64)
     work2 = torch.empty((n, n), **f64) if not lib.eg_prep_uses_i8(n) else None
 
-    def to_eig(v):                                                               # U^T v for an n-vector on the host
+    def apply_U(v, to_eigenbasis):
         d_in = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
         d_out = torch.empty(n, **f64)
-        _lib.check(lib.eg_dev_eigbasis_apply(p(U), n, p(d_in), 1, 1, p(d_out), st()))
+        _lib.check(lib.eg_dev_eigbasis_apply(p(U), n, p(d_in), 1, 1 if to_eigenbasis else 0, p(d_out), st()))
         return d_out.cpu().numpy()
 
-    yt = to_eig(y)
-    Xt = np.column_stack([to_eig(X[:, c]) for c in range(X.shape[1])])
+    def to_eig(v):
+        """Coordinates of a vector on the eigen directions.  No Z: U^T v.  With Z (v has one entry per record): on the t
+        directions Z C^-1/2 h_j, i.e. h_j^T C^-1/2 Z^T v = A^T C^-1 Z^T v; returns also the part of v outside their span."""
+        if zidx is None:
+            return apply_U(v, True)
+        top = apply_U(np.bincount(zidx, weights=v, minlength=n) / cnt, True)
+        return top, v - (apply_U(top, False) / cnt)[zidx]
+
+    if zidx is None:
+        yt = to_eig(y)
+        Xt = np.column_stack([to_eig(X[:, c]) for c in range(X.shape[1])])
+        Res = None
+    else:
+        yt, ry = to_eig(y)
+        tops = [to_eig(X[:, c]) for c in range(X.shape[1])]
+        Xt = np.column_stack([a for a, _ in tops])
+        Res = [r for _, r in tops]                                               # residuals of the columns of X (and of y: ry)
     timed("eigen_K_s", t0)
     emma = _Emma(None, stats)
     emma._xi = xi
@@ -398,29 +501,57 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
             else:
                 col = shard.fetch_col(lambda j: device.extract_col(store_kb, n, j, kblocked=True), n, g, dev)
             xnew = col.cpu().numpy().astype(np.float64)
-            X = np.column_stack([X, xnew])
-            Xt = np.column_stack([Xt, to_eig(xnew)])
+            if zidx is None:
+                X = np.column_stack([X, xnew])
+                Xt = np.column_stack([Xt, to_eig(xnew)])
+            else:
+                xnew = xnew[zidx]                                                # Z m: the marker's genotype of every record
+                X = np.column_stack([X, xnew])
+                top, r = to_eig(xnew)
+                Xt = np.column_stack([Xt, top])
+                Res.append(r)
             timed("extract_s", t0)
         q = X.shape[1]
         # ---- emma.REMLE and emma.MLE share eigen(S (K + I) S) of this iteration
         t0 = time.perf_counter()
-        lam, et = np.empty(n - q), np.empty(n - q)
         s4 = (C.c_int64 * 4)()
-        Xtf = np.asfortranarray(Xt)
-        _lib.check(lib.eg_emma_eigen_R_wo_Z_eigbasis(dp(xi), dp(Xtf), dp(yt), n, q, dp(lam), dp(et), s4))
+        if zidx is None:
+            lam, et = np.empty(n - q), np.empty(n - q)
+            Xtf = np.asfortranarray(Xt)
+            _lib.check(lib.eg_emma_eigen_R_wo_Z_eigbasis(dp(xi), dp(Xtf), dp(yt), n, q, dp(lam), dp(et), s4))
+            emma._last = (q, lam, et * et)
+        else:
+            # the n - t directions outside range(Z) carry the eigenvalue 0; X and y only reach the q + 1 of them that
+            # their own residuals span: t + q + 1 poles describe the whole compression (R/emma_eigen_R_w_Z.R:10-21)
+            Qr, Rr = np.linalg.qr(np.column_stack(Res + [ry]))
+            m = n + q + 1
+            xi_x = np.concatenate([xi, np.zeros(q + 1)])
+            Xt_x = np.asfortranarray(np.vstack([Xt, Rr[:, :q]]))
+            yt_x = np.concatenate([yt, Rr[:, q]])
+            val_x, et_x = np.empty(m - q), np.empty(m - q)
+            _lib.check(lib.eg_emma_eigen_R_wo_Z_eigbasis(dp(xi_x), dp(Xt_x), dp(yt_x), m, q, dp(val_x), dp(et_x), s4))
+            lam, e1sq, e2sq = val_x[: n - q], et_x[: n - q] ** 2, float((et_x[n - q:] ** 2).sum())
         sec_stats.append(list(s4))
-        emma._last = (q, lam, et * et)
         timed("emma_eigen_s", t0)
         t0 = time.perf_counter()
-        vc = emma.REMLE(y, X)                                                     # AM.R:428
-        ml = emma.MLE(y, X, llim=-100.0, ulim=100.0)                             # calc_extBIC.R:6
+        if zidx is None:
+            vc = emma.REMLE(y, X)                                                 # AM.R:428
+            ml = emma.MLE(y, X, llim=-100.0, ulim=100.0)                         # calc_extBIC.R:6
+        elif np.linalg.det(X.T @ X) == 0:
+            vc, ml = dict(REML=0.0, delta=0.0, ve=0.0, vg=0.0), dict(ML=0.0, delta=0.0, ve=0.0, vg=0.0)
+        else:
+            vc = emma_w_Z(nrec, n, q, lam, e1sq, e2sq)
+            ml = emma_w_Z(nrec, n, q, lam, e1sq, e2sq, xi=xi, llim=-100.0, ulim=100.0)
         stats["emma_search_s"] += time.perf_counter() - t0
-        bic = -2 * ml["ML"] + (q + 1) * math.log(n)
+        bic = -2 * ml["ML"] + (q + 1) * math.log(nrec)
         extBIC.append(bic + 2 * _lchoose(L, q - 1))
         say(f" iteration {itnum}: extBIC = {extBIC[-1]:.4f}")
         if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) == len(extBIC) - 1:   # AM.R:448
             t0 = time.perf_counter()
-            w, Et, vt = eigbasis_inputs(xi, Xt, yt, float(vc["ve"]), float(vc["vg"]))
+            if zidx is None:
+                w, Et, vt = eigbasis_inputs(xi, Xt, yt, float(vc["ve"]), float(vc["vg"]))
+            else:
+                w, Et, vt = eigbasis_inputs(xi, Xt, yt, float(vc["ve"]), float(vc["vg"]), XtX=X.T @ X, Xty=X.T @ y)
             d_w = torch.from_numpy(w).to(dev)
             d_Et = torch.from_numpy(Et.T.copy()).to(dev)                         # q x n row-major = n x q column-major
             d_vt = torch.from_numpy(vt).to(dev)

@@ -303,8 +303,9 @@ def scan_inputs_Z(K, Z, X, y, ve, vg):
 
 
 def AM_Z(backend_M, y, X0, Z, L, maxit=20):
-    """The forward search with repeated measures: EMMA with Z as the reference has it (AM.R:428,436), the Z-aware scan
-    inputs above, dense numpy throughout.  backend_M: the t x L matrix of -1/0/1 genotypes."""
+    """The forward search with repeated measures: AM()'s loop control (AM.R:395-492), EMMA with Z as the reference has it
+    (AM.R:428,436), the Z-aware scan inputs above; dense numpy throughout.  backend_M: the t x L matrix of -1/0/1
+    genotypes."""
     y = np.asarray(y, dtype=np.float64)
     M = np.asarray(backend_M, dtype=np.float64)
     n = len(y)
@@ -312,18 +313,23 @@ def AM_Z(backend_M, y, X0, Z, L, maxit=20):
     MMt = M @ M.T
     K = MMt / MMt.max() + np.diag(np.full(M.shape[0], 0.95))
     picked, extBIC, vc = [], [], None
-    for _ in range(maxit):
+    itnum, cont = 1, True
+    while cont:
         vc = emma_REMLE_Z(y, X, K, Z)
         ml = emma_MLE_Z(y, X, K, Z, llim=-100.0, ulim=100.0)
         extBIC.append(-2 * ml["ML"] + (X.shape[1] + 1) * math.log(n) + 2 * lchoose(L, X.shape[1] - 1))
-        if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) != len(extBIC) - 1:
-            break
-        W, v = scan_inputs_Z(K, Z, X, y, vc["ve"], vc["vg"])
-        a = M.T @ v
-        vara = np.einsum("ij,ij->j", M, W @ M)
-        picked.append(pick_locus(a, vara)[0])
-        X = np.column_stack([X, Z @ M[:, picked[-1] - 1]])
-    sel = picked if len(extBIC) == maxit and len(picked) == maxit else picked[:-1] if len(picked) > 0 and len(extBIC) > len(picked) else picked
+        if int(np.flatnonzero(np.asarray(extBIC) == min(extBIC))[0]) == len(extBIC) - 1:
+            W, v = scan_inputs_Z(K, Z, X, y, vc["ve"], vc["vg"])
+            a = M.T @ v
+            vara = np.einsum("ij,ij->j", M, W @ M)
+            picked.append(pick_locus(a, vara)[0])
+            X = np.column_stack([X, Z @ M[:, picked[-1] - 1]])
+        else:
+            cont = False
+        itnum += 1
+        if itnum > maxit:
+            cont = False
+    sel = picked if itnum > maxit else picked[:-1] if picked else picked
     return dict(all_picked=picked, selected=sel, extBIC=extBIC, vc=vc)
 
 

@@ -78,3 +78,35 @@ def test_search_with_everything_resident_in_hbm(am, demo, synth_small):
     rf = am.AM(am.FileGeno(s["M"], s["Mt"], (s["n"], s["L"])), y, maxit=6)
     assert rr["all_picked"] == rf["all_picked"] and rr["selected"] == rf["selected"]
     np.testing.assert_allclose(rr["extBIC"], rf["extBIC"], rtol=1e-8)
+
+
+def test_repeated_measures_search(am):
+    """BASELINE config 5's model at test size: records x individuals incidence matrix Z and fixed-effect covariates.
+    am.AM_resident(Z = ...) -- EMMA's Z branches through the secular solve, the Z-aware scan -- against the dense
+    restatement (oracle/am_driver.py::AM_Z: R/emma_eigen_R_w_Z.R, R/emma_REMLE.R:78-131, R/emma_MLE.R:57-117 and
+    H = ve I + vg Z K Z'): same picks, extBIC to 1e-8, and the same with Z given as an index vector."""
+    import torch
+    from eagleeverything_b200 import device
+    from oracle import am_driver as oam
+    rng = np.random.default_rng(21)
+    t, L, nrec = 150, 2000, 230
+    G = synth.genotypes(t, L, seed=77)
+    idx = np.concatenate([np.arange(t), rng.integers(0, t, nrec - t)])
+    rng.shuffle(idx)
+    Z = np.zeros((nrec, t))
+    Z[np.arange(nrec), idx] = 1
+    X0 = np.column_stack([np.ones(nrec), rng.standard_normal(nrec), rng.integers(0, 2, nrec).astype(float)])
+    M = G.astype(np.float64) - 1.0
+    y = 3.0 + 0.4 * X0[:, 1] + rng.standard_normal(nrec) + Z @ (1.2 * M[:, 300] - 0.9 * M[:, 1500])
+    ro = oam.AM_Z(M, y, X0, Z, L, maxit=4)
+    img = torch.from_numpy(np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    kb, err = device.decode_kb(img, L + 1, t, L)
+    tT = device.transpose_kb(kb, t, L)
+    rr = am.AM_resident(kb, tT, t, L, y, X0=X0, maxit=4, Z=Z)
+    assert rr["all_picked"] == ro["all_picked"] and rr["selected"] == ro["selected"], (rr["all_picked"], ro["all_picked"])
+    assert 301 in rr["all_picked"] and 1501 in rr["all_picked"]
+    np.testing.assert_allclose(rr["extBIC"], ro["extBIC"], rtol=1e-8)
+    r2 = am.AM_resident(kb, tT, t, L, y, X0=X0, maxit=4, Z=idx)
+    assert r2["all_picked"] == rr["all_picked"] and r2["extBIC"] == rr["extBIC"]
+    with pytest.raises(ValueError):
+        am.AM_resident(kb, tT, t, L, y[:-1], X0=X0[:-1], maxit=2, Z=Z[:-1][:, : t - 1])

@@ -169,3 +169,82 @@ def test_forward_search_in_the_eigenbasis_reproduces_the_golden_demo(sec, demo):
     picked2, ext2 = search(z["trait2"], np.column_stack([np.ones(n), z["pc1"], z["pc2"]]))
     assert picked2 == list(z["am2_all_picked"])
     np.testing.assert_allclose(ext2, z["am2_extBIC"], rtol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Repeated measures (Z): EMMA's Z branches and the Z-aware scan inputs in the basis of eigen(C^1/2 K C^1/2), C = Z'Z
+def _z_problem(seed=3, t=70, L=500, nrec=110, q=2):
+    rng = np.random.default_rng(seed)
+    G = rng.integers(0, 3, (t, L))
+    idx = np.concatenate([np.arange(t), rng.integers(0, t, nrec - t)])
+    rng.shuffle(idx)
+    Z = np.zeros((nrec, t))
+    Z[np.arange(nrec), idx] = 1
+    X = np.column_stack([np.ones(nrec)] + [rng.standard_normal(nrec) for _ in range(q - 1)])
+    y = rng.standard_normal(nrec) + 0.9 * (Z @ (G[:, 11] - 1.0))
+    return G, Z, idx, X, y
+
+
+def _z_basis(K, idx, t):
+    cnt = np.bincount(idx, minlength=t).astype(np.float64)
+    sc = np.sqrt(cnt)
+    xi, Hm = oam.r_eigen_sym(K * sc[:, None] * sc[None, :])
+    return cnt, xi, sc[:, None] * Hm              # A = C^1/2 H
+
+
+def _z_coords(A, cnt, idx, v):
+    top = A.T @ (np.bincount(idx, weights=v, minlength=len(cnt)) / cnt)
+    return top, v - ((A @ top) / cnt)[idx]
+
+
+def test_emma_with_Z_through_the_secular_solve_equals_the_dense_restatement(sec):
+    G, Z, idx, X, y = _z_problem()
+    t, q, nrec = G.shape[0], X.shape[1], len(y)
+    K = _K_of(G)
+    cnt, xi, A = _z_basis(K, idx, t)
+    tops = [_z_coords(A, cnt, idx, X[:, c]) for c in range(q)]
+    yt, ry = _z_coords(A, cnt, idx, y)
+    Xt = np.column_stack([a for a, _ in tops])
+    _, Rr = np.linalg.qr(np.column_stack([r for _, r in tops] + [ry]))
+    rc, vals, etas, _st = sec(np.concatenate([xi, np.zeros(q + 1)]), np.vstack([Xt, Rr[:, :q]]), np.concatenate([yt, Rr[:, q]]))
+    assert rc == 0
+    lam, e1sq, e2sq = vals[: t - q], etas[: t - q] ** 2, float((etas[t - q:] ** 2).sum())
+    lam_ref, U_ref = oam.emma_eigen_R_w_Z(Z, K, X)                     # R/emma_eigen_R_w_Z.R:2-23 (dense, non-symmetric eigen)
+    np.testing.assert_allclose(np.sort(lam), np.sort(lam_ref), rtol=1e-9, atol=1e-11)
+    e_ref = U_ref.T @ y
+    np.testing.assert_allclose(e2sq, (e_ref[t - q:] ** 2).sum(), rtol=1e-9)
+    np.testing.assert_allclose(np.sort(xi), np.sort(oam.emma_eigen_L_w_Z(Z, K)), rtol=1e-9)
+    r, ro = am.emma_w_Z(nrec, t, q, lam, e1sq, e2sq), oam.emma_REMLE_Z(y, X, K, Z)
+    m = am.emma_w_Z(nrec, t, q, lam, e1sq, e2sq, xi=xi, llim=-100.0, ulim=100.0)
+    mo = oam.emma_MLE_Z(y, X, K, Z, llim=-100.0, ulim=100.0)
+    for k in ("REML", "delta", "ve", "vg"):
+        np.testing.assert_allclose(r[k], ro[k], rtol=1e-7)
+    for k in ("ML", "delta", "ve", "vg"):
+        np.testing.assert_allclose(m[k], mo[k], rtol=1e-7)
+
+
+def test_Z_aware_scan_inputs_equal_the_dense_model():
+    G, Z, idx, X, y = _z_problem(seed=8, q=3)
+    t = G.shape[0]
+    K = _K_of(G)
+    cnt, xi, A = _z_basis(K, idx, t)
+    Xt = np.column_stack([_z_coords(A, cnt, idx, X[:, c])[0] for c in range(X.shape[1])])
+    yt = _z_coords(A, cnt, idx, y)[0]
+    ve, vg = 0.6, 1.4
+    w, Et, vt = am.eigbasis_inputs(xi, Xt, yt, ve, vg, XtX=X.T @ X, Xty=X.T @ y)
+    E = A @ Et
+    W, v = (A * w) @ A.T - E @ E.T, A @ vt
+    W_ref, v_ref = oam.scan_inputs_Z(K, Z, X, y, ve, vg)                 # H = ve I + vg Z K Z', dense
+    assert np.abs(W - W_ref).max() <= 1e-9 * np.abs(W_ref).max()
+    assert np.abs(v - v_ref).max() <= 1e-9 * np.abs(v_ref).max()
+    # Z = I falls back to the formulas without Z
+    n = t
+    Xi, yi = X[:n], y[:n]
+    xi0, U0 = oam.r_eigen_sym(K)
+    a0 = am.eigbasis_inputs(xi0, U0.T @ Xi, U0.T @ yi, ve, vg)
+    a1 = am.eigbasis_inputs(xi0, U0.T @ Xi, U0.T @ yi, ve, vg, XtX=Xi.T @ Xi, Xty=Xi.T @ yi)
+    for p0, p1 in zip(a0, a1):
+        np.testing.assert_allclose(p0, p1, rtol=1e-9, atol=1e-12)
+    with pytest.raises(ValueError):
+        am.z_index(np.delete(Z, 3, axis=1), t)
+    assert np.array_equal(am.z_index(Z, t), idx)
