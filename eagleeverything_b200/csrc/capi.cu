@@ -535,9 +535,10 @@ static int cache_key(const char* path, int64_t rows, int64_t cols, bool kblocked
     }
     char* rp = realpath(path, nullptr);
     char buf[4400];
-    snprintf(buf, sizeof(buf), "%s|%lld|%lld.%09ld|%016llx|%lldx%lld|%c", rp ? rp : path, (long long)st.st_size,
-             (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (unsigned long long)h, (long long)rows, (long long)cols,
-             kblocked ? 'K' : 'R');
+    // inode and ctime as well: a file replaced by rename(), or rewritten in place inside one mtime tick, changes them
+    snprintf(buf, sizeof(buf), "%s|%lld|%lld.%09ld|%llu|%lld.%09ld|%016llx|%lldx%lld|%c", rp ? rp : path, (long long)st.st_size,
+             (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (unsigned long long)st.st_ino, (long long)st.st_ctim.tv_sec,
+             (long)st.st_ctim.tv_nsec, (unsigned long long)h, (long long)rows, (long long)cols, kblocked ? 'K' : 'R');
     free(rp);
     key = buf;
     return EG_OK;
@@ -545,8 +546,16 @@ static int cache_key(const char* path, int64_t rows, int64_t cols, bool kblocked
 static void cache_insert(const std::string& key, eg_store* s) {
     const char* envmax = getenv("EAGLE_GPU_CACHE_ENTRIES");
     const size_t maxe = envmax ? (size_t)atoi(envmax) : 4;
-    for (size_t i = 0; i < g_ctx.cache.size();)   // a rewritten file: the entry under the same key is stale by construction
-        if (g_ctx.cache[i].key == key && g_ctx.cache[i].store->pins == 0) {
+    // entries of the same file (same path, dims, layout) under an older stamp are stale: a rewritten file must not keep
+    // 10 GB resident until the LRU rule reaches it
+    auto same_file = [](const std::string& a, const std::string& b) {
+        const size_t pa = a.find('|'), pb = b.find('|');
+        if (pa == std::string::npos || pa != pb || a.compare(0, pa, b, 0, pb) != 0) return false;
+        const size_t ta = a.rfind('|', a.rfind('|') - 1), tb = b.rfind('|', b.rfind('|') - 1);   // "|rowsxcols|layout"
+        return a.substr(ta) == b.substr(tb);
+    };
+    for (size_t i = 0; i < g_ctx.cache.size();)
+        if (same_file(g_ctx.cache[i].key, key) && g_ctx.cache[i].store->pins == 0) {
             free_store_tree(g_ctx.cache[i].store);
             g_ctx.cache.erase(g_ctx.cache.begin() + i);
         } else i++;
