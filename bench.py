@@ -455,9 +455,9 @@ def run_gpu(args):
     if mode == 1:
         roofline = {"kernel": "scan_i8_kernel", "bound": "tensor", "achieved": k_rate, "peak": int8_peak,
                     "unit": "TOP/s (int8)", **int8_fracs(k_rate), "executed_ops": k_ops,
-                    "algorithmic_ops": 7.0 * Lg * n * (n + 1),
+                    "digits": int(lib.eg_get_scan_digits()), "algorithmic_ops": float(lib.eg_get_scan_digits()) * Lg * n * (n + 1),
                     "traffic": None, "kernel_ms": k_ms,
-                    "ops_convention": "executed int8 ops: 7 balanced-byte slices x symmetric-half contraction, 2 ops per MAC "
+                    "ops_convention": "executed int8 ops: `digits` balanced-byte slices x symmetric-half contraction, 2 ops per MAC "
                                       "(DESIGN.md section 4)",
                     "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
                     "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas,
@@ -525,7 +525,7 @@ def run_gpu(args):
                           "note": "dtype f64 = the scan's results (a, var(a)); decode is u8, M.Mt is s8 x s8 -> s32 "
                                   "(bit-exact); var(a) is contracted on int8 slices of the FP64 matrix (exact) or on FP64 DMMA"},
         "stage_ms": stages, "mmt_int8_tops": syrk_tops, "decode_gbs": dec_gbs,
-        "scan_mode": "int8 slices (tcgen05)" if mode == 1 else "fp64 (DMMA)", "scan_reference_equiv_fp64_tflops": scan_tf,
+        "scan_mode": f"int8 slices (tcgen05), {int(lib.eg_get_scan_digits())} digits per column" if mode == 1 else "fp64 (DMMA)", "scan_reference_equiv_fp64_tflops": scan_tf,
         "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "allreduce": (None if world == 1 else {
             "bytes": 4 * n * n, "ms": stages["allreduce"],

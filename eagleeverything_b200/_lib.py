@@ -98,6 +98,8 @@ SIGNATURES = {
     "eg_dev_synth_ascii": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, C.c_uint64, _vp]),
     "eg_set_scan_mode": (C.c_int, [C.c_int]),
     "eg_get_scan_mode": (C.c_int, []),
+    "eg_set_scan_digits": (C.c_int, [C.c_int]),
+    "eg_get_scan_digits": (C.c_int, []),
     "eg_calculateMMt_sqrt_and_sqrtinv": (C.c_int, [_dp, _i64, C.c_int, MESSAGE_FN, _vp, _dp, _dp, C.POINTER(C.c_int)]),
     "eg_calculateH": (C.c_int, [_dp, _i64, C.c_double, C.c_double, MESSAGE_FN, _vp, _dp, C.POINTER(C.c_int)]),
     "eg_calculateP": (C.c_int, [_dp, _dp, _i64, C.c_int, _dp]),

@@ -341,6 +341,15 @@ def set_scan_mode(mode):
     _lib.check(_lib.load().eg_set_scan_mode(int(m)))
 
 
+def set_scan_digits(digits):
+    """6 (default) or 7 balanced base-256 digits per column of U in the int8 scan (include/eagle_gpu.h)."""
+    _lib.check(_lib.load().eg_set_scan_digits(int(digits)))
+
+
+def get_scan_digits():
+    return int(_lib.load().eg_get_scan_digits())
+
+
 def get_scan_mode():
     return int(_lib.load().eg_get_scan_mode())
 

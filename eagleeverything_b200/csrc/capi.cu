@@ -1336,6 +1336,16 @@ extern "C" int eg_set_scan_mode(int mode) {
     return EG_OK;
 }
 extern "C" int eg_get_scan_mode(void) { return scan_mode(); }
+namespace eg {
+int scan_i8_digits();
+void scan_i8_set_digits(int d);
+}
+extern "C" int eg_set_scan_digits(int digits) {
+    if (digits != 6 && digits != 7) return set_error(EG_ERR_ARG, "eg_set_scan_digits: 6 or 7 balanced base-256 digits per column");
+    scan_i8_set_digits(digits);
+    return EG_OK;
+}
+extern "C" int eg_get_scan_digits(void) { return scan_i8_digits(); }
 
 namespace eg {
 // CUDA events around the dominant scan kernel of the last eg_dev_scan call (for roofline reporting)

@@ -34,23 +34,40 @@
 namespace eg {
 
 constexpr int SI_BM = 128;
-constexpr int SI_SLICES = 7;
 constexpr int SI_GCOLS = 32;                  // columns of U per group
-constexpr int SI_BN = SI_GCOLS * SI_SLICES;   // 224 rows of Q per group = one UMMA N
 constexpr int SI_ACC_COLS = 256;              // TMEM columns between the two accumulators
-constexpr int SI_CHUNK = 4 * SI_SLICES;       // TMEM columns of one 4-column chunk
 constexpr int SI_BK = 128;
 constexpr int SI_STAGES = 5;
 constexpr int SI_A_BYTES = SI_BM * SI_BK;
-constexpr int SI_B_BYTES = SI_BN * SI_BK;
-constexpr int SI_STAGE_BYTES = SI_A_BYTES + SI_B_BYTES;
 constexpr int SI_THREADS = 320;        // TMA warp, UMMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int SI_TMEM_COLS = 512;
 constexpr int SI_MSUP_DEFAULT = 37;  // super-tile: marker blocks (their Mt rows stay L2-resident over the group sweep)
 constexpr int SI_GSUP_DEFAULT = 4;   //             x groups  (~ one wave of 148 CTAs)
 constexpr int SI_PHASE = 16;
 constexpr int SI_LAG = 4;
-constexpr int SI_SMEM_BYTES = SI_STAGES * SI_STAGE_BYTES + 1024 + 256;
+constexpr int SP_STAGES = 7;
+constexpr int SP_MSUP_DEFAULT = 18;  // super-tile in units of 256-marker blocks x groups (see SI_MSUP_DEFAULT)
+constexpr int SP_GSUP_DEFAULT = 4;
+constexpr int SP_A_BYTES = SI_BM * SI_BK;               // 128 marker rows
+// Everything that depends on the number of digits S per column of U.  S = 7: the full significand of the column's
+// largest entry (55 bits + sign), one rounding per entry of Mt U.  S = 6 (default): 47 bits + sign, the recombination is
+// exact (48 bits fit a double), the truncation of U is bounded by 2^(e_k - 48) per entry -- 32 units in the last place of
+// the column maximum, the size of an FP64 GEMM's own accumulation error at these n and four orders of magnitude inside
+// the 1e-9 tolerance -- and every k-block costs 6/7 of the tensor work and of the shared-memory fill.
+template <int S>
+struct SiT {
+    static_assert(S == 6 || S == 7, "digits per column");
+    static constexpr int SLICES = S;
+    static constexpr int BITS = 8 * S - 1;                   // scale_k = 2^(e_k - BITS)
+    static constexpr int BN = SI_GCOLS * S;                  // rows of Q per group = one UMMA N (224 / 192)
+    static constexpr int CHUNK = 4 * S;                      // TMEM columns of one 4-column chunk
+    static constexpr int B_BYTES = BN * SI_BK;
+    static constexpr int STAGE_BYTES = SI_A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = SI_STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SP_B_BYTES = (BN / 2) * SI_BK;      // CTA pair: half of the slice rows per CTA
+    static constexpr int SP_STAGE_BYTES = SP_A_BYTES + SP_B_BYTES;
+    static constexpr int SP_SMEM_BYTES = SP_STAGES * SP_STAGE_BYTES + 1024 + 256;
+};
 
 struct ScanI8Params {
     int64_t L, n;
@@ -95,15 +112,19 @@ __device__ __forceinline__ double si_i2d(int x) {
 // Measured (EG_SI_PROFILE): ~6,000 clk per unit whatever the arithmetic (9 FP64 operations per column or 2 plus
 // integer normalisation): the 114 KB of TMEM reads per unit, competing with the MMAs for the TMEM port, set the
 // pace.  Units with fewer than ~14 k-blocks are therefore epilogue-bound (3 % of the time at n = 10k).
+template <int S>
 __device__ __forceinline__ double si_recombine_rowdot(uint32_t taddr, const uint32_t (&mw)[4], const double* __restrict__ sc,
                                                       bool wide /* P0*256+P1 leaves int32 beyond n = 65280 */) {
     double sum[4] = {0.0, 0.0, 0.0, 0.0};
     uint32_t v4[4][32];
 #pragma unroll
-    for (int c = 0; c < 4; c++) ptx::tmem_ld_32x28(taddr + (uint32_t)(c * SI_CHUNK), v4[c]);  // all 112 columns in flight
+    for (int c = 0; c < 4; c++) {  // all 4 S columns of the four chunks in flight before the first use
+        if (S == 7) ptx::tmem_ld_32x28(taddr + (uint32_t)(c * SiT<S>::CHUNK), v4[c]);
+        else ptx::tmem_ld_32x24(taddr + (uint32_t)(c * SiT<S>::CHUNK), v4[c]);
+    }
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 4; c++) {  // 28 TMEM columns = 7 slices x 4 columns (kk = 4c .. 4c+3)
+    for (int c = 0; c < 4; c++) {  // 4 S TMEM columns = S slices x 4 columns (kk = 4c .. 4c+3)
         uint32_t(&v)[32] = v4[c];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
@@ -118,8 +139,13 @@ __device__ __forceinline__ double si_recombine_rowdot(uint32_t taddr, const uint
                 y45 = fma(si_i2d((int)v[4 * 4 + e]), 256.0, si_i2d((int)v[5 * 4 + e]));
             }
             const double hi = fma(y01, 65536.0, y23);                      // exact (< 2^48)
-            const double lo = fma(y45, 256.0, si_i2d((int)v[6 * 4 + e]));  // exact
-            const double x = fma(hi, 16777216.0, lo);                      // the one rounding
+            double x;
+            if (S == 7) {
+                const double lo = fma(y45, 256.0, si_i2d((int)v[6 * 4 + e]));  // exact
+                x = fma(hi, 16777216.0, lo);                                   // the one rounding
+            } else {
+                x = fma(hi, 65536.0, y45);                                     // exact: 48 bits
+            }
             const double t = x * __ldg(sc + c * 4 + e);                    // power-of-two scale: exact
             sum[e] = fma(t, si_s8_to_f64(mw[c], e), sum[e]);               // row-dot with m_kj in {-1,0,1}
         }
@@ -127,12 +153,13 @@ __device__ __forceinline__ double si_recombine_rowdot(uint32_t taddr, const uint
     return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
+template <int S>
 __global__ void __launch_bounds__(SI_THREADS, 1)
 scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const ScanI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SI_STAGES * SI_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SI_STAGES * SiT<S>::STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + SI_STAGES;
     uint64_t* tmem_full = bars + 2 * SI_STAGES;
@@ -193,12 +220,12 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                         }
                     }
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sA = smem + stage * SI_STAGE_BYTES;
+                    uint8_t* sA = smem + stage * SiT<S>::STAGE_BYTES;
                     uint8_t* sB = sA + SI_A_BYTES;
-                    ptx::mbar_expect_tx(&full[stage], SI_STAGE_BYTES);
+                    ptx::mbar_expect_tx(&full[stage], SiT<S>::STAGE_BYTES);
                     ptx::tma_load_2d(sA, &tmapA, kb * SI_BK, un.x * SI_BM, &full[stage]);
-                    ptx::tma_load_2d(sB, &tmapB, kb * SI_BK, un.y * SI_BN, &full[stage]);
-                    ptx::tma_load_2d(sB + SI_B_BYTES / 2, &tmapB, kb * SI_BK, un.y * SI_BN + SI_BN / 2, &full[stage]);
+                    ptx::tma_load_2d(sB, &tmapB, kb * SI_BK, un.y * SiT<S>::BN, &full[stage]);
+                    ptx::tma_load_2d(sB + SiT<S>::B_BYTES / 2, &tmapB, kb * SI_BK, un.y * SiT<S>::BN + SiT<S>::BN / 2, &full[stage]);
                     if (++stage == SI_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -206,7 +233,7 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------ UMMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_i8(SI_BM, SI_BN);
+            constexpr uint32_t idesc = ptx::make_idesc_i8(SI_BM, SiT<S>::BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -244,7 +271,7 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                             for (int q = ph + 1; q < p.phases_per_unit; q++) si_red_add(c + q, 1u);
                     }
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem + stage * SI_STAGE_BYTES);
+                    const uint32_t a_addr = ptx::smem_u32(smem + stage * SiT<S>::STAGE_BYTES);
                     const uint64_t a_desc = ptx::make_desc_k_sw128(a_addr);
                     const uint64_t b_desc = ptx::make_desc_k_sw128(a_addr + SI_A_BYTES);
 #pragma unroll
@@ -299,8 +326,8 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             t0 = clock64();
 #endif
             ptx::tc_fence_after();
-            const double sum = si_recombine_rowdot(
-                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SI_CHUNK), mw, sc, p.n > 65000);
+            const double sum = si_recombine_rowdot<S>(
+                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SiT<S>::CHUNK), mw, sc, p.n > 65000);
             ptx::tc_fence_before();
             __syncwarp();
 #ifdef EG_SI_PROFILE
@@ -334,20 +361,13 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 // Barrier protocol: full[s] lives in the leader (rank 0) and collects the bytes of both CTAs' TMA loads; the
 // leader's UMMA thread frees a stage / publishes an accumulator in BOTH CTAs with a multicast commit; the epilogue
 // warps of both CTAs release an accumulator by arriving on the leader's tmem_empty (count 8).
-constexpr int SP_STAGES = 7;
-constexpr int SP_MSUP_DEFAULT = 18;  // super-tile in units of 256-marker blocks x groups (see SI_MSUP_DEFAULT)
-constexpr int SP_GSUP_DEFAULT = 4;
-constexpr int SP_A_BYTES = SI_BM * SI_BK;               // 128 marker rows
-constexpr int SP_B_BYTES = (SI_BN / 2) * SI_BK;         // 112 slice rows
-constexpr int SP_STAGE_BYTES = SP_A_BYTES + SP_B_BYTES; // 30 KB
-constexpr int SP_SMEM_BYTES = SP_STAGES * SP_STAGE_BYTES + 1024 + 256;
-
+template <int S>
 __global__ void __launch_bounds__(SI_THREADS, 1)
 scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const ScanI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_STAGES * SP_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_STAGES * SiT<S>::SP_STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + SP_STAGES;
     uint64_t* tmem_full = bars + 2 * SP_STAGES;
@@ -411,12 +431,12 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                         }
                     }
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sA = smem + stage * SP_STAGE_BYTES;
+                    uint8_t* sA = smem + stage * SiT<S>::SP_STAGE_BYTES;
                     uint8_t* sB = sA + SP_A_BYTES;
                     const uint32_t lead_full = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
-                    if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * SP_STAGE_BYTES);
+                    if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * SiT<S>::SP_STAGE_BYTES);
                     ptx::tma_load_2d_pair(sA, &tmapA, kb * SI_BK, un.x * (2 * SI_BM) + (int)rank * SI_BM, lead_full);
-                    ptx::tma_load_2d_pair(sB, &tmapB, kb * SI_BK, un.y * SI_BN + (int)rank * (SI_BN / 2), lead_full);
+                    ptx::tma_load_2d_pair(sB, &tmapB, kb * SI_BK, un.y * SiT<S>::BN + (int)rank * (SiT<S>::BN / 2), lead_full);
                     if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -424,7 +444,7 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     } else if (warp == 1) {
         // ------------------------------------------------------------ UMMA issuer (leader CTA only)
         if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_i8(2 * SI_BM, SI_BN);
+            constexpr uint32_t idesc = ptx::make_idesc_i8(2 * SI_BM, SiT<S>::BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -446,7 +466,7 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                             for (int q = ph + 1; q < p.phases_per_unit; q++) si_red_add(c + q, 1u);
                     }
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem + stage * SP_STAGE_BYTES);
+                    const uint32_t a_addr = ptx::smem_u32(smem + stage * SiT<S>::SP_STAGE_BYTES);
                     const uint64_t a_desc = ptx::make_desc_k_sw128(a_addr);
                     const uint64_t b_desc = ptx::make_desc_k_sw128(a_addr + SP_A_BYTES);
 #pragma unroll
@@ -483,8 +503,8 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             const double* sc = p.scale + (int64_t)un.y * SI_GCOLS + half * 16;
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
-            const double sum = si_recombine_rowdot(
-                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SI_CHUNK), mw, sc, p.n > 65000);
+            const double sum = si_recombine_rowdot<S>(
+                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SiT<S>::CHUNK), mw, sc, p.n > 65000);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
@@ -506,7 +526,7 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 // stays <= 127); scale_k = 2^(e_k - 55)
 __global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
                                                           int32_t* __restrict__ expo, double* __restrict__ scale,
-                                                          int64_t ncols_pad) {
+                                                          int64_t ncols_pad, int bits) {
     // |x| bit patterns order like unsigned integers and NaN > Inf > finite: an integer max finds the column's largest
     // magnitude AND lets a NaN / Inf through (fmax would drop a NaN and turn a poisoned column into zeros)
     const int64_t k = blockIdx.x;
@@ -532,13 +552,14 @@ __global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restri
             s = __longlong_as_double(0x7FF8000000000000LL);  // NaN / Inf in U poisons the column, as in the reference's product
         } else if (k < n && m) {
             if (frexp(__longlong_as_double((long long)m), &e) >= 0.9921875) e++;
-            s = ldexp(1.0, e - 55);
+            s = ldexp(1.0, e - bits);
         }
         expo[k] = e;
         scale[k] = s;
     }
 }
 // Q rows for column k = 32 g + kk: g*224 + (kk>>2)*28 + s*4 + (kk&3); thread -> 4 consecutive i
+template <int S>
 __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
                                                        const int32_t* __restrict__ expo, int8_t* __restrict__ Q,
                                                        int64_t Kp) {
@@ -547,20 +568,20 @@ __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict_
     if (i0 >= Kp) return;
     const int64_t g = k / SI_GCOLS;
     const int kk = (int)(k - g * SI_GCOLS);
-    int8_t* base = Q + (g * SI_BN + (kk >> 2) * SI_CHUNK + (kk & 3)) * Kp + i0;
-    uint32_t out[SI_SLICES];
+    int8_t* base = Q + (g * SiT<S>::BN + (kk >> 2) * SiT<S>::CHUNK + (kk & 3)) * Kp + i0;
+    uint32_t out[S];
 #pragma unroll
-    for (int s = 0; s < SI_SLICES; s++) out[s] = 0;
+    for (int s = 0; s < S; s++) out[s] = 0;
     if (k < n) {
         const int e = expo[k];
 #pragma unroll
         for (int d = 0; d < 4; d++) {
             const int64_t i = i0 + d;
             if (i <= k && i < n) {
-                const double xs = ldexp(Wp[i + k * ld], 55 - e);  // |xs| <= 127 * 2^48 (exact scaling)
-                long long X = fabs(xs) < 3.6e16 ? __double2ll_rn(xs) : 0;  // NaN / Inf: the column's scale is NaN
+                const double xs = ldexp(Wp[i + k * ld], SiT<S>::BITS - e);  // |xs| <= 127 * 2^(8 S - 8) (exact scaling)
+                long long X = fabs(xs) < 3.6e16 ? __double2ll_rn(xs) : 0;  // rint: |residual| <= 1/2 unit = 2^(e - 8 S)  // NaN / Inf: the column's scale is NaN
 #pragma unroll
-                for (int s = SI_SLICES - 1; s > 0; s--) {          // balanced digits, least significant first
+                for (int s = S - 1; s > 0; s--) {          // balanced digits, least significant first
                     const int q = (int)(int8_t)(X & 0xFF);
                     out[s] |= ((uint32_t)q & 0xFFu) << (8 * d);
                     X = (X - q) >> 8;                              // exact: X - q is a multiple of 256
@@ -570,7 +591,7 @@ __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict_
         }
     }
 #pragma unroll
-    for (int s = 0; s < SI_SLICES; s++) *reinterpret_cast<uint32_t*>(base + (int64_t)s * 4 * Kp) = out[s];
+    for (int s = 0; s < S; s++) *reinterpret_cast<uint32_t*>(base + (int64_t)s * 4 * Kp) = out[s];
 }
 
 // (mb, g) -> position in the super-tile order
@@ -659,9 +680,21 @@ static int si_grow(T** p, size_t* cap, size_t need, const char* what) {
     return EG_OK;
 }
 
+// digits per column of U: 6 (default) or 7 (EAGLE_SCAN_DIGITS=7: the full significand of every column's largest entry)
+static int g_si_digits = 0;
+int scan_i8_digits() {
+    if (!g_si_digits) {
+        const char* e = getenv("EAGLE_SCAN_DIGITS");
+        g_si_digits = (e && e[0] == '7') ? 7 : 6;
+    }
+    return g_si_digits;
+}
+void scan_i8_set_digits(int d) { g_si_digits = d == 7 ? 7 : 6; }
+
 // vara for all rows of an Mt store from the folded matrix U (columns 0..n-1 of Wp)
-int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp, int64_t Kpad,
-                   const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st) {
+template <int S>
+static int launch_scan_i8_t(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp, int64_t Kpad,
+                            const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st) {
     int dev = 0;
     EG_CUDA(cudaGetDevice(&dev));
     if (g_si.device != dev) {
@@ -677,7 +710,7 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
     const int KB = (int)(Kp / SI_BK);
     if (pitch < Kp || pitch < (int64_t)G * SI_GCOLS)
         return set_error(EG_ERR_ARG, "scan_i8: Mt pitch %lld too small for n=%lld", (long long)pitch, (long long)n);
-    EG_TRY(si_grow(&g_si.Q, &g_si.q_cap, (size_t)G * SI_BN * Kp, "sliced U"));
+    EG_TRY(si_grow(&g_si.Q, &g_si.q_cap, (size_t)G * SiT<S>::BN * Kp, "sliced U"));
     EG_TRY(si_grow(&g_si.scale, &g_si.sc_cap, (size_t)G * SI_GCOLS, "column scales"));
     EG_TRY(si_grow(&g_si.expo, &g_si.expo_cap, (size_t)G * SI_GCOLS, "column exponents"));
     EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)2 * G * L, "per-group partial sums"));
@@ -695,15 +728,15 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
         g_si.units_shape = shape_key;
     }
     // 1. slice U
-    si_colscale_kernel<<<(unsigned)(G * SI_GCOLS), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo, g_si.scale, (int64_t)G * SI_GCOLS);
+    si_colscale_kernel<<<(unsigned)(G * SI_GCOLS), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo, g_si.scale, (int64_t)G * SI_GCOLS, SiT<S>::BITS);
     EG_TRY(check_launch("si_colscale_kernel"));
-    si_slice_kernel<<<dim3((unsigned)((Kp / 4 + 255) / 256), (unsigned)(G * SI_GCOLS)), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo,
+    si_slice_kernel<S><<<dim3((unsigned)((Kp / 4 + 255) / 256), (unsigned)(G * SI_GCOLS)), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo,
                                                                                                    g_si.Q, Kp);
     EG_TRY(check_launch("si_slice_kernel"));
     // 2. the int8 contraction with fused recombination + row-dot
     CUtensorMap tA, tB;
     EG_TRY(si_make_map(&tA, d_Mt, Kp, L, pitch, SI_BM));
-    EG_TRY(si_make_map(&tB, g_si.Q, Kp, (int64_t)G * SI_BN, Kp, SI_BN / 2));
+    EG_TRY(si_make_map(&tB, g_si.Q, Kp, (int64_t)G * SiT<S>::BN, Kp, SiT<S>::BN / 2));
     ScanI8Params p;
     p.L = L; p.n = n; p.G = G; p.MB = MB; p.KB = KB;
     p.Mt = d_Mt; p.pitch = pitch; p.scale = g_si.scale; p.partial = g_si.partial;
@@ -722,9 +755,9 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
         EG_CUDA(cudaMemsetAsync(g_si.phase, 0, nctr * sizeof(uint32_t), st));
         p.phase_ctr = g_si.phase;
     }
-    const int smem_bytes = pair ? SP_SMEM_BYTES : SI_SMEM_BYTES;
-    if (pair) EG_CUDA(cudaFuncSetAttribute(scan_i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    else EG_CUDA(cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int smem_bytes = pair ? SiT<S>::SP_SMEM_BYTES : SiT<S>::SMEM_BYTES;
+    if (pair) EG_CUDA(cudaFuncSetAttribute(scan_i8_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else EG_CUDA(cudaFuncSetAttribute(scan_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(pair ? 2 * workers : workers));
     cfg.blockDim = dim3(SI_THREADS);
@@ -744,14 +777,20 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
         const int kb = (g * SI_GCOLS + SI_GCOLS + SI_BK - 1) / SI_BK;
         kblocks += kb < KB ? kb : KB;
     }
-    scan_kernel_mark(0, st, kblocks * MB * 2.0 * rows_per_unit * SI_BN * SI_BK);
-    if (pair) EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_pair_kernel, tA, tB, p));
-    else EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel, tA, tB, p));
+    scan_kernel_mark(0, st, kblocks * MB * 2.0 * rows_per_unit * SiT<S>::BN * SI_BK);
+    if (pair) EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_pair_kernel<S>, tA, tB, p));
+    else EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel<S>, tA, tB, p));
     EG_TRY(check_launch("scan_i8_kernel"));
     scan_kernel_mark(1, st, 0.0);
     // 3. groups summed in index order
     si_reduce_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(g_si.partial, L, 2 * G, d_zero_rows, n_zero, d_vara);
     return check_launch("si_reduce_kernel");
+}
+
+int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp, int64_t Kpad,
+                   const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st) {
+    return scan_i8_digits() == 7 ? launch_scan_i8_t<7>(d_Mt, L, n, pitch, d_Wp, Kpad, d_zero_rows, n_zero, d_vara, st)
+                                 : launch_scan_i8_t<6>(d_Mt, L, n, pitch, d_Wp, Kpad, d_zero_rows, n_zero, d_vara, st);
 }
 
 }  // namespace eg
