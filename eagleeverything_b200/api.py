@@ -342,7 +342,7 @@ def set_scan_mode(mode):
 
 
 def set_scan_digits(digits):
-    """6 (default) or 7 balanced base-256 digits per column of U in the int8 scan (include/eagle_gpu.h)."""
+    """7 (default) or 6 balanced base-256 digits per column of U in the int8 scan (include/eagle_gpu.h)."""
     _lib.check(_lib.load().eg_set_scan_digits(int(digits)))
 
 

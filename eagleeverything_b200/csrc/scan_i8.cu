@@ -49,11 +49,12 @@ constexpr int SP_STAGES = 7;
 constexpr int SP_MSUP_DEFAULT = 18;  // super-tile in units of 256-marker blocks x groups (see SI_MSUP_DEFAULT)
 constexpr int SP_GSUP_DEFAULT = 4;
 constexpr int SP_A_BYTES = SI_BM * SI_BK;               // 128 marker rows
-// Everything that depends on the number of digits S per column of U.  S = 7: the full significand of the column's
-// largest entry (55 bits + sign), one rounding per entry of Mt U.  S = 6 (default): 47 bits + sign, the recombination is
-// exact (48 bits fit a double), the truncation of U is bounded by 2^(e_k - 48) per entry -- 32 units in the last place of
-// the column maximum, the size of an FP64 GEMM's own accumulation error at these n and four orders of magnitude inside
-// the 1e-9 tolerance -- and every k-block costs 6/7 of the tensor work and of the shared-memory fill.
+// Everything that depends on the number of digits S per column of U.  S = 7 (default): the full significand of the
+// column's largest entry (55 bits + sign), one rounding per entry of Mt U.  S = 6 (opt-in): 47 bits + sign, the
+// recombination is exact (48 bits fit a double), the truncation of U is bounded by 2^(e_k - 48) per entry -- inside an FP64
+// GEMM's worst-case accumulation bound at these n and five orders of magnitude inside the 1e-9 tolerance -- and every
+// k-block costs 6/7 of the tensor work.  Measured at config 3: 260 -> 248 ms (the fill of the A tile does not shrink), and
+// 16 x the error of an FP64 evaluation on the adversarial test: not worth being the default.
 template <int S>
 struct SiT {
     static_assert(S == 6 || S == 7, "digits per column");
@@ -680,16 +681,16 @@ static int si_grow(T** p, size_t* cap, size_t need, const char* what) {
     return EG_OK;
 }
 
-// digits per column of U: 6 (default) or 7 (EAGLE_SCAN_DIGITS=7: the full significand of every column's largest entry)
+// digits per column of U: 7 (default: the full significand of every column's largest entry) or 6 (EAGLE_SCAN_DIGITS=6)
 static int g_si_digits = 0;
 int scan_i8_digits() {
     if (!g_si_digits) {
         const char* e = getenv("EAGLE_SCAN_DIGITS");
-        g_si_digits = (e && e[0] == '7') ? 7 : 6;
+        g_si_digits = (e && e[0] == '6') ? 6 : 7;
     }
     return g_si_digits;
 }
-void scan_i8_set_digits(int d) { g_si_digits = d == 7 ? 7 : 6; }
+void scan_i8_set_digits(int d) { g_si_digits = d == 6 ? 6 : 7; }
 
 // vara for all rows of an Mt store from the folded matrix U (columns 0..n-1 of Wp)
 template <int S>

@@ -349,10 +349,10 @@ int eg_dev_scan_prepare_eig(const double* d_U, const double* d_Ut, int64_t n, co
 int eg_set_scan_mode(int mode);
 int eg_get_scan_mode(void);
 /* Digits (balanced base-256, int8) that mode 1 keeps of every column of the folded matrix U:
- *   6 (default; EAGLE_SCAN_DIGITS=6)  47 bits + sign relative to the column's largest entry: truncation <= 2^(e_k - 48) per
- *       entry, exact integer accumulation and an exact recombination -- the accuracy of an FP64 GEMM's own accumulation at
- *       these sizes, four orders of magnitude inside the 1e-9 tolerance, at 6/7 of the tensor work;
- *   7 (EAGLE_SCAN_DIGITS=7)  the full significand of the column's largest entry, one rounding per entry of Mt U. */
+ *   7 (default)  the full significand of the column's largest entry, one rounding per entry of Mt U: more accurate than the
+ *       FP64 accumulation it replaces;
+ *   6 (EAGLE_SCAN_DIGITS=6)  47 bits + sign: truncation <= 2^(e_k - 48) per entry, exact accumulation and recombination --
+ *       inside an FP64 GEMM's worst-case bound, five orders of magnitude inside the 1e-9 tolerance, 5 % faster. */
 int eg_set_scan_digits(int digits);
 int eg_get_scan_digits(void);
 /* Device time of the dominant kernel of the last eg_dev_scan (scan_i8_kernel or scan_f64_kernel),
