@@ -512,7 +512,7 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_reference_sample(n, L, steps=3, warmup=0)
+            cpu = cpu_reference_sample(n, L, steps=3, warmup=1)   # the same passes as --impl reference: warm-up, then the median
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     out = {
