@@ -976,11 +976,13 @@ def run_forward_search(args, torch, dist, egd, n, L, Lg, c0, world, rank, img):
         else:
             col = shard.fetch_col(lambda jj: device.extract_col(kb, n, jj, kblocked=True), n, int(j), "cuda")
         y = y + b * col.cpu().numpy().astype(np.float64)
-    # warm-up on a small data set: library handles, lazily loaded kernels (cuSOLVER, the secular-solve kernels)
-    Gw = synth.genotypes(512, 4096, seed=5)
+    # warm-up on a smaller data set: library handles and the lazily loaded kernels of cuSOLVER's large-matrix paths, of the
+    # digit-slice product and of the secular solve (a cold first dsyevd of order 10,000 takes 2 s instead of 0.86)
+    nw = min(n, 4096)
+    Gw = synth.genotypes(nw, 2048, seed=5)
     imgw = torch.from_numpy(np.concatenate([synth.ascii_image(Gw).reshape(-1), np.zeros(64, np.uint8)])).cuda()
-    kbw = device.decode_kb(imgw, 4097, 512, 4096)[0]
-    am.AM_resident(kbw, device.transpose_kb(kbw, 512, 4096), 512, 4096, synth.phenotype(Gw)[0], maxit=2)
+    kbw = device.decode_kb(imgw, 2049, nw, 2048)[0]
+    am.AM_resident(kbw, device.transpose_kb(kbw, nw, 2048), nw, 2048, synth.phenotype(Gw)[0], maxit=2)
     del kbw, imgw
     if world > 1:
         torch.cuda.synchronize(); dist.barrier()
