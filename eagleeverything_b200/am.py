@@ -389,6 +389,18 @@ def eigbasis_inputs(xi, Xt, yt, ve, vg, XtX=None, Xty=None):
 
 
 def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None, Z=None):
+    """See _AM_resident.  The host side of the loop only touches n-vectors and n x q panels: BLAS worker threads would
+    gain nothing there, and their spin-waiting after every small product delays the thread that launches the kernels
+    (measured at config 3: 0.3 - 0.8 s of the search with 16 OpenBLAS threads, 0.07 s with one)."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:
+        return _AM_resident(store_kb, storeT, n, L, y, X0, maxit, message, shard, Z)
+    with threadpool_limits(limits=1):
+        return _AM_resident(store_kb, storeT, n, L, y, X0, maxit, message, shard, Z)
+
+
+def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None, Z=None):
     """AM()'s forward search (R/AM.R:260, 395-504) with the genotypes resident in HBM and the n x n algebra of every
     iteration carried out in the basis of eigen(K) (csrc/eigbasis.cu): K = MMt/max(MMt) + 0.95 I never changes after the
     first iteration (R/AM.R:414-423), so it is decomposed ONCE; after that an iteration costs
@@ -453,6 +465,8 @@ def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shar
         sc_d = torch.from_numpy(np.sqrt(cnt)).to(dev)
         U.mul_(sc_d[:, None]).mul_(sc_d[None, :])
     _lib.check(lib.eg_dev_eigen_sym(p(U), n, p(vals), st()))                     # values decreasing, as R's eigen()
+    torch.cuda.synchronize()
+    stats["dsyevd_s"] = round(time.perf_counter() - t0, 4)                       # the one library factorisation of the search
     xi = vals.cpu().numpy().copy()
     if not np.all(np.where(np.abs(xi) < 1e-8, 0.0, xi) > 0):                     # matrixcalc::is.positive.definite's screen
         raise ValueError("M %*% t(M) is not positive definite")                  # calculateMMt_sqrt_and_sqrtinv.R:15-23
