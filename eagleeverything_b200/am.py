@@ -545,7 +545,9 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
             val_x, et_x = np.empty(m - q), np.empty(m - q)
             _lib.check(lib.eg_emma_eigen_R_wo_Z_eigbasis(dp(xi_x), dp(Xt_x), dp(yt_x), m, q, dp(val_x), dp(et_x), s4))
             lam, e1sq, e2sq = val_x[: n - q], et_x[: n - q] ** 2, float((et_x[n - q:] ** 2).sum())
-        sec_stats.append(list(s4))
+        t2 = (C.c_double * 2)()
+        lib.eg_last_secular_times(t2)
+        sec_stats.append(list(s4) + [t2[0], t2[1], time.perf_counter() - t0])
         timed("emma_eigen_s", t0)
         t0 = time.perf_counter()
         if zidx is None:
@@ -601,7 +603,9 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
                 all_picked=[int(s) for s in selected if not math.isnan(s)], extBIC=extBIC, vc=vc,
                 iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()},
                 secular={"max_root_iterations": max(s[2] for s in sec_stats), "deflated_poles": sum(s[1] for s in sec_stats),
-                         "roots": sum(s[3] for s in sec_stats)})
+                         "roots": sum(s[3] for s in sec_stats),
+                         "seconds_per_call": [dict(device_back_end=round(s[4], 4), library_call=round(s[5], 4), with_python=round(s[6], 4))
+                                              for s in sec_stats]})
 
 
 # ----------------------------------------------------------------------------- everything resident in HBM

@@ -17,6 +17,8 @@
 // kernels below.
 #include <cublas_v2.h>
 
+#include <time.h>
+
 #include <cstring>
 #include <vector>
 
@@ -147,11 +149,26 @@ void eigbasis_release() {
     g_sec = SecWorkspace();
 }
 
+static double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static thread_local double g_sec_times[2] = {0.0, 0.0};   // seconds of the last solve: inside the device back end, in total
+
 struct CudaBackend {
     cudaStream_t st;
     int err = EG_OK;
+    double busy = 0.0;
     int solve(int m, const double* d, const double* z, const double* V, int r, int* origin, double* mu, double* Vout,
               int* max_iters) {
+        const double t_in = now_s();
+        const int rc = solve_(m, d, z, V, r, origin, mu, Vout, max_iters);
+        busy += now_s() - t_in;
+        return rc;
+    }
+    int solve_(int m, const double* d, const double* z, const double* V, int r, int* origin, double* mu, double* Vout,
+               int* max_iters) {
         const size_t need = (size_t)m * 4 + (size_t)m * r * 2, ineed = (size_t)m + 1;
         if (need > g_sec.cap) {
             cudaFree(g_sec.buf);
@@ -270,7 +287,10 @@ extern "C" int eg_emma_eigen_R_wo_Z_eigbasis(const double* xi, const double* Xt,
     EG_TRY(ensure_init_pub());
     CudaBackend be{ctx_stream()};
     sec::Stats st;
+    const double t_all = now_s();
     const int rc = sec::compress(be, n, q, xi, Xt, yt, out_values, out_etas, &st);
+    g_sec_times[0] = be.busy;
+    g_sec_times[1] = now_s() - t_all;
     if (stats4) {
         stats4[0] = st.steps;
         stats4[1] = st.deflated;
@@ -280,6 +300,14 @@ extern "C" int eg_emma_eigen_R_wo_Z_eigbasis(const double* xi, const double* Xt,
     if (rc >= 100) return be.err != EG_OK ? be.err : set_error(EG_ERR_CUDA, "secular solve failed");
     if (rc == 1) return set_error(EG_ERR_ARG, "emma.eigen.R.wo.Z: the design matrix X is rank deficient");
     if (rc) return set_error(EG_ERR_ARG, "emma.eigen.R.wo.Z: secular solve lost the ordering of its poles (%d)", rc);
+    return EG_OK;
+}
+
+// seconds of the calling thread's last eg_emma_eigen_R_wo_Z_eigbasis: [0] uploads + kernels + downloads, [1] the whole call
+extern "C" int eg_last_secular_times(double* out2) {
+    if (!out2) return set_error(EG_ERR_ARG, "eg_last_secular_times: null");
+    out2[0] = g_sec_times[0];
+    out2[1] = g_sec_times[1];
     return EG_OK;
 }
 

@@ -333,6 +333,8 @@ int eg_dev_calculate_reduced_vara(const double* d_X, int q, double varE, double 
  * Host pointers.  stats4 (may be NULL): compressions done, poles deflated, worst root-finder iteration count, roots. */
 int eg_emma_eigen_R_wo_Z_eigbasis(const double* xi, const double* Xt, const double* yt, int64_t n, int q, double* out_values,
                                   double* out_etas, int64_t* stats4);
+/* seconds of the calling thread's last secular solve: [0] inside the device back end, [1] the whole call */
+int eg_last_secular_times(double* out2);
 int eg_dev_transpose_f64(const double* d_in, int64_t n, double* d_out, void* stream);
 /* d_out (n x r) = U^T d_in (to_eigenbasis != 0) or U d_in */
 int eg_dev_eigbasis_apply(const double* d_U, int64_t n, const double* d_in, int r, int to_eigenbasis, double* d_out, void* stream);
