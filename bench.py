@@ -976,13 +976,15 @@ def run_forward_search(args, torch, dist, egd, n, L, Lg, c0, world, rank, img):
         else:
             col = shard.fetch_col(lambda jj: device.extract_col(kb, n, jj, kblocked=True), n, int(j), "cuda")
         y = y + b * col.cpu().numpy().astype(np.float64)
-    # warm-up on a smaller data set: library handles and the lazily loaded kernels of cuSOLVER's large-matrix paths, of the
-    # digit-slice product and of the secular solve (a cold first dsyevd of order 10,000 takes 2 s instead of 0.86)
-    nw = min(n, 4096)
-    Gw = synth.genotypes(nw, 2048, seed=5)
-    imgw = torch.from_numpy(np.concatenate([synth.ascii_image(Gw).reshape(-1), np.zeros(64, np.uint8)])).cuda()
-    kbw = device.decode_kb(imgw, 2049, nw, 2048)[0]
-    am.AM_resident(kbw, device.transpose_kb(kbw, nw, 2048), nw, 2048, synth.phenotype(Gw)[0], maxit=2)
+    # warm-up (untimed, like the W warm-up steps of the timed region): two iterations of the same search on the same
+    # individuals and 4,096 markers -- library handles, lazily loaded kernels, and every workspace that depends on n at
+    # its final size (a workspace that grows inside the timed search costs a cudaFree + cudaMalloc next to the memory
+    # pools: dsyevd 1.5 - 2.0 s instead of 0.8, a secular solve 0.5 s instead of 0.01)
+    Lw = 4096
+    imgw = device.synth_ascii(n, Lw, GENO_SEED + 1)
+    kbw = device.decode_kb(imgw, Lw + 1, n, Lw)[0]
+    yw = np.random.default_rng(3).standard_normal(n) + device.extract_col(kbw, n, 17, kblocked=True).cpu().numpy()
+    am.AM_resident(kbw, device.transpose_kb(kbw, n, Lw), n, Lw, yw, maxit=2)
     del kbw, imgw
     if world > 1:
         torch.cuda.synchronize(); dist.barrier()
