@@ -116,6 +116,8 @@ SIGNATURES = {
     "eg_dev_calculate_reduced_a": (C.c_int, [C.c_double, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "eg_dev_calculate_reduced_vara": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _i64, _vp, _vp, _vp, _vp]),
     "eg_emma_eigen_R_wo_Z_eigbasis": (C.c_int, [_dp, _dp, _dp, _i64, C.c_int, _dp, _dp, _lp]),
+    "eg_dev_project_i8": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "eg_dev_bscan": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "eg_last_secular_times": (C.c_int, [_dp]),
     "eg_dev_transpose_f64": (C.c_int, [_vp, _i64, _vp, _vp]),
     "eg_dev_eigbasis_apply": (C.c_int, [_vp, _i64, _vp, C.c_int, C.c_int, _vp, _vp]),

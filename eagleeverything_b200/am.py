@@ -388,19 +388,19 @@ def eigbasis_inputs(xi, Xt, yt, ve, vg, XtX=None, Xty=None):
     return vg * vg * Dh, np.asfortranarray(Et), vt
 
 
-def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None, Z=None):
+def AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None, Z=None, bcache="auto"):
     """See _AM_resident.  The host side of the loop only touches n-vectors and n x q panels: BLAS worker threads would
     gain nothing there, and their spin-waiting after every small product delays the thread that launches the kernels
     (measured at config 3: 0.3 - 0.8 s of the search with 16 OpenBLAS threads, 0.07 s with one)."""
     try:
         from threadpoolctl import threadpool_limits
     except ImportError:
-        return _AM_resident(store_kb, storeT, n, L, y, X0, maxit, message, shard, Z)
+        return _AM_resident(store_kb, storeT, n, L, y, X0, maxit, message, shard, Z, bcache)
     with threadpool_limits(limits=1):
-        return _AM_resident(store_kb, storeT, n, L, y, X0, maxit, message, shard, Z)
+        return _AM_resident(store_kb, storeT, n, L, y, X0, maxit, message, shard, Z, bcache)
 
 
-def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None, Z=None):
+def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, shard=None, Z=None, bcache="auto"):
     """AM()'s forward search (R/AM.R:260, 395-504) with the genotypes resident in HBM and the n x n algebra of every
     iteration carried out in the basis of eigen(K) (csrc/eigbasis.cu): K = MMt/max(MMt) + 0.95 I never changes after the
     first iteration (R/AM.R:414-423), so it is decomposed ONCE; after that an iteration costs
@@ -420,7 +420,14 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
     (R/emma_eigen_L_w_Z.R:2-14, R/emma_eigen_R_w_Z.R:2-23, R/emma_REMLE.R:78-131, R/emma_MLE.R:57-117) run on the
     eigenpairs of C^1/2 K C^1/2 (C = Z'Z, computed once) through the same secular solve, and the scan is fed the Z-aware
     H = ve I + vg Z K Z' (in the reference snapshot Z stops at EMMA and a non-square Z cannot
-    pass find_qtl: R/AM.R:450-452, R/calculateP.R:22-25)."""
+    pass find_qtl: R/AM.R:450-452, R/calculateP.R:22-25).
+
+    bcache ("auto" / True / False): K -- hence U -- is the same in every iteration, so the projection B = M^T U of this
+    rank's markers (L_local x n doubles: 80 GB at config 3) can be computed ONCE, by the scan's own int8 digit-slice
+    contraction in projection mode (eg_dev_project_i8); every later scan is then
+    var(a)_j = sum_k w_k B_jk^2 - sum_c (E_c^T m_j)^2, a_j = m_j^T v: one HBM-bound pass over B plus q + 1 exact int8
+    matrix-vector products, instead of the n^2 L contraction of src/calculate_a_and_vara_rcpp.cpp:103-112 per iteration
+    (and no n^3 product for W at all).  "auto": when B fits in the free device memory with 12 GB to spare."""
     import ctypes as C
 
     import torch
@@ -441,7 +448,8 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
     X = np.ones((nrec, 1)) if X0 is None else np.asarray(X0, dtype=np.float64).reshape(nrec, -1)
     cnt = None if zidx is None else np.bincount(zidx, minlength=n).astype(np.float64)
     Lloc = storeT.shape[0]
-    stats = dict(mmt_s=0.0, eigen_K_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0, extract_s=0.0, total_s=0.0)
+    stats = dict(mmt_s=0.0, eigen_K_s=0.0, dsyevd_s=0.0, project_s=0.0, emma_eigen_s=0.0, emma_search_s=0.0, algebra_s=0.0, scan_s=0.0,
+                 extract_s=0.0, total_s=0.0)
 
     def timed(key, t0):
         torch.cuda.synchronize()
@@ -472,10 +480,19 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
         raise ValueError("M %*% t(M) is not positive definite")                  # calculateMMt_sqrt_and_sqrtinv.R:15-23
     if zidx is not None:
         U.mul_(sc_d[None, :])                                                    # A = C^1/2 [h_1 .. h_t] (rows of the torch view = columns)
-    Ut = torch.empty((n, n), **f64)
-    _lib.check(lib.eg_dev_transpose_f64(p(U), n, p(Ut), st()))
-    Wp = torch.empty(lib.eg_scan_wp_elems(n), **f64)
-    work2 = torch.empty((n, n), **f64) if not lib.eg_prep_uses_i8(n) else None
+    ldb = (n + 1) // 2 * 2
+    if bcache == "auto":
+        free_b, _tot = torch.cuda.mem_get_info()
+        use_b = Lloc * ldb * 8 + (12 << 30) < free_b
+    else:
+        use_b = bool(bcache)
+    if use_b:
+        Ut = Wp = work2 = None
+    else:
+        Ut = torch.empty((n, n), **f64)
+        _lib.check(lib.eg_dev_transpose_f64(p(U), n, p(Ut), st()))
+        Wp = torch.empty(lib.eg_scan_wp_elems(n), **f64)
+        work2 = torch.empty((n, n), **f64) if not lib.eg_prep_uses_i8(n) else None
 
     def apply_U(v, to_eigenbasis):
         d_in = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
@@ -501,6 +518,12 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
         Xt = np.column_stack([a for a, _ in tops])
         Res = [r for _, r in tops]                                               # residuals of the columns of X (and of y: ry)
     timed("eigen_K_s", t0)
+    if use_b:
+        t0 = time.perf_counter()
+        Bc = torch.empty((Lloc, ldb), **f64)
+        _lib.check(lib.eg_dev_project_i8(p(storeT), Lloc, n, storeT.stride(0), p(U), p(Bc), ldb, st()))
+        tmpL = torch.empty(Lloc, **f64)
+        timed("project_s", t0)
     emma = _Emma(None, stats)
     emma._xi = xi
     selected, new_locus, extBIC = [NA], NA, []
@@ -571,12 +594,26 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
             d_w = torch.from_numpy(w).to(dev)
             d_Et = torch.from_numpy(Et.T.copy()).to(dev)                         # q x n row-major = n x q column-major
             d_vt = torch.from_numpy(vt).to(dev)
-            work = torch.empty(n * q, **f64)
-            _lib.check(lib.eg_dev_scan_prepare_eig(p(U), p(Ut), n, p(d_w), p(d_Et), q, p(d_vt), p(work),
-                                                   p(work2) if work2 is not None else None, p(Wp), st()))
-            timed("algebra_s", t0)
-            t0 = time.perf_counter()
-            a, vara = device.scan(storeT, Lloc, n, Wp)
+            if use_b:
+                d_E = torch.empty((q, n), **f64)                                 # E = U Et, column c = row c of the torch view
+                d_v = torch.empty(n, **f64)
+                _lib.check(lib.eg_dev_eigbasis_apply(p(U), n, p(d_Et), q, 0, p(d_E), st()))
+                _lib.check(lib.eg_dev_eigbasis_apply(p(U), n, p(d_vt), 1, 0, p(d_v), st()))
+                timed("algebra_s", t0)
+                t0 = time.perf_counter()
+                e = torch.empty((q, Lloc), **f64)
+                a, vara = torch.empty(Lloc, **f64), torch.empty(Lloc, **f64)
+                for c in range(q):                                               # e_c = Mt E_c: exact int8 digit products (DP4A)
+                    _lib.check(lib.eg_dev_gemv_i8(p(storeT), Lloc, n, storeT.stride(0), p(d_E[c]), 1.0, p(e[c]), st()))
+                _lib.check(lib.eg_dev_gemv_i8(p(storeT), Lloc, n, storeT.stride(0), p(d_v), 1.0, p(a), st()))
+                _lib.check(lib.eg_dev_bscan(p(Bc), Lloc, n, ldb, p(d_w), p(e), q, p(tmpL), p(vara), st()))
+            else:
+                work = torch.empty(n * q, **f64)
+                _lib.check(lib.eg_dev_scan_prepare_eig(p(U), p(Ut), n, p(d_w), p(d_Et), q, p(d_vt), p(work),
+                                                       p(work2) if work2 is not None else None, p(Wp), st()))
+                timed("algebra_s", t0)
+                t0 = time.perf_counter()
+                a, vara = device.scan(storeT, Lloc, n, Wp)
             best, idx = device.argmax_tsq(a, vara)
             if shard is None:
                 new_locus = int(idx.item()) + 1
@@ -602,6 +639,7 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
     return dict(selected=[int(s) for s in final if not math.isnan(s)],
                 all_picked=[int(s) for s in selected if not math.isnan(s)], extBIC=extBIC, vc=vc,
                 iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()},
+                scan_route="cached projection B = M^T U (one HBM-bound pass per iteration)" if use_b else "n^2 L contraction per iteration",
                 secular={"max_root_iterations": max(s[2] for s in sec_stats), "deflated_poles": sum(s[1] for s in sec_stats),
                          "roots": sum(s[3] for s in sec_stats),
                          "seconds_per_call": [dict(device_back_end=round(s[4], 4), library_call=round(s[5], 4), with_python=round(s[6], 4))

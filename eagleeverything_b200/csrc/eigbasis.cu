@@ -32,6 +32,8 @@ cudaStream_t ctx_stream();
 cublasHandle_t ctx_cublas();
 int launch_prepare_eig_i8(const double* d_Ut, const double* d_rs, int64_t n, double* d_Wp, int64_t Kpad, cudaStream_t st,
                           bool* done);
+int launch_project_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_U, int64_t ld, double* d_B,
+                      int64_t ldb, cudaStream_t st);
 
 // ------------------------------------------------------------------ block-wide reductions (fixed tree: deterministic)
 constexpr int SEC_THREADS = 128;
@@ -273,6 +275,47 @@ __global__ void __launch_bounds__(256) eig_fold_kernel(double* __restrict__ Wp, 
     }
 }
 
+// s_j = sum_k w_k B_jk^2 for every marker row of B (L x n doubles, row pitch ldb): one warp per row, lane-strided
+// partial sums over 4 independent accumulators, then a fixed shuffle tree -- the same order for every row, so identical
+// markers give identical bits.  HBM-bound: 8 n bytes per marker.
+__global__ void __launch_bounds__(256) bscan_kernel(const double* __restrict__ B, int64_t L, int64_t n, int64_t ldb,
+                                                    const double* __restrict__ w, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < L; j += warps) {
+        const double* row = B + j * ldb;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        int64_t k = 2 * lane;
+        for (; k + 192 + 1 < n; k += 256) {   // 4 x (2 doubles per lane): 16-byte loads, 512 B per warp and step
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double2 b = *reinterpret_cast<const double2*>(row + k + 64 * u);
+                const double2 ww = *reinterpret_cast<const double2*>(w + k + 64 * u);
+                acc[u] = fma(ww.x * b.x, b.x, acc[u]);
+                acc[u] = fma(ww.y * b.y, b.y, acc[u]);
+            }
+        }
+        for (; k < n; k += 64) {              // tail, same lane -> column assignment
+            const double b0 = row[k], b1 = k + 1 < n ? row[k + 1] : 0.0;
+            const double w0 = w[k], w1 = k + 1 < n ? w[k + 1] : 0.0;
+            acc[0] = fma(w0 * b0, b0, acc[0]);
+            acc[0] = fma(w1 * b1, b1, acc[0]);
+        }
+        double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        s = warp_sum(s);
+        if (lane == 0) out[j] = s;
+    }
+}
+// vara_j = s_j - sum_c e_cj^2   (e: q vectors of length L, row-major q x L)
+__global__ void __launch_bounds__(256) bscan_combine_kernel(const double* __restrict__ s, const double* __restrict__ e, int q, int64_t L,
+                                                            double* __restrict__ vara) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= L) return;
+    double c = 0.0;
+    for (int k = 0; k < q; k++) c = fma(e[(int64_t)k * L + j], e[(int64_t)k * L + j], c);
+    vara[j] = s[j] - c;
+}
+
 }  // namespace eg
 
 using namespace eg;
@@ -374,4 +417,29 @@ extern "C" int eg_dev_scan_prepare_eig(const double* d_U, const double* d_Ut, in
     // v = U vt -> column n of Wp   (src/calculate_a_and_vara_rcpp.cpp:90: v = inv_MMt_sqrt * a_hat)
     EGB_BLAS(cublasDgemv(ctx_cublas(), CUBLAS_OP_N, (int)n, (int)n, &one, d_U, (int)n, d_vt, 1, &zero, d_Wp + n * Kpad, 1));
     return EG_OK;
+}
+
+// ================================================================== the scan from a cached projection B = M^T U
+// (am.AM_resident, bcache route).  K is fixed for the whole search, so B = M^T U (L x n doubles: 80 GB at config 3) is
+// computed ONCE, by the scan's own int8 digit-slice contraction in projection mode; after that
+//     var(a)_j = m_j^T W m_j = sum_k w_k B_jk^2 - sum_c (E_c^T m_j)^2,      a_j = m_j^T v
+// is one HBM-bound pass over B plus q + 1 exact int8 matrix-vector products with Mt, instead of the n^2 L contraction of
+// src/calculate_a_and_vara_rcpp.cpp:103-112 in every forward iteration.
+extern "C" int eg_dev_project_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_U, double* d_B,
+                                 int64_t ldb, void* stream) {
+    if (!d_Mt || !d_U || !d_B || L <= 0 || n <= 0 || ldb < n || (ldb & 1))
+        return set_error(EG_ERR_ARG, "eg_dev_project_i8: bad argument (ldb >= n and even)");
+    EG_TRY(ensure_init_pub());
+    return launch_project_i8(d_Mt, L, n, pitch, d_U, n, d_B, ldb, (cudaStream_t)stream);
+}
+extern "C" int eg_dev_bscan(const double* d_B, int64_t L, int64_t n, int64_t ldb, const double* d_w, const double* d_e, int q,
+                            double* d_tmp_L, double* d_vara, void* stream) {
+    if (!d_B || !d_w || !d_tmp_L || !d_vara || L <= 0 || n <= 0 || ldb < n || (ldb & 1) || q < 0 || (q > 0 && !d_e))
+        return set_error(EG_ERR_ARG, "eg_dev_bscan: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t blocks = (L + 7) / 8;
+    bscan_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(d_B, L, n, ldb, d_w, d_tmp_L);
+    EG_TRY(check_launch("bscan_kernel"));
+    bscan_combine_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(d_tmp_L, d_e, q, L, d_vara);
+    return check_launch("bscan_combine_kernel");
 }

@@ -81,6 +81,11 @@ struct ScanI8Params {
     int64_t nunits;
     uint32_t* phase_ctr;
     int32_t phases_per_unit;
+    // projection mode (launch_project_i8): the right-hand matrix is FULL (no triangular cut of the K loop) and the
+    // recombined products are stored, Bout[j * ldb + k] = (Mt U)_jk, instead of being folded into the row-dot
+    int32_t full;
+    double* Bout;
+    int64_t ldb;
 };
 
 __device__ __forceinline__ void si_red_add(uint32_t* p, uint32_t v) {
@@ -91,9 +96,9 @@ __device__ __forceinline__ uint32_t si_ld(const uint32_t* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ int si_kb_end(int g, int KB) {
+__device__ __forceinline__ int si_kb_end(int g, int KB, int full) {
     const int kb = (g * SI_GCOLS + SI_GCOLS + SI_BK - 1) / SI_BK;  // rows i <= k of U only
-    return kb < KB ? kb : KB;
+    return (full || kb >= KB) ? KB : kb;
 }
 __device__ __forceinline__ double si_s8_to_f64(uint32_t w, int b) {
     const uint32_t g = (uint32_t)((int32_t)(w << (24 - 8 * b)) >> 24);
@@ -154,6 +159,50 @@ __device__ __forceinline__ double si_recombine_rowdot(uint32_t taddr, const uint
     return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
+// The same recombination, the 16 values of the row stored instead of summed (projection mode, S = 7 only in practice)
+template <int S>
+__device__ __forceinline__ void si_recombine_store(uint32_t taddr, const double* __restrict__ sc, bool wide, double* __restrict__ out,
+                                                   int ncols) {
+    uint32_t v4[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (S == 7) ptx::tmem_ld_32x28(taddr + (uint32_t)(c * SiT<S>::CHUNK), v4[c]);
+        else ptx::tmem_ld_32x24(taddr + (uint32_t)(c * SiT<S>::CHUNK), v4[c]);
+    }
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t(&v)[32] = v4[c];
+        double t[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            double y01, y23, y45;
+            if (!wide) {
+                y01 = si_i2d((int)v[0 * 4 + e] * 256 + (int)v[1 * 4 + e]);
+                y23 = si_i2d((int)v[2 * 4 + e] * 256 + (int)v[3 * 4 + e]);
+                y45 = si_i2d((int)v[4 * 4 + e] * 256 + (int)v[5 * 4 + e]);
+            } else {
+                y01 = fma(si_i2d((int)v[0 * 4 + e]), 256.0, si_i2d((int)v[1 * 4 + e]));
+                y23 = fma(si_i2d((int)v[2 * 4 + e]), 256.0, si_i2d((int)v[3 * 4 + e]));
+                y45 = fma(si_i2d((int)v[4 * 4 + e]), 256.0, si_i2d((int)v[5 * 4 + e]));
+            }
+            const double hi = fma(y01, 65536.0, y23);
+            double x;
+            if (S == 7) x = fma(hi, 16777216.0, fma(y45, 256.0, si_i2d((int)v[6 * 4 + e])));   // the one rounding
+            else x = fma(hi, 65536.0, y45);
+            t[e] = x * __ldg(sc + c * 4 + e);
+        }
+        if (c * 4 + 3 < ncols) {
+            *reinterpret_cast<double2*>(out + c * 4) = make_double2(t[0], t[1]);
+            *reinterpret_cast<double2*>(out + c * 4 + 2) = make_double2(t[2], t[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (c * 4 + e < ncols) out[c * 4 + e] = t[e];
+        }
+    }
+}
+
 template <int S>
 __global__ void __launch_bounds__(SI_THREADS, 1)
 scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
@@ -199,7 +248,7 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             };
             for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
                 const int2 un = p.units[u];
-                const int kb1 = si_kb_end(un.y, p.KB);
+                const int kb1 = si_kb_end(un.y, p.KB, p.full);
                 for (int kb = 0; kb < kb1; kb++) {
                     if (p.phase_ctr && (kb % SI_PHASE) == 0) {
                         const int gp = round * p.phases_per_unit + kb / SI_PHASE;
@@ -245,7 +294,7 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #endif
             for (int64_t u = blockIdx.x; u < p.nunits; u += gridDim.x, round++) {
                 const int2 un = p.units[u];
-                const int kb1 = si_kb_end(un.y, p.KB);
+                const int kb1 = si_kb_end(un.y, p.KB, p.full);
 #ifdef EG_SI_PROFILE
                 long long t0 = clock64();
 #endif
@@ -327,15 +376,23 @@ scan_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             t0 = clock64();
 #endif
             ptx::tc_fence_after();
-            const double sum = si_recombine_rowdot<S>(
-                tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SiT<S>::CHUNK), mw, sc, p.n > 65000);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * SI_ACC_COLS + half * 4 * SiT<S>::CHUNK);
+            double sum = 0.0;
+            if (p.Bout) {   // projection mode: 16 products of this marker row go to B (lanes beyond L still read TMEM)
+                const int64_t col0 = (int64_t)un.y * SI_GCOLS + half * 16;
+                const int64_t left = p.n - col0;
+                double* out = p.Bout + (j < p.L ? j : 0) * p.ldb + col0;
+                si_recombine_store<S>(taddr, sc, p.n > 65000, out, j < p.L ? (left > 16 ? 16 : (int)(left < 0 ? 0 : left)) : 0);
+            } else {
+                sum = si_recombine_rowdot<S>(taddr, mw, sc, p.n > 65000);
+            }
             ptx::tc_fence_before();
             __syncwarp();
 #ifdef EG_SI_PROFILE
             e_work += clock64() - t0;
 #endif
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-            if (j < p.L) p.partial[((int64_t)un.y * 2 + half) * p.L + j] = sum;
+            if (j < p.L && !p.Bout) p.partial[((int64_t)un.y * 2 + half) * p.L + j] = sum;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
 #ifdef EG_SI_PROFILE
@@ -410,7 +467,7 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             };
             for (int64_t u = cid; u < p.nunits; u += ncl, round++) {
                 const int2 un = p.units[u];
-                const int kb1 = si_kb_end(un.y, p.KB);
+                const int kb1 = si_kb_end(un.y, p.KB, p.full);
                 for (int kb = 0; kb < kb1; kb++) {
                     if (rank == 0 && p.phase_ctr && (kb % SI_PHASE) == 0) {
                         const int gp = round * p.phases_per_unit + kb / SI_PHASE;
@@ -453,7 +510,7 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             int round = 0;
             for (int64_t u = cid; u < p.nunits; u += ncl, round++) {
                 const int2 un = p.units[u];
-                const int kb1 = si_kb_end(un.y, p.KB);
+                const int kb1 = si_kb_end(un.y, p.KB, p.full);
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SI_ACC_COLS);
@@ -527,13 +584,13 @@ scan_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 // stays <= 127); scale_k = 2^(e_k - 55)
 __global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
                                                           int32_t* __restrict__ expo, double* __restrict__ scale,
-                                                          int64_t ncols_pad, int bits) {
+                                                          int64_t ncols_pad, int bits, int full) {
     // |x| bit patterns order like unsigned integers and NaN > Inf > finite: an integer max finds the column's largest
     // magnitude AND lets a NaN / Inf through (fmax would drop a NaN and turn a poisoned column into zeros)
     const int64_t k = blockIdx.x;
     unsigned long long m = 0;
     if (k < n)
-        for (int64_t i = threadIdx.x; i <= k; i += 256) {
+        for (int64_t i = threadIdx.x; i <= (full ? n - 1 : k); i += 256) {
             const unsigned long long b = (unsigned long long)__double_as_longlong(Wp[i + k * ld]) & 0x7FFFFFFFFFFFFFFFull;
             m = b > m ? b : m;
         }
@@ -563,7 +620,7 @@ __global__ void __launch_bounds__(256) si_colscale_kernel(const double* __restri
 template <int S>
 __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict__ Wp, int64_t n, int64_t ld,
                                                        const int32_t* __restrict__ expo, int8_t* __restrict__ Q,
-                                                       int64_t Kp) {
+                                                       int64_t Kp, int full) {
     const int64_t k = blockIdx.y;
     const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (i0 >= Kp) return;
@@ -578,7 +635,7 @@ __global__ void __launch_bounds__(256) si_slice_kernel(const double* __restrict_
 #pragma unroll
         for (int d = 0; d < 4; d++) {
             const int64_t i = i0 + d;
-            if (i <= k && i < n) {
+            if ((full || i <= k) && i < n) {
                 const double xs = ldexp(Wp[i + k * ld], SiT<S>::BITS - e);  // |xs| <= 127 * 2^(8 S - 8) (exact scaling)
                 long long X = fabs(xs) < 3.6e16 ? __double2ll_rn(xs) : 0;  // rint: |residual| <= 1/2 unit = 2^(e - 8 S)  // NaN / Inf: the column's scale is NaN
 #pragma unroll
@@ -695,7 +752,9 @@ void scan_i8_set_digits(int d) { g_si_digits = d == 6 ? 6 : 7; }
 // vara for all rows of an Mt store from the folded matrix U (columns 0..n-1 of Wp)
 template <int S>
 static int launch_scan_i8_t(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_Wp, int64_t Kpad,
-                            const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st) {
+                            const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st, double* d_Bout = nullptr,
+                            int64_t ldb = 0) {
+    const int full = d_Bout ? 1 : 0;
     int dev = 0;
     EG_CUDA(cudaGetDevice(&dev));
     if (g_si.device != dev) {
@@ -704,7 +763,7 @@ static int launch_scan_i8_t(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pi
     }
     const int G = (int)((n + SI_GCOLS - 1) / SI_GCOLS);
     const char* env_pair = getenv("EAGLE_SI_PAIR");
-    const bool pair = env_pair && env_pair[0] == '1';      // CTA pairs (cta_group::2): opt-in, see the kernel's header
+    const bool pair = env_pair && env_pair[0] == '1' && !full;   // CTA pairs (cta_group::2): opt-in, see the kernel's header
     const int rows_per_unit = pair ? 2 * SI_BM : SI_BM;
     const int MB = (int)((L + rows_per_unit - 1) / rows_per_unit);
     const int64_t Kp = round_up(n, 128);
@@ -714,7 +773,7 @@ static int launch_scan_i8_t(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pi
     EG_TRY(si_grow(&g_si.Q, &g_si.q_cap, (size_t)G * SiT<S>::BN * Kp, "sliced U"));
     EG_TRY(si_grow(&g_si.scale, &g_si.sc_cap, (size_t)G * SI_GCOLS, "column scales"));
     EG_TRY(si_grow(&g_si.expo, &g_si.expo_cap, (size_t)G * SI_GCOLS, "column exponents"));
-    EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)2 * G * L, "per-group partial sums"));
+    if (!full) EG_TRY(si_grow(&g_si.partial, &g_si.part_cap, (size_t)2 * G * L, "per-group partial sums"));
     const int64_t nunits = (int64_t)MB * G;
     int msup = pair ? SP_MSUP_DEFAULT : SI_MSUP_DEFAULT, gsup = pair ? SP_GSUP_DEFAULT : SI_GSUP_DEFAULT;
     if (const char* e = getenv("EAGLE_SI_MSUP")) msup = atoi(e) > 0 ? atoi(e) : msup;
@@ -729,10 +788,10 @@ static int launch_scan_i8_t(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pi
         g_si.units_shape = shape_key;
     }
     // 1. slice U
-    si_colscale_kernel<<<(unsigned)(G * SI_GCOLS), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo, g_si.scale, (int64_t)G * SI_GCOLS, SiT<S>::BITS);
+    si_colscale_kernel<<<(unsigned)(G * SI_GCOLS), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo, g_si.scale, (int64_t)G * SI_GCOLS, SiT<S>::BITS, full);
     EG_TRY(check_launch("si_colscale_kernel"));
     si_slice_kernel<S><<<dim3((unsigned)((Kp / 4 + 255) / 256), (unsigned)(G * SI_GCOLS)), 256, 0, st>>>(d_Wp, n, Kpad, g_si.expo,
-                                                                                                   g_si.Q, Kp);
+                                                                                                   g_si.Q, Kp, full);
     EG_TRY(check_launch("si_slice_kernel"));
     // 2. the int8 contraction with fused recombination + row-dot
     CUtensorMap tA, tB;
@@ -742,6 +801,7 @@ static int launch_scan_i8_t(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pi
     p.L = L; p.n = n; p.G = G; p.MB = MB; p.KB = KB;
     p.Mt = d_Mt; p.pitch = pitch; p.scale = g_si.scale; p.partial = g_si.partial;
     p.units = g_si.units; p.nunits = nunits;
+    p.full = full; p.Bout = d_Bout; p.ldb = ldb;
     const int sms = num_sms();
     const int workers_max = pair ? sms / 2 : sms;          // CTAs, or CTA pairs
     const int workers = nunits < workers_max ? (int)nunits : workers_max;
@@ -776,13 +836,14 @@ static int launch_scan_i8_t(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pi
     double kblocks = 0.0;  // executed int8 ops: 2 * rows * 224 * 128 per (marker block, k-block of a group)
     for (int g = 0; g < G; g++) {
         const int kb = (g * SI_GCOLS + SI_GCOLS + SI_BK - 1) / SI_BK;
-        kblocks += kb < KB ? kb : KB;
+        kblocks += (full || kb >= KB) ? KB : kb;
     }
     scan_kernel_mark(0, st, kblocks * MB * 2.0 * rows_per_unit * SiT<S>::BN * SI_BK);
     if (pair) EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_pair_kernel<S>, tA, tB, p));
     else EG_CUDA(cudaLaunchKernelEx(&cfg, scan_i8_kernel<S>, tA, tB, p));
     EG_TRY(check_launch("scan_i8_kernel"));
     scan_kernel_mark(1, st, 0.0);
+    if (full) return EG_OK;
     // 3. groups summed in index order
     si_reduce_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(g_si.partial, L, 2 * G, d_zero_rows, n_zero, d_vara);
     return check_launch("si_reduce_kernel");
@@ -792,6 +853,14 @@ int launch_scan_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, cons
                    const int64_t* d_zero_rows, int n_zero, double* d_vara, cudaStream_t st) {
     return scan_i8_digits() == 7 ? launch_scan_i8_t<7>(d_Mt, L, n, pitch, d_Wp, Kpad, d_zero_rows, n_zero, d_vara, st)
                                  : launch_scan_i8_t<6>(d_Mt, L, n, pitch, d_Wp, Kpad, d_zero_rows, n_zero, d_vara, st);
+}
+
+// B = Mt * U for a full n x n FP64 matrix U (column-major, ld): every entry exact up to one rounding (7 digits per
+// column of U).  d_B: L rows, row pitch ldb >= n doubles.  What am.AM_resident computes once per search (B = M^T U, U the
+// eigenvectors of K) so that every later scan is one pass over B instead of an n^2 L contraction.
+int launch_project_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_U, int64_t ld, double* d_B,
+                      int64_t ldb, cudaStream_t st) {
+    return launch_scan_i8_t<7>(d_Mt, L, n, pitch, d_U, ld, nullptr, 0, nullptr, st, d_B, ldb);
 }
 
 }  // namespace eg

@@ -345,6 +345,15 @@ int eg_dev_eigbasis_apply(const double* d_U, int64_t n, const double* d_in, int 
 int eg_dev_scan_prepare_eig(const double* d_U, const double* d_Ut, int64_t n, const double* d_w, const double* d_Et, int q,
                             const double* d_vt, double* d_work, double* d_work2, double* d_Wp, void* stream);
 
+/* The scan from a cached projection (am.AM_resident's bcache route): K is fixed for the whole search, so B = M^T U (U the
+ * eigenvectors of K; L x n doubles, row pitch ldb) is computed ONCE by the int8 digit-slice contraction in projection mode
+ * (one rounding per entry); afterwards var(a)_j = sum_k w_k B_jk^2 - sum_c e_cj^2 with e_c = Mt E_c (eg_dev_gemv_i8) is one
+ * HBM-bound pass over B instead of the n^2 L contraction per forward iteration.  d_e: q x L row-major; d_tmp_L: L doubles. */
+int eg_dev_project_i8(const int8_t* d_Mt, int64_t L, int64_t n, int64_t pitch, const double* d_U, double* d_B, int64_t ldb,
+                      void* stream);
+int eg_dev_bscan(const double* d_B, int64_t L, int64_t n, int64_t ldb, const double* d_w, const double* d_e, int q,
+                 double* d_tmp_L, double* d_vara, void* stream);
+
 /* How var(a) is contracted (same result within the stated tolerance, both deterministic):
  *   1  exact int8 slices of U on the tcgen05 int8 tensor cores, scan_i8.cu -- the default;
  *   0  FP64 tensor cores (DMMA), scan_f64.cu (also: environment EAGLE_SCAN_MODE=f64). */

@@ -246,3 +246,81 @@ def test_emma_eigen_R_resident_with_many_fixed_effects():
     lam, Ur = am.emma_eigen_R_wo_Z(K, X)
     np.testing.assert_allclose(vals[: n - q].cpu().numpy(), lam, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(etas[: n - q].cpu().numpy() ** 2, (Ur.T @ y) ** 2, rtol=1e-7, atol=1e-10)
+
+
+def test_scan_from_the_cached_projection_equals_the_contraction(problem):
+    """B = M^T U once (eg_dev_project_i8: the scan's int8 contraction in projection mode), then
+    var(a)_j = sum_k w_k B_jk^2 - sum_c (E_c^T m_j)^2 and a_j = m_j^T v (eg_dev_bscan + eg_dev_gemv_i8) against the scan on
+    the explicit W (eg_dev_scan_prepare_eig + eg_dev_scan), and B itself against an FP64 product."""
+    import ctypes as C
+    import torch
+    from eagleeverything_b200 import _lib, am as pam, device
+    from oracle import am_driver as am
+    lib = device.init(0)
+    K, X, y, ve, vg, n, q = (problem[k] for k in ("K", "X", "y", "ve", "vg", "n", "q"))
+    xi, U = am.r_eigen_sym(K)
+    w, Et, vt = pam.eigbasis_inputs(xi, U.T @ X, U.T @ y, ve, vg)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    f64 = dict(dtype=torch.float64, device="cuda")
+    dU, dUt = cu(U.T.copy()), cu(U.copy())
+    L = 1700
+    G = synth.genotypes(n, L, seed=n + 9)
+    G[:, 40] = G[:, 1500]                                                   # identical markers far apart
+    img = torch.from_numpy(np.concatenate([synth.ascii_image(G).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    kb, _ = device.decode_kb(img, L + 1, n, L)
+    tT = device.transpose_kb(kb, n, L)
+    # explicit W route
+    d_w, d_Et, d_vt = cu(w), cu(Et.T.copy()), cu(vt)
+    Wp = torch.empty(lib.eg_scan_wp_elems(n), **f64)
+    _lib.check(lib.eg_dev_scan_prepare_eig(p(dU), p(dUt), n, p(d_w), p(d_Et), q, p(d_vt), p(torch.empty(n * q, **f64)),
+                                           p(torch.empty(n * n, **f64)), p(Wp), None))
+    a0, v0 = device.scan(tT, L, n, Wp)
+    # cached projection route
+    ldb = (n + 1) // 2 * 2
+    B = torch.full((L, ldb), float("nan"), **f64)
+    _lib.check(lib.eg_dev_project_i8(p(tT), L, n, tT.stride(0), p(dU), p(B), ldb, None))
+    torch.cuda.synchronize()
+    Mt = 1.0 - G.T.astype(np.float64)                                        # the store holds the negated genotype
+    Bref = Mt @ U
+    Bh = B.cpu().numpy()[:, :n]
+    assert np.abs(Bh - Bref).max() <= 4 * n * np.finfo(float).eps * (np.abs(Mt) @ np.abs(U)).max()
+    d_E, d_v = torch.empty((q, n), **f64), torch.empty(n, **f64)
+    _lib.check(lib.eg_dev_eigbasis_apply(p(dU), n, p(d_Et), q, 0, p(d_E), None))
+    _lib.check(lib.eg_dev_eigbasis_apply(p(dU), n, p(d_vt), 1, 0, p(d_v), None))
+    e = torch.empty((q, L), **f64)
+    a1, v1, tmpL = torch.empty(L, **f64), torch.empty(L, **f64), torch.empty(L, **f64)
+    for c in range(q):
+        _lib.check(lib.eg_dev_gemv_i8(p(tT), L, n, tT.stride(0), p(d_E[c]), 1.0, p(e[c]), None))
+    _lib.check(lib.eg_dev_gemv_i8(p(tT), L, n, tT.stride(0), p(d_v), 1.0, p(a1), None))
+    _lib.check(lib.eg_dev_bscan(p(B), L, n, ldb, p(d_w), p(e), q, p(tmpL), p(v1), None))
+    a0, v0, a1, v1 = (t.cpu().numpy() for t in (a0, v0, a1, v1))
+    E = U @ Et
+    cond_v = ((np.abs(Mt) @ np.abs(U)) ** 2 * w).sum(1) + ((Mt @ E) ** 2).sum(1)
+    assert (np.abs(v1 - v0) <= 1e-9 * np.abs(v0) + 4 * (n + 10) * np.finfo(float).eps * cond_v).all()
+    assert np.abs(a1 - a0).max() <= 1e-12 * np.abs(a0).max()
+    assert v1[40] == v1[1500] and a1[40] == a1[1500]                        # identical rows, identical bits
+
+
+def test_search_routes_agree(synth_small):
+    """am.AM_resident with the cached projection against the contraction per iteration, without and with Z."""
+    import torch
+    from eagleeverything_b200 import am as pam, device
+    device.init(0)
+    s = synth_small
+    y, _ = synth.phenotype(s["G"])
+    img = torch.from_numpy(np.concatenate([synth.ascii_image(s["G"]).reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    kb, _ = device.decode_kb(img, s["L"] + 1, s["n"], s["L"])
+    tT = device.transpose_kb(kb, s["n"], s["L"])
+    r1 = pam.AM_resident(kb, tT, s["n"], s["L"], y, maxit=6, bcache=True)
+    r0 = pam.AM_resident(kb, tT, s["n"], s["L"], y, maxit=6, bcache=False)
+    assert "cached projection" in r1["scan_route"] and "contraction" in r0["scan_route"]
+    assert r1["all_picked"] == r0["all_picked"] and r1["selected"] == r0["selected"]
+    np.testing.assert_allclose(r1["extBIC"], r0["extBIC"], rtol=1e-12)
+    rng = np.random.default_rng(2)
+    idx = np.concatenate([np.arange(s["n"]), rng.integers(0, s["n"], 90)])
+    yz = y[idx] + 0.3 * rng.standard_normal(len(idx))
+    z1 = pam.AM_resident(kb, tT, s["n"], s["L"], yz, maxit=4, Z=idx, bcache=True)
+    z0 = pam.AM_resident(kb, tT, s["n"], s["L"], yz, maxit=4, Z=idx, bcache=False)
+    assert z1["all_picked"] == z0["all_picked"]
+    np.testing.assert_allclose(z1["extBIC"], z0["extBIC"], rtol=1e-12)
