@@ -306,14 +306,21 @@ __global__ void __launch_bounds__(256) bscan_kernel(const double* __restrict__ B
         if (lane == 0) out[j] = s;
     }
 }
-// vara_j = s_j - sum_c e_cj^2   (e: q vectors of length L, row-major q x L)
+// vara_j = s_j - sum_c e_cj^2   (e: q vectors of length L, row-major q x L).
+// A marker that lies in the span of the fixed effects (a locus already in the model, or an identical copy of one) has
+// var(a) = 0 and a = 0 exactly: tsq = 0 / 0, which R's which(tsq == max(tsq, na.rm = TRUE)) ignores.  The dense route
+// returns rounding noise there (|var(a)| ~ 1e-13 of its scale, tsq ~ 1e-14: never the maximum); this route cancels two
+// accurately computed sums and can land on +-1e-17 or on 0, i.e. on a huge or infinite tsq.  So a difference below
+// 1e-10 of s_j -- fifty times the rounding level n eps, a squared multiple correlation with the model above
+// 1 - 1e-10 -- is reported as what it is in exact arithmetic: NaN (not testable).
 __global__ void __launch_bounds__(256) bscan_combine_kernel(const double* __restrict__ s, const double* __restrict__ e, int q, int64_t L,
                                                             double* __restrict__ vara) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (j >= L) return;
     double c = 0.0;
     for (int k = 0; k < q; k++) c = fma(e[(int64_t)k * L + j], e[(int64_t)k * L + j], c);
-    vara[j] = s[j] - c;
+    const double v = s[j] - c;
+    vara[j] = (q > 0 && s[j] > 0.0 && v <= 1e-10 * s[j]) ? __longlong_as_double(0x7FF8000000000000LL) : v;
 }
 
 }  // namespace eg
