@@ -427,7 +427,8 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
     contraction in projection mode (eg_dev_project_i8); every later scan is then
     var(a)_j = sum_k w_k B_jk^2 - sum_c (E_c^T m_j)^2, a_j = m_j^T v: one HBM-bound pass over B plus q + 1 exact int8
     matrix-vector products, instead of the n^2 L contraction of src/calculate_a_and_vara_rcpp.cpp:103-112 per iteration
-    (and no n^3 product for W at all).  "auto": when B fits in the free device memory with 12 GB to spare."""
+    (and no n^3 product for W at all).  "auto": when B fits in the free device memory with 12 GB to spare and at least three
+    iterations are allowed (the projection costs as much as two scans)."""
     import ctypes as C
 
     import torch
@@ -483,7 +484,7 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
     ldb = (n + 1) // 2 * 2
     if bcache == "auto":
         free_b, _tot = torch.cuda.mem_get_info()
-        use_b = Lloc * ldb * 8 + (12 << 30) < free_b
+        use_b = maxit >= 3 and Lloc * ldb * 8 + (12 << 30) < free_b   # the projection costs two scans: pays from the third
     else:
         use_b = bool(bcache)
     if use_b:
