@@ -597,6 +597,22 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
                 "note": f"could not pin host buffers: {ex}"}
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
+    try:
+        return _run_e2e_rank0(args, torch, dist, lib, device, n, L, world, rank, img, img_h, S_h, V_h, a_h, K_h, oa_h, ov_h)
+    finally:
+        if world > 1:
+            try:   # back to this rank's own GPU whatever happened, and release the ranks that wait on the TCP store
+                lib.eg_shutdown()
+                lib.eg_init(int(os.environ.get("LOCAL_RANK", "0")))
+            finally:
+                _wait_rank0(dist, rank, world, "e2e_done")
+
+
+def _run_e2e_rank0(args, torch, dist, lib, device, n, L, world, rank, img, img_h, S_h, V_h, a_h, K_h, oa_h, ov_h):
+    from eagleeverything_b200 import _lib
+    vp = C.c_void_p
+    dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))  # noqa: E731
+    img_bytes = n * (L + 1)
     if world > 1:   # the other ranks have released their memory
         from datetime import timedelta
         store = dist.distributed_c10d._get_default_store()
@@ -678,10 +694,6 @@ def run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img,
                 "container": "2-bit packed genotypes (RcppFunctions.cpp.gpu:224-345 layout) instead of the ASCII image"}
         except Exception as ex:  # noqa: BLE001
             out["from_packed_container"] = {"value": None, "note": f"{type(ex).__name__}: {ex}"}
-    if world > 1:
-        _lib.check(lib.eg_shutdown())
-        _lib.check(lib.eg_init(int(os.environ.get("LOCAL_RANK", "0"))))
-    _wait_rank0(dist, rank, world, "e2e_done")
     return out
 
 

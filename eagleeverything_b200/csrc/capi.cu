@@ -1271,7 +1271,19 @@ extern "C" int eg_init_multi(int ngpu, const int* devs) {
             return rc;
         }
     }
-    EG_NCCL(g_nccl.CommInitAll(g_multi.comm, ngpu, g_multi.devs));
+    {
+        const int nrc = g_nccl.CommInitAll(g_multi.comm, ngpu, g_multi.devs);
+        if (nrc != 0) {   // leave nothing half-built behind
+            const int rc = check_nccl(nrc, "ncclCommInitAll");
+            const std::string msg = g_err;
+            for (int r = 0; r < ngpu; r++) {
+                t_ctx = &g_ctxs[r];
+                shutdown_slot();
+            }
+            t_ctx = &g_ctxs[0];
+            return set_error(rc, "%s", msg.c_str());
+        }
+    }
     g_multi.n = ngpu;
     g_multi.pool = new WorkerPool();
     g_multi.pool->rc.assign(ngpu, EG_OK);
@@ -1307,7 +1319,7 @@ extern "C" int eg_shutdown(void) {
         eg_cache_clear();   // composite stores: parts are freed on their own threads
         // the calling thread's own workspaces on device 0 (single-GPU entry points it ran itself)
         cudaSetDevice(g_ctxs[0].device);
-        syrk_release_cache(); scan_i8_release(); prep_i8_release(); algebra_release(); eigbasis_release();
+        syrk_release_cache(); scan_i8_release(); prep_i8_release(); algebra_release(); eigbasis_release(); hostio_release();
         run_all([](int r) {
             if (g_multi.comm[r]) g_nccl.CommDestroy(g_multi.comm[r]);
             g_multi.comm[r] = nullptr;
