@@ -170,18 +170,23 @@ def scan_prepare_sharded(S, V, a, n, rank, world, Wp=None, tmp=None):
         tmp = torch.empty(need, dtype=torch.float64, device=S.device)
     Wp.zero_()
     _lib.check(lib.eg_dev_scan_prepare_cols(_ptr(S), _ptr(V), n, c0, c1, sym, _ptr(tmp), _ptr(Wp), _stream()))
-    # ONE collective when its staging buffers are small: the column blocks (contiguous ranges of the column-major Wp,
-    # unequal widths) are all-gathered at the width of the widest one and copied into place.  At n = 50,000 those buffers
-    # would be 36 GB and push the digit slices of the pre-products out of memory: one broadcast per block there.
-    wmax = max(cuts[r + 1] - cuts[r] for r in range(world))
-    if (world + 1) * wmax * Kpad * 8 <= (4 << 30):
-        mine = torch.zeros(wmax * Kpad, dtype=torch.float64, device=S.device)
-        mine[: (c1 - c0) * Kpad].copy_(Wp[c0 * Kpad:c1 * Kpad])
-        allb = torch.empty(world * wmax * Kpad, dtype=torch.float64, device=S.device)
+    # ONE collective when its staging buffers are small.  W is symmetric here and only rows 0 .. c1-1 of the columns
+    # [c0, c1) were computed (the rest of Wp is zero), so the UPPER TRAPEZOID of every column block is what travels:
+    # packed (width x c1 doubles per block, unequal), all-gathered at the size of the largest block and copied into
+    # place -- 55 % of the bytes of whole column blocks.  At n = 50,000 the staging buffers would be tens of GB and push
+    # the digit slices of the pre-products out of memory: one broadcast per block there.
+    Wv = Wp[: (Wp.numel() // Kpad) * Kpad].view(-1, Kpad)          # row r of this view = column r of W
+    sizes = [(cuts[r + 1] - cuts[r]) * cuts[r + 1] for r in range(world)]
+    smax = max(sizes)
+    if (world + 1) * smax * 8 <= (4 << 30):
+        mine = torch.zeros(smax, dtype=torch.float64, device=S.device)
+        if c1 > c0:
+            mine[: sizes[rank]].view(c1 - c0, c1).copy_(Wv[c0:c1, :c1])
+        allb = torch.empty(world * smax, dtype=torch.float64, device=S.device)
         dist.all_gather_into_tensor(allb, mine)
         for r in range(world):
             if r != rank and cuts[r + 1] > cuts[r]:
-                Wp[cuts[r] * Kpad:cuts[r + 1] * Kpad].copy_(allb[r * wmax * Kpad:r * wmax * Kpad + (cuts[r + 1] - cuts[r]) * Kpad])
+                Wv[cuts[r]:cuts[r + 1], :cuts[r + 1]].copy_(allb[r * smax:r * smax + sizes[r]].view(cuts[r + 1] - cuts[r], cuts[r + 1]))
         del mine, allb
     else:
         for r in range(world):
