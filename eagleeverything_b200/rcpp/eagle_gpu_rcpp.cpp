@@ -182,3 +182,12 @@ Eigen::MatrixXd calculate_reduced_vara_gpu(Eigen::Map<Eigen::MatrixXd> X, double
     check(eg_calculate_reduced_vara(X.data(), MMtsqrt.rows(), (int)X.cols(), varE, varG, MMtsqrt.data(), V.data()));
     return V;
 }
+
+// The reference's `ngpu` argument made live (R/AM.R:185-196; forced to 0 at R/AM.R:214).  One NEW export: AM() calls it
+// where it sets ngpu; every other export above then works on the marker-sharded stores unchanged (include/eagle_gpu.h,
+// eg_init_multi).  Returns the number of GPUs in use.
+// [[Rcpp::export]]
+int eagle_gpu_init(int ngpu) {
+    check(ngpu > 1 ? eg_init_multi(ngpu, NULL) : eg_init(0));
+    return eg_gpu_count();
+}

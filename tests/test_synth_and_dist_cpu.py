@@ -68,7 +68,16 @@ def _worker(rank, world, port, n, L, ret):
         best, idx = egd.global_argmax(torch.tensor([loc[k]]), torch.tensor([k]), c0)
         vec = egd.gather_sharded(torch.from_numpy(loc.copy()), L, world)
         ok_gather = bool(np.array_equal(np.nan_to_num(vec.numpy(), nan=-1), np.nan_to_num(tsq, nan=-1)))
-        ret[rank] = (ok_mmt, best, idx, ok_gather)
+        # dist.Shard: what the sharded forward search uses (owner of a marker, its column broadcast, the sharded pick)
+        sh = egd.Shard(L, world, rank)
+        cols = {}
+        first_end = egd.shard_range(L, world, 0)[1]
+        for gidx in (0, first_end - 1, first_end, L - 1, 128):          # the same markers on every rank (collective)
+            col = sh.fetch_col(lambda j: torch.from_numpy(G[:, c0 + j].astype(np.int32)), n, gidx, "cpu")
+            cols[gidx] = bool(np.array_equal(col.numpy(), G[:, gidx].astype(np.int32)))
+        owners = [sh.owner(0), sh.owner(L - 1)]
+        b2, i2 = sh.global_argmax(torch.tensor([loc[k]]), torch.tensor([k]))
+        ret[rank] = (ok_mmt, best, idx, ok_gather, all(cols.values()), owners, b2, i2)
     finally:
         dist.destroy_process_group()
 
@@ -80,6 +89,7 @@ def test_world_size_2_gloo():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n, L, ret), nprocs=world, join=True)
     for r in range(world):
-        ok_mmt, best, idx, ok_gather = ret[r]
-        assert ok_mmt and ok_gather
-        assert best == 2.0 and idx == 3
+        ok_mmt, best, idx, ok_gather, ok_cols, owners, b2, i2 = ret[r]
+        assert ok_mmt and ok_gather and ok_cols
+        assert best == 2.0 and idx == 3 and b2 == 2.0 and i2 == 3
+        assert owners == [0, world - 1]
