@@ -913,7 +913,10 @@ def run_extra_workload(args, wl, torch, dist, device, egd, lib, world, rank):
     V = (V + V.T) * (0.5 / n ** 0.5); V.diagonal().add_(1.5)
     ah = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
     # one untimed pass of the two stages whose workspaces depend on n (digit slices of S, V, X: 8 - 52 GB here; partial
-    # sums of the scan): their first allocation is not part of a step
+    # sums of the scan): their first allocation is not part of a step.  torch's cache is emptied first: the library sizes
+    # its digit-slice workspace by the FREE device memory, and at n = 50,000 the 14 GB of released image / int32 product
+    # blocks that torch still held made it fall back to two library DGEMMs (1.4 s instead of 0.64 s).
+    torch.cuda.empty_cache()
     Wp = device.scan_prepare_sharded(S, V, ah, n, rank, world)
     device.scan(tT, min(Lg, 4096), n, Wp)
     del Wp
