@@ -1026,7 +1026,7 @@ def run_forward_search(args, torch, dist, egd, n, L, Lg, c0, world, rank, img):
            "iterations": rr["iterations"], "selected_loci_1based": rr["selected"], "all_picked_1based": rr["all_picked"],
            "planted_qtl_1based": [int(j) + 1 for j in qtl],
            "planted_recovered": int(sum(1 for j in qtl if int(j) + 1 in rr["selected"])),
-           "extBIC": [round(x, 6) for x in rr["extBIC"]], "seconds": secs, "secular": rr["secular"], "scan_route": rr.get("scan_route"),
+           "extBIC": [round(x, 6) for x in rr["extBIC"]], "seconds": secs, "secular": rr["secular"], "scan_route": rr.get("scan_route"), "scan_kernels": rr.get("scan_kernels"),
            "decode_transpose_s": round(t_stores, 4), "scans": len(rr["all_picked"]),
            "markers_per_s_whole_search": len(rr["all_picked"]) * L / secs["total_s"],
            "path": "am.AM_resident (mirror of R/AM.R:395-504): device-level C ABI; eigen(K) once, then per iteration a secular "

@@ -457,6 +457,7 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
         stats[key] += time.perf_counter() - t0
 
     t_all = time.perf_counter()
+    kern = {}
     # ---- M M^T (AM.R:414-417), K (calcMMt.R:13), eigen(K) once
     t0 = time.perf_counter()
     U = torch.empty((n, n), **f64)           # K, then its eigenvectors (columns; column-major)
@@ -522,11 +523,17 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
     if use_b:
         t0 = time.perf_counter()
         Bc = torch.empty((Lloc, ldb), **f64)
+        ev_p = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev_p[0].record()
         _lib.check(lib.eg_dev_project_i8(p(storeT), Lloc, n, storeT.stride(0), p(U), p(Bc), ldb, st()))
+        ev_p[1].record()
         tmpL = torch.empty(Lloc, **f64)
         timed("project_s", t0)
+        kern["project_ms"] = ev_p[0].elapsed_time(ev_p[1])
+        kern["project_int8_tops"] = 2.0 * 7 * Lloc * n * n / (kern["project_ms"] * 1e-3) / 1e12   # 7 digit slices of the full U
     emma = _Emma(None, stats)
     emma._xi = xi
+    bscan_ms, gemv_ms = [], []
     selected, new_locus, extBIC = [NA], NA, []
     itnum, cont, vc = 1, True, None
     sec_stats = []
@@ -604,10 +611,17 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
                 t0 = time.perf_counter()
                 e = torch.empty((q, Lloc), **f64)
                 a, vara = torch.empty(Lloc, **f64), torch.empty(Lloc, **f64)
+                ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev_b[0].record()
                 for c in range(q):                                               # e_c = Mt E_c: exact int8 digit products (DP4A)
                     _lib.check(lib.eg_dev_gemv_i8(p(storeT), Lloc, n, storeT.stride(0), p(d_E[c]), 1.0, p(e[c]), st()))
                 _lib.check(lib.eg_dev_gemv_i8(p(storeT), Lloc, n, storeT.stride(0), p(d_v), 1.0, p(a), st()))
+                ev_b[1].record()
                 _lib.check(lib.eg_dev_bscan(p(Bc), Lloc, n, ldb, p(d_w), p(e), q, p(tmpL), p(vara), st()))
+                ev_b[2].record()
+                ev_b[2].synchronize()
+                gemv_ms.append(ev_b[0].elapsed_time(ev_b[1]))
+                bscan_ms.append(ev_b[1].elapsed_time(ev_b[2]))
             else:
                 work = torch.empty(n * q, **f64)
                 _lib.check(lib.eg_dev_scan_prepare_eig(p(U), p(Ut), n, p(d_w), p(d_Et), q, p(d_vt), p(work),
@@ -641,6 +655,10 @@ def _AM_resident(store_kb, storeT, n, L, y, X0=None, maxit=20, message=None, sha
                 all_picked=[int(s) for s in selected if not math.isnan(s)], extBIC=extBIC, vc=vc,
                 iterations=itnum - 1, seconds={k: round(v, 4) for k, v in stats.items()},
                 scan_route="cached projection B = M^T U (one HBM-bound pass per iteration)" if use_b else "n^2 L contraction per iteration",
+                scan_kernels=(dict(kern, bscan_ms=[round(x, 3) for x in bscan_ms], gemv_ms=[round(x, 3) for x in gemv_ms],
+                                   bscan_gbs=(8.0 * Lloc * n / (min(bscan_ms) * 1e-3) / 1e9) if bscan_ms else None,
+                                   bscan_bytes="8 n bytes per marker (B read once); gemv: (q + 1) passes over the int8 Mt store")
+                              if use_b else None),
                 secular={"max_root_iterations": max(s[2] for s in sec_stats), "deflated_poles": sum(s[1] for s in sec_stats),
                          "roots": sum(s[3] for s in sec_stats),
                          "seconds_per_call": [dict(device_back_end=round(s[4], 4), library_call=round(s[5], 4), with_python=round(s[6], 4))

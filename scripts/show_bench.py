@@ -20,6 +20,6 @@ for path in sys.argv[1:]:
     print("  e2e ms", e.get("ms_per_step"), "dropin", {k: v.get("ms_per_step") for k, v in (e.get("dropin_files") or {}).items() if isinstance(v, dict)})
     fs = d.get("forward_search") or {}
     print("  search", fs.get("seconds"), fs.get("all_picked_1based"), fs.get("extBIC"), fs.get("note"))
-    print("  secular", (fs.get("secular") or {}))
+    print("  scan_kernels", fs.get("scan_kernels"))
     print("  checks", d.get("checks"))
     print("  cpu", (d.get("cpu_baseline") or {}).get("value"), "clocks", d.get("clocks"))
