@@ -52,7 +52,7 @@ static int alg_work(size_t doubles) {
     cudaFree(g_alg.work);
     g_alg.work = nullptr;
     g_alg.work_cap = 0;
-    if (cudaMalloc(&g_alg.work, (doubles ? doubles : 1) * sizeof(double)) != cudaSuccess) {
+    if (malloc_retry((void**)&g_alg.work, (doubles ? doubles : 1) * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         return set_error(EG_ERR_ALLOC, "out of device memory for the LAPACK workspace (%zu bytes)", doubles * 8);
     }
@@ -409,7 +409,7 @@ struct HostDev {
     double* p = nullptr;
     ~HostDev() { cudaFree(p); }
     int alloc(size_t doubles, const char* what) {
-        if (cudaMalloc(&p, (doubles ? doubles : 1) * 8) != cudaSuccess) {
+        if (malloc_retry((void**)&p, (doubles ? doubles : 1) * 8) != cudaSuccess) {
             cudaGetLastError();
             p = nullptr;
             return set_error(EG_ERR_ALLOC, "out of device memory allocating %zu bytes for %s", doubles * 8, what);

@@ -201,6 +201,16 @@ static void pool_flush() {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     pool_flush_locked();
 }
+// For the plain cudaMalloc users of the library (LAPACK workspace, digit slices, host-level algebra buffers): when the
+// device is out of memory, hand the recycled blocks and the cached part of the stream-ordered pool back to the driver --
+// those bytes are invisible to cudaMalloc -- so that the caller can retry once.
+void pool_give_back() {
+    if (!g_ctx.ready) return;
+    pool_flush();
+    cudaStreamSynchronize(g_ctx.stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
 
 // RAII device buffer (valid on g_ctx.stream)
 struct DevBuf {

@@ -12,6 +12,17 @@ int set_error(int code, const char* fmt, ...);   // stores the message for eg_la
 int check_cuda(cudaError_t e, const char* what); // EG_OK or EG_ERR_CUDA (+message)
 int check_launch(const char* kernel);            // cudaGetLastError() after a launch
 int num_sms();                                   // SM count of the current device (148 on B200)
+void pool_give_back();                           // release the library's cached device memory to the driver (retry after an OOM)
+// cudaMalloc with one retry after pool_give_back()
+static inline cudaError_t malloc_retry(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_give_back();
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
 
 #define EG_TRY(expr)                 \
     do {                             \

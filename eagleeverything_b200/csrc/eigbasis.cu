@@ -179,7 +179,7 @@ struct CudaBackend {
             cudaFree(g_sec.buf);
             g_sec.buf = nullptr;
             g_sec.cap = 0;
-            if (cudaMalloc(&g_sec.buf, need * 8) != cudaSuccess) { cudaGetLastError(); err = set_error(EG_ERR_ALLOC, "secular solve: out of device memory"); return 1; }
+            if (malloc_retry((void**)&g_sec.buf, need * 8) != cudaSuccess) { cudaGetLastError(); err = set_error(EG_ERR_ALLOC, "secular solve: out of device memory"); return 1; }
             g_sec.cap = need;
         }
         if (ineed > g_sec.icap) {

@@ -383,7 +383,7 @@ static bool pi_grow(T** ptr, size_t* cap, size_t need) {
     if (*ptr) cudaFree(*ptr);
     *ptr = nullptr;
     *cap = 0;
-    if (cudaMalloc(ptr, need * sizeof(T)) != cudaSuccess) {
+    if (malloc_retry((void**)ptr, need * sizeof(T)) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }

@@ -730,7 +730,7 @@ static int si_grow(T** p, size_t* cap, size_t need, const char* what) {
     if (*p) cudaFree(*p);
     *p = nullptr;
     *cap = 0;
-    if (cudaMalloc(p, need * sizeof(T)) != cudaSuccess) {
+    if (malloc_retry((void**)p, need * sizeof(T)) != cudaSuccess) {
         cudaGetLastError();
         return set_error(EG_ERR_ALLOC, "out of device memory for %s (%zu bytes)", what, need * sizeof(T));
     }
