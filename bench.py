@@ -257,6 +257,38 @@ def measure_library_ceilings(torch):
     return out
 
 
+class TailGuard:
+    """Watchdog over the legs that follow the timed region.  Rank 0 holds the output line; when the deadline passes with
+    a leg still running (a rank that failed inside a collective leaves the others waiting), rank 0 prints the line with
+    the legs that did finish and a note naming the one that did not, and every rank leaves with status 0."""
+
+    def __init__(self, rank, out, seconds):
+        import threading
+        self.rank, self.out, self.leg, self.lock, self.done = rank, out, None, threading.Lock(), False
+        self.timer = threading.Timer(seconds + (0.0 if rank == 0 else 10.0), self._expired)
+        self.timer.daemon = True
+        self.timer.start()
+
+    def _expired(self):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            if self.out is not None:
+                self.out["tail_note"] = f"leg '{self.leg}' did not finish before the deadline; the line is printed without it"
+                jprint(self.out)
+        os._exit(0)
+
+    def finish(self):
+        with self.lock:
+            if self.done:       # the watchdog is printing
+                time.sleep(3600)
+            self.done = True
+            self.timer.cancel()
+        if self.out is not None:
+            jprint(self.out)
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -389,6 +421,118 @@ def run_gpu(args):
             dist.destroy_process_group()
         sys.exit(3)
 
+    # ---------------- the line as far as the timed region decides it; the legs below fill in their parts.  They use
+    # collectives and one process driving every GPU: should one of them stall, the guard prints the line with what is
+    # there instead of losing the measurement to NCCL's ten-minute timeout
+    out = None
+    if rank == 0:
+        stages = dict(zip(STAGES, stage_ms))
+        k_ms, k_ops = k_ms.value, k_ops.value
+        # reference-equivalent FP64 work of the scan (full T = Mt*W, row-dot): 2n(n+1)+2n flops per marker
+        scan_ref_flops = (2.0 * n * (n + 1) + 2.0 * n) * Lg
+        syrk_ops = float(Lg) * n * (n + 1)                      # symmetric half, 2 ops per MAC
+        dec_bytes = float(n) * (Lg + 1) + float(n) * Lg
+        syrk_tops = syrk_ops / (stages["syrk"] * 1e-3) / 1e12
+        dec_gbs = dec_bytes / (stages["decode"] * 1e-3) / 1e9
+        dgemm = ceil.get("dgemm_tflops") or 37.0
+        int8_meas = ceil.get("int8_gemm_tops")
+        # int8 denominators.  MEASURED_PEAKS.json has no int8 entry: the peak of the line is the cuBLASLt int8 GEMM measured
+        # in THIS run -- its sustained figure (~1.5 s back to back), since these kernels are timed inside a long power-capped
+        # step -- with the burst figure, the 2 x bf16 proxies from MEASURED_PEAKS.json and the nominal 4500 beside it
+        proxy_sust, proxy_burst = 2.0 * peaks["bf16_tflops_sustained"], 2.0 * peaks["bf16_tflops"]
+        int8_peak = ceil.get("int8_gemm_tops_sustained") or proxy_sust
+        int8_burst = int8_meas or proxy_burst
+        int8_src = ("cuBLASLt int8 GEMM 8192^3 measured in this run, sustained over ~1.5 s (burst: %.0f); proxies 2 x measured bf16 "
+                    "from MEASURED_PEAKS.json: %.0f sustained / %.0f burst; nominal 4500" % (int8_burst, proxy_sust, proxy_burst)
+                    if ceil.get("int8_gemm_tops_sustained") else
+                    "2 x measured sustained bf16 (no int8 entry in MEASURED_PEAKS.json, in-run int8 GEMM unavailable); 2 x burst bf16 = %.0f, "
+                    "nominal 4500" % proxy_burst)
+
+        def int8_fracs(rate):
+            return {"frac": rate / int8_peak, "frac_of_burst_peak": rate / int8_burst,
+                    "frac_of_2x_bf16_sustained": rate / proxy_sust, "frac_of_2x_bf16_burst": rate / proxy_burst, "frac_of_nominal_4500": rate / 4500.0}
+        k_rate = k_ops / (k_ms * 1e-3) / 1e12
+        if mode == 1:
+            roofline = {"kernel": "scan_i8_kernel", "bound": "tensor", "achieved": k_rate, "peak": int8_peak,
+                        "unit": "TOP/s (int8)", **int8_fracs(k_rate), "executed_ops": k_ops,
+                        "digits": int(lib.eg_get_scan_digits()), "algorithmic_ops": float(lib.eg_get_scan_digits()) * Lg * n * (n + 1),
+                        "traffic": None, "kernel_ms": k_ms,
+                        "ops_convention": "executed int8 ops: `digits` balanced-byte slices x symmetric-half contraction, 2 ops per MAC "
+                                          "(DESIGN.md section 4)",
+                        "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
+                        "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas,
+                        "cublaslt_int8_gemm_tops_sustained_this_run": ceil.get("int8_gemm_tops_sustained")}
+        else:
+            roofline = {"kernel": "scan_f64_kernel", "bound": "tensor", "achieved": k_rate, "peak": dgemm,
+                        "unit": "TFLOP/s (fp64)", "frac": k_rate / dgemm, "traffic": None, "kernel_ms": k_ms,
+                        "ops_convention": "executed FP64 flops of the symmetric-half contraction (DESIGN.md section 4)",
+                        "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
+                        "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 "
+                                       "entry); B200 FP64 nominal 37-40 TFLOP/s"}
+        rooflines = {
+            "decode_kb_kernel": {"bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": dec_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                                 "timed_alone_gbs": dec_bytes / (decode_alone_ms * 1e-3) / 1e9,
+                                 "timed_alone_frac": dec_bytes / (decode_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                 "note": "achieved/frac = inside the step (power-capped clocks inherited from the previous "
+                                         "step's scan); timed_alone = 5 back-to-back launches after an idle gap"},
+            "transpose_kb128_kernel": {"bound": "hbm", "achieved": 2.0 * n * Lg / (stages["transpose"] * 1e-3) / 1e9,
+                                       "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": 2.0 * n * Lg / (stages["transpose"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                       "peak_source": peaks["source"]},
+            "syrk_i8_kernel": {"bound": "tensor", "achieved": syrk_tops, "unit": "TOP/s (int8, symmetric-half ops)",
+                               "full_product_equiv_tops": 2.0 * n * n * Lg / (stages["syrk"] * 1e-3) / 1e12,
+                               "peak": int8_peak, **int8_fracs(syrk_tops), "algorithmic_ops": syrk_ops,
+                               "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas},
+            roofline["kernel"]: roofline,
+        }
+        if p_ms.value > 0:
+            p_rate = p_ops.value / (p_ms.value * 1e-3) / 1e12
+            rooflines["prep_i8_kernel"] = {"bound": "tensor", "achieved": p_rate, "unit": "TOP/s (int8)", "peak": int8_peak,
+                                           **int8_fracs(p_rate), "executed_ops": p_ops.value,
+                                           "kernel_ms": p_ms.value, "peak_source": int8_src,
+                                           "ops_convention": "executed int8 ops of the 28 + 28 digit-slice products of "
+                                                             "X = V S and upper(W = S X); reference-equivalent FP64: 3 n^3 flops",
+                                           "reference_equiv_fp64_tflops": 3.0 * n ** 3 / (stages["prepare"] * 1e-3) / 1e12}
+        scan_tf = scan_ref_flops / (stages["scan"] * 1e-3) / 1e12
+        # DRAM traffic per launch from the committed `ncu --set full` capture of the same kernel at the same shape
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:  # noqa: BLE001
+            tr = {}
+        for kname, rf in rooflines.items():
+            rec = tr.get(kname)
+            if rec and rec.get("workload") == args.workload and rec.get("n_gpus") == world:
+                rf["traffic"] = rec["dram_bytes_per_launch"]
+                rf["traffic_source"] = rec.get("source")
+                if "tensor_pipe_active_pct" in rec:
+                    rf["tensor_pipe_active_pct_ncu"] = rec["tensor_pipe_active_pct"]
+            else:
+                rf.setdefault("traffic", None)
+        out = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": bench_config(w, n, L, world),
+            "config_detail": {"markers_per_gpu": Lg, "parallelism": f"markers/{world}",
+                              "l2": f"inputs larger than L2 ({(dec_bytes + 16.0 * n * n) / 1e9:.1f} GB streamed per step)",
+                              "note": "dtype f64 = the scan's results (a, var(a)); decode is u8, M.Mt is s8 x s8 -> s32 "
+                                      "(bit-exact); var(a) is contracted on int8 slices of the FP64 matrix (exact) or on FP64 DMMA"},
+            "stage_ms": stages, "mmt_int8_tops": syrk_tops, "decode_gbs": dec_gbs,
+            "scan_mode": f"int8 slices (tcgen05), {int(lib.eg_get_scan_digits())} digits per column" if mode == 1 else "fp64 (DMMA)", "scan_reference_equiv_fp64_tflops": scan_tf,
+            "roofline": roofline, "rooflines": rooflines, "cpu_baseline": None, "e2e": None, "clocks": clocks,
+            "allreduce": (None if world == 1 else {
+                "bytes": 4 * n * n, "ms": stages["allreduce"],
+                "algbw_gbs": 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
+                "busbw_gbs": 2.0 * (world - 1) / world * 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
+                "note": "NCCL int32 sum of the n x n partial M.Mt; measured reference on this pool: 725 GB/s bus bandwidth "
+                        "for an 8-rank all-reduce at 1 GiB (B200_PROFILING.md)"}),
+            "gpu_launches": launches, "library_ceilings": ceil, "forward_search": None, "checks": checks,
+            "extra_workloads": None,
+            "picked_marker": int(res[1]) if not hasattr(res[1], "item") else int(res[1].item()),
+        }
+    guard = TailGuard(rank, out, float(os.environ.get("EAGLE_BENCH_TAIL_S", "900")))
+
     # ---------------- end to end with host buffers (H2D of the image / S / V / a, D2H of K, a, vara)
     if args.no_e2e:
         e2e = {"value": None, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "skipped (--no-e2e)"}
@@ -398,23 +542,33 @@ def run_gpu(args):
         if world > 1 and rank != 0:   # the ranks' GPUs are driven by rank 0 alone in this leg; inputs are rebuilt after it
             img = S = V = ah = None
             torch.cuda.empty_cache()
+        guard.leg = "e2e"
         e2e = run_e2e(args, torch, dist, lib, device, egd, n, L, Lg, c0, world, rank, img, S, V, ah)
         if world > 1 and rank != 0:
             img = device.synth_ascii(n, Lg, GENO_SEED, col_offset=c0, n_total=n)
 
+    if out is not None:
+        out["e2e"] = e2e
+
     # BASELINE config 3 as it is worded: the full forward search, marker-sharded at N > 1 (collective calls: every rank)
     search = None
     if not args.no_search and args.workload in ("c2", "c3"):
+        guard.leg = "forward_search"
         try:
             search = run_forward_search(args, torch, dist, egd, n, L, Lg, c0, world, rank, img)
         except Exception as ex:  # noqa: BLE001
             search = {"note": f"failed: {type(ex).__name__}: {ex}"}
+    if out is not None:
+        out["forward_search"] = search
     extras = None
     if (world >= 8 or os.environ.get("EAGLE_BENCH_EXTRAS_SHRINK")) and world > 1 and args.workload == "c3" and not args.no_extras:
         del img, S, V, ah
         torch.cuda.empty_cache()
         extras = {}
+        if out is not None:
+            out["extra_workloads"] = extras
         for wl in ("c5", "c4"):
+            guard.leg = "extra_workloads." + wl
             try:
                 extras[wl] = run_extra_workload(args, wl, torch, dist, device, egd, lib, world, rank)
             except Exception as ex:  # noqa: BLE001
@@ -422,122 +576,20 @@ def run_gpu(args):
             torch.cuda.empty_cache()
 
     if rank != 0:
+        guard.finish()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    stages = dict(zip(STAGES, stage_ms))
-    k_ms, k_ops = k_ms.value, k_ops.value
-    # reference-equivalent FP64 work of the scan (full T = Mt*W, row-dot): 2n(n+1)+2n flops per marker
-    scan_ref_flops = (2.0 * n * (n + 1) + 2.0 * n) * Lg
-    syrk_ops = float(Lg) * n * (n + 1)                      # symmetric half, 2 ops per MAC
-    dec_bytes = float(n) * (Lg + 1) + float(n) * Lg
-    syrk_tops = syrk_ops / (stages["syrk"] * 1e-3) / 1e12
-    dec_gbs = dec_bytes / (stages["decode"] * 1e-3) / 1e9
-    dgemm = ceil.get("dgemm_tflops") or 37.0
-    int8_meas = ceil.get("int8_gemm_tops")
-    # int8 denominators.  MEASURED_PEAKS.json has no int8 entry: the peak of the line is the cuBLASLt int8 GEMM measured
-    # in THIS run -- its sustained figure (~1.5 s back to back), since these kernels are timed inside a long power-capped
-    # step -- with the burst figure, the 2 x bf16 proxies from MEASURED_PEAKS.json and the nominal 4500 beside it
-    proxy_sust, proxy_burst = 2.0 * peaks["bf16_tflops_sustained"], 2.0 * peaks["bf16_tflops"]
-    int8_peak = ceil.get("int8_gemm_tops_sustained") or proxy_sust
-    int8_burst = int8_meas or proxy_burst
-    int8_src = ("cuBLASLt int8 GEMM 8192^3 measured in this run, sustained over ~1.5 s (burst: %.0f); proxies 2 x measured bf16 "
-                "from MEASURED_PEAKS.json: %.0f sustained / %.0f burst; nominal 4500" % (int8_burst, proxy_sust, proxy_burst)
-                if ceil.get("int8_gemm_tops_sustained") else
-                "2 x measured sustained bf16 (no int8 entry in MEASURED_PEAKS.json, in-run int8 GEMM unavailable); 2 x burst bf16 = %.0f, "
-                "nominal 4500" % proxy_burst)
-
-    def int8_fracs(rate):
-        return {"frac": rate / int8_peak, "frac_of_burst_peak": rate / int8_burst,
-                "frac_of_2x_bf16_sustained": rate / proxy_sust, "frac_of_2x_bf16_burst": rate / proxy_burst, "frac_of_nominal_4500": rate / 4500.0}
-    k_rate = k_ops / (k_ms * 1e-3) / 1e12
-    if mode == 1:
-        roofline = {"kernel": "scan_i8_kernel", "bound": "tensor", "achieved": k_rate, "peak": int8_peak,
-                    "unit": "TOP/s (int8)", **int8_fracs(k_rate), "executed_ops": k_ops,
-                    "digits": int(lib.eg_get_scan_digits()), "algorithmic_ops": float(lib.eg_get_scan_digits()) * Lg * n * (n + 1),
-                    "traffic": None, "kernel_ms": k_ms,
-                    "ops_convention": "executed int8 ops: `digits` balanced-byte slices x symmetric-half contraction, 2 ops per MAC "
-                                      "(DESIGN.md section 4)",
-                    "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
-                    "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas,
-                    "cublaslt_int8_gemm_tops_sustained_this_run": ceil.get("int8_gemm_tops_sustained")}
-    else:
-        roofline = {"kernel": "scan_f64_kernel", "bound": "tensor", "achieved": k_rate, "peak": dgemm,
-                    "unit": "TFLOP/s (fp64)", "frac": k_rate / dgemm, "traffic": None, "kernel_ms": k_ms,
-                    "ops_convention": "executed FP64 flops of the symmetric-half contraction (DESIGN.md section 4)",
-                    "reference_equiv_fp64_tflops": scan_ref_flops / (k_ms * 1e-3) / 1e12,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 "
-                                   "entry); B200 FP64 nominal 37-40 TFLOP/s"}
-    rooflines = {
-        "decode_kb_kernel": {"bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": dec_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                             "timed_alone_gbs": dec_bytes / (decode_alone_ms * 1e-3) / 1e9,
-                             "timed_alone_frac": dec_bytes / (decode_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                             "note": "achieved/frac = inside the step (power-capped clocks inherited from the previous "
-                                     "step's scan); timed_alone = 5 back-to-back launches after an idle gap"},
-        "transpose_kb128_kernel": {"bound": "hbm", "achieved": 2.0 * n * Lg / (stages["transpose"] * 1e-3) / 1e9,
-                                   "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                   "frac": 2.0 * n * Lg / (stages["transpose"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                   "peak_source": peaks["source"]},
-        "syrk_i8_kernel": {"bound": "tensor", "achieved": syrk_tops, "unit": "TOP/s (int8, symmetric-half ops)",
-                           "full_product_equiv_tops": 2.0 * n * n * Lg / (stages["syrk"] * 1e-3) / 1e12,
-                           "peak": int8_peak, **int8_fracs(syrk_tops), "algorithmic_ops": syrk_ops,
-                           "peak_source": int8_src, "cublaslt_int8_gemm_tops_this_run": int8_meas},
-        roofline["kernel"]: roofline,
-    }
-    if p_ms.value > 0:
-        p_rate = p_ops.value / (p_ms.value * 1e-3) / 1e12
-        rooflines["prep_i8_kernel"] = {"bound": "tensor", "achieved": p_rate, "unit": "TOP/s (int8)", "peak": int8_peak,
-                                       **int8_fracs(p_rate), "executed_ops": p_ops.value,
-                                       "kernel_ms": p_ms.value, "peak_source": int8_src,
-                                       "ops_convention": "executed int8 ops of the 28 + 28 digit-slice products of "
-                                                         "X = V S and upper(W = S X); reference-equivalent FP64: 3 n^3 flops",
-                                       "reference_equiv_fp64_tflops": 3.0 * n ** 3 / (stages["prepare"] * 1e-3) / 1e12}
-    scan_tf = scan_ref_flops / (stages["scan"] * 1e-3) / 1e12
-    # DRAM traffic per launch from the committed `ncu --set full` capture of the same kernel at the same shape
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    except Exception:  # noqa: BLE001
-        tr = {}
-    for kname, rf in rooflines.items():
-        rec = tr.get(kname)
-        if rec and rec.get("workload") == args.workload and rec.get("n_gpus") == world:
-            rf["traffic"] = rec["dram_bytes_per_launch"]
-            rf["traffic_source"] = rec.get("source")
-            if "tensor_pipe_active_pct" in rec:
-                rf["tensor_pipe_active_pct_ncu"] = rec["tensor_pipe_active_pct"]
-        else:
-            rf.setdefault("traffic", None)
+    guard.leg = "cpu_baseline"
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
             cpu = cpu_reference_sample(n, L, steps=3, warmup=1)   # the same passes as --impl reference: warm-up, then the median
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
-    out = {
-        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": bench_config(w, n, L, world),
-        "config_detail": {"markers_per_gpu": Lg, "parallelism": f"markers/{world}",
-                          "l2": f"inputs larger than L2 ({(dec_bytes + 16.0 * n * n) / 1e9:.1f} GB streamed per step)",
-                          "note": "dtype f64 = the scan's results (a, var(a)); decode is u8, M.Mt is s8 x s8 -> s32 "
-                                  "(bit-exact); var(a) is contracted on int8 slices of the FP64 matrix (exact) or on FP64 DMMA"},
-        "stage_ms": stages, "mmt_int8_tops": syrk_tops, "decode_gbs": dec_gbs,
-        "scan_mode": f"int8 slices (tcgen05), {int(lib.eg_get_scan_digits())} digits per column" if mode == 1 else "fp64 (DMMA)", "scan_reference_equiv_fp64_tflops": scan_tf,
-        "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "allreduce": (None if world == 1 else {
-            "bytes": 4 * n * n, "ms": stages["allreduce"],
-            "algbw_gbs": 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
-            "busbw_gbs": 2.0 * (world - 1) / world * 4.0 * n * n / (stages["allreduce"] * 1e-3) / 1e9,
-            "note": "NCCL int32 sum of the n x n partial M.Mt; measured reference on this pool: 725 GB/s bus bandwidth "
-                    "for an 8-rank all-reduce at 1 GiB (B200_PROFILING.md)"}),
-        "gpu_launches": launches, "library_ceilings": ceil, "forward_search": search, "checks": checks,
-        "extra_workloads": extras,
-        "picked_marker": int(res[1]) if not hasattr(res[1], "item") else int(res[1].item()),
-    }
-    jprint(out)
+    out["cpu_baseline"] = cpu
+    guard.finish()
     if world > 1:
         dist.destroy_process_group()
 
