@@ -511,7 +511,8 @@ extern "C" int eg_dev_syrk_zero_cols(const int8_t* d_M, int64_t n, int64_t pitch
     int64_t* d_cols = nullptr;
     int8_t* d_G = nullptr;
     EG_CUDA(cudaMalloc(&d_cols, k * sizeof(int64_t)));
-    if (cudaMalloc(&d_G, (size_t)n * k) != cudaSuccess) {
+    if (malloc_retry((void**)&d_G, (size_t)n * k) != cudaSuccess) {
+        cudaGetLastError();
         cudaFree(d_cols);
         return set_error(EG_ERR_ALLOC, "eg_dev_syrk_zero_cols: out of device memory");
     }
