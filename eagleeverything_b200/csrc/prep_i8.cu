@@ -249,6 +249,197 @@ prep_i8_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------ the same product on CTA pairs (tcgen05 cta_group::2)
+// Output tile 256 x 256 over a cluster of two CTAs: each CTA stages its own 128 left rows and HALF of the 256 right rows
+// (32 KB per k-block and SM instead of 48 KB, six ring stages instead of four) -- the kernel above is bound by the bytes it
+// can keep in flight from L2, not by power (ncu: 52 % tensor pipe at 1.79 GHz, DRAM 19 %).  Roles as in scan_i8_pair_kernel:
+// both CTAs run a TMA producer whose loads complete on the LEADER's `full` barrier, the leader's thread issues the M = 256
+// MMAs and multicasts its commits to both CTAs, both CTAs' epilogue warps hand the accumulator back on the leader's barrier.
+constexpr int PP_STAGES = 6;
+constexpr int PP_B_BYTES = 128 * PI_BK;                       // this CTA's half of the right operand
+constexpr int PP_STAGE_BYTES = PI_A_BYTES + PP_B_BYTES;       // 32 KB
+constexpr int PP_SMEM_BYTES = PP_STAGES * PP_STAGE_BYTES + 1024 + 256;
+constexpr int PP_BM = 2 * PI_BM;                              // tile rows of the pair
+
+__global__ void __launch_bounds__(PI_THREADS, 1)
+prep_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constant__ CUtensorMap tmapR, const PrepParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PP_STAGES * PP_STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + PP_STAGES;
+    uint64_t* tmem_full = bars + 2 * PP_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int cid = (int)ptx::cluster_id_x();
+    const int ncl = (int)gridDim.x / 2;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmapL);
+        ptx::prefetch_tmap(&tmapR);
+        for (int s = 0; s < PP_STAGES; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&tmem_full[a], 1);
+            ptx::mbar_init(&tmem_empty[a], 8);   // 4 epilogue warps in each CTA
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc_pair<PI_TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // unit (group gi, chunk c) of this cluster: tile gi * ncl + cid, chunks in order
+    const int nun = p.ngroups * p.nchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int known = -1, r = 0;
+            auto need_of = [&](int gp) -> uint32_t {
+                const int left = p.ntiles - (gp / p.phases_per_tile) * ncl;
+                return (uint32_t)(left < ncl ? left : ncl);
+            };
+            for (int u = 0; u < nun; u++) {
+                const int gi = u / p.nchunks, c = u - gi * p.nchunks;
+                const int tile = gi * ncl + cid;
+                if (tile >= p.ntiles) break;
+                const int2 t = p.tiles[tile];
+                if (c == 0) r = 0;
+                for (int term = p.cbeg[c]; term < p.cbeg[c + 1]; term++) {
+                    const int sp = p.tp[term], sq = p.tq[term];
+                    for (int kb = 0; kb < p.KB; kb++, r++) {
+                        if (rank == 0 && p.phase_ctr && (r % p.phase_len) == 0) {
+                            const int gp = gi * p.phases_per_tile + r / p.phase_len;
+                            if (gp - p.lag > known) {
+                                uint32_t v[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) v[q] = q < p.lag ? pi_ld(p.phase_ctr + max(gp - 1 - q, 0)) : 0u;
+#pragma unroll
+                                for (int q = 7; q >= 0; q--)
+                                    if (q < p.lag && gp - 1 - q >= 0 && gp - 1 - q > known && v[q] >= need_of(gp - 1 - q)) known = gp - 1 - q;
+                                uint32_t spins = 0;
+                                while (gp - p.lag > known) {
+                                    if (pi_ld(p.phase_ctr + gp - p.lag) >= need_of(gp - p.lag)) known = gp - p.lag;
+                                    else if (++spins > (1u << 24)) {
+                                        printf("eagle: prep_i8 (pair) flow control timed out (cluster %d phase %d)\n", cid, gp);
+                                        __trap();
+                                    }
+                                }
+                            }
+                        }
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * PP_STAGE_BYTES;
+                        uint8_t* sB = sA + PI_A_BYTES;
+                        const uint32_t lead_full = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+                        if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * PP_STAGE_BYTES);
+                        ptx::tma_load_3d_pair(sA, &tmapL, kb * PI_BK, p.lrow0 + t.x * PP_BM + (int)rank * PI_BM, sp, lead_full);
+                        ptx::tma_load_3d_pair(sB, &tmapR, kb * PI_BK, p.rrow0 + t.y * PI_BN + (int)rank * 128, sq, lead_full);
+                        if (++stage == PP_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_i8(PP_BM, PI_BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            int r = 0;
+            const int rtot = (int)p.cbeg[p.nchunks] * p.KB;
+            for (int u = 0; u < nun; u++) {
+                const int gi = u / p.nchunks, c = u - gi * p.nchunks;
+                const int tile = gi * ncl + cid;
+                if (tile >= p.ntiles) break;
+                if (c == 0) r = 0;
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * PI_BN);
+                bool first = true;
+                for (int term = p.cbeg[c]; term < p.cbeg[c + 1]; term++) {
+                    for (int kb = 0; kb < p.KB; kb++, r++) {
+                        ptx::mbar_wait(&full[stage], phase);
+                        if (p.phase_ctr && ((r % p.phase_len) == p.phase_len - 1 || r == rtot - 1))
+                            pi_red_add(p.phase_ctr + (int64_t)gi * p.phases_per_tile + r / p.phase_len, 1u);
+                        ptx::tc_fence_after();
+                        const uint32_t a_addr = ptx::smem_u32(smem + stage * PP_STAGE_BYTES);
+                        const uint64_t a_desc = ptx::make_desc_k_sw128(a_addr);
+                        const uint64_t b_desc = ptx::make_desc_k_sw128(a_addr + PI_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < PI_BK / 32; k++) {
+                            ptx::umma_i8_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                            first = false;
+                        }
+                        ptx::umma_commit_pair(&empty[stage], 3);
+                        if (++stage == PP_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                ptx::umma_commit_pair(&tmem_full[acc], 3);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // epilogue: thread = one output row of this CTA's half of the tile; running FP64 sum kept in the output itself
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int u = 0; u < nun; u++) {
+            const int gi = u / p.nchunks, c = u - gi * p.nchunks;
+            const int tile = gi * ncl + cid;
+            if (tile >= p.ntiles) break;
+            const int2 t = p.tiles[tile];
+            const bool first = c == 0, last = c == p.nchunks - 1;
+            const double w = p.cw[c];
+            const int64_t row0 = (int64_t)t.x * PP_BM + (int64_t)rank * PI_BM + q * 32;
+            const int64_t row = row0 + lane;
+            const double srow = (last && row < p.M) ? p.sL[row] * 281474976710656.0 /* 256^6 */ : 0.0;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < PI_BN / 32; cc++) {
+                const int64_t col0 = (int64_t)t.y * PI_BN + cc * 32;
+                if (col0 >= p.N) continue;
+                if (p.upper_only && col0 + 31 + p.diag_shift < row0) continue;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * PI_BN + cc * 32), v);
+                ptx::tmem_ld_wait();
+                if (row < p.M) {
+                    double* o = p.out + row + col0 * p.ld;
+#pragma unroll 8
+                    for (int j = 0; j < 32; j++) {
+                        if (col0 + j < p.N) {
+                            double x = w * (double)(int)v[j];          // exact: |D| < 2^31, w a power of two
+                            if (!first) x += o[(int64_t)j * p.ld];     // one rounding per level
+                            if (last) x *= srow * __ldg(p.sR + col0 + j);
+                            o[(int64_t)j * p.ld] = x;
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // no CTA leaves while its peer can still signal it or read its shared memory
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_pair<PI_TMEM_COLS>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------ slicing of the columns of a column-major matrix
 // |x| bit patterns order like unsigned integers, and NaN > Inf > finite: a plain integer max finds the column's
 // largest magnitude and lets a NaN / Inf poison the column.
@@ -347,6 +538,12 @@ static int pi_make_map(CUtensorMap* m, const void* base, int64_t Kp, int64_t row
     return EG_OK;
 }
 
+// EAGLE_PREP_PAIR=1: the CTA-pair kernel (read at every call)
+static bool prep_i8_pair() {
+    const char* e = getenv("EAGLE_PREP_PAIR");
+    return e && e[0] == '1';
+}
+
 struct PrepWorkspace {
     int device = -1;
     int8_t* qS = nullptr;  size_t qS_cap = 0;
@@ -406,14 +603,17 @@ static int pi_product(const int8_t* qL, int64_t lrows, const double* sL, int64_t
                       int64_t rrows, const double* sR, int64_t rrow0, int64_t N, int64_t n, int64_t Kp, double* out,
                       int64_t ld, bool upper_only, int64_t diag_shift, cudaStream_t st) {
     // tiles ordered in compact blocks of 12 tile rows so that a wave of CTAs shares its operand rows through L2
-    const int TM = (int)((M + PI_BM - 1) / PI_BM), TN = (int)((N + PI_BN - 1) / PI_BN);
+    const bool pair = prep_i8_pair();
+    const int BMt = pair ? PP_BM : PI_BM;                                          // tile rows: 256 over a CTA pair
+    const int TM = (int)((M + BMt - 1) / BMt), TN = (int)((N + PI_BN - 1) / PI_BN);
     std::vector<int2> h;
     int srows = PI_SROWS;
     if (const char* e = getenv("EAGLE_PREP_SROWS")) srows = atoi(e) > 0 ? atoi(e) : srows;
+    if (pair) srows = (srows + 1) / 2;                                             // the same rows per super-row
     for (int sr = 0; sr < TM; sr += srows)
         for (int tj = 0; tj < TN; tj++)
             for (int ti = sr; ti < TM && ti < sr + srows; ti++) {
-                if (upper_only && (int64_t)(tj + 1) * PI_BN - 1 + diag_shift < (int64_t)ti * PI_BM) continue;
+                if (upper_only && (int64_t)(tj + 1) * PI_BN - 1 + diag_shift < (int64_t)ti * BMt) continue;
                 h.push_back(make_int2(ti, tj));
             }
     if (h.empty()) return EG_OK;
@@ -452,13 +652,16 @@ static int pi_product(const int8_t* qL, int64_t lrows, const double* sL, int64_t
     p.cbeg[nc] = (uint8_t)nt;
     p.nchunks = nc;
     const int sms = num_sms();
-    const int grid = p.ntiles < sms ? p.ntiles : sms;
-    p.ngroups = (p.ntiles + grid - 1) / grid;
+    const int workers_max = pair ? sms / 2 : sms;                                  // CTAs, or CTA pairs
+    const int workers = p.ntiles < workers_max ? p.ntiles : workers_max;
+    const int grid = pair ? 2 * workers : workers;
+    p.ngroups = (p.ntiles + workers - 1) / workers;
 
     CUtensorMap tL, tR;
     EG_TRY(pi_make_map(&tL, qL, Kp, lrows));
     EG_TRY(pi_make_map(&tR, qR, Kp, rrows));
-    EG_CUDA(cudaFuncSetAttribute(prep_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PI_SMEM_BYTES));
+    if (pair) EG_CUDA(cudaFuncSetAttribute(prep_i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
+    else EG_CUDA(cudaFuncSetAttribute(prep_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PI_SMEM_BYTES));
     p.phase_len = PI_PHASE;
     p.lag = PI_LAG;
     if (const char* e = getenv("EAGLE_PREP_PHASE")) p.phase_len = atoi(e) > 0 ? atoi(e) : p.phase_len;
@@ -466,7 +669,7 @@ static int pi_product(const int8_t* qL, int64_t lrows, const double* sL, int64_t
     p.phases_per_tile = (nt * p.KB + p.phase_len - 1) / p.phase_len;
     const size_t nctr = (size_t)p.ngroups * p.phases_per_tile;
     const char* env_fc = getenv("EAGLE_PREP_FLOWCTL");
-    const bool flow = !(env_fc && env_fc[0] == '0') && grid > 1;
+    const bool flow = !(env_fc && env_fc[0] == '0') && workers > 1;
     p.phase_ctr = nullptr;
     if (flow) {
         if (!pi_grow(&g_pi.phase, &g_pi.phase_cap, nctr)) return set_error(EG_ERR_ALLOC, "prep_i8: flow-control counters");
@@ -476,20 +679,25 @@ static int pi_product(const int8_t* qL, int64_t lrows, const double* sL, int64_t
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(PI_THREADS);
-    cfg.dynamicSmemBytes = PI_SMEM_BYTES;
+    cfg.dynamicSmemBytes = pair ? PP_SMEM_BYTES : PI_SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the soft barrier cannot deadlock
     attr[0].val.cooperative = flow ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pair ? 2 : 1;
     if (!g_pi_ev[0])
         for (int i = 0; i < 4; i++) cudaEventCreate(&g_pi_ev[i]);
     if (g_pi_marks <= 2) {
         cudaEventRecord(g_pi_ev[g_pi_marks], st);
-        g_pi_ops += (double)p.ntiles * nt * p.KB * 2.0 * PI_BM * PI_BN * PI_BK;  // executed int8 ops
+        g_pi_ops += (double)p.ntiles * nt * p.KB * 2.0 * BMt * PI_BN * PI_BK;  // executed int8 ops
     }
-    EG_CUDA(cudaLaunchKernelEx(&cfg, prep_i8_kernel, tL, tR, p));
+    if (pair) EG_CUDA(cudaLaunchKernelEx(&cfg, prep_i8_pair_kernel, tL, tR, p));
+    else EG_CUDA(cudaLaunchKernelEx(&cfg, prep_i8_kernel, tL, tR, p));
     if (g_pi_marks <= 2) {
         cudaEventRecord(g_pi_ev[g_pi_marks + 1], st);
         g_pi_marks += 2;

@@ -140,8 +140,9 @@ def test_preproducts_int8_slices_match_float64(dev, n, cuts, monkeypatch):
     Kpad = (n + 31) // 32 * 32
     tmp = torch.empty(n * n, dtype=torch.float64, device="cuda")
 
-    def run(mode):
+    def run(mode, pair="0"):
         monkeypatch.setenv("EAGLE_PREP_MODE", mode)
+        monkeypatch.setenv("EAGLE_PREP_PAIR", pair)
         Wp = torch.zeros(lib.eg_scan_wp_elems(n), dtype=torch.float64, device="cuda")
         for c0, c1 in zip(cuts[:-1], cuts[1:]):
             _lib.check(lib.eg_dev_scan_prepare_cols(C.c_void_p(Sd.data_ptr()), C.c_void_p(Vd.data_ptr()), n, c0, c1, 1,
@@ -150,6 +151,8 @@ def test_preproducts_int8_slices_match_float64(dev, n, cuts, monkeypatch):
         return Wp[: Kpad * n].view(n, Kpad).T[:n, :]     # column-major content -> W[i, j]
     Wi, Wi2, Wf = run("i8"), run("i8"), run("f64")
     assert torch.equal(torch.triu(Wi), torch.triu(Wi2))
+    # the CTA-pair kernel (256-row tiles over two SMs) forms the same integer sums and combines them in the same order
+    assert torch.equal(torch.triu(Wi), torch.triu(run("i8", pair="1")))
     X = Vd @ Sd
     ref = Sd @ X
     eps = np.finfo(np.float64).eps
