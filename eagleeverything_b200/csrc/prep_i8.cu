@@ -220,14 +220,20 @@ prep_i8_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constant_
                 if (p.upper_only && col0 + 31 + p.diag_shift < row0) continue;
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * PI_BN + cc * 32), v);
+                // the 32 running sums of this thread are fetched together, under the TMEM load: read one by one between
+                // the stores (which the compiler must assume to alias) they cost 256 serial L2 round trips per chunk
+                double* o = p.out + row + col0 * p.ld;
+                const bool live = row < p.M;
+                double run[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) run[j] = (live && !first && col0 + j < p.N) ? o[(int64_t)j * p.ld] : 0.0;
                 ptx::tmem_ld_wait();
-                if (row < p.M) {
-                    double* o = p.out + row + col0 * p.ld;
-#pragma unroll 8
+                if (live) {
+#pragma unroll
                     for (int j = 0; j < 32; j++) {
                         if (col0 + j < p.N) {
                             double x = w * (double)(int)v[j];          // exact: |D| < 2^31, w a power of two
-                            if (!first) x += o[(int64_t)j * p.ld];     // one rounding per level
+                            if (!first) x += run[j];                   // one rounding per level
                             if (last) x *= srow * __ldg(p.sR + col0 + j);
                             o[(int64_t)j * p.ld] = x;
                         }
@@ -411,14 +417,20 @@ prep_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_cons
                 if (p.upper_only && col0 + 31 + p.diag_shift < row0) continue;
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * PI_BN + cc * 32), v);
+                // the 32 running sums of this thread are fetched together, under the TMEM load: read one by one between
+                // the stores (which the compiler must assume to alias) they cost 256 serial L2 round trips per chunk
+                double* o = p.out + row + col0 * p.ld;
+                const bool live = row < p.M;
+                double run[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) run[j] = (live && !first && col0 + j < p.N) ? o[(int64_t)j * p.ld] : 0.0;
                 ptx::tmem_ld_wait();
-                if (row < p.M) {
-                    double* o = p.out + row + col0 * p.ld;
-#pragma unroll 8
+                if (live) {
+#pragma unroll
                     for (int j = 0; j < 32; j++) {
                         if (col0 + j < p.N) {
                             double x = w * (double)(int)v[j];          // exact: |D| < 2^31, w a power of two
-                            if (!first) x += o[(int64_t)j * p.ld];     // one rounding per level
+                            if (!first) x += run[j];                   // one rounding per level
                             if (last) x *= srow * __ldg(p.sR + col0 + j);
                             o[(int64_t)j * p.ld] = x;
                         }
