@@ -274,10 +274,20 @@ class TailGuard:
             if self.done:
                 return
             self.done = True
-            if self.out is not None:
-                self.out["tail_note"] = f"leg '{self.leg}' did not finish before the deadline; the line is printed without it"
-                jprint(self.out)
-        os._exit(0)
+            try:
+                if self.out is not None:
+                    self.out["tail_note"] = f"leg '{self.leg}' did not finish before the deadline; the line is printed without it"
+                    for _ in range(3):          # the main thread may be filling in a leg's dictionary right now
+                        try:
+                            line = json.dumps(self.out)
+                            break
+                        except RuntimeError:
+                            time.sleep(0.05)
+                    else:
+                        line = json.dumps({k: v for k, v in self.out.items() if k != "extra_workloads"})
+                    print(line, flush=True)
+            finally:
+                os._exit(0)
 
     def finish(self):
         with self.lock:
